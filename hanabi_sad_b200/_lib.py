@@ -1,0 +1,81 @@
+"""ctypes binding of libhanabi_b200.so (C ABI: include/hanabi_b200.h).
+
+There is no CPU implementation behind this module: if the CUDA library cannot be built/loaded, or no GPU is
+present when an engine is created, the call fails loudly."""
+import ctypes
+import os
+
+from . import build as _build
+
+c_int, c_void_p, c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_float
+c_i32, c_i64, c_u64, c_u32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint32
+
+
+class HbConfig(ctypes.Structure):
+    _fields_ = [
+        ("device", c_i32), ("num_games", c_i32), ("players", c_i32), ("hand_size", c_i32), ("bomb", c_i32),
+        ("max_len", c_i32), ("sad", c_i32), ("shuffle_color", c_i32), ("num_eps", c_i32),
+        ("eps_list", ctypes.POINTER(c_float)), ("seed", c_u64),
+        ("vdn", c_i32), ("multi_step", c_i32), ("gamma", c_float), ("eta", c_float), ("seq_len", c_i32),
+        ("replay_capacity", c_i32), ("alpha", c_float), ("beta", c_float), ("hid_dim", c_i32),
+        ("num_lstm_layer", c_i32), ("num_fc_layer", c_i32), ("skip_connect", c_i32), ("priority_mode", c_i32),
+        ("reserved", c_i32 * 7),
+    ]
+
+
+class HbGameInfo(ctypes.Structure):
+    _fields_ = [
+        ("cur_player", c_i32), ("score", c_i32), ("life", c_i32), ("info", c_i32), ("deck_size", c_i32),
+        ("num_step", c_i32), ("terminated", c_i32), ("last_score", c_i32), ("illegal", c_i32),
+        ("fireworks", c_i32 * 5), ("hand_len", c_i32 * 5), ("hand_card", (c_i32 * 5) * 5), ("eps_idx", c_i32 * 5),
+        ("perm", (c_i32 * 5) * 5), ("episode", c_u32),
+    ]
+
+
+# name -> (restype, argtypes); the list tests/test_abi.py checks against include/hanabi_b200.h
+SIGNATURES = {
+    "hb_last_error": (ctypes.c_char_p, []),
+    "hb_version": (c_int, []),
+    "hb_create": (c_int, [ctypes.POINTER(HbConfig), ctypes.POINTER(c_void_p)]),
+    "hb_destroy": (None, [c_void_p]),
+    "hb_feature_size": (c_int, [c_void_p]),
+    "hb_num_action": (c_int, [c_void_p]),
+    "hb_num_games": (c_int, [c_void_p]),
+    "hb_env_inject": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "hb_env_reset": (c_int, [c_void_p]),
+    "hb_env_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hb_env_observe": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hb_env_observe_dev": (c_int, [c_void_p] + [ctypes.POINTER(c_void_p)] * 6),
+    "hb_env_step_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hb_env_any_terminated": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "hb_env_query": (c_int, [c_void_p, c_int, ctypes.POINTER(HbGameInfo)]),
+    "hb_env_random_actions": (c_int, [c_void_p, c_u64]),
+    "hb_sync": (c_int, [c_void_p]),
+    "hb_stream": (c_void_p, [c_void_p]),
+    "hb_kernel_launches": (c_i64, [c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (building first if the sources are newer) libhanabi_b200.so; raises if that is impossible."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class HbError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise HbError("libhanabi_b200: %s (code %d)" % (lib().hb_last_error().decode(), rc))

@@ -1,0 +1,72 @@
+// hb_engine.h -- internal (C++) definition of hb_engine shared by the translation units of libhanabi_b200.so.
+// Not part of the ABI; the ABI is include/hanabi_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/hanabi_b200.h"
+#include "hb_env.cuh"
+
+#define HB_DECK_STRIDE 64  // bytes per game in the deck / injected-deck arrays (50 used)
+
+// Randomness of the next episode fixed from the host (hb_env_inject); consumed by one reset.
+struct HbInject {
+  uint8_t flag;
+  uint8_t eps_idx[HB_MAX_P];
+  uint16_t perm[HB_MAX_P], inv_perm[HB_MAX_P];
+  uint8_t deck[HB_DECK];
+  uint8_t pad[HB_DECK_STRIDE * 2 - 1 - HB_MAX_P - 4 * HB_MAX_P - HB_DECK];
+};
+static_assert(sizeof(HbInject) == 128, "HbInject must be 128 bytes");
+
+// Device pointers of the "current observation" in the reference's obs-dict layout (hanabi_env.cc:195-204).
+struct HbObsPtrs {
+  float* priv_s;     // [G,P,F]
+  float* legal_move; // [G,P,A]
+  float* own_hand;   // [G,P,3H]
+  float* eps;        // [G,P]
+};
+
+struct hb_engine {
+  hb_config cfg;
+  HbEnvCfg env;
+  int G, P, H, F, A, rows;
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  int64_t launches;
+
+  // ---- environment
+  HbGame* d_games;       // [G]
+  uint8_t* d_decks;      // [G][HB_DECK_STRIDE]
+  HbInject* d_inject;    // [G]
+  float* d_eps_list;     // [num_eps]
+  HbObsPtrs obs;
+  float* d_reward;       // [G]
+  uint8_t* d_terminal;   // [G]
+  int64_t* d_a;          // [G,P]
+  int64_t* d_greedy_a;   // [G,P]
+  int* d_flags;          // [4]: 0 any_terminated, 1 illegal count
+  int* h_flags;          // pinned mirror
+
+  // ---- policy / replay (hb_policy.cu, hb_replay.cu) -- opaque here
+  struct HbPolicy* policy;
+  struct HbReplay* replay;
+};
+
+void hb_set_error(const char* fmt, ...);
+
+#define HB_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (call);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      hb_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e));        \
+      return -2;                                                                                        \
+    }                                                                                                   \
+  } while (0)
+
+// hb_env_kernels.cu
+int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev);
+int hb_launch_random_actions(hb_engine* e, uint64_t counter);

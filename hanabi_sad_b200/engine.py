@@ -1,0 +1,105 @@
+"""Engine -- thin Python owner of one hb_engine (one GPU): numpy in / numpy out over the C ABI
+(include/hanabi_b200.h).  The reference-shaped classes in hanalearn.py / rela.py are built on it."""
+import ctypes
+
+import numpy as np
+
+from ._lib import HbConfig, HbGameInfo, check, lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    def __init__(self, num_games, players=2, hand_size=5, bomb=0, max_len=80, sad=True, shuffle_color=False,
+                 eps_list=(0.0,), seed=1, device=0, vdn=True, multi_step=3, gamma=0.999, eta=0.9, seq_len=80,
+                 replay_capacity=0, alpha=0.6, beta=0.4, hid_dim=512, num_lstm_layer=2, num_fc_layer=1,
+                 skip_connect=False, priority_mode=0):
+        L = lib()
+        self._eps = np.ascontiguousarray(eps_list, dtype=np.float32)
+        cfg = HbConfig()
+        cfg.device, cfg.num_games, cfg.players, cfg.hand_size = int(device), int(num_games), int(players), int(hand_size)
+        cfg.bomb, cfg.max_len, cfg.sad, cfg.shuffle_color = int(bomb), int(max_len), int(bool(sad)), int(bool(shuffle_color))
+        cfg.num_eps = len(self._eps)
+        cfg.eps_list = self._eps.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.vdn, cfg.multi_step, cfg.gamma, cfg.eta = int(bool(vdn)), int(multi_step), float(gamma), float(eta)
+        cfg.seq_len, cfg.replay_capacity, cfg.alpha, cfg.beta = int(seq_len), int(replay_capacity), float(alpha), float(beta)
+        cfg.hid_dim, cfg.num_lstm_layer, cfg.num_fc_layer = int(hid_dim), int(num_lstm_layer), int(num_fc_layer)
+        cfg.skip_connect, cfg.priority_mode = int(bool(skip_connect)), int(priority_mode)
+        self.cfg = cfg
+        h = ctypes.c_void_p()
+        check(L.hb_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        self.G, self.P, self.H = int(num_games), int(players), int(hand_size)
+        self.F = L.hb_feature_size(h)
+        self.A = L.hb_num_action(h)
+        self.rows = self.G * self.P
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ---- environment (VectorEnv semantics) ----------------------------------------------------------
+    def inject(self, game, deck50, eps_idx, perms=None):
+        deck = np.ascontiguousarray(deck50, dtype=np.int8)
+        ei = np.ascontiguousarray(eps_idx, dtype=np.int32)
+        pm = None if perms is None else np.ascontiguousarray(perms, dtype=np.int32)
+        assert deck.shape == (50,) and ei.shape[0] >= self.P
+        check(lib().hb_env_inject(self._h, int(game), _ptr(deck), _ptr(ei), _ptr(pm)))
+
+    def reset(self):
+        check(lib().hb_env_reset(self._h))
+
+    def step(self, a, greedy_a=None):
+        a = np.ascontiguousarray(a, dtype=np.int64).reshape(self.G, self.P)
+        ga = a if greedy_a is None else np.ascontiguousarray(greedy_a, dtype=np.int64).reshape(self.G, self.P)
+        reward = np.empty((self.G,), np.float32)
+        terminal = np.empty((self.G,), np.uint8)
+        check(lib().hb_env_step(self._h, _ptr(a), _ptr(ga), _ptr(reward), _ptr(terminal)))
+        return reward, terminal.astype(bool)
+
+    def observe(self):
+        priv_s = np.empty((self.G, self.P, self.F), np.float32)
+        legal = np.empty((self.G, self.P, self.A), np.float32)
+        own = np.empty((self.G, self.P, 3 * self.H), np.float32)
+        eps = np.empty((self.G, self.P), np.float32)
+        check(lib().hb_env_observe(self._h, _ptr(priv_s), _ptr(legal), _ptr(own), _ptr(eps)))
+        return {"priv_s": priv_s, "legal_move": legal, "own_hand": own, "eps": eps}
+
+    def step_dev(self):
+        check(lib().hb_env_step_dev(self._h, None, None))
+
+    def random_actions(self, counter):
+        check(lib().hb_env_random_actions(self._h, int(counter)))
+
+    def any_terminated(self):
+        out = ctypes.c_int()
+        check(lib().hb_env_any_terminated(self._h, ctypes.byref(out)))
+        return bool(out.value)
+
+    def query(self, game):
+        info = HbGameInfo()
+        check(lib().hb_env_query(self._h, int(game), ctypes.byref(info)))
+        return info
+
+    def sync(self):
+        check(lib().hb_sync(self._h))
+
+    def stream(self):
+        return lib().hb_stream(self._h)
+
+    def kernel_launches(self):
+        return int(lib().hb_kernel_launches(self._h))

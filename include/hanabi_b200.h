@@ -1,0 +1,126 @@
+/*
+ * hanabi_b200.h -- C ABI of libhanabi_b200.so, the B200 (sm_100a) Hanabi actor hot path.
+ *
+ * One hb_engine owns, on ONE GPU: `num_games` board states, the per-agent LSTM hidden state, the policy
+ * weights (online + target), the per-game episode under construction and the prioritized episode replay.
+ * It replaces, as one unit, what the reference spreads over
+ *     cpp/hanabi_env.{h,cc}  + hanabi-learning-environment/hanabi_lib/       (simulator + encoder)
+ *     rela/env.h VectorEnv, cpp/thread_loop.h HanabiThreadLoop                (tick loop)
+ *     rela/batcher.h, rela/batch_runner.h + TorchScript R2D2Agent.act         (policy forward)
+ *     rela/r2d2_actor.h, rela/transition_buffer.h                             (n-step, episode assembly, priority)
+ *     rela/prioritized_replay.h                                               (replay add / sample / update)
+ * (paths relative to the reference root).  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain C types only; every function returns 0 on success and a negative code on failure
+ * (hb_last_error() gives the message); no exceptions cross this boundary; the caller owns every buffer it
+ * passes, the engine owns all device memory.  "host" pointers are ordinary (ideally pinned) host memory,
+ * "dev" pointers are device memory on the engine's GPU.  All calls on one engine must come from one thread
+ * at a time (same rule as the reference's sample/update alternation, rela/prioritized_replay.h:209-212).
+ */
+#ifndef HANABI_B200_H_
+#define HANABI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_engine hb_engine;
+
+/* Everything the reference passes to HanabiEnv (cpp/hanabi_env.h:19-48), create_envs/create_threads
+ * (pyhanabi/create.py:24-76), R2D2Actor (rela/r2d2_actor.h:25-58), R2D2Agent (pyhanabi/r2d2.py:163-206) and
+ * RNNPrioritizedReplay (rela/prioritized_replay.h:176-190) for one act device. */
+typedef struct hb_config {
+  int32_t device;          /* CUDA ordinal */
+  int32_t num_games;       /* num_thread * num_game_per_thread on this device */
+  int32_t players;         /* 2..5 */
+  int32_t hand_size;       /* 2..5 (selfplay.py passes it explicitly, create.py:40) */
+  int32_t bomb;            /* 0 | 1 | -1  (hanabi_state.cc:362-376) */
+  int32_t max_len;         /* <=0: no forced termination; also the replay sequence length when > 0 */
+  int32_t sad;             /* append the greedy-action block (hanabi_env.cc:154-160) */
+  int32_t shuffle_color;   /* Other-Play colour permutation */
+  int32_t num_eps;         /* length of eps_list */
+  const float* eps_list;   /* host; copied */
+  uint64_t seed;           /* production RNG (Philox) seed; game g uses stream (seed, g) */
+  /* actor / replay (ignored until hb_policy_* / hb_rollout are used) */
+  int32_t vdn;             /* 1: one replay entry per game (players axis kept); 0: IQL, one per player */
+  int32_t multi_step;      /* n of the n-step return */
+  float gamma;
+  float eta;               /* priority = eta*max + (1-eta)*mean (r2d2_actor.h:10-21) */
+  int32_t seq_len;         /* episode slots T in the replay (reference: max_len = 80) */
+  int32_t replay_capacity; /* episodes; 0 = no replay (eval-style actors) */
+  float alpha, beta;       /* prioritized_replay.h:176-190 */
+  int32_t hid_dim;         /* 512 */
+  int32_t num_lstm_layer;  /* 2 */
+  int32_t num_fc_layer;    /* 1 (r2d2.py:42-46) */
+  int32_t skip_connect;    /* r2d2.py:74-75 */
+  int32_t priority_mode;   /* 0: reference semantics (online + target forward every tick); 1: uniform priority */
+  int32_t reserved[7];
+} hb_config;
+
+/* Snapshot of one game, for tests / eval (HanabiEnv getters, cpp/pybind.cc:23-38). */
+typedef struct hb_game_info {
+  int32_t cur_player;      /* -1 while a deal is pending (only visible at terminal states) */
+  int32_t score, life, info, deck_size, num_step, terminated, last_score, illegal;
+  int32_t fireworks[5];
+  int32_t hand_len[5];
+  int32_t hand_card[5][5]; /* colour*5+rank, -1 = empty */
+  int32_t eps_idx[5];
+  int32_t perm[5][5];      /* colour permutation per observer (identity unless shuffle_color) */
+  uint32_t episode;        /* episodes started on this seat */
+} hb_game_info;
+
+const char* hb_last_error(void);
+int hb_version(void);
+
+/* HanabiEnv ctor x num_games + HanabiVecEnv.append (cpp/pybind.cc:15-43, create.py:36-53,63-71). */
+int hb_create(const hb_config* cfg, hb_engine** out);
+void hb_destroy(hb_engine* e);
+
+int hb_feature_size(const hb_engine* e); /* HanabiEnv::featureSize, hanabi_env.h:52-59 */
+int hb_num_action(const hb_engine* e);   /* HanabiEnv::numAction,   hanabi_env.h:61-63 */
+int hb_num_games(const hb_engine* e);
+
+/* ---- environment, VectorEnv semantics (rela/env.h:48-104); host buffers ---------------------------- */
+
+/* Parity hook: fix the randomness of the NEXT episode of `game` (deck order, per-player eps index, per-player
+ * colour permutation real->shown [P][5], NULL = identity).  Replaces the mt19937 draws of HanabiEnv::reset
+ * (hanabi_env.cc:12-44) and ApplyRandomChance (hanabi_state.cc:285-289).  Without it Philox supplies them. */
+int hb_env_inject(hb_engine* e, int game, const int8_t* deck50, const int32_t* eps_idx, const int32_t* perms);
+
+/* VectorEnv::reset (env.h:48-60): start a new episode on every terminated game, then encode every game. */
+int hb_env_reset(hb_engine* e);
+
+/* VectorEnv::step (env.h:66-87) -> HanabiEnv::step (hanabi_env.cc:49-113).  a / greedy_a: host int64 [G,P]
+ * (only the entry of each game's current player is read); reward: host float [G]; terminal: host uint8 [G].
+ * An illegal action marks the game (hb_game_info.illegal) and returns -3 where the reference aborts. */
+int hb_env_step(hb_engine* e, const int64_t* a, const int64_t* greedy_a, float* reward, uint8_t* terminal);
+
+/* The obs dict of the last reset/step (hanabi_env.cc:195-204): host float priv_s [G,P,F], legal_move [G,P,A],
+ * own_hand [G,P,3H], eps [G,P].  Any pointer may be NULL. */
+int hb_env_observe(hb_engine* e, float* priv_s, float* legal_move, float* own_hand, float* eps);
+
+/* Same data without the host copy: device pointers valid until hb_destroy (layouts as above). */
+int hb_env_observe_dev(hb_engine* e, const float** priv_s, const float** legal_move, const float** own_hand,
+                       const float** eps, const float** reward, const uint8_t** terminal);
+
+/* Device-resident variant of hb_env_step: a / greedy_a are device int64 [G,P]; results stay on the device. */
+int hb_env_step_dev(hb_engine* e, const int64_t* a_dev, const int64_t* greedy_a_dev);
+
+/* VectorEnv::anyTerminated (env.h:89-96) and the getters of cpp/pybind.cc:23-38. */
+int hb_env_any_terminated(hb_engine* e, int* out);
+int hb_env_query(hb_engine* e, int game, hb_game_info* out);
+
+/* Uniform-random legal policy on the device (test / benchmark driver, the analogue of random_action in
+ * r2d2.py:273): fills the engine's own action buffers for the next hb_env_step_dev(e, NULL, NULL). */
+int hb_env_random_actions(hb_engine* e, uint64_t counter);
+
+int hb_sync(hb_engine* e); /* cudaStreamSynchronize on the engine stream */
+void* hb_stream(hb_engine* e); /* cudaStream_t the engine launches on (for CUDA-event timing) */
+int64_t hb_kernel_launches(const hb_engine* e); /* kernels launched by this engine so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANABI_B200_H_ */
