@@ -49,6 +49,10 @@ SIGNATURES = {
     "hb_env_step_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hb_env_any_terminated": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "hb_env_query": (c_int, [c_void_p, c_int, ctypes.POINTER(HbGameInfo)]),
+    "hb_env_get_deck": (c_int, [c_void_p, c_int, c_void_p]),
+    "hb_env_check_invariants": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "hb_env_get_actions": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hb_env_get_result": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hb_env_random_actions": (c_int, [c_void_p, c_u64]),
     "hb_sync": (c_int, [c_void_p]),
     "hb_stream": (c_void_p, [c_void_p]),

@@ -262,6 +262,45 @@ int hb_env_query(hb_engine* e, int game, hb_game_info* out) {
   return 0;
 }
 
+int hb_env_get_deck(hb_engine* e, int game, int8_t* deck50) {
+  if (!e || !deck50) return hb_fail(-1, "hb_env_get_deck: null argument");
+  if (game < 0 || game >= e->G) return hb_fail(-1, "hb_env_get_deck: game out of range");
+  HB_CUDA(cudaSetDevice(e->device));
+  HB_CUDA(cudaMemcpyAsync(deck50, e->d_decks + (size_t)game * HB_DECK_STRIDE, HB_DECK, cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int hb_env_check_invariants(hb_engine* e, int* num_bad) {
+  if (!e || !num_bad) return hb_fail(-1, "hb_env_check_invariants: null argument");
+  HB_CUDA(cudaSetDevice(e->device));
+  int rc = hb_launch_check_invariants(e);
+  if (rc) return rc;
+  HB_CUDA(cudaMemcpyAsync(e->h_flags + 2, e->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  *num_bad = e->h_flags[2];
+  return 0;
+}
+
+int hb_env_get_actions(hb_engine* e, int64_t* a, int64_t* greedy_a) {
+  if (!e) return hb_fail(-1, "hb_env_get_actions: null engine");
+  HB_CUDA(cudaSetDevice(e->device));
+  const size_t nb = (size_t)e->rows * sizeof(int64_t);
+  if (a) HB_CUDA(cudaMemcpyAsync(a, e->d_a, nb, cudaMemcpyDeviceToHost, e->stream));
+  if (greedy_a) HB_CUDA(cudaMemcpyAsync(greedy_a, e->d_greedy_a, nb, cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int hb_env_get_result(hb_engine* e, float* reward, uint8_t* terminal) {
+  if (!e) return hb_fail(-1, "hb_env_get_result: null engine");
+  HB_CUDA(cudaSetDevice(e->device));
+  if (reward) HB_CUDA(cudaMemcpyAsync(reward, e->d_reward, (size_t)e->G * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  if (terminal) HB_CUDA(cudaMemcpyAsync(terminal, e->d_terminal, (size_t)e->G, cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 int hb_env_random_actions(hb_engine* e, uint64_t counter) {
   if (!e) return hb_fail(-1, "hb_env_random_actions: null engine");
   HB_CUDA(cudaSetDevice(e->device));

@@ -70,3 +70,4 @@ void hb_set_error(const char* fmt, ...);
 // hb_env_kernels.cu
 int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev);
 int hb_launch_random_actions(hb_engine* e, uint64_t counter);
+int hb_launch_check_invariants(hb_engine* e);

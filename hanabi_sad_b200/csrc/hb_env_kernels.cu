@@ -71,6 +71,47 @@ __global__ void hb_k_random_actions(const float* __restrict__ legal, int rows, i
   greedy_a[r] = a2;
 }
 
+// Audit kernel: one thread per game (see hb_env_check_invariants in include/hanabi_b200.h).
+__global__ void hb_k_check_invariants(const HbGame* __restrict__ games, const uint8_t* __restrict__ decks, int G, HbGeom geo,
+                                      int* __restrict__ flags) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const HbGame& s = games[g];
+  if (s.episode == 0) return;  // never reset: nothing to audit
+  int cnt[HB_NCARD];
+  for (int i = 0; i < HB_NCARD; ++i) cnt[i] = s.discard_count[i];
+  bool bad = false;
+  for (int c = 0; c < HB_NC; ++c) {
+    bad |= s.fireworks[c] > HB_NR;
+    for (int r = 0; r < s.fireworks[c] && r < HB_NR; ++r) ++cnt[c * HB_NR + r];
+  }
+  for (int p = 0; p < geo.P; ++p) {
+    bad |= s.hand_len[p] > geo.H;
+    for (int i = 0; i < HB_MAX_H; ++i) {
+      const int card = s.hand_card[p][i];
+      if (i < s.hand_len[p]) { if (card < HB_NCARD) ++cnt[card]; else bad = true; }
+      else bad |= card != HB_NO_CARD;
+    }
+  }
+  bad |= s.deck_pos > HB_DECK;
+  for (int i = s.deck_pos; i < HB_DECK; ++i) {
+    const int card = decks[(size_t)g * HB_DECK_STRIDE + i];
+    if (card < HB_NCARD) ++cnt[card]; else bad = true;
+  }
+  for (int i = 0; i < HB_NCARD; ++i) bad |= cnt[i] != hb_card_mult(i % HB_NR);
+  bad |= s.info > HB_MAX_INFO || s.life > HB_MAX_LIFE || s.turns_to_play > geo.P || s.illegal != 0;
+  if (!s.terminated) bad |= s.cur_player >= geo.P || s.next_player >= geo.P;
+  if (bad) atomicAdd(&flags[2], 1);
+}
+
+int hb_launch_check_invariants(hb_engine* e) {
+  HB_CUDA(cudaMemsetAsync(e->d_flags + 2, 0, sizeof(int), e->stream));
+  hb_k_check_invariants<<<(e->G + 127) / 128, 128, 0, e->stream>>>(e->d_games, e->d_decks, e->G, e->env.g, e->d_flags);
+  HB_CUDA(cudaGetLastError());
+  e->launches += 1;
+  return 0;
+}
+
 int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev) {
   HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
   hb_k_env<<<e->G, HB_ENV_THREADS, 0, e->stream>>>(e->d_games, e->d_decks, e->d_inject, e->env, e->cfg.seed, do_reset, do_step,

@@ -1,0 +1,310 @@
+// hb_gemm.cuh -- the dense contraction of the R2D2 act forward (pyhanabi/r2d2.py:65-78: Linear+ReLU, 2-layer
+// LSTM cell) as ONE sm_100a kernel template: TMA-staged 128B-swizzled shared-memory tiles, tcgen05.mma with the
+// accumulator in TMEM, and the layer's pointwise tail (bias+ReLU, or the LSTM gate non-linearities and state
+// update) fused into the TMEM->register epilogue.
+//
+// Precision: the reference network is fp32 (contract: 1e-4 against CPU fp32 nn.LSTM).  Tensor
+// cores are fed a 2-term bf16 split of both operands, x = hi + lo with hi = bf16(x), lo = bf16(x - hi), and the
+// product is accumulated in fp32 as  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is < 2^-16 relative), i.e.
+// three tcgen05.mma per K-slice ("bf16x3").  Activations are produced already split by the previous layer's
+// epilogue; weights are split once when they are uploaded.
+//
+// Tile: BM=128 rows (agents) x BN=256 output columns, K streamed in 64-wide chunks.  For an LSTM layer the 256
+// columns of a tile are [gate i|f|g|o][64 hidden units] (weights are stored gate-interleaved per tile), so one
+// epilogue thread (= one TMEM lane = one agent row) holds all four gates of a hidden unit.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hbg {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 2;
+constexpr int A_TILE = BM * BK * 2;                  // 16 KB
+constexpr int B_TILE = BN * BK * 2;                  // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE; // hi+lo of both operands: 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TMEM_COLS = 256;
+constexpr int HID = 512;
+
+enum { EPI_F32 = 0, EPI_RELU = 1, EPI_LSTM = 2 };
+
+struct __align__(64) Params {
+  CUtensorMap a_hi[2], a_lo[2];  // A operand [rows][K] bf16, K contiguous; segment 0 then segment 1 along K
+  CUtensorMap b_hi, b_lo;        // B operand [N][K] bf16 (= nn.Linear / nn.LSTM weight layout), K contiguous
+  int k_chunks;                  // total K / 64
+  int k_chunks_seg0;             // chunks taken from a_*[0]; the rest come from a_*[1] (its own column 0 onward)
+  int lo_first, lo_last;         // K-chunk range [first,last) in which the A operand has a non-zero lo part
+  const float* bias;             // [N]
+  // EPI_F32: plain fp32 result (diagnostics / self-test)
+  float* c_f32;
+  int ldc;
+  // EPI_RELU / EPI_LSTM: result written as a bf16 hi/lo pair, [rows][out_ld], starting at column out_col0
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int out_ld;
+  int out_col0;
+  // EPI_LSTM: cell state in / out [rows][512] fp32 (c_out may be null: the target-network pass keeps no state),
+  // optional fp32 copy of h' [rows][512] (feeds the advantage head)
+  const float* c_in;
+  float* c_out;
+  float* h_f32;
+  int* error_flag;               // set to 1 if a barrier wait ran into the spin guard (never in a healthy run)
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU (the box is shared); it raises error_flag instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, bool& dead) {
+  if (dead) return;
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 21)) {
+      if (error_flag) atomicExch(error_flag, 1);
+      dead = true;  // stop waiting on anything else in this thread: finish fast, report through error_flag
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor: K-major operand tile of [rows][64] bf16, 128-byte swizzle (what TMA's
+// CU_TENSOR_MAP_SWIZZLE_128B writes): 8-row groups are 1024 bytes apart (SBO), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // leading byte offset: unused for swizzled K-major layouts
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
+  d |= (uint64_t)1 << 46;            // version
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::f16: D fp32, A and B bf16, both K-major, M=128, N=BN.
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+__device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi_ptr, __nv_bfloat16* lo_ptr) {
+  __align__(16) __nv_bfloat16 h[16], l[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split_bf16(v[i], h[i], l[i]);
+  reinterpret_cast<uint4*>(hi_ptr)[0] = reinterpret_cast<const uint4*>(h)[0];
+  reinterpret_cast<uint4*>(hi_ptr)[1] = reinterpret_cast<const uint4*>(h)[1];
+  reinterpret_cast<uint4*>(lo_ptr)[0] = reinterpret_cast<const uint4*>(l)[0];
+  reinterpret_cast<uint4*>(lo_ptr)[1] = reinterpret_cast<const uint4*>(l)[1];
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+// grid = (N / BN, rows_padded / BM).  One output tile per CTA.
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers: full[s] at +8s, empty[s] at +16+8s, tmem_full at +32, tmem base slot at +40
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * STAGES, bar_tmem = bar_base + 16 * STAGES;
+  const uint32_t tmem_slot = bar_tmem + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool dead = false;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_hi[0]); tma_prefetch_desc(&p.a_lo[0]); tma_prefetch_desc(&p.b_hi); tma_prefetch_desc(&p.b_lo);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, dead);  // slot free (first pass: passes immediately)
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        const bool need_lo = kc >= p.lo_first && kc < p.lo_last;
+        mbar_expect_tx(bar_full + 8 * s, (need_lo ? 2 : 1) * A_TILE + 2 * B_TILE);
+        const int seg = kc >= p.k_chunks_seg0 ? 1 : 0;
+        const int kx = (seg ? kc - p.k_chunks_seg0 : kc) * BK;
+        tma_load_2d(st, &p.a_hi[seg], bar_full + 8 * s, kx, m_tile * BM);
+        if (need_lo) tma_load_2d(st + A_TILE, &p.a_lo[seg], bar_full + 8 * s, kx, m_tile * BM);
+        tma_load_2d(st + 2 * A_TILE, &p.b_hi, bar_full + 8 * s, kc * BK, n_tile * BN);
+        tma_load_2d(st + 2 * A_TILE + B_TILE, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc();
+      uint32_t acc = 0;
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, ph, p.error_flag, dead);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        const bool need_lo = kc >= p.lo_first && kc < p.lo_last;
+        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
+        const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE), b_lo = make_desc_sw128(st + 2 * A_TILE + B_TILE);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance the start address inside the swizzle span
+          umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, acc);
+          acc = 1;
+          if (need_lo) umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+        }
+        umma_commit(bar_empty + 8 * s);  // the smem slot is free once these MMAs have read it
+      }
+      umma_commit(bar_tmem);             // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> pointwise tail -> global =====================
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const size_t row = (size_t)m_tile * BM + row_in_tile;
+    mbar_wait(bar_tmem, 0, p.error_flag, dead);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (EPI == EPI_F32) {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        float* dst = p.c_f32 + row * p.ldc + (size_t)n_tile * BN + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += p.bias ? __ldg(p.bias + n_tile * BN + c0 + i) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    } else if (EPI == EPI_RELU) {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        const int col = n_tile * BN + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + col + i), 0.f);
+        const size_t o = row * p.out_ld + p.out_col0 + col;
+        store_split16(v, p.out_hi + o, p.out_lo + o);
+      }
+    } else {
+      // tile columns: [gate i | f | g | o][64 hidden units]; hidden unit = n_tile*64 + u
+      for (int u0 = 0; u0 < 64; u0 += 16) {
+        float gi[16], gf[16], gg[16], go[16], c[16], h[16];
+        tmem_ld16(taddr + 0 * 64 + u0, gi);
+        tmem_ld16(taddr + 1 * 64 + u0, gf);
+        tmem_ld16(taddr + 2 * 64 + u0, gg);
+        tmem_ld16(taddr + 3 * 64 + u0, go);
+        const int unit = n_tile * 64 + u0;
+        const float* bias = p.bias + n_tile * BN + u0;
+        const float4* cin = reinterpret_cast<const float4*>(p.c_in + row * HID + unit);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 t = cin[i]; c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w; }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float ig = sigmoid_f(gi[i] + __ldg(bias + i));
+          const float fg = sigmoid_f(gf[i] + __ldg(bias + 64 + i));
+          const float g_ = tanh_f(gg[i] + __ldg(bias + 128 + i));
+          const float og = sigmoid_f(go[i] + __ldg(bias + 192 + i));
+          c[i] = fg * c[i] + ig * g_;
+          h[i] = og * tanh_f(c[i]);
+        }
+        if (p.c_out) {
+          float4* cout = reinterpret_cast<float4*>(p.c_out + row * HID + unit);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cout[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+        }
+        if (p.h_f32) {
+          float4* ho = reinterpret_cast<float4*>(p.h_f32 + row * HID + unit);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ho[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        }
+        const size_t o = row * p.out_ld + p.out_col0 + unit;
+        store_split16(h, p.out_hi + o, p.out_lo + o);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace hbg

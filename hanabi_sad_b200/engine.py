@@ -95,6 +95,29 @@ class Engine:
         check(lib().hb_env_query(self._h, int(game), ctypes.byref(info)))
         return info
 
+    def get_deck(self, game):
+        out = np.empty((50,), np.int8)
+        check(lib().hb_env_get_deck(self._h, int(game), _ptr(out)))
+        return out
+
+    def check_invariants(self):
+        out = ctypes.c_int()
+        check(lib().hb_env_check_invariants(self._h, ctypes.byref(out)))
+        return int(out.value)
+
+    def actions(self):
+        """The engine's own device action buffers (filled by random_actions / the policy): (a, greedy_a) [G,P]."""
+        a = np.empty((self.G, self.P), np.int64)
+        g = np.empty((self.G, self.P), np.int64)
+        check(lib().hb_env_get_actions(self._h, _ptr(a), _ptr(g)))
+        return a, g
+
+    def result(self):
+        r = np.empty((self.G,), np.float32)
+        t = np.empty((self.G,), np.uint8)
+        check(lib().hb_env_get_result(self._h, _ptr(r), _ptr(t)))
+        return r, t.astype(bool)
+
     def sync(self):
         check(lib().hb_sync(self._h))
 

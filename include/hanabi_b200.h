@@ -112,9 +112,24 @@ int hb_env_step_dev(hb_engine* e, const int64_t* a_dev, const int64_t* greedy_a_
 int hb_env_any_terminated(hb_engine* e, int* out);
 int hb_env_query(hb_engine* e, int game, hb_game_info* out);
 
+/* The 50-card deal order of `game`'s current episode (card id colour*5+rank), whether injected or drawn from the
+ * engine's Philox stream -- what ApplyRandomChance (hanabi_state.cc:285-289) would have produced one draw at a
+ * time.  Together with hb_env_query's eps_idx / perm it lets a test replay the same episode on the CPU oracle. */
+int hb_env_get_deck(hb_engine* e, int game, int8_t* deck50);
+
+/* Device-side audit of every board record: card conservation (hands + discards + fireworks + undealt = the 50-card
+ * multiset), token / hand-length / turn ranges.  *num_bad = number of games violating an invariant.  Plays the role
+ * of the reference's live asserts (hanabi_state.cc:225, hanabi_hand.cc:85-97) for the batched state. */
+int hb_env_check_invariants(hb_engine* e, int* num_bad);
+
 /* Uniform-random legal policy on the device (test / benchmark driver, the analogue of random_action in
  * r2d2.py:273): fills the engine's own action buffers for the next hb_env_step_dev(e, NULL, NULL). */
 int hb_env_random_actions(hb_engine* e, uint64_t counter);
+
+/* Host copies of the engine's device-resident action buffers (the reply of R2D2Actor::act, r2d2_actor.h:78-96:
+ * a / greedy_a int64 [G,P]) and of the last step's result (reward float [G], terminal uint8 [G]).  NULL skips. */
+int hb_env_get_actions(hb_engine* e, int64_t* a, int64_t* greedy_a);
+int hb_env_get_result(hb_engine* e, float* reward, uint8_t* terminal);
 
 int hb_sync(hb_engine* e); /* cudaStreamSynchronize on the engine stream */
 void* hb_stream(hb_engine* e); /* cudaStream_t the engine launches on (for CUDA-event timing) */

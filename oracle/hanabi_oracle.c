@@ -838,6 +838,25 @@ void orc_env_perms(const OrcEnv* e, int* out) {
 }
 uint64_t orc_env_rng_draws(const OrcEnv* e) { return e->rng.draws; }
 
+/* Full 50-card order of the CURRENT episode: the cards dealt so far followed by the cards the mt19937 stream
+ * would deal next.  The chance draws depend only on the remaining counts (hanabi_state.cc:316-328), never on the
+ * players' moves, so the order is fixed once the episode's reset has run; computed on a COPY of the rng.
+ * (In inject mode it is simply the injected deck.)  Lets a test replay the reference's own randomness on the GPU. */
+void orc_env_peek_deck(const OrcEnv* e, int8_t* out50) {
+  if (e->inject) { memcpy(out50, e->inj_deck, ORC_DECK); return; }
+  memcpy(out50, e->dealt, (size_t)e->n_dealt);
+  orc_mt19937 g = e->rng;
+  int cnt[ORC_NUM_CARDS], total = e->state.total_count, n = e->n_dealt;
+  for (int i = 0; i < ORC_NUM_CARDS; ++i) cnt[i] = e->state.card_count[i];
+  while (total > 0) {
+    int uids[ORC_NUM_CARDS]; double probs[ORC_NUM_CARDS]; int k = 0;
+    for (int uid = 0; uid < ORC_NUM_CARDS; ++uid)
+      if (cnt[uid] > 0) { uids[k] = uid; probs[k] = (double)cnt[uid] / (double)total; ++k; }
+    int idx = uids[discrete_draw(&g, probs, k)];
+    out50[n++] = (int8_t)idx; --cnt[idx]; --total;
+  }
+}
+
 /* ---------------------------------------------------------------- CPU baseline driver ("port" kind)
  * Runs `num_env` envs for `num_steps` steps each with a uniformly random legal policy (LCG), doing exactly
  * what one HanabiVecEnv thread does per tick minus the network: step + full observation encode + auto-reset.

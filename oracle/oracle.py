@@ -54,6 +54,7 @@ def lib():
         L.orc_env_eps_idx.argtypes = [vp, vp]
         L.orc_env_perms.argtypes = [vp, vp]
         L.orc_env_rng_draws.argtypes = [vp]
+        L.orc_env_peek_deck.argtypes = [vp, vp]
         L.orc_env_rng_draws.restype = ctypes.c_uint64
         L.orc_bench_random_rollout.restype = ctypes.c_long
         L.orc_bench_random_rollout.argtypes = [ci, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_double)]
@@ -155,6 +156,12 @@ class OracleEnv:
         out = np.zeros(50, np.int8)
         n = lib().orc_env_dealt(self._h, out.ctypes.data)
         return out[:n].copy()
+
+    def peek_deck(self):
+        """Full 50-card order of the current episode (dealt + what the rng stream will deal next)."""
+        out = np.zeros(50, np.int8)
+        lib().orc_env_peek_deck(self._h, out.ctypes.data)
+        return out
 
     def eps_idx(self):
         out = np.zeros(self.players, np.int32)
