@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- Hanabi env-steps/s at 4096 concurrent games (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libhanabi_b200.so)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the path
+
+A "step" is one tick of the actor loop (cpp/thread_loop.h:42-88) over every game of the rank: G env-steps.
+`value` = env-steps of all ranks / max-over-ranks device time.  See DESIGN.md "Measurement" for the byte / flop
+accounting behind `roofline`.  Only the cpu_baseline leg and --impl reference touch oracle/ (never timed as the
+product).  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hanabi_env_steps_per_s_4096_games"
+UNIT = "env-steps/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games PER GPU (weak scaling)")
+    ap.add_argument("--players", type=int, default=2)
+    ap.add_argument("--hand_size", type=int, default=5)
+    ap.add_argument("--sad", type=int, default=1)
+    ap.add_argument("--shuffle_color", type=int, default=0)
+    ap.add_argument("--mode", default="auto", choices=["auto", "rollout", "env"],
+                    help="rollout: fused env+policy+replay tick; env: env step/encode + random-legal policy only")
+    ap.add_argument("--precision", default="x3", choices=["x3", "x1"], help="rollout policy GEMM: bf16x3 split (fp32-class) or bf16")
+    ap.add_argument("--cpu_seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--ref_seconds", type=float, default=6.0, help="--impl reference: wall seconds per step sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def eps_list():
+    # utils.generate_explore_eps(0.1, 7, 80) (pyhanabi/utils.py:367-379)
+    return [0.1 ** (1 + i / 79.0 * 7) for i in range(80)]
+
+
+# ---------------------------------------------------------------------------------------------- CPU legs
+def cpu_port_sample(args, seconds, threads):
+    """The oracle's C restatement of HanabiVecEnv stepping (step + encode + auto-reset, random-legal policy),
+    `threads` host threads (ctypes releases the GIL), sized to ~`seconds` of wall time."""
+    from oracle import oracle as orc
+
+    orc.lib()
+    P, H = args.players, args.hand_size
+    t0 = time.perf_counter()
+    n, _ = orc.bench_random_rollout(P, H, args.sad, args.shuffle_color, 80, 8, 250, 1)
+    rate1 = n / (time.perf_counter() - t0)
+    per_thread_steps = max(2000, int(rate1 * seconds))
+    envs = max(1, min(args.games // max(threads, 1), 64))
+    steps_per_env = max(50, per_thread_steps // envs)
+    out = [0] * threads
+
+    def work(i):
+        k, _ = orc.bench_random_rollout(P, H, args.sad, args.shuffle_color, 80, envs, steps_per_env, 100 + i)
+        out[i] = k
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    total = sum(out)
+    return total / dt, dt, "oracle C port, env step+encode+auto-reset with a random-legal policy (no network): %d threads x %d envs x %d steps = %d env-steps in %.1f s" % (
+        threads, envs, steps_per_env, total, dt)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, dt, sample = cpu_port_sample(args, args.ref_seconds, cores)
+        if i >= args.warmup:
+            vals.append((v, dt))
+        if sum(d for _, d in vals) > 150:
+            break
+    value = sum(v * d for v, d in vals) / max(1e-9, sum(d for _, d in vals))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(d for _, d in vals) / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "games": args.games, "players": args.players, "hand_size": args.hand_size, "sad": args.sad},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(args):
+    return "C2: %d-player SAD=%d self-play, %d concurrent games/GPU, hid=512, seq_len=80" % (args.players, args.sad, args.games)
+
+
+# ---------------------------------------------------------------------------------------------- GPU path
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import hanabi_sad_b200 as hb
+
+    G, P, H = args.games, args.players, args.hand_size
+    mode = args.mode
+    if mode == "auto":
+        mode = "rollout" if hasattr(hb.Engine, "rollout") else "env"
+    eng = hb.Engine(G, P, H, 0, 80, bool(args.sad), bool(args.shuffle_color), eps_list(), seed=1 + 1000 * rank, device=local,
+                    replay_capacity=(16384 if mode == "rollout" else 0))
+    stream = torch.cuda.ExternalStream(eng.stream(), device=local)
+    F, A = eng.F, eng.A
+    peaks = load_peaks()
+    flush = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device="cuda")
+
+    if mode == "rollout":
+        runner = hb.bench_support.RolloutBench(eng, args)  # noqa: F821  (added with the fused rollout)
+    else:
+        runner = EnvBench(eng)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement: K steps, each bracketed by its own event pair, L2 flushed between steps
+    for i in range(args.warmup):
+        runner.step(i)
+    eng.sync()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = eng.kernel_launches()
+    evs = []
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            if runner.flush_between_steps:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            runner.step(args.warmup + i)
+            e1.record(stream)
+            evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.kernel_launches() - l0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    # ---- back-to-back (no flush), one event pair around all K steps
+    barrier()
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            runner.step(args.warmup + args.steps + i)
+        e1.record(stream)
+    barrier()
+    b2b_ms = e0.elapsed_time(e1)
+    # ---- e2e through the host-buffer C ABI
+    e2e_steps = max(5, min(args.steps, 200))
+    barrier()
+    t_e2e, h2d, d2h = runner.e2e(e2e_steps, stream)
+    barrier()
+    assert eng.check_invariants() == 0, "board-state audit failed after the timed region"
+
+    t = torch.tensor([total_ms, b2b_ms, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, b2b_ms, t_e2e = [float(x) for x in t.tolist()]
+    units = float(G) * world * args.steps
+    value = units / (total_ms * 1e-3)
+    dom = runner.dominant(step_ms, peaks)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": runner.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(args), "mode": mode, "games_per_gpu": G, "players": P, "hand_size": H, "sad": args.sad,
+                   "shuffle_color": args.shuffle_color, "feature_size": F, "num_action": A, "policy": runner.policy,
+                   "l2": runner.l2_note, "back_to_back_env_steps_per_s": units / (b2b_ms * 1e-3)},
+        "clocks": clocks,
+        "e2e": {"value": float(G) * world * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": runner.e2e_note},
+        "gpu_launches": int(launches),
+        "roofline": dom,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, sample = cpu_port_sample(args, args.cpu_seconds, os.cpu_count() or 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+class EnvBench:
+    """Environment-only tick: device random-legal policy -> VectorEnv::step -> VectorEnv::reset (3 launches)."""
+
+    flush_between_steps = True
+    dtype = "f32"
+    policy = "uniform-random legal (device Philox); no network"
+    l2_note = "L2 flushed (252 MB memset) between timed steps; each step timed with its own CUDA-event pair"
+    e2e_note = "hb_env_step with pinned host int64 actions [G,P] in, host reward/terminal + full obs dict (hb_env_observe) out, every step"
+
+    def __init__(self, eng):
+        self.eng = eng
+        eng.reset()
+
+    def step(self, i):
+        self.eng.random_actions(i)
+        self.eng.step_dev()
+        self.eng.reset()
+
+    def e2e(self, steps, stream):
+        import numpy as np
+        import torch
+
+        eng = self.eng
+        eng.reset()
+        obs = eng.observe()
+        a = torch.empty((eng.G, eng.P), dtype=torch.int64).pin_memory().numpy()
+        bufs = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory().numpy() for k, v in obs.items()}
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            # host policy: first legal move of every agent (vectorised; this leg measures the boundary, not the policy)
+            a[...] = obs["legal_move"].argmax(-1)
+            eng.step(a, a)      # H2D actions, step kernel, D2H reward/terminal (VectorEnv::step)
+            eng.reset()         # VectorEnv::reset: restart finished games
+            obs = eng.observe_into(bufs)  # D2H of the whole obs dict into pinned host buffers
+        dt = (time.perf_counter() - t0) * 1e3
+        h2d = 2 * a.nbytes
+        d2h = sum(v.nbytes for v in obs.values()) + eng.G * 5
+        return dt, h2d, d2h
+
+    def dominant(self, step_ms, peaks):
+        eng = self.eng
+        per_game = eng.P * (eng.F + eng.A + 3 * eng.H + 1) * 4 + 2 * (256 + 64) + eng.P * 16 + 5
+        bytes_per_launch = per_game * eng.G
+        # the step kernel is 1 of 3 launches per tick; its own duration is measured by profiles/ (ncu); here the tick time bounds it
+        ms = sum(step_ms) / len(step_ms)
+        ach = bytes_per_launch * 2 / (ms * 1e-3) / 1e9  # step + reset both run the encoder over every game
+        return {"bound": "hbm", "kernel": "hb_k_env (step+encode, reset+encode)", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_env_step": per_game}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

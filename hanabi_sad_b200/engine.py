@@ -79,6 +79,11 @@ class Engine:
         check(lib().hb_env_observe(self._h, _ptr(priv_s), _ptr(legal), _ptr(own), _ptr(eps)))
         return {"priv_s": priv_s, "legal_move": legal, "own_hand": own, "eps": eps}
 
+    def observe_into(self, bufs):
+        """observe() into caller-owned (ideally pinned) numpy buffers: dict with the four obs keys."""
+        check(lib().hb_env_observe(self._h, _ptr(bufs["priv_s"]), _ptr(bufs["legal_move"]), _ptr(bufs["own_hand"]), _ptr(bufs["eps"])))
+        return bufs
+
     def step_dev(self):
         check(lib().hb_env_step_dev(self._h, None, None))
 

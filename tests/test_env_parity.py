@@ -148,6 +148,7 @@ def test_batch_lockstep_with_auto_reset(hb, cfg):
         for g in range(G):
             if terminal[g]:
                 info = eng.query(g)
+                assert orcs[g].terminated()  # the reference captures last_score inside terminated() (hanabi_env.h:92-94)
                 assert info.terminated == 1 and info.last_score == orcs[g].last_score()
                 assert info.cur_player == orcs[g].get_current_player()
         if terminal.any():
