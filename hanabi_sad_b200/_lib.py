@@ -32,6 +32,13 @@ class HbGameInfo(ctypes.Structure):
     ]
 
 
+class HbWeights(ctypes.Structure):
+    _fields_ = [
+        ("fc_w", c_void_p), ("fc_b", c_void_p), ("w_ih", c_void_p * 2), ("w_hh", c_void_p * 2), ("b_ih", c_void_p * 2),
+        ("b_hh", c_void_p * 2), ("fc_a_w", c_void_p), ("fc_a_b", c_void_p), ("fc_v_w", c_void_p), ("fc_v_b", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); the list tests/test_abi.py checks against include/hanabi_b200.h
 SIGNATURES = {
     "hb_last_error": (ctypes.c_char_p, []),
@@ -54,6 +61,10 @@ SIGNATURES = {
     "hb_env_get_actions": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hb_env_get_result": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hb_env_random_actions": (c_int, [c_void_p, c_u64]),
+    "hb_policy_set_weights": (c_int, [c_void_p, c_int, ctypes.POINTER(HbWeights)]),
+    "hb_policy_act": (c_int, [c_void_p, c_int]),
+    "hb_policy_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hb_debug_gemm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     "hb_sync": (c_int, [c_void_p]),
     "hb_stream": (c_void_p, [c_void_p]),
     "hb_kernel_launches": (c_i64, [c_void_p]),

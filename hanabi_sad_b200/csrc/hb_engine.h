@@ -1,6 +1,7 @@
 // hb_engine.h -- internal (C++) definition of hb_engine shared by the translation units of libhanabi_b200.so.
 // Not part of the ABI; the ABI is include/hanabi_b200.h.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -27,6 +28,19 @@ struct HbObsPtrs {
   float* legal_move; // [G,P,A]
   float* own_hand;   // [G,P,3H]
   float* eps;        // [G,P]
+  // the same priv_s as the policy's first GEMM operand: bf16 hi / lo split, [rows_pad][KS] (null without a policy)
+  __nv_bfloat16* s_hi;
+  __nv_bfloat16* s_lo;
+  int KS;
+};
+
+// The CURRENT half of the policy's recurrent state, so that the kernel that restarts a game can zero its agents'
+// rows (R2D2Actor::postAct, rela/r2d2_actor.h:113-126).  All null without a policy.
+struct HbHidPtrs {
+  __nv_bfloat16* h_hi;  // [L][rows_pad][512]
+  __nv_bfloat16* h_lo;
+  float* c;             // [L][rows_pad][512]
+  int rows_pad;
 };
 
 struct hb_engine {
@@ -67,6 +81,7 @@ void hb_set_error(const char* fmt, ...);
     }                                                                                                   \
   } while (0)
 
+HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e);  // hb_policy.cu
 // hb_env_kernels.cu
 int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev);
 int hb_launch_random_actions(hb_engine* e, uint64_t counter);

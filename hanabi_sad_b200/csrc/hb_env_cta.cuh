@@ -99,17 +99,42 @@ __device__ __forceinline__ void hb_cta_build_totals(const HbGame& s, HbEncTables
 __device__ __forceinline__ void hb_cta_write_obs(const HbGame& s, const HbEncTables& t, const HbEnvCfg& cfg,
                                                  float* __restrict__ priv_s, float* __restrict__ legal,
                                                  float* __restrict__ own, float* __restrict__ eps,
-                                                 const float* __restrict__ eps_list) {
+                                                 const float* __restrict__ eps_list,
+                                                 __nv_bfloat16* __restrict__ s_hi = nullptr, __nv_bfloat16* __restrict__ s_lo = nullptr,
+                                                 int KS = 0) {
   const HbGeom& g = cfg.g;
   const int nt = blockDim.x, tid = threadIdx.x;
   const int PF = g.P * g.F;
   for (int i = tid; i < PF; i += nt) {
     const int o = i / g.F, f = i - o * g.F;
-    priv_s[i] = hb_feature(s, t, cfg, o, f);
+    const float v = hb_feature(s, t, cfg, o, f);
+    priv_s[i] = v;
+    if (s_hi != nullptr) {  // GEMM operand: everything outside the belief block is 0/1, i.e. exact in bf16 (lo stays 0)
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      s_hi[o * KS + f] = hi;
+      if (f >= g.off_belief && f < g.off_sad) s_lo[o * KS + f] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
   }
   const int PA = g.P * g.A;
   for (int i = tid; i < PA; i += nt) legal[i] = hb_legal_elem(s, cfg, i / g.A, i % g.A);
   const int PO = g.P * 3 * g.H;
   for (int i = tid; i < PO; i += nt) own[i] = hb_own_hand_elem(s, i / (3 * g.H), i % (3 * g.H));
   if (tid < g.P) eps[tid] = eps_list[s.eps_idx[tid]];
+}
+
+// Zero the recurrent state of one game's agents (rows g*P .. g*P+P-1, every layer) -- all threads of the CTA.
+__device__ __forceinline__ void hb_cta_zero_hidden(const HbHidPtrs& hp, int g, int P) {
+  if (hp.c == nullptr) return;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const int per_row_c = HB_HID * 4 / 16, per_row_h = HB_HID * 2 / 16;  // uint4 stores per row
+  for (int l = 0; l < HB_LAYERS; ++l) {
+    for (int p = 0; p < P; ++p) {
+      const size_t row = (size_t)l * hp.rows_pad + (size_t)g * P + p;
+      uint4* c4 = reinterpret_cast<uint4*>(hp.c + row * HB_HID);
+      uint4* hh = reinterpret_cast<uint4*>(hp.h_hi + row * HB_HID);
+      uint4* hl = reinterpret_cast<uint4*>(hp.h_lo + row * HB_HID);
+      for (int i = threadIdx.x; i < per_row_c; i += blockDim.x) c4[i] = z;
+      for (int i = threadIdx.x; i < per_row_h; i += blockDim.x) { hh[i] = z; hl[i] = z; }
+    }
+  }
 }

@@ -10,8 +10,9 @@ __global__ void __launch_bounds__(HB_ENV_THREADS)
 hb_k_env(HbGame* __restrict__ games, uint8_t* __restrict__ decks, HbInject* __restrict__ inject, HbEnvCfg cfg,
          uint64_t seed, int do_reset, int do_step, const int64_t* __restrict__ a, const int64_t* __restrict__ greedy_a,
          HbObsPtrs obs, const float* __restrict__ eps_list, float* __restrict__ reward, uint8_t* __restrict__ terminal,
-         int* __restrict__ flags) {
+         int* __restrict__ flags, HbHidPtrs hid) {
   __shared__ HbGame s;
+  __shared__ int did_reset;
   __shared__ HbEncTables tab;
   __shared__ __align__(16) uint8_t deck[HB_DECK_STRIDE];
   const int g = blockIdx.x, tid = threadIdx.x;
@@ -20,6 +21,7 @@ hb_k_env(HbGame* __restrict__ games, uint8_t* __restrict__ decks, HbInject* __re
   else if (tid < 20) reinterpret_cast<uint4*>(deck)[tid - 16] = reinterpret_cast<const uint4*>(decks + (size_t)g * HB_DECK_STRIDE)[tid - 16];
   __syncthreads();
   if (tid == 0) {
+    did_reset = 0;
     if (do_step) {
       if (!s.terminated) {
         const int cur = s.cur_player < geo.P ? s.cur_player : 0;
@@ -34,16 +36,18 @@ hb_k_env(HbGame* __restrict__ games, uint8_t* __restrict__ decks, HbInject* __re
         terminal[g] = 1;
       }
     }
-    if (do_reset && s.terminated) hb_begin_episode(s, deck, inject + g, cfg, seed, g);
+    if (do_reset && s.terminated) { hb_begin_episode(s, deck, inject + g, cfg, seed, g); did_reset = 1; }
     if (s.terminated) atomicOr(&flags[0], 1);
   }
   __syncthreads();
+  if (did_reset) hb_cta_zero_hidden(hid, g, geo.P);
   hb_cta_build_tables(s, tab, geo);
   __syncthreads();
   hb_cta_build_totals(s, tab, geo);
   __syncthreads();
   hb_cta_write_obs(s, tab, cfg, obs.priv_s + (size_t)g * geo.P * geo.F, obs.legal_move + (size_t)g * geo.P * geo.A,
-                   obs.own_hand + (size_t)g * geo.P * 3 * geo.H, obs.eps + (size_t)g * geo.P, eps_list);
+                   obs.own_hand + (size_t)g * geo.P * 3 * geo.H, obs.eps + (size_t)g * geo.P, eps_list,
+                   obs.s_hi ? obs.s_hi + (size_t)g * geo.P * obs.KS : nullptr, obs.s_lo ? obs.s_lo + (size_t)g * geo.P * obs.KS : nullptr, obs.KS);
   if (tid < 16) reinterpret_cast<uint4*>(games + g)[tid] = reinterpret_cast<const uint4*>(&s)[tid];
   else if (tid < 20) reinterpret_cast<uint4*>(decks + (size_t)g * HB_DECK_STRIDE)[tid - 16] = reinterpret_cast<const uint4*>(deck)[tid - 16];
 }
@@ -116,7 +120,7 @@ int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev,
   HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
   hb_k_env<<<e->G, HB_ENV_THREADS, 0, e->stream>>>(e->d_games, e->d_decks, e->d_inject, e->env, e->cfg.seed, do_reset, do_step,
                                                    a_dev, greedy_a_dev, e->obs, e->d_eps_list, e->d_reward, e->d_terminal,
-                                                   e->d_flags);
+                                                   e->d_flags, hb_policy_hidden_ptrs(e));
   HB_CUDA(cudaGetLastError());
   e->launches += 1;
   return 0;

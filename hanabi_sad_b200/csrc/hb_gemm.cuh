@@ -41,6 +41,7 @@ struct __align__(64) Params {
   int k_chunks;                  // total K / 64
   int k_chunks_seg0;             // chunks taken from a_*[0]; the rest come from a_*[1] (its own column 0 onward)
   int lo_first, lo_last;         // K-chunk range [first,last) in which the A operand has a non-zero lo part
+  int split;                     // 1: bf16x3 (hi*lo + lo*hi + hi*hi); 0: plain bf16 (hi*hi only, lo operands never loaded)
   const float* bias;             // [N]
   // EPI_F32: plain fp32 result (diagnostics / self-test)
   float* c_f32;
@@ -159,9 +160,12 @@ __device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi_
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-// grid = (N / BN, rows_padded / BM).  One output tile per CTA.
+// grid = (N / BN, rows_padded / BM, number of Params records).  One output tile per CTA; blockIdx.z picks the
+// problem (online / target network), so both networks' layer runs as one launch.  Params records live in global
+// memory (the tensor maps inside them are read by the TMA unit through their generic address).
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restrict__ ps) {
+  const Params& p = ps[blockIdx.z];
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -173,6 +177,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool dead = false;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int k_chunks = p.k_chunks, lo_first = p.lo_first, lo_last = p.lo_last;
+  const bool split = p.split != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_hi[0]); tma_prefetch_desc(&p.a_lo[0]); tma_prefetch_desc(&p.b_hi); tma_prefetch_desc(&p.b_lo);
@@ -193,19 +199,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
+      const int seg0 = p.k_chunks_seg0;
+      for (int kc = 0; kc < k_chunks; ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
         mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, dead);  // slot free (first pass: passes immediately)
         const uint32_t st = smem_base + s * STAGE_BYTES;
-        const bool need_lo = kc >= p.lo_first && kc < p.lo_last;
-        mbar_expect_tx(bar_full + 8 * s, (need_lo ? 2 : 1) * A_TILE + 2 * B_TILE);
-        const int seg = kc >= p.k_chunks_seg0 ? 1 : 0;
-        const int kx = (seg ? kc - p.k_chunks_seg0 : kc) * BK;
+        const bool need_lo = split && kc >= lo_first && kc < lo_last;
+        mbar_expect_tx(bar_full + 8 * s, (need_lo ? 2 : 1) * A_TILE + (split ? 2 : 1) * B_TILE);
+        const int seg = kc >= seg0 ? 1 : 0;
+        const int kx = (seg ? kc - seg0 : kc) * BK;
         tma_load_2d(st, &p.a_hi[seg], bar_full + 8 * s, kx, m_tile * BM);
         if (need_lo) tma_load_2d(st + A_TILE, &p.a_lo[seg], bar_full + 8 * s, kx, m_tile * BM);
         tma_load_2d(st + 2 * A_TILE, &p.b_hi, bar_full + 8 * s, kc * BK, n_tile * BN);
-        tma_load_2d(st + 2 * A_TILE + B_TILE, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN);
+        if (split) tma_load_2d(st + 2 * A_TILE + B_TILE, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN);
       }
     }
   } else if (warp == 1) {
@@ -213,22 +220,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc();
       uint32_t acc = 0;
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
+      for (int kc = 0; kc < k_chunks; ++kc) {
         const int s = kc % STAGES;
         const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
         mbar_wait(bar_full + 8 * s, ph, p.error_flag, dead);
         tc_fence_after();
         const uint32_t st = smem_base + s * STAGE_BYTES;
-        const bool need_lo = kc >= p.lo_first && kc < p.lo_last;
+        const bool need_lo = split && kc >= lo_first && kc < lo_last;
         const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
         const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE), b_lo = make_desc_sw128(st + 2 * A_TILE + B_TILE);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance the start address inside the swizzle span
-          umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, acc);
-          acc = 1;
+          if (split) { umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, acc); acc = 1; }  // small terms first
           if (need_lo) umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
-          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
+          acc = 1;
         }
         umma_commit(bar_empty + 8 * s);  // the smem slot is free once these MMAs have read it
       }
@@ -294,8 +301,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i) ho[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
         }
-        const size_t o = row * p.out_ld + p.out_col0 + unit;
-        store_split16(h, p.out_hi + o, p.out_lo + o);
+        if (p.out_hi) {
+          const size_t o = row * p.out_ld + p.out_col0 + unit;
+          store_split16(h, p.out_hi + o, p.out_lo + o);
+        }
       }
     }
     tc_fence_before();

@@ -1,6 +1,534 @@
-// hb_policy.cu -- R2D2 policy forward on the device (placeholder until the kernels land).
+// hb_policy.cu -- the R2D2 act forward on the device (pyhanabi/r2d2.py:65-78 R2D2Net.act, :234-303 greedy_act / act,
+// and the Q-values compute_priority needs, :305-361), for the online and the target network at once:
+//
+//   fc    : x  = ReLU(W0 s + b0)                     tcgen05 GEMM, epilogue bias+ReLU          (hb_gemm.cuh, EPI_RELU)
+//   lstm l: [x | h_l] [W_ih | W_hh]^T + b -> gates   tcgen05 GEMM, epilogue = LSTM cell update  (EPI_LSTM)
+//   head  : adv = W_a h + b_a, v = W_v h + b_v, masked argmax, eps-greedy, dueling Q            (hb_k_head_act, fp32 CUDA cores)
+//
+// State lives in two ping-pong halves (h as bf16 hi/lo pairs = the next tick's GEMM operand, c in fp32): a tick reads
+// half `parity` and writes half `parity^1`, so the target network (which is fed the ONLINE hidden state,
+// r2d2_actor.h:139-152) can run in the same launches as the online network without a hazard.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+#include <vector>
+
 #include "hb_engine.h"
-extern "C" {
-int hb_policy_create(hb_engine* e) { e->policy = nullptr; return 0; }
-void hb_policy_destroy(hb_engine* e) { (void)e; }
+#include "hb_env_cta.cuh"
+#include "hb_gemm.cuh"
+#include "hb_policy.h"
+
+using hbg::Params;
+
+// ---------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled hb_get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
 }
+
+// [rows][cols] bf16, cols contiguous; box = 64 columns (128 bytes, one swizzle span) x box_rows rows.
+static int hb_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_tmapEncodeTiled enc = hb_get_encode();
+  if (!enc) { hb_set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)hbg::BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { hb_set_error("cuTensorMapEncodeTiled failed with code %d", (int)r); return -2; }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- weight preparation
+// fp32 [n][k] (nn.Linear / nn.LSTM layout) -> bf16 hi/lo [n_out][k_out]; rows optionally re-ordered so that every
+// 256-row tile holds [gate i|f|g|o][64 hidden units] (hb_gemm.cuh EPI_LSTM), columns placed at col0, rest zero.
+__global__ void hb_k_prep_weight(const float* __restrict__ w, int n, int k, int lstm_order, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int ld_out, int col0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * k) return;
+  const int r = idx / k, c = idx - r * k;
+  int ro = r;
+  if (lstm_order) {  // r = gate*512 + unit  ->  tile (unit/64), inside the tile gate*64 + unit%64
+    const int gate = r / HB_HID, unit = r % HB_HID;
+    ro = (unit / 64) * 256 + gate * 64 + (unit % 64);
+  }
+  const float v = w[idx];
+  __nv_bfloat16 h, l;
+  hbg::split_bf16(v, h, l);
+  hi[(size_t)ro * ld_out + col0 + c] = h;
+  lo[(size_t)ro * ld_out + col0 + c] = l;
+}
+
+__global__ void hb_k_prep_lstm_bias(const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 4 * HB_HID) return;
+  const int gate = r / HB_HID, unit = r % HB_HID;
+  out[(unit / 64) * 256 + gate * 64 + (unit % 64)] = b_ih[r] + b_hh[r];
+}
+
+// ---------------------------------------------------------------------------------------- head + action selection
+struct HbHeadArgs {
+  int rows, A, have_target;
+  const float* htop[2];       // [rows_pad][512] top-layer h' of the online / target network
+  const float* wa[2];         // [A][512]
+  const float* ba[2];
+  const float* wv[2];         // [512]
+  const float* bv[2];
+  const float* legal;         // [rows][A]
+  const float* eps;           // [rows]
+  int64_t* a;                 // [rows]
+  int64_t* greedy_a;          // [rows]
+  float* adv;                 // [rows][A] online advantages
+  float* oq;                  // [rows] online dueling Q of the chosen action          (r2d2.py:344, :124-131)
+  float* tq;                  // [rows] target dueling Q of the online greedy action   (r2d2.py:345-348)
+  uint64_t seed;
+  uint32_t tick;
+  int greedy_only;            // eval actors: eps ignored
+};
+
+#define HB_HEAD_WARPS 8
+
+__global__ void __launch_bounds__(HB_HEAD_WARPS * 32) hb_k_head_act(HbHeadArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * HB_HEAD_WARPS + warp;
+  if (row >= p.rows) return;
+  const int A = p.A;
+  const unsigned FULL = 0xffffffffu;
+  // legal mask: lane holds outputs lane and lane+32
+  const float* lm = p.legal + (size_t)row * A;
+  const float l0 = lane < A ? lm[lane] : 0.f;
+  const float l1 = lane + 32 < A ? lm[lane + 32] : 0.f;
+
+  int greedy = A - 1;
+  int action = A - 1;
+  for (int net = 0; net < (p.have_target ? 2 : 1); ++net) {
+    const float4* h4 = reinterpret_cast<const float4*>(p.htop[net] + (size_t)row * HB_HID);
+    float4 h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = h4[j * 32 + lane];
+    float o0 = 0.f, o1 = 0.f, v = 0.f;
+    for (int o = 0; o <= A; ++o) {
+      const float4* w4 = reinterpret_cast<const float4*>(o < A ? p.wa[net] + (size_t)o * HB_HID : p.wv[net]);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = __ldg(w4 + j * 32 + lane);
+        acc = fmaf(h[j].x, w.x, acc); acc = fmaf(h[j].y, w.y, acc); acc = fmaf(h[j].z, w.z, acc); acc = fmaf(h[j].w, w.w, acc);
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(FULL, acc, s);
+      if (o < A) {
+        acc += __ldg(p.ba[net] + o);
+        if (o == lane) o0 = acc;
+        if (o == lane + 32) o1 = acc;
+      } else {
+        v = acc + __ldg(p.bv[net]);
+      }
+    }
+    // mean over ALL A entries of adv*legal (r2d2.py:129-130)
+    float s = o0 * l0 + o1 * l1;
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(FULL, s, k);
+    const float mean = s / (float)A;
+    if (net == 0) {
+
+      if (lane < A) p.adv[(size_t)row * A + lane] = o0;
+      if (lane + 32 < A) p.adv[(size_t)row * A + lane + 32] = o1;
+      // greedy = first index of the largest advantage among legal moves (r2d2.py:242-243)
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      if (l0 != 0.f) { best = o0; bi = lane; }
+      if (l1 != 0.f && (o1 > best || bi == 0x7fffffff)) { best = o1; bi = lane + 32; }
+#pragma unroll
+      for (int k = 16; k > 0; k >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, k);
+        const int oi = __shfl_xor_sync(FULL, bi, k);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+      }
+      greedy = bi == 0x7fffffff ? A - 1 : bi;
+      // eps-greedy: uniform over legal moves with probability eps (r2d2.py:273-277)
+      action = greedy;
+      if (!p.greedy_only) {
+        const unsigned m0 = __ballot_sync(FULL, l0 != 0.f), m1 = __ballot_sync(FULL, l1 != 0.f);
+        const int n_legal = __popc(m0) + __popc(m1);
+        HbRng rng(p.seed, (uint32_t)row, p.tick, HB_RNG_ACT);
+        const float u = rng.uniform();
+        int k = n_legal > 0 ? (int)rng.below((uint32_t)n_legal) : 0;
+        if (u < p.eps[row] && n_legal > 0) {
+          int ra;
+          if (k < __popc(m0)) { unsigned m = m0; for (int i = 0; i < k; ++i) m &= m - 1; ra = __ffs(m) - 1; }
+          else { k -= __popc(m0); unsigned m = m1; for (int i = 0; i < k; ++i) m &= m - 1; ra = 32 + __ffs(m) - 1; }
+          action = ra;
+        }
+      }
+      // Q_online(s, a) for the action actually taken
+      const float qa_src = action < 32 ? __shfl_sync(FULL, o0 * l0, action) : __shfl_sync(FULL, o1 * l1, action - 32);
+      if (lane == 0) {
+        p.a[row] = action;
+        p.greedy_a[row] = greedy;
+        p.oq[row] = v + qa_src - mean;
+      }
+    } else {
+      const float qa_src = greedy < 32 ? __shfl_sync(FULL, o0 * l0, greedy) : __shfl_sync(FULL, o1 * l1, greedy - 32);
+      if (lane == 0) p.tq[row] = v + qa_src - mean;
+    }
+  }
+
+}
+
+// ---------------------------------------------------------------------------------------- host side
+static int hb_alloc_zero(void** p, size_t bytes, cudaStream_t st) {
+  HB_CUDA(cudaMalloc(p, bytes));
+  HB_CUDA(cudaMemsetAsync(*p, 0, bytes, st));
+  return 0;
+}
+#define HB_ALLOC(ptr, bytes)                                                   \
+  do {                                                                         \
+    int _rc = hb_alloc_zero((void**)&(ptr), (bytes), e->stream);               \
+    if (_rc) return _rc;                                                       \
+  } while (0)
+
+static int hb_build_params(hb_engine* e) {
+  HbPolicy* P = e->policy;
+  const int rp = P->rows_pad, KS = P->KS;
+  std::vector<Params> hp(2 * 3 * 2);
+  memset(hp.data(), 0, hp.size() * sizeof(Params));
+  for (int par = 0; par < 2; ++par) {
+    const int cur = par, nxt = par ^ 1;
+    for (int net = 0; net < 2; ++net) {
+      const HbNetWeights& W = P->net[net];
+      const size_t lsz = (size_t)rp * HB_HID;  // one layer of one state half
+      int rc = 0;
+      // ---- fc
+      Params& f = hp[(par * 3 + 0) * 2 + net];
+      rc |= hb_make_tmap(&f.a_hi[0], P->s_hi, rp, KS, hbg::BM);
+      rc |= hb_make_tmap(&f.a_lo[0], P->s_lo, rp, KS, hbg::BM);
+      f.a_hi[1] = f.a_hi[0]; f.a_lo[1] = f.a_lo[0];
+      rc |= hb_make_tmap(&f.b_hi, W.w0_hi, HB_HID, KS, hbg::BN);
+      rc |= hb_make_tmap(&f.b_lo, W.w0_lo, HB_HID, KS, hbg::BN);
+      f.k_chunks = KS / hbg::BK; f.k_chunks_seg0 = f.k_chunks;
+      f.lo_first = e->env.g.off_belief / hbg::BK;
+      f.lo_last = (e->env.g.off_sad + hbg::BK - 1) / hbg::BK;
+      f.bias = W.b0;
+      f.out_hi = P->x_hi[net]; f.out_lo = P->x_lo[net]; f.out_ld = HB_HID; f.out_col0 = 0;
+      // ---- lstm layer 0
+      Params& l0 = hp[(par * 3 + 1) * 2 + net];
+      rc |= hb_make_tmap(&l0.a_hi[0], P->x_hi[net], rp, HB_HID, hbg::BM);
+      rc |= hb_make_tmap(&l0.a_lo[0], P->x_lo[net], rp, HB_HID, hbg::BM);
+      rc |= hb_make_tmap(&l0.a_hi[1], P->h_hi[cur], rp, HB_HID, hbg::BM);
+      rc |= hb_make_tmap(&l0.a_lo[1], P->h_lo[cur], rp, HB_HID, hbg::BM);
+      rc |= hb_make_tmap(&l0.b_hi, W.wl_hi[0], 4 * HB_HID, 2 * HB_HID, hbg::BN);
+      rc |= hb_make_tmap(&l0.b_lo, W.wl_lo[0], 4 * HB_HID, 2 * HB_HID, hbg::BN);
+      l0.k_chunks = 2 * HB_HID / hbg::BK; l0.k_chunks_seg0 = HB_HID / hbg::BK; l0.lo_first = 0; l0.lo_last = l0.k_chunks;
+      l0.bias = W.bl[0];
+      l0.c_in = P->c[cur];
+      if (net == 0) { l0.c_out = P->c[nxt]; l0.out_hi = P->h_hi[nxt]; l0.out_lo = P->h_lo[nxt]; }
+      else { l0.c_out = nullptr; l0.out_hi = P->th_hi; l0.out_lo = P->th_lo; }
+      l0.out_ld = HB_HID; l0.out_col0 = 0; l0.h_f32 = nullptr;
+      // ---- lstm layer 1
+      Params& l1 = hp[(par * 3 + 2) * 2 + net];
+      if (net == 0) {
+        rc |= hb_make_tmap(&l1.a_hi[0], P->h_hi[nxt], rp, HB_HID, hbg::BM);
+        rc |= hb_make_tmap(&l1.a_lo[0], P->h_lo[nxt], rp, HB_HID, hbg::BM);
+      } else {
+        rc |= hb_make_tmap(&l1.a_hi[0], P->th_hi, rp, HB_HID, hbg::BM);
+        rc |= hb_make_tmap(&l1.a_lo[0], P->th_lo, rp, HB_HID, hbg::BM);
+      }
+      rc |= hb_make_tmap(&l1.a_hi[1], P->h_hi[cur] + lsz, rp, HB_HID, hbg::BM);
+      rc |= hb_make_tmap(&l1.a_lo[1], P->h_lo[cur] + lsz, rp, HB_HID, hbg::BM);
+      rc |= hb_make_tmap(&l1.b_hi, W.wl_hi[1], 4 * HB_HID, 2 * HB_HID, hbg::BN);
+      rc |= hb_make_tmap(&l1.b_lo, W.wl_lo[1], 4 * HB_HID, 2 * HB_HID, hbg::BN);
+      l1.k_chunks = 2 * HB_HID / hbg::BK; l1.k_chunks_seg0 = HB_HID / hbg::BK; l1.lo_first = 0; l1.lo_last = l1.k_chunks;
+      l1.bias = W.bl[1];
+      l1.c_in = P->c[cur] + lsz;
+      if (net == 0) { l1.c_out = P->c[nxt] + lsz; l1.out_hi = P->h_hi[nxt] + lsz; l1.out_lo = P->h_lo[nxt] + lsz; }
+      else { l1.c_out = nullptr; l1.out_hi = nullptr; l1.out_lo = nullptr; }
+      l1.out_ld = HB_HID; l1.out_col0 = 0; l1.h_f32 = P->htop[net];
+      if (rc) return -2;
+      for (Params* q : {&f, &l0, &l1}) {
+        q->split = (net == 0 || P->target_split) ? 1 : 0;
+        q->error_flag = P->d_error;
+      }
+    }
+  }
+  HB_CUDA(cudaMemcpyAsync(P->d_params, hp.data(), hp.size() * sizeof(Params), cudaMemcpyHostToDevice, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" {
+
+int hb_policy_create(hb_engine* e) {
+  e->policy = nullptr;
+  const hb_config& c = e->cfg;
+  if (c.hid_dim == 0) return 0;  // environment-only engine
+  if (c.hid_dim != HB_HID || c.num_lstm_layer != HB_LAYERS || c.num_fc_layer != 1 || c.skip_connect != 0) {
+    hb_set_error("hb_create: the device policy serves hid_dim=512, num_lstm_layer=2, num_fc_layer=1, skip_connect=0 (got %d, %d, %d, %d)",
+                 c.hid_dim, c.num_lstm_layer, c.num_fc_layer, c.skip_connect);
+    return -1;
+  }
+  if (e->A > 63) { hb_set_error("hb_create: num_action > 63 is not supported by the head kernel"); return -1; }
+  HbPolicy* P = new HbPolicy();
+  memset(P, 0, sizeof(*P));
+  e->policy = P;
+  P->rows = e->rows;
+  P->rows_pad = (e->rows + hbg::BM - 1) / hbg::BM * hbg::BM;
+  P->KS = (e->F + hbg::BK - 1) / hbg::BK * hbg::BK;
+  P->target_split = c.priority_mode == 2 ? 0 : 1;
+  const size_t rp = P->rows_pad, KS = P->KS, bf = sizeof(__nv_bfloat16);
+  HB_ALLOC(P->s_hi, rp * KS * bf);
+  HB_ALLOC(P->s_lo, rp * KS * bf);
+  for (int n = 0; n < 2; ++n) {
+    HB_ALLOC(P->x_hi[n], rp * HB_HID * bf);
+    HB_ALLOC(P->x_lo[n], rp * HB_HID * bf);
+    HB_ALLOC(P->htop[n], rp * HB_HID * sizeof(float));
+    HB_ALLOC(P->h_hi[n], HB_LAYERS * rp * HB_HID * bf);
+    HB_ALLOC(P->h_lo[n], HB_LAYERS * rp * HB_HID * bf);
+    HB_ALLOC(P->c[n], HB_LAYERS * rp * HB_HID * sizeof(float));
+    HbNetWeights& W = P->net[n];
+    HB_ALLOC(W.w0_hi, (size_t)HB_HID * KS * bf);
+    HB_ALLOC(W.w0_lo, (size_t)HB_HID * KS * bf);
+    HB_ALLOC(W.b0, HB_HID * sizeof(float));
+    for (int l = 0; l < HB_LAYERS; ++l) {
+      HB_ALLOC(W.wl_hi[l], (size_t)4 * HB_HID * 2 * HB_HID * bf);
+      HB_ALLOC(W.wl_lo[l], (size_t)4 * HB_HID * 2 * HB_HID * bf);
+      HB_ALLOC(W.bl[l], 4 * HB_HID * sizeof(float));
+    }
+    HB_ALLOC(W.wa, (size_t)e->A * HB_HID * sizeof(float));
+    HB_ALLOC(W.ba, e->A * sizeof(float));
+    HB_ALLOC(W.wv, HB_HID * sizeof(float));
+    HB_ALLOC(W.bv, sizeof(float));
+    size_t raw = (size_t)HB_HID * e->F;
+    if (raw < (size_t)4 * HB_HID * HB_HID) raw = (size_t)4 * HB_HID * HB_HID;
+    HB_ALLOC(W.raw, raw * sizeof(float));
+    HB_ALLOC(W.raw2, (size_t)4 * HB_HID * sizeof(float) * 2);
+  }
+  HB_ALLOC(P->th_hi, rp * HB_HID * bf);
+  HB_ALLOC(P->th_lo, rp * HB_HID * bf);
+  HB_ALLOC(P->adv, (size_t)e->rows * e->A * sizeof(float));
+  HB_ALLOC(P->oq, e->rows * sizeof(float));
+  HB_ALLOC(P->tq, e->rows * sizeof(float));
+  HB_ALLOC(P->d_error, sizeof(int));
+  HB_ALLOC(P->d_params, 12 * sizeof(Params));
+  e->obs.s_hi = P->s_hi; e->obs.s_lo = P->s_lo; e->obs.KS = P->KS;
+  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
+  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
+  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
+  return hb_build_params(e);
+}
+
+void hb_policy_destroy(hb_engine* e) {
+  HbPolicy* P = e->policy;
+  if (!P) return;
+  cudaFree(P->s_hi); cudaFree(P->s_lo); cudaFree(P->th_hi); cudaFree(P->th_lo);
+  for (int n = 0; n < 2; ++n) {
+    cudaFree(P->x_hi[n]); cudaFree(P->x_lo[n]); cudaFree(P->htop[n]); cudaFree(P->h_hi[n]); cudaFree(P->h_lo[n]); cudaFree(P->c[n]);
+    HbNetWeights& W = P->net[n];
+    cudaFree(W.w0_hi); cudaFree(W.w0_lo); cudaFree(W.b0);
+    for (int l = 0; l < HB_LAYERS; ++l) { cudaFree(W.wl_hi[l]); cudaFree(W.wl_lo[l]); cudaFree(W.bl[l]); }
+    cudaFree(W.wa); cudaFree(W.ba); cudaFree(W.wv); cudaFree(W.bv); cudaFree(W.raw); cudaFree(W.raw2);
+  }
+  cudaFree(P->adv); cudaFree(P->oq); cudaFree(P->tq); cudaFree(P->d_error); cudaFree(P->d_params);
+  delete P;
+  e->policy = nullptr;
+}
+
+// R2D2Agent state_dict -> device operands (BatchRunner::updateModel, rela/batch_runner.h:74-77, without the
+// TorchScript module: the tensors may live on the host or on any device -- cudaMemcpyDefault).
+int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w) {
+  if (!e || !w) { hb_set_error("hb_policy_set_weights: null argument"); return -1; }
+  HbPolicy* P = e->policy;
+  if (!P) { hb_set_error("hb_policy_set_weights: this engine was created without a policy (hid_dim = 0)"); return -1; }
+  if (net < 0 || net > 1) { hb_set_error("hb_policy_set_weights: net must be 0 (online) or 1 (target)"); return -1; }
+  const void* need[] = {w->fc_w, w->fc_b, w->w_ih[0], w->w_hh[0], w->b_ih[0], w->b_hh[0], w->w_ih[1], w->w_hh[1], w->b_ih[1], w->b_hh[1],
+                        w->fc_a_w, w->fc_a_b, w->fc_v_w, w->fc_v_b};
+  for (const void* p : need)
+    if (!p) { hb_set_error("hb_policy_set_weights: a weight pointer is null"); return -1; }
+  HB_CUDA(cudaSetDevice(e->device));
+  HbNetWeights& W = P->net[net];
+  cudaStream_t st = e->stream;
+  const int F = e->F, A = e->A, KS = P->KS;
+  auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+  HB_CUDA(cudaMemcpyAsync(W.raw, w->fc_w, (size_t)HB_HID * F * sizeof(float), cudaMemcpyDefault, st));
+  hb_k_prep_weight<<<blocks((size_t)HB_HID * F), 256, 0, st>>>(W.raw, HB_HID, F, 0, W.w0_hi, W.w0_lo, KS, 0);
+  HB_CUDA(cudaMemcpyAsync(W.b0, w->fc_b, HB_HID * sizeof(float), cudaMemcpyDefault, st));
+  for (int l = 0; l < HB_LAYERS; ++l) {
+    const size_t n = (size_t)4 * HB_HID * HB_HID;
+    HB_CUDA(cudaMemcpyAsync(W.raw, w->w_ih[l], n * sizeof(float), cudaMemcpyDefault, st));
+    hb_k_prep_weight<<<blocks(n), 256, 0, st>>>(W.raw, 4 * HB_HID, HB_HID, 1, W.wl_hi[l], W.wl_lo[l], 2 * HB_HID, 0);
+    HB_CUDA(cudaMemcpyAsync(W.raw, w->w_hh[l], n * sizeof(float), cudaMemcpyDefault, st));
+    hb_k_prep_weight<<<blocks(n), 256, 0, st>>>(W.raw, 4 * HB_HID, HB_HID, 1, W.wl_hi[l], W.wl_lo[l], 2 * HB_HID, HB_HID);
+    HB_CUDA(cudaMemcpyAsync(W.raw2, w->b_ih[l], 4 * HB_HID * sizeof(float), cudaMemcpyDefault, st));
+    HB_CUDA(cudaMemcpyAsync(W.raw2 + 4 * HB_HID, w->b_hh[l], 4 * HB_HID * sizeof(float), cudaMemcpyDefault, st));
+    hb_k_prep_lstm_bias<<<blocks(4 * HB_HID), 256, 0, st>>>(W.raw2, W.raw2 + 4 * HB_HID, W.bl[l]);
+    e->launches += 3;
+  }
+  e->launches += 1;
+  HB_CUDA(cudaMemcpyAsync(W.wa, w->fc_a_w, (size_t)A * HB_HID * sizeof(float), cudaMemcpyDefault, st));
+  HB_CUDA(cudaMemcpyAsync(W.ba, w->fc_a_b, A * sizeof(float), cudaMemcpyDefault, st));
+  HB_CUDA(cudaMemcpyAsync(W.wv, w->fc_v_w, HB_HID * sizeof(float), cudaMemcpyDefault, st));
+  HB_CUDA(cudaMemcpyAsync(W.bv, w->fc_v_b, sizeof(float), cudaMemcpyDefault, st));
+  HB_CUDA(cudaGetLastError());
+  HB_CUDA(cudaStreamSynchronize(st));  // the caller may free / overwrite its tensors once this returns
+  P->have_weights[net] = 1;
+  return 0;
+}
+
+}  // extern "C"
+
+HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e) {
+  HbHidPtrs h = {nullptr, nullptr, nullptr, 0};
+  if (e->policy) { HbPolicy* P = e->policy; h.h_hi = P->h_hi[P->parity]; h.h_lo = P->h_lo[P->parity]; h.c = P->c[P->parity]; h.rows_pad = P->rows_pad; }
+  return h;
+}
+
+// One act forward over the CURRENT observation operands (s_hi / s_lo, legal_move, eps) and state half `parity`:
+// 3 GEMM launches (both networks each) + the head kernel.  Leaves the new state in half parity^1 and flips parity.
+int hb_policy_forward(hb_engine* e, int greedy_only) {
+  HbPolicy* P = e->policy;
+  if (!P || !P->have_weights[0]) { hb_set_error("policy forward without online weights (call hb_policy_set_weights first)"); return -1; }
+  const int nets = P->have_weights[1] && e->cfg.priority_mode != 1 ? 2 : 1;
+  const int mt = P->rows_pad / hbg::BM;
+  const Params* base = P->d_params + (size_t)P->parity * 6;
+  hbg::gemm3_kernel<hbg::EPI_RELU><<<dim3(HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 0);
+  hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 2);
+  hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 4);
+  HbHeadArgs a;
+  a.rows = e->rows; a.A = e->A; a.have_target = nets == 2;
+  for (int n = 0; n < 2; ++n) {
+    a.htop[n] = P->htop[n]; a.wa[n] = P->net[n].wa; a.ba[n] = P->net[n].ba; a.wv[n] = P->net[n].wv; a.bv[n] = P->net[n].bv;
+  }
+  a.legal = e->obs.legal_move; a.eps = e->obs.eps; a.a = e->d_a; a.greedy_a = e->d_greedy_a;
+  a.adv = P->adv; a.oq = P->oq; a.tq = P->tq; a.seed = e->cfg.seed; a.tick = (uint32_t)P->act_count; a.greedy_only = greedy_only;
+  hb_k_head_act<<<(e->rows + HB_HEAD_WARPS - 1) / HB_HEAD_WARPS, HB_HEAD_WARPS * 32, 0, e->stream>>>(a);
+  HB_CUDA(cudaGetLastError());
+  e->launches += 4;
+  P->parity ^= 1;
+  P->act_count += 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- diagnostics
+__global__ void hb_k_split_rows(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ hi,
+                                __nv_bfloat16* __restrict__ lo, int ld) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * cols) return;
+  const int r = (int)(idx / cols), c = (int)(idx % cols);
+  __nv_bfloat16 h, l;
+  hbg::split_bf16(src[idx], h, l);
+  hi[(size_t)r * ld + c] = h;
+  lo[(size_t)r * ld + c] = l;
+}
+
+__global__ void hb_k_merge_hidden(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int rows, int rows_pad,
+                                  float* __restrict__ out) {  // [L][rows_pad][512] hi/lo -> [L][rows][512] fp32
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)HB_LAYERS * rows * HB_HID) return;
+  const int l = (int)(idx / ((size_t)rows * HB_HID));
+  const size_t rem = idx % ((size_t)rows * HB_HID);
+  const size_t src = (size_t)l * rows_pad * HB_HID + rem;
+  out[idx] = __bfloat162float(hi[src]) + __bfloat162float(lo[src]);
+}
+
+extern "C" {
+
+// Stand-alone run of the tcgen05 GEMM template: C[M,N] = A[M,K] B[N,K]^T + bias (host fp32 in/out), `split` = bf16x3.
+int hb_debug_gemm(int device, const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int split) {
+  if (!A || !B || !C) { hb_set_error("hb_debug_gemm: null argument"); return -1; }
+  if (M % hbg::BM || N % hbg::BN || K % hbg::BK) { hb_set_error("hb_debug_gemm: M, N, K must be multiples of 128, 256, 64"); return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { hb_set_error("hb_debug_gemm: no CUDA device"); return -2; }
+  HB_CUDA(cudaSetDevice(device));
+  float *dA, *dB, *dC, *dbias;
+  __nv_bfloat16 *ah, *al, *bh, *bl;
+  Params* dp;
+  int* derr;
+  const size_t bf = sizeof(__nv_bfloat16);
+  HB_CUDA(cudaMalloc(&dA, (size_t)M * K * 4)); HB_CUDA(cudaMalloc(&dB, (size_t)N * K * 4)); HB_CUDA(cudaMalloc(&dC, (size_t)M * N * 4));
+  HB_CUDA(cudaMalloc(&dbias, (size_t)N * 4));
+  HB_CUDA(cudaMalloc(&ah, (size_t)M * K * bf)); HB_CUDA(cudaMalloc(&al, (size_t)M * K * bf));
+  HB_CUDA(cudaMalloc(&bh, (size_t)N * K * bf)); HB_CUDA(cudaMalloc(&bl, (size_t)N * K * bf));
+  HB_CUDA(cudaMalloc(&dp, sizeof(Params))); HB_CUDA(cudaMalloc(&derr, sizeof(int)));
+  HB_CUDA(cudaMemset(derr, 0, sizeof(int)));
+  HB_CUDA(cudaMemcpy(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(dB, B, (size_t)N * K * 4, cudaMemcpyHostToDevice));
+  if (bias) HB_CUDA(cudaMemcpy(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+  else HB_CUDA(cudaMemset(dbias, 0, (size_t)N * 4));
+  hb_k_split_rows<<<(unsigned)(((size_t)M * K + 255) / 256), 256>>>(dA, M, K, ah, al, K);
+  hb_k_split_rows<<<(unsigned)(((size_t)N * K + 255) / 256), 256>>>(dB, N, K, bh, bl, K);
+  Params hp;
+  memset(&hp, 0, sizeof(hp));
+  int rc = 0;
+  rc |= hb_make_tmap(&hp.a_hi[0], ah, M, K, hbg::BM); rc |= hb_make_tmap(&hp.a_lo[0], al, M, K, hbg::BM);
+  hp.a_hi[1] = hp.a_hi[0]; hp.a_lo[1] = hp.a_lo[0];
+  rc |= hb_make_tmap(&hp.b_hi, bh, N, K, hbg::BN); rc |= hb_make_tmap(&hp.b_lo, bl, N, K, hbg::BN);
+  if (rc) return rc;
+  hp.k_chunks = K / hbg::BK; hp.k_chunks_seg0 = hp.k_chunks; hp.lo_first = 0; hp.lo_last = hp.k_chunks; hp.split = split;
+  hp.bias = dbias; hp.c_f32 = dC; hp.ldc = N; hp.error_flag = derr;
+  HB_CUDA(cudaMemcpy(dp, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
+  hbg::gemm3_kernel<hbg::EPI_F32><<<dim3(N / hbg::BN, M / hbg::BM, 1), hbg::THREADS, hbg::SMEM_BYTES>>>(dp);
+  HB_CUDA(cudaGetLastError());
+  HB_CUDA(cudaDeviceSynchronize());
+  int herr = 0;
+  HB_CUDA(cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dbias); cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl); cudaFree(dp); cudaFree(derr);
+  if (herr) { hb_set_error("hb_debug_gemm: a pipeline barrier timed out (spin guard)"); return -4; }
+  return 0;
+}
+
+// R2D2Actor::act without the environment (r2d2_actor.h:61-100): one policy forward on the engine's current
+// observation; the reply (a, greedy_a) lands in the engine's action buffers, the hidden state advances.
+int hb_policy_act(hb_engine* e, int greedy_only) {
+  if (!e) { hb_set_error("hb_policy_act: null engine"); return -1; }
+  HB_CUDA(cudaSetDevice(e->device));
+  return hb_policy_forward(e, greedy_only);
+}
+
+// Host copies of the policy's outputs of the last forward: adv [rows,A] (online advantages), online_q / target_q
+// [rows] (dueling Q of the taken action / of the greedy action under the target net), and the CURRENT hidden state
+// h, c as [L, rows, 512] fp32 (R2D2Actor::hidden_, r2d2_actor.h:186).  NULL skips.
+int hb_policy_get(hb_engine* e, float* adv, float* online_q, float* target_q, float* h, float* c) {
+  if (!e || !e->policy) { hb_set_error("hb_policy_get: no policy"); return -1; }
+  HbPolicy* P = e->policy;
+  HB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  const size_t R = e->rows;
+  if (adv) HB_CUDA(cudaMemcpyAsync(adv, P->adv, R * e->A * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (online_q) HB_CUDA(cudaMemcpyAsync(online_q, P->oq, R * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (target_q) HB_CUDA(cudaMemcpyAsync(target_q, P->tq, R * sizeof(float), cudaMemcpyDeviceToHost, st));
+  const int cur = P->parity;
+  if (h) {
+    float* tmp;
+    HB_CUDA(cudaMalloc(&tmp, HB_LAYERS * R * HB_HID * sizeof(float)));
+    hb_k_merge_hidden<<<(unsigned)((HB_LAYERS * R * HB_HID + 255) / 256), 256, 0, st>>>(P->h_hi[cur], P->h_lo[cur], (int)R, P->rows_pad, tmp);
+    HB_CUDA(cudaMemcpyAsync(h, tmp, HB_LAYERS * R * HB_HID * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    e->launches += 1;
+  }
+  if (c) {
+    for (int l = 0; l < HB_LAYERS; ++l)
+      HB_CUDA(cudaMemcpyAsync(c + (size_t)l * R * HB_HID, P->c[cur] + (size_t)l * P->rows_pad * HB_HID, R * HB_HID * sizeof(float),
+                              cudaMemcpyDeviceToHost, st));
+  }
+  HB_CUDA(cudaStreamSynchronize(st));
+  int herr = 0;
+  HB_CUDA(cudaMemcpy(&herr, P->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr) { hb_set_error("policy GEMM: a pipeline barrier timed out (spin guard)"); return -4; }
+  return 0;
+}
+
+}  // extern "C"

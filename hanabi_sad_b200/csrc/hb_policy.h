@@ -1,0 +1,38 @@
+// hb_policy.h -- device-side policy state shared by hb_policy.cu (forward), hb_env_kernels.cu / hb_rollout.cu (the
+// encoder writes the GEMM operand directly, the tick zeroes the hidden state of finished games).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "hb_types.h"
+
+namespace hbg { struct Params; }
+
+struct HbNetWeights {                   // one network (online or target) in GEMM operand form
+  __nv_bfloat16 *w0_hi, *w0_lo;         // [512][KS]        net.0.weight, K zero-padded to a multiple of 64
+  float* b0;                            // [512]
+  __nv_bfloat16 *wl_hi[HB_LAYERS], *wl_lo[HB_LAYERS];  // [2048][1024] = [W_ih | W_hh], rows in gate-interleaved tile order
+  float* bl[HB_LAYERS];                 // [2048]           b_ih + b_hh in the same row order
+  float *wa, *ba, *wv, *bv;             // fc_a [A][512], [A]; fc_v [512], [1]  (fp32, CUDA-core head)
+  float *raw, *raw2;                    // upload staging
+};
+
+struct HbPolicy {
+  int rows, rows_pad, KS;
+  int parity;                           // state half holding the CURRENT hidden state
+  int target_split;                     // 1: the target network also runs bf16x3
+  int have_weights[2];
+  int64_t act_count;                    // forwards so far (Philox counter of the eps-greedy draw)
+  HbNetWeights net[2];
+  __nv_bfloat16 *s_hi, *s_lo;           // [rows_pad][KS]   priv_s as the fc GEMM operand (written by the encoder)
+  __nv_bfloat16 *x_hi[2], *x_lo[2];     // [rows_pad][512]  per network
+  __nv_bfloat16 *h_hi[2], *h_lo[2];     // ping-pong halves: [L][rows_pad][512]
+  float* c[2];                          // ping-pong halves: [L][rows_pad][512]
+  __nv_bfloat16 *th_hi, *th_lo;         // target network layer-0 output
+  float* htop[2];                       // [rows_pad][512]  top-layer h' per network, fp32
+  float *adv, *oq, *tq;                 // [rows][A], [rows], [rows]
+  hbg::Params* d_params;                // [2 parity][3 layers][2 nets]
+  int* d_error;
+};
+
+int hb_policy_forward(struct hb_engine* e, int greedy_only);

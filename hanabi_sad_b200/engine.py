@@ -4,7 +4,7 @@ import ctypes
 
 import numpy as np
 
-from ._lib import HbConfig, HbGameInfo, check, lib
+from ._lib import HbConfig, HbGameInfo, HbWeights, check, lib
 
 
 def _ptr(a):
@@ -122,6 +122,50 @@ class Engine:
         t = np.empty((self.G,), np.uint8)
         check(lib().hb_env_get_result(self._h, _ptr(r), _ptr(t)))
         return r, t.astype(bool)
+
+    # ---- policy ---------------------------------------------------------------------------------------
+    WEIGHT_KEYS = ("net.0.weight", "net.0.bias", "lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
+                   "lstm.weight_ih_l1", "lstm.weight_hh_l1", "lstm.bias_ih_l1", "lstm.bias_hh_l1", "fc_a.weight", "fc_a.bias",
+                   "fc_v.weight", "fc_v.bias")
+
+    def set_weights(self, net, state_dict):
+        """`state_dict` = R2D2Net.state_dict() (torch tensors on any device, or numpy arrays); net 0 online, 1 target."""
+        keep, ptr = [], {}
+        for k in self.WEIGHT_KEYS:
+            v = state_dict[k]
+            if hasattr(v, "data_ptr"):
+                v = v.detach().float().contiguous()
+                ptr[k] = v.data_ptr()
+            else:
+                v = np.ascontiguousarray(v, dtype=np.float32)
+                ptr[k] = v.ctypes.data
+            keep.append(v)
+        shapes = {"net.0.weight": (512, self.F), "lstm.weight_ih_l0": (2048, 512), "lstm.weight_hh_l1": (2048, 512), "fc_a.weight": (self.A, 512),
+                  "fc_v.weight": (1, 512)}
+        for k, shp in shapes.items():
+            assert tuple(state_dict[k].shape) == shp, "%s has shape %s, the engine needs %s" % (k, tuple(state_dict[k].shape), shp)
+        w = HbWeights()
+        w.fc_w, w.fc_b = ptr["net.0.weight"], ptr["net.0.bias"]
+        for l in range(2):
+            w.w_ih[l], w.w_hh[l] = ptr["lstm.weight_ih_l%d" % l], ptr["lstm.weight_hh_l%d" % l]
+            w.b_ih[l], w.b_hh[l] = ptr["lstm.bias_ih_l%d" % l], ptr["lstm.bias_hh_l%d" % l]
+        w.fc_a_w, w.fc_a_b, w.fc_v_w, w.fc_v_b = ptr["fc_a.weight"], ptr["fc_a.bias"], ptr["fc_v.weight"], ptr["fc_v.bias"]
+        check(lib().hb_policy_set_weights(self._h, int(net), ctypes.byref(w)))
+        del keep
+
+    def policy_act(self, greedy_only=False):
+        check(lib().hb_policy_act(self._h, int(bool(greedy_only))))
+
+    def policy_get(self, hidden=False):
+        out = {"adv": np.empty((self.G, self.P, self.A), np.float32), "online_q": np.empty((self.G, self.P), np.float32),
+               "target_q": np.empty((self.G, self.P), np.float32)}
+        h = c = None
+        if hidden:
+            h = np.empty((2, self.rows, 512), np.float32)
+            c = np.empty((2, self.rows, 512), np.float32)
+            out["h"], out["c"] = h, c
+        check(lib().hb_policy_get(self._h, _ptr(out["adv"]), _ptr(out["online_q"]), _ptr(out["target_q"]), _ptr(h), _ptr(c)))
+        return out
 
     def sync(self):
         check(lib().hb_sync(self._h))

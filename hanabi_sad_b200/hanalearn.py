@@ -66,7 +66,7 @@ class HanabiEnv:
     def _eng(self):
         if self._engine is None:
             self._engine = Engine(1, self.players, self.hand_size, self.bomb, self.max_len, self.sad, self.shuffle_color,
-                                  self.eps_list, seed=self.seed)
+                                  self.eps_list, seed=self.seed, hid_dim=0)
             self._slot = 0
             assert self._engine.F == self._F and self._engine.A == self._A
         return self._engine

@@ -55,7 +55,9 @@ typedef struct hb_config {
   int32_t num_lstm_layer;  /* 2 */
   int32_t num_fc_layer;    /* 1 (r2d2.py:42-46) */
   int32_t skip_connect;    /* r2d2.py:74-75 */
-  int32_t priority_mode;   /* 0: reference semantics (online + target forward every tick); 1: uniform priority */
+  int32_t priority_mode;   /* 0: reference semantics (online + target forward every tick, both fp32-class);
+                            * 1: uniform priority (R2D2Agent uniform_priority, r2d2.py:310-311: no target forward);
+                            * 2: as 0 but the target forward runs in plain bf16 (priorities are heuristics) */
   int32_t reserved[7];
 } hb_config;
 
@@ -130,6 +132,36 @@ int hb_env_random_actions(hb_engine* e, uint64_t counter);
  * a / greedy_a int64 [G,P]) and of the last step's result (reward float [G], terminal uint8 [G]).  NULL skips. */
 int hb_env_get_actions(hb_engine* e, int64_t* a, int64_t* greedy_a);
 int hb_env_get_result(hb_engine* e, float* reward, uint8_t* terminal);
+
+/* ---- policy: the R2D2 act forward (pyhanabi/r2d2.py:65-78, 234-303) ---------------------------------- */
+
+/* One network's parameters in the layouts of R2D2Net.state_dict() (fp32, row-major, host OR device pointers):
+ * net.0.{weight [512,F], bias}, lstm.{weight_ih, weight_hh [2048,512], bias_ih, bias_hh [2048]}_l{0,1},
+ * fc_a.{weight [A,512], bias}, fc_v.{weight [1,512], bias}. */
+typedef struct hb_weights {
+  const float* fc_w; const float* fc_b;
+  const float* w_ih[2]; const float* w_hh[2]; const float* b_ih[2]; const float* b_hh[2];
+  const float* fc_a_w; const float* fc_a_b;
+  const float* fc_v_w; const float* fc_v_b;
+} hb_weights;
+
+/* BatchRunner::updateModel (rela/batch_runner.h:74-77) / R2D2Agent.sync_target_with_online: net 0 = online_net,
+ * 1 = target_net.  Synchronous: the caller's tensors may be released when it returns. */
+int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w);
+
+/* R2D2Actor::act minus the environment (rela/r2d2_actor.h:61-100 -> R2D2Agent.act): one forward of both networks
+ * over the engine's current observation; (a, greedy_a) land in the engine's action buffers, the hidden state
+ * advances.  greedy_only != 0 ignores eps (eval actors). */
+int hb_policy_act(hb_engine* e, int greedy_only);
+
+/* Host copies of the last forward's outputs (NULL skips): adv float [G*P,A] online advantages; online_q / target_q
+ * float [G*P] = the dueling Q-values compute_priority uses (r2d2.py:344-348); h, c float [2, G*P, 512] = the
+ * CURRENT hidden state (R2D2Actor::hidden_). */
+int hb_policy_get(hb_engine* e, float* adv, float* online_q, float* target_q, float* h, float* c);
+
+/* Diagnostic: run the tcgen05 GEMM template alone, C[M,N] = A[M,K] B[N,K]^T + bias on host fp32 buffers
+ * (M % 128 == N % 256 == K % 64 == 0; split != 0 selects the bf16x3 fp32-class mode). */
+int hb_debug_gemm(int device, const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int split);
 
 int hb_sync(hb_engine* e); /* cudaStreamSynchronize on the engine stream */
 void* hb_stream(hb_engine* e); /* cudaStream_t the engine launches on (for CUDA-event timing) */
