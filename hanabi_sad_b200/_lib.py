@@ -39,6 +39,11 @@ class HbWeights(ctypes.Structure):
     ]
 
 
+class HbBatch(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in ("priv_s", "legal_move", "own_hand", "eps", "a", "greedy_a", "reward", "bootstrap", "terminal",
+                                        "seq_len", "weight", "ids")]
+
+
 # name -> (restype, argtypes); the list tests/test_abi.py checks against include/hanabi_b200.h
 SIGNATURES = {
     "hb_last_error": (ctypes.c_char_p, []),
@@ -64,6 +69,10 @@ SIGNATURES = {
     "hb_policy_set_weights": (c_int, [c_void_p, c_int, ctypes.POINTER(HbWeights)]),
     "hb_policy_act": (c_int, [c_void_p, c_int]),
     "hb_policy_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hb_rollout": (c_int, [c_void_p, c_int]),
+    "hb_counters": (c_int, [c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "hb_replay_sample": (c_int, [c_void_p, c_int, ctypes.POINTER(HbBatch)]),
+    "hb_replay_update_priority": (c_int, [c_void_p, c_void_p, c_int]),
     "hb_debug_gemm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     "hb_sync": (c_int, [c_void_p]),
     "hb_stream": (c_void_p, [c_void_p]),

@@ -185,6 +185,7 @@ int hb_env_step_dev(hb_engine* e, const int64_t* a_dev, const int64_t* greedy_a_
   if (!e) return hb_fail(-1, "hb_env_step_dev: null engine");
   HB_CUDA(cudaSetDevice(e->device));
   if (!a_dev) { a_dev = e->d_a; greedy_a_dev = e->d_greedy_a; }
+  e->pending_actions = 0;
   return hb_launch_env(e, 0, 1, a_dev, greedy_a_dev);
 }
 
@@ -194,6 +195,7 @@ int hb_env_step(hb_engine* e, const int64_t* a, const int64_t* greedy_a, float* 
   const size_t nb = (size_t)e->rows * sizeof(int64_t);
   HB_CUDA(cudaMemcpyAsync(e->d_a, a, nb, cudaMemcpyHostToDevice, e->stream));
   HB_CUDA(cudaMemcpyAsync(e->d_greedy_a, greedy_a ? greedy_a : a, nb, cudaMemcpyHostToDevice, e->stream));
+  e->pending_actions = 0;
   int rc = hb_launch_env(e, 0, 1, e->d_a, e->d_greedy_a);
   if (rc) return rc;
   if (reward) HB_CUDA(cudaMemcpyAsync(reward, e->d_reward, (size_t)e->G * sizeof(float), cudaMemcpyDeviceToHost, e->stream));

@@ -51,6 +51,8 @@ struct hb_engine {
   int sm_count;
   cudaStream_t stream;
   int64_t launches;
+  int pending_actions;   // d_a / d_greedy_a hold a reply the environment has not consumed yet
+  int64_t num_act;       // sum of R2D2Actor::numAct_ (r2d2_actor.h:98): env-steps acted on
 
   // ---- environment
   HbGame* d_games;       // [G]
@@ -82,6 +84,7 @@ void hb_set_error(const char* fmt, ...);
   } while (0)
 
 HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e);  // hb_policy.cu
+int hb_launch_tick(hb_engine* e, int do_step, int do_reset);  // hb_rollout.cu
 // hb_env_kernels.cu
 int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev);
 int hb_launch_random_actions(hb_engine* e, uint64_t counter);

@@ -494,6 +494,7 @@ int hb_debug_gemm(int device, const float* A, const float* B, const float* bias,
 int hb_policy_act(hb_engine* e, int greedy_only) {
   if (!e) { hb_set_error("hb_policy_act: null engine"); return -1; }
   HB_CUDA(cudaSetDevice(e->device));
+  e->pending_actions = 1;
   return hb_policy_forward(e, greedy_only);
 }
 

@@ -1,6 +1,270 @@
-// hb_replay.cu -- device-resident prioritized episode replay (placeholder until the kernels land).
+// hb_replay.cu -- host side and learner-facing kernels of the device replay (hb_replay.h): allocation of the
+// episode ring, stratified priority sampling + importance weights (PrioritizedReplay::sample_,
+// rela/prioritized_replay.h:274-345), batch assembly in the learner's [T, B, ...] layout with terminal padding
+// (RNNTransition::makeBatch, rela/transition.cc:160-202; FFTransition::padLike, :29-40) and priority write-back
+// (ConcurrentQueue::update, prioritized_replay.h:106-120).  The producer side (append / finalize / commit) is part of
+// the fused tick in hb_rollout.cu.
+#include <string.h>
+
 #include "hb_engine.h"
-extern "C" {
-int hb_replay_create(hb_engine* e) { e->replay = nullptr; return 0; }
-void hb_replay_destroy(hb_engine* e) { (void)e; }
+#include "hb_env_cta.cuh"
+#include "hb_replay.h"
+
+#define HB_SCAN_THREADS 1024
+
+__device__ __forceinline__ float hb_entry_weight(const HbRing& R, int i, long long oldest) {
+  const int slot = i / R.NE;
+  if (R.state[slot] != HB_SLOT_COMMITTED) return 0.f;
+  if (R.commit_seq[slot] < oldest) return 0.f;  // beyond `capacity` most recent episodes: evicted (prioritized_replay.h:329-332)
+  return R.weight[i];
 }
+
+// Inclusive prefix sums (double, like the reference's running accSum) of the sampleable weights; out[0] = total,
+// out[1] = number of sampleable entries.
+__global__ void __launch_bounds__(HB_SCAN_THREADS) hb_k_replay_prefix(HbRing R, double* __restrict__ prefix, double* __restrict__ out) {
+  __shared__ double part[HB_SCAN_THREADS];
+  __shared__ int cnt[HB_SCAN_THREADS];
+  const int n = R.phys_slots * R.NE, tid = threadIdx.x;
+  const long long commits = (long long)R.counters[HB_CNT_COMMIT];
+  const long long oldest = commits - R.cap_slots;
+  const int chunk = (n + HB_SCAN_THREADS - 1) / HB_SCAN_THREADS;
+  const int lo = tid * chunk, hi = min(n, lo + chunk);
+  double s = 0;
+  int c = 0;
+  for (int i = lo; i < hi; ++i) { const float w = hb_entry_weight(R, i, oldest); s += w; c += w > 0.f; }
+  part[tid] = s; cnt[tid] = c;
+  __syncthreads();
+  for (int off = 1; off < HB_SCAN_THREADS; off <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
+    double v = 0; int cv = 0;
+    if (tid >= off) { v = part[tid - off]; cv = cnt[tid - off]; }
+    __syncthreads();
+    part[tid] += v; cnt[tid] += cv;
+    __syncthreads();
+  }
+  double acc = tid > 0 ? part[tid - 1] : 0.0;
+  for (int i = lo; i < hi; ++i) { acc += hb_entry_weight(R, i, oldest); prefix[i] = acc; }
+  if (tid == HB_SCAN_THREADS - 1) { out[0] = part[tid]; out[1] = (double)cnt[tid]; }
+}
+
+// One thread per batch element: stratified draw, binary search, importance weight.
+__global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, const double* __restrict__ tot, int B, float beta, uint64_t seed,
+                                 unsigned long long draw, int* __restrict__ idx_out, long long* __restrict__ seq_out, float* __restrict__ w_out,
+                                 float* __restrict__ is_weight) {
+  __shared__ float red[32];
+  const int b = threadIdx.x, n = R.phys_slots * R.NE;
+  const float sum = (float)tot[0];
+  const float size = (float)tot[1];
+  float isw = 0.f;
+  if (b < B) {
+    const float segment = sum / (float)B;
+    HbRng rng(seed, (uint32_t)b, (uint32_t)draw, HB_RNG_SAMPLE);
+    float r = rng.uniform() * segment + (float)b * segment;   // dist(rng_) + i * segment (prioritized_replay.h:296)
+    r = fminf(sum - 0.1f, r);
+    int lo = 0, hi = n - 1;                                   // first i with prefix[i] > 0 and prefix[i] >= r
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const double p = prefix[mid];
+      if (p > 0.0 && p >= (double)r) hi = mid; else lo = mid + 1;
+    }
+    const float w = (float)(prefix[lo] - (lo > 0 ? prefix[lo - 1] : 0.0));
+    idx_out[b] = lo;
+    seq_out[b] = R.commit_seq[lo / R.NE];
+    w_out[b] = w;
+    isw = powf(size * (w / sum), -beta);                      // prioritized_replay.h:337-338
+  }
+  float m = isw;
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if (threadIdx.x == 0) red[0] = m;
+  }
+  __syncthreads();
+  if (b < B) is_weight[b] = isw / red[0];                     // weights /= weights.max()
+}
+
+struct HbBatchPtrs {
+  float* priv_s; float* legal; float* own_hand; float* eps; int64_t* a; int64_t* greedy_a;
+  float* reward; float* bootstrap; uint8_t* terminal; float* seq_len;
+};
+
+// grid (B, T): one CTA copies step t of sampled entry b into the [T, B, (P,) ...] batch; steps at or beyond the episode
+// length are the reference's padding (zeros, terminal = 1).
+__global__ void __launch_bounds__(128) hb_k_replay_gather(HbRing R, const int* __restrict__ idx, int B, HbBatchPtrs out) {
+  const int b = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+  const int entry = idx[b], slot = entry / R.NE, e = entry % R.NE;
+  const int PP = R.NE == 1 ? R.P : 1;          // players kept in one entry
+  const int p0 = R.NE == 1 ? 0 : e;
+  const int len = R.seq_len[slot];
+  const bool live = t < len;
+  const size_t src = ((size_t)slot * R.T + t) * R.P + p0;   // (slot, t, p0) in units of one player's row
+  const size_t dst = ((size_t)t * B + b) * PP;
+  const int nF = PP * R.F, nA = PP * R.A, nO = PP * R.OH;
+  for (int i = tid; i < nF; i += blockDim.x) out.priv_s[dst * R.F + i] = live ? R.priv_s[src * R.F + i] : 0.f;
+  for (int i = tid; i < nA; i += blockDim.x) out.legal[dst * R.A + i] = live ? R.legal[src * R.A + i] : 0.f;
+  for (int i = tid; i < nO; i += blockDim.x) out.own_hand[dst * R.OH + i] = live ? R.own_hand[src * R.OH + i] : 0.f;
+  if (tid < PP) {
+    out.eps[dst + tid] = live ? R.eps[src + tid] : 0.f;
+    out.a[dst + tid] = live ? R.a[src + tid] : 0;
+    out.greedy_a[dst + tid] = live ? R.greedy_a[src + tid] : 0;
+  }
+  if (tid == 0) {
+    out.reward[(size_t)t * B + b] = live ? R.reward[(size_t)slot * R.T + t] : 0.f;
+    out.bootstrap[(size_t)t * B + b] = live ? R.bootstrap[(size_t)slot * R.T + t] : 0.f;
+    out.terminal[(size_t)t * B + b] = t >= len - 1 ? 1 : 0;
+    if (t == 0) out.seq_len[b] = (float)len;
+  }
+}
+
+__global__ void hb_k_replay_update(HbRing R, const int* __restrict__ idx, const long long* __restrict__ seq, const float* __restrict__ prio, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int entry = idx[i], slot = entry / R.NE;
+  if (R.state[slot] == HB_SLOT_COMMITTED && R.commit_seq[slot] == seq[i]) R.weight[entry] = powf(prio[i], R.alpha);
+}
+
+HbRing hb_replay_ring(hb_engine* e) { return e->replay->ring; }
+
+#define HB_RALLOC(ptr, bytes)                                        \
+  do {                                                               \
+    HB_CUDA(cudaMalloc((void**)&(ptr), (bytes)));                    \
+    HB_CUDA(cudaMemsetAsync((ptr), 0, (bytes), e->stream));          \
+  } while (0)
+
+extern "C" {
+
+int hb_replay_create(hb_engine* e) {
+  e->replay = nullptr;
+  const hb_config& c = e->cfg;
+  if (c.replay_capacity <= 0) return 0;
+  if (!e->policy) { hb_set_error("hb_create: a replay needs the device policy (hid_dim = 512)"); return -1; }
+  if (c.seq_len < 1 || c.multi_step < 1) { hb_set_error("hb_create: seq_len and multi_step must be >= 1"); return -1; }
+  if (c.max_len <= 0 || c.max_len > c.seq_len) {
+    hb_set_error("hb_create: with a replay, 0 < max_len <= seq_len is required (the reference asserts it, transition_buffer.h:143)");
+    return -1;
+  }
+  HbReplay* Q = new HbReplay();
+  memset(Q, 0, sizeof(*Q));
+  e->replay = Q;
+  HbRing& R = Q->ring;
+  R.T = c.seq_len; R.P = e->P; R.F = e->F; R.A = e->A; R.OH = 3 * e->H;
+  R.NE = c.vdn ? 1 : e->P;
+  Q->capacity = c.replay_capacity;
+  R.cap_slots = (c.replay_capacity + R.NE - 1) / R.NE;
+  R.phys_slots = R.cap_slots + 2 * e->G + 64;
+  R.n_step = c.multi_step; R.gamma = c.gamma; R.eta = c.eta; R.alpha = c.alpha;
+  double gn = 1.0;
+  for (int i = 0; i < c.multi_step; ++i) gn *= (double)c.gamma;  // python: self.gamma ** self.multi_step
+  R.gamma_n = (float)gn;
+  R.uniform_priority = c.priority_mode == 1;
+  Q->beta = c.beta; Q->seed = c.seed ^ 0x5851F42D4C957F2DULL;
+  const size_t S = R.phys_slots, T = R.T, P = R.P, G = e->G;
+  HB_RALLOC(R.priv_s, S * T * P * R.F * sizeof(float));
+  HB_RALLOC(R.legal, S * T * P * R.A * sizeof(float));
+  HB_RALLOC(R.own_hand, S * T * P * R.OH * sizeof(float));
+  HB_RALLOC(R.eps, S * T * P * sizeof(float));
+  HB_RALLOC(R.a, S * T * P * sizeof(int64_t));
+  HB_RALLOC(R.greedy_a, S * T * P * sizeof(int64_t));
+  HB_RALLOC(R.reward, S * T * sizeof(float));
+  HB_RALLOC(R.bootstrap, S * T * sizeof(float));
+  HB_RALLOC(R.seq_len, S * sizeof(int));
+  HB_RALLOC(R.weight, S * R.NE * sizeof(float));
+  HB_RALLOC(R.commit_seq, S * sizeof(long long));
+  HB_RALLOC(R.state, S * sizeof(int));
+  HB_CUDA(cudaMalloc((void**)&R.game_slot, G * sizeof(int)));
+  HB_CUDA(cudaMemsetAsync(R.game_slot, 0xFF, G * sizeof(int), e->stream));  // -1: no slot yet
+  HB_RALLOC(R.sc_reward, G * T * sizeof(float));
+  HB_RALLOC(R.sc_oq, G * T * P * sizeof(float));
+  HB_RALLOC(R.sc_tq, G * T * P * sizeof(float));
+  HB_RALLOC(R.counters, HB_CNT_N * sizeof(unsigned long long));
+  Q->max_batch = 1024;
+  HB_RALLOC(Q->prefix, (S * R.NE + 2) * sizeof(double));
+  HB_RALLOC(Q->sampled_idx, Q->max_batch * sizeof(int));
+  HB_RALLOC(Q->sampled_seq, Q->max_batch * sizeof(long long));
+  HB_RALLOC(Q->sampled_w, Q->max_batch * sizeof(float));
+  HB_RALLOC(Q->d_prio, Q->max_batch * sizeof(float));
+  HB_CUDA(cudaMallocHost((void**)&Q->h_counters, (HB_CNT_N + 2) * sizeof(unsigned long long)));
+  return 0;
+}
+
+void hb_replay_destroy(hb_engine* e) {
+  HbReplay* Q = e->replay;
+  if (!Q) return;
+  HbRing& R = Q->ring;
+  cudaFree(R.priv_s); cudaFree(R.legal); cudaFree(R.own_hand); cudaFree(R.eps); cudaFree(R.a); cudaFree(R.greedy_a); cudaFree(R.reward);
+  cudaFree(R.bootstrap); cudaFree(R.seq_len); cudaFree(R.weight); cudaFree(R.commit_seq); cudaFree(R.state); cudaFree(R.game_slot);
+  cudaFree(R.sc_reward); cudaFree(R.sc_oq); cudaFree(R.sc_tq); cudaFree(R.counters);
+  cudaFree(Q->prefix); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio);
+  cudaFreeHost(Q->h_counters);
+  delete Q;
+  e->replay = nullptr;
+}
+
+int hb_counters(hb_engine* e, int64_t* size, int64_t* num_add, int64_t* num_act) {
+  if (!e) { hb_set_error("hb_counters: null engine"); return -1; }
+  if (num_act) *num_act = e->num_act;
+  if (size) *size = 0;
+  if (num_add) *num_add = 0;
+  HbReplay* Q = e->replay;
+  if (!Q) return 0;
+  HB_CUDA(cudaSetDevice(e->device));
+  HB_CUDA(cudaMemcpyAsync(Q->h_counters, Q->ring.counters, HB_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  const long long commits = (long long)Q->h_counters[HB_CNT_COMMIT];
+  const long long held = commits < Q->ring.cap_slots ? commits : Q->ring.cap_slots;
+  if (size) *size = held * Q->ring.NE;
+  if (num_add) *num_add = commits * Q->ring.NE;
+  return 0;
+}
+
+int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) {
+  if (!e || !out) { hb_set_error("hb_replay_sample: null argument"); return -1; }
+  HbReplay* Q = e->replay;
+  if (!Q) { hb_set_error("hb_replay_sample: this engine has no replay (replay_capacity = 0)"); return -1; }
+  if (batchsize < 1 || batchsize > Q->max_batch) { hb_set_error("hb_replay_sample: batchsize must be 1..%d", Q->max_batch); return -1; }
+  if (Q->n_sampled != 0) {  // prioritized_replay.h:209-212
+    hb_set_error("hb_replay_sample: previous samples' priority has not been updated");
+    return -3;
+  }
+  int64_t size = 0;
+  int rc = hb_counters(e, &size, nullptr, nullptr);
+  if (rc) return rc;
+  if (size < batchsize) { hb_set_error("hb_replay_sample: replay holds %lld entries, fewer than the batch size %d", (long long)size, batchsize); return -3; }
+  HbRing& R = Q->ring;
+  double* tot = Q->prefix + (size_t)R.phys_slots * R.NE;
+  hb_k_replay_prefix<<<1, HB_SCAN_THREADS, 0, e->stream>>>(R, Q->prefix, tot);
+  const int threads = (batchsize + 31) / 32 * 32;
+  hb_k_replay_draw<<<1, threads, 0, e->stream>>>(R, Q->prefix, tot, batchsize, Q->beta, Q->seed, Q->sample_count, Q->sampled_idx, Q->sampled_seq,
+                                                 Q->sampled_w, out->weight);
+  HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
+  hb_k_replay_gather<<<dim3(batchsize, R.T), 128, 0, e->stream>>>(R, Q->sampled_idx, batchsize, bp);
+  HB_CUDA(cudaGetLastError());
+  if (out->ids) HB_CUDA(cudaMemcpyAsync(out->ids, Q->sampled_idx, batchsize * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));  // the batch tensors are consumed on the caller's own stream
+  e->launches += 3;
+  Q->sample_count += 1;
+  Q->n_sampled = batchsize;
+  return 0;
+}
+
+int hb_replay_update_priority(hb_engine* e, const float* priority, int n) {
+  if (!e) { hb_set_error("hb_replay_update_priority: null engine"); return -1; }
+  HbReplay* Q = e->replay;
+  if (!Q) { hb_set_error("hb_replay_update_priority: this engine has no replay"); return -1; }
+  if (n == 0) { Q->n_sampled = 0; return 0; }  // prioritized_replay.h:243-246
+  if (!priority || n != Q->n_sampled) { hb_set_error("hb_replay_update_priority: expected %d priorities, got %d", Q->n_sampled, n); return -1; }
+  HB_CUDA(cudaSetDevice(e->device));
+  HB_CUDA(cudaMemcpyAsync(Q->d_prio, priority, n * sizeof(float), cudaMemcpyDefault, e->stream));
+  hb_k_replay_update<<<(n + 127) / 128, 128, 0, e->stream>>>(Q->ring, Q->sampled_idx, Q->sampled_seq, Q->d_prio, n);
+  HB_CUDA(cudaGetLastError());
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  e->launches += 1;
+  Q->n_sampled = 0;
+  return 0;
+}
+
+}  // extern "C"

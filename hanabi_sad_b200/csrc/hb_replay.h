@@ -1,0 +1,55 @@
+// hb_replay.h -- device-resident prioritized episode replay: what rela/transition_buffer.h (MultiStepBuffer,
+// R2D2Buffer), rela/r2d2_actor.h postAct and rela/prioritized_replay.h keep in host deques of tensor dicts lives here
+// as one ring of fixed-size episode slots in HBM.  A game writes its observations straight into the slot it claimed
+// when its episode began; at the terminal step its CTA turns the raw rewards into n-step returns, computes the
+// per-step priorities from the Q-values the policy kernel left behind, aggregates them and commits the slot.
+#pragma once
+#include <stdint.h>
+
+#include "hb_types.h"
+
+enum { HB_SLOT_FREE = 0, HB_SLOT_INFLIGHT = 1, HB_SLOT_COMMITTED = 2 };
+enum { HB_CNT_HEAD = 0, HB_CNT_COMMIT = 1, HB_CNT_DROPPED = 2, HB_CNT_TICK = 3, HB_CNT_N = 8 };
+
+struct HbRing {                 // device pointers + geometry, passed by value to kernels
+  int T, P, F, A, OH;           // seq_len, players, feature size, num_action, 3*hand_size
+  int NE;                       // replay entries per episode slot: 1 (vdn) or P (iql, one per player)
+  int cap_slots, phys_slots;
+  int n_step;
+  float gamma, gamma_n, eta, alpha;
+  int uniform_priority;
+  float* priv_s;                // [phys][T][P][F]
+  float* legal;                 // [phys][T][P][A]
+  float* own_hand;              // [phys][T][P][OH]
+  float* eps;                   // [phys][T][P]
+  int64_t* a;                   // [phys][T][P]
+  int64_t* greedy_a;            // [phys][T][P]
+  float* reward;                // [phys][T]   n-step return (transition_buffer.h:83-90)
+  float* bootstrap;             // [phys][T]
+  int* seq_len;                 // [phys]
+  float* weight;                // [phys][NE]  priority^alpha (prioritized_replay.h:192-197); 0 = not sampleable
+  long long* commit_seq;        // [phys]      order of arrival (ConcurrentQueue order), -1 while in flight
+  int* state;                   // [phys]      HB_SLOT_*
+  int* game_slot;               // [G]         slot under construction
+  float* sc_reward;             // [G][T]      raw per-step reward
+  float* sc_oq;                 // [G][T][P]   Q_online(s_t, a_t)          per agent
+  float* sc_tq;                 // [G][T][P]   Q_target(s_t, greedy_t)     per agent
+  unsigned long long* counters; // [HB_CNT_N]
+};
+
+struct HbReplay {
+  HbRing ring;
+  int capacity;                 // entries
+  float beta;
+  uint64_t seed;
+  unsigned long long sample_count;
+  // sampling scratch
+  double* prefix;               // [phys*NE]
+  int* sampled_idx;             // [max_batch] entry index = slot*NE + e
+  long long* sampled_seq;       // [max_batch] commit_seq at sampling time (evicted-since check, prioritized_replay.h:106-120)
+  float* sampled_w;             // [max_batch]
+  float* d_prio;                // [max_batch] staging for update_priority
+  int n_sampled;
+  int max_batch;
+  unsigned long long* h_counters;  // pinned mirror
+};

@@ -1,0 +1,232 @@
+// hb_rollout.cu -- the fused actor tick: one launch of hb_k_tick does, for every game of the engine, what one
+// iteration of HanabiThreadLoop::mainLoop (cpp/thread_loop.h:42-88) spreads over VectorEnv::step, R2D2Actor::postAct,
+// MultiStepBuffer / R2D2Buffer, PrioritizedReplay::add and VectorEnv::reset:
+//
+//   1. apply the action the policy chose last tick (HanabiEnv::step, hanabi_env.cc:49-108): reward, terminal;
+//   2. record (a, greedy_a, reward, Q_online, Q_target) of that step in the episode slot of the replay ring;
+//   3. on terminal: n-step returns + bootstrap flags (transition_buffer.h:51-99), per-step priorities
+//      (r2d2.py:344-358), eta-aggregate (r2d2_actor.h:10-21), weight = priority^alpha, commit the slot
+//      (prioritized_replay.h:192-197); zero the agents' LSTM state (r2d2_actor.h:113-126); start the next episode
+//      (HanabiEnv::reset, hanabi_env.cc:9-47) in a freshly claimed slot;
+//   4. encode the observation (hanabi_env.cc:115-205) ONCE into three places: the obs dict buffers, the replay slot
+//      at step index ep_len, and the bf16 hi/lo operand of the policy's first GEMM.
+//
+// The policy forward (hb_policy.cu: 3 tcgen05 GEMM launches + head/act kernel) follows on the same stream; nothing
+// returns to the host between ticks.
+#include "hb_engine.h"
+#include "hb_env_cta.cuh"
+#include "hb_policy.h"
+#include "hb_replay.h"
+
+#define HB_TICK_THREADS 128
+
+struct HbTickArgs {
+  HbGame* games;
+  uint8_t* decks;
+  HbInject* inject;
+  HbEnvCfg cfg;
+  uint64_t seed;
+  int do_step, do_reset, has_replay;
+  const int64_t* a;
+  const int64_t* greedy_a;
+  HbObsPtrs obs;
+  const float* eps_list;
+  float* reward;
+  uint8_t* terminal;
+  int* flags;
+  HbHidPtrs hid;
+  const float* oq;
+  const float* tq;
+  HbRing ring;
+};
+
+__device__ __forceinline__ int hb_claim_slot(const HbRing& R) {
+  for (int tries = 0; tries < 4 * R.phys_slots; ++tries) {
+    const unsigned long long id = atomicAdd(&R.counters[HB_CNT_HEAD], 1ULL);
+    const int slot = (int)(id % (unsigned long long)R.phys_slots);
+    const int old = atomicCAS(&R.state[slot], HB_SLOT_FREE, HB_SLOT_INFLIGHT);
+    if (old == HB_SLOT_FREE) return slot;
+    if (old == HB_SLOT_COMMITTED && atomicCAS(&R.state[slot], HB_SLOT_COMMITTED, HB_SLOT_INFLIGHT) == HB_SLOT_COMMITTED) {
+      for (int e = 0; e < R.NE; ++e) R.weight[(size_t)slot * R.NE + e] = 0.f;  // evicted: the oldest episode makes room
+      R.commit_seq[slot] = -1;
+      return slot;
+    }
+  }
+  return -1;
+}
+
+// Turn the finished episode of game g (length Len, raw data in the sc_* scratch rows) into replay form and commit it.
+// All threads of the CTA; `red` is shared scratch of 2 * (blockDim.x / 32) floats.
+__device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, int slot, int Len, float* red) {
+  const int T = R.T, P = R.P, n = R.n_step;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const float* r = R.sc_reward + (size_t)g * T;
+  for (int e = 0; e < R.NE; ++e) {
+    float pmax = 0.f, psum = 0.f;
+    for (int t = tid; t < T; t += nt) {
+      float rew = 0.f, boot = 0.f, prio = 0.f;
+      if (t < Len) {
+        boot = t < Len - n ? 1.f : 0.f;                       // no terminal inside the next n steps (transition_buffer.h:66-79)
+        const int K = min(n - 1, Len - 1 - t);
+        float acc = 0.f;
+        // Horner from the far end (transition_buffer.h:83-90); separately rounded multiply and add, as the
+        // reference compiled without FMA contraction (the oracle/_ref build) computes it
+        for (int s = K; s >= 0; --s) acc = __fadd_rn(r[t + s], __fmul_rn(R.gamma, acc));
+        rew = acc;
+        if (R.uniform_priority) {
+          prio = 1.f;
+        } else {
+          float oq = 0.f, tq = 0.f;
+          if (R.NE == 1) {                                    // VDN: Q summed over the players (r2d2.py:351-354)
+            for (int p = 0; p < P; ++p) oq += R.sc_oq[((size_t)g * T + t) * P + p];
+            if (boot != 0.f) for (int p = 0; p < P; ++p) tq += R.sc_tq[((size_t)g * T + t + n) * P + p];
+          } else {
+            oq = R.sc_oq[((size_t)g * T + t) * P + e];
+            if (boot != 0.f) tq = R.sc_tq[((size_t)g * T + t + n) * P + e];
+          }
+          prio = fabsf(rew + boot * R.gamma_n * tq - oq);     // r2d2.py:356-357
+        }
+      }
+      if (e == 0) { R.reward[(size_t)slot * T + t] = rew; R.bootstrap[(size_t)slot * T + t] = boot; }
+      pmax = fmaxf(pmax, prio);
+      psum += prio;
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) { pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, k)); psum += __shfl_xor_sync(0xffffffffu, psum, k); }
+    if (lane == 0) { red[warp] = pmax; red[nw + warp] = psum; }
+    __syncthreads();
+    if (tid == 0) {
+      float m = 0.f, s = 0.f;
+      for (int w = 0; w < nw; ++w) { m = fmaxf(m, red[w]); s += red[nw + w]; }
+      const float agg = R.eta * m + (1.f - R.eta) * (s / (float)Len);  // aggregatePriority (r2d2_actor.h:10-21)
+      R.weight[(size_t)slot * R.NE + e] = powf(agg, R.alpha);           // PrioritizedReplay::add (prioritized_replay.h:192-197)
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    R.seq_len[slot] = Len;
+    __threadfence();
+    R.commit_seq[slot] = (long long)atomicAdd(&R.counters[HB_CNT_COMMIT], 1ULL);
+    __threadfence();
+    atomicExch(&R.state[slot], HB_SLOT_COMMITTED);
+  }
+}
+
+__global__ void __launch_bounds__(HB_TICK_THREADS) hb_k_tick(const __grid_constant__ HbTickArgs A) {
+  __shared__ HbGame s;
+  __shared__ HbEncTables tab;
+  __shared__ __align__(16) uint8_t deck[HB_DECK_STRIDE];
+  __shared__ int sh_did_step, sh_t, sh_term, sh_reset, sh_slot, sh_drop;
+  __shared__ float red[2 * HB_TICK_THREADS / 32];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const HbEnvCfg& cfg = A.cfg;
+  const HbGeom& geo = cfg.g;
+  const HbRing& R = A.ring;
+  const int P = geo.P;
+  if (tid < 16) reinterpret_cast<uint4*>(&s)[tid] = reinterpret_cast<const uint4*>(A.games + g)[tid];
+  else if (tid < 20) reinterpret_cast<uint4*>(deck)[tid - 16] = reinterpret_cast<const uint4*>(A.decks + (size_t)g * HB_DECK_STRIDE)[tid - 16];
+  __syncthreads();
+  if (tid == 0) {
+    sh_did_step = 0; sh_term = 0; sh_reset = 0; sh_drop = 0; sh_t = 0;
+    sh_slot = A.has_replay ? R.game_slot[g] : -1;
+    if (g == 0 && A.has_replay) atomicAdd(&R.counters[HB_CNT_TICK], 1ULL);
+    if (A.do_step && !s.terminated) {
+      const int t = s.ep_len;
+      const int cur = s.cur_player < P ? s.cur_player : 0;
+      const bool term = hb_step_game(s, cfg, deck, (int)A.a[g * P + cur], (int)A.greedy_a[g * P + cur]);
+      s.ep_len = (int16_t)(t + 1);
+      sh_did_step = 1; sh_t = t; sh_term = term ? 1 : 0;
+      A.reward[g] = s.reward;
+      A.terminal[g] = term ? 1 : 0;
+      if (s.illegal) { atomicAdd(&A.flags[1], 1); sh_drop = 1; }
+    } else if (A.do_step) {
+      A.reward[g] = 0.f;
+      A.terminal[g] = 1;
+    }
+  }
+  __syncthreads();
+  int slot = sh_slot;
+  if (sh_did_step && slot >= 0 && !sh_drop) {
+    const int t = sh_t;
+    if (t < R.T) {
+      if (tid < P) {
+        const size_t o = ((size_t)slot * R.T + t) * P + tid;
+        R.a[o] = A.a[g * P + tid];
+        R.greedy_a[o] = A.greedy_a[g * P + tid];
+        R.sc_oq[((size_t)g * R.T + t) * P + tid] = A.oq[g * P + tid];
+        R.sc_tq[((size_t)g * R.T + t) * P + tid] = A.tq != nullptr ? A.tq[g * P + tid] : 0.f;
+      }
+      if (tid == 0) R.sc_reward[(size_t)g * R.T + t] = s.reward;
+    }
+    if (sh_term) {
+      __syncthreads();  // the scratch rows written above are read by other threads below
+      hb_cta_finalize_episode(R, g, slot, min(t + 1, R.T), red);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (sh_drop && slot >= 0) { atomicExch(&R.state[slot], HB_SLOT_FREE); atomicAdd(&R.counters[HB_CNT_DROPPED], 1ULL); }
+    if (A.do_reset && s.terminated) {
+      hb_begin_episode(s, deck, A.inject + g, cfg, A.seed, g);
+      sh_reset = 1;
+      if (A.has_replay) { sh_slot = hb_claim_slot(R); R.game_slot[g] = sh_slot; }
+    }
+    if (s.terminated) atomicOr(&A.flags[0], 1);
+  }
+  __syncthreads();
+  slot = sh_slot;
+  if (sh_reset) hb_cta_zero_hidden(A.hid, g, P);
+  hb_cta_build_tables(s, tab, geo);
+  __syncthreads();
+  hb_cta_build_totals(s, tab, geo);
+  __syncthreads();
+  const HbObsPtrs& O = A.obs;
+  const int t_obs = s.ep_len;
+  const bool to_ring = slot >= 0 && !s.terminated && t_obs < R.T;
+  const size_t ro = ((size_t)(to_ring ? slot : 0) * R.T + (to_ring ? t_obs : 0)) * P;
+  hb_cta_write_obs(s, tab, cfg, O.priv_s + (size_t)g * P * geo.F, O.legal_move + (size_t)g * P * geo.A, O.own_hand + (size_t)g * P * 3 * geo.H,
+                   O.eps + (size_t)g * P, A.eps_list, O.s_hi ? O.s_hi + (size_t)g * P * O.KS : nullptr,
+                   O.s_lo ? O.s_lo + (size_t)g * P * O.KS : nullptr, O.KS, to_ring ? R.priv_s + ro * geo.F : nullptr,
+                   to_ring ? R.legal + ro * geo.A : nullptr, to_ring ? R.own_hand + ro * 3 * geo.H : nullptr, to_ring ? R.eps + ro : nullptr);
+  if (tid < 16) reinterpret_cast<uint4*>(A.games + g)[tid] = reinterpret_cast<const uint4*>(&s)[tid];
+  else if (tid < 20) reinterpret_cast<uint4*>(A.decks + (size_t)g * HB_DECK_STRIDE)[tid - 16] = reinterpret_cast<const uint4*>(deck)[tid - 16];
+}
+
+HbRing hb_replay_ring(hb_engine* e);  // hb_replay.cu
+
+int hb_launch_tick(hb_engine* e, int do_step, int do_reset) {
+  HbTickArgs a;
+  memset(&a, 0, sizeof(a));
+  a.games = e->d_games; a.decks = e->d_decks; a.inject = e->d_inject; a.cfg = e->env; a.seed = e->cfg.seed;
+  a.do_step = do_step; a.do_reset = do_reset; a.has_replay = e->replay != nullptr;
+  a.a = e->d_a; a.greedy_a = e->d_greedy_a; a.obs = e->obs; a.eps_list = e->d_eps_list; a.reward = e->d_reward; a.terminal = e->d_terminal;
+  a.flags = e->d_flags; a.hid = hb_policy_hidden_ptrs(e);
+  a.oq = e->policy ? e->policy->oq : nullptr;
+  a.tq = e->policy && e->policy->have_weights[1] && e->cfg.priority_mode != 1 ? e->policy->tq : nullptr;
+  if (e->replay) a.ring = hb_replay_ring(e);
+  HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
+  hb_k_tick<<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a);
+  HB_CUDA(cudaGetLastError());
+  e->launches += 1;
+  return 0;
+}
+
+extern "C" {
+
+// n iterations of HanabiThreadLoop::mainLoop (cpp/thread_loop.h:42-88) for every game at once, entirely on the device.
+int hb_rollout(hb_engine* e, int n_ticks) {
+  if (!e) { hb_set_error("hb_rollout: null engine"); return -1; }
+  if (!e->policy || !e->policy->have_weights[0]) { hb_set_error("hb_rollout: no policy weights (hb_policy_set_weights)"); return -1; }
+  HB_CUDA(cudaSetDevice(e->device));
+  for (int i = 0; i < n_ticks; ++i) {
+    int rc = hb_launch_tick(e, e->pending_actions, 1);
+    if (rc) return rc;
+    rc = hb_policy_forward(e, 0);
+    if (rc) return rc;
+    e->pending_actions = 1;
+    e->num_act += e->G;
+  }
+  return 0;
+}
+
+}  // extern "C"

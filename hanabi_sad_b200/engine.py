@@ -4,7 +4,7 @@ import ctypes
 
 import numpy as np
 
-from ._lib import HbConfig, HbGameInfo, HbWeights, check, lib
+from ._lib import HbBatch, HbConfig, HbGameInfo, HbWeights, check, lib
 
 
 def _ptr(a):
@@ -166,6 +166,53 @@ class Engine:
             out["h"], out["c"] = h, c
         check(lib().hb_policy_get(self._h, _ptr(out["adv"]), _ptr(out["online_q"]), _ptr(out["target_q"]), _ptr(h), _ptr(c)))
         return out
+
+    # ---- fused actor loop + replay ------------------------------------------------------------------------
+    def rollout(self, n_ticks):
+        check(lib().hb_rollout(self._h, int(n_ticks)))
+
+    def counters(self):
+        """(replay size, num_add, num_act) -- RNNPrioritizedReplay.size()/num_add(), sum of R2D2Actor.num_act()."""
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib().hb_counters(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
+    def sample(self, batchsize, device=None):
+        """PrioritizedReplay::sample: torch tensors on the engine's GPU in the learner's layout + importance weights."""
+        import torch
+
+        dev = torch.device("cuda", self.cfg.device)
+        T, B = self.cfg.seq_len, int(batchsize)
+        pp = (self.P,) if self.cfg.vdn else ()
+        f32 = dict(dtype=torch.float32, device=dev)
+        t = {
+            "priv_s": torch.empty((T, B) + pp + (self.F,), **f32), "legal_move": torch.empty((T, B) + pp + (self.A,), **f32),
+            "own_hand": torch.empty((T, B) + pp + (3 * self.H,), **f32), "eps": torch.empty((T, B) + pp, **f32),
+            "a": torch.empty((T, B) + pp, dtype=torch.int64, device=dev), "greedy_a": torch.empty((T, B) + pp, dtype=torch.int64, device=dev),
+            "reward": torch.empty((T, B), **f32), "bootstrap": torch.empty((T, B), **f32),
+            "terminal": torch.empty((T, B), dtype=torch.uint8, device=dev), "seq_len": torch.empty((B,), **f32),
+            "weight": torch.empty((B,), **f32), "ids": torch.empty((B,), dtype=torch.int32, device=dev),
+        }
+        hb = HbBatch()
+        for k, v in t.items():
+            setattr(hb, k, v.data_ptr())
+        torch.cuda.current_stream(dev).synchronize()  # the allocator may hand back memory still in use on torch's stream
+        check(lib().hb_replay_sample(self._h, B, ctypes.byref(hb)))
+        t["terminal"] = t["terminal"].bool()
+        return t
+
+    def update_priority(self, priority):
+        """PrioritizedReplay::updatePriority: `priority` = torch tensor (any device) or numpy array, float32 [B]."""
+        if hasattr(priority, "data_ptr"):
+            p = priority.detach().float().contiguous()
+            if p.is_cuda:
+                import torch
+
+                torch.cuda.current_stream(p.device).synchronize()
+            check(lib().hb_replay_update_priority(self._h, p.data_ptr(), int(p.numel())))
+        else:
+            p = np.ascontiguousarray(priority, dtype=np.float32)
+            check(lib().hb_replay_update_priority(self._h, _ptr(p), int(p.size)))
 
     def sync(self):
         check(lib().hb_sync(self._h))

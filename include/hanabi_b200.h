@@ -159,6 +159,36 @@ int hb_policy_act(hb_engine* e, int greedy_only);
  * CURRENT hidden state (R2D2Actor::hidden_). */
 int hb_policy_get(hb_engine* e, float* adv, float* online_q, float* target_q, float* h, float* c);
 
+/* ---- fused actor loop + replay -------------------------------------------------------------------------- */
+
+/* n iterations of HanabiThreadLoop::mainLoop (cpp/thread_loop.h:42-88) for every game of the engine, on the device:
+ * VectorEnv::step with the pending reply, R2D2Actor::postAct (n-step return, priority, episode assembly,
+ * PrioritizedReplay::add when an episode ends, hidden-state reset), VectorEnv::reset of finished games, observation
+ * encoding, R2D2Actor::act (policy forward, eps-greedy).  Asynchronous: returns once the work is queued. */
+int hb_rollout(hb_engine* e, int n_ticks);
+
+/* RNNPrioritizedReplay::size / numAdd (rela/prioritized_replay.h:259-265) and the sum of R2D2Actor::numAct
+ * (rela/r2d2_actor.h:57-59) in env-steps.  NULL skips.  Synchronises with the engine stream. */
+int hb_counters(hb_engine* e, int64_t* size, int64_t* num_add, int64_t* num_act);
+
+/* Destination of one sampled batch: DEVICE pointers owned by the caller, in the layouts RNNTransition::makeBatch
+ * produces (rela/transition.cc:160-202).  With vdn: priv_s [T,B,P,F], legal_move [T,B,P,A], own_hand [T,B,P,3H],
+ * eps [T,B,P], a / greedy_a int64 [T,B,P]; without (iql): the same without the P axis.  reward, bootstrap float [T,B];
+ * terminal uint8 [T,B]; seq_len float [B]; weight float [B] (importance weights); ids int32 [B] or NULL. */
+typedef struct hb_batch {
+  float* priv_s; float* legal_move; float* own_hand; float* eps;
+  int64_t* a; int64_t* greedy_a;
+  float* reward; float* bootstrap; uint8_t* terminal; float* seq_len;
+  float* weight; int32_t* ids;
+} hb_batch;
+
+/* PrioritizedReplay::sample (rela/prioritized_replay.h:208-240, 274-345).  Returns -3 if the replay holds fewer than
+ * `batchsize` entries or the previous batch's priorities were not written back. */
+int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out);
+
+/* PrioritizedReplay::updatePriority (rela/prioritized_replay.h:242-257): `priority` float [n], host or device. */
+int hb_replay_update_priority(hb_engine* e, const float* priority, int n);
+
 /* Diagnostic: run the tcgen05 GEMM template alone, C[M,N] = A[M,K] B[N,K]^T + bias on host fp32 buffers
  * (M % 128 == N % 256 == K % 64 == 0; split != 0 selects the bf16x3 fp32-class mode). */
 int hb_debug_gemm(int device, const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int split);
