@@ -38,7 +38,9 @@ def parse():
     ap.add_argument("--shuffle_color", type=int, default=0)
     ap.add_argument("--mode", default="auto", choices=["auto", "rollout", "env"],
                     help="rollout: fused env+policy+replay tick; env: env step/encode + random-legal policy only")
-    ap.add_argument("--precision", default="x3", choices=["x3", "x1"], help="rollout policy GEMM: bf16x3 split (fp32-class) or bf16")
+    ap.add_argument("--target_precision", default="x3", choices=["x3", "x1", "uniform"],
+                    help="priority (target-network) forward: bf16x3 like the online net, plain bf16, or none (uniform priority)")
+    ap.add_argument("--replay_capacity", type=int, default=16384, help="episodes held by the device replay (563 KB each at C2)")
     ap.add_argument("--cpu_seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--ref_seconds", type=float, default=6.0, help="--impl reference: wall seconds per step sample")
@@ -191,16 +193,14 @@ def run_b200(args):
     if mode == "auto":
         mode = "rollout" if hasattr(hb.Engine, "rollout") else "env"
     eng = hb.Engine(G, P, H, 0, 80, bool(args.sad), bool(args.shuffle_color), eps_list(), seed=1 + 1000 * rank, device=local,
-                    replay_capacity=(16384 if mode == "rollout" else 0))
+                    vdn=True, multi_step=3, gamma=0.999, eta=0.9, seq_len=80, replay_capacity=(args.replay_capacity if mode == "rollout" else 0),
+                    priority_mode={"x3": 0, "x1": 2, "uniform": 1}[args.target_precision], hid_dim=(512 if mode == "rollout" else 0))
     stream = torch.cuda.ExternalStream(eng.stream(), device=local)
     F, A = eng.F, eng.A
     peaks = load_peaks()
     flush = torch.empty(L2_BYTES * 2, dtype=torch.uint8, device="cuda")
 
-    if mode == "rollout":
-        runner = hb.bench_support.RolloutBench(eng, args)  # noqa: F821  (added with the fused rollout)
-    else:
-        runner = EnvBench(eng)
+    runner = RolloutBench(eng, args) if mode == "rollout" else EnvBench(eng)
 
     def barrier():
         torch.cuda.synchronize()
@@ -277,6 +277,87 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def random_weights(F, A, H, seed):
+    """R2D2Net parameters with nn.Linear / nn.LSTM default-init ranges (synthetic: there are no checkpoints offline)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    hid = 512
+
+    def u(shape, fan):
+        b = 1.0 / np.sqrt(fan)
+        return rng.uniform(-b, b, size=shape).astype(np.float32)
+
+    sd = {"net.0.weight": u((hid, F), F), "net.0.bias": u((hid,), F), "fc_v.weight": u((1, hid), hid), "fc_v.bias": u((1,), hid),
+          "fc_a.weight": u((A, hid), hid), "fc_a.bias": u((A,), hid)}
+    for l in range(2):
+        for k, shp in (("weight_ih", (4 * hid, hid)), ("weight_hh", (4 * hid, hid)), ("bias_ih", (4 * hid,)), ("bias_hh", (4 * hid,))):
+            sd["lstm.%s_l%d" % (k, l)] = u(shp, hid)
+    return sd
+
+
+class RolloutBench:
+    """The fused actor tick: env step + replay append / finalize + reset + encode (1 launch), policy forward of the online
+    and the target network (3 tcgen05 GEMM launches) and head / eps-greedy (1 launch)."""
+
+    flush_between_steps = False
+    dtype = "bf16x3 (fp32-class split accumulate), fp32 state"
+
+    def __init__(self, eng, args):
+        import torch
+
+        self.eng, self.args = eng, args
+        self.sd = random_weights(eng.F, eng.A, eng.H, 1)
+        self.sd_t = random_weights(eng.F, eng.A, eng.H, 2)
+        self.pinned = {k: torch.from_numpy(v).pin_memory() for k, v in self.sd.items()}
+        eng.set_weights(0, self.sd)
+        eng.set_weights(1, self.sd_t)
+        self.policy = "R2D2 online + target forward every tick (priority_mode %s), eps-greedy eps=generate_explore_eps(0.1,7,80), random-init weights" % args.target_precision
+        rows = eng.G * eng.P
+        ws = (rows * eng.F * 4 * 2 + rows * 896 * 2 * 2 + rows * 512 * (2 * 2 * 2 + 2 * 2 * 2 * 2 + 4 * 2 * 2 + 4 * 2) + 2 * 18.6e6 * 2) / 1e6
+        self.l2_note = "no flush: per-step working set ~%.0f MB (obs + GEMM operands + both halves of the recurrent state + 2 networks' weights) exceeds the 126 MB L2; consecutive ticks are the workload" % ws
+        self.e2e_note = ("hb_rollout(1) per step through the C ABI, host sync every step, D2H of reward/terminal/actions every step, "
+                         "H2D re-upload of the online weights from pinned host memory every 10th step (actor_sync_freq)")
+
+    def step(self, i):
+        self.eng.rollout(1)
+
+    def e2e(self, steps, stream):
+        eng = self.eng
+        sd_bytes = sum(v.numel() * 4 for v in self.pinned.values())
+        t0 = time.perf_counter()
+        for i in range(steps):
+            if i % 10 == 0:
+                eng.set_weights(0, self.pinned)
+            eng.rollout(1)
+            eng.result()
+            eng.actions()
+        dt = (time.perf_counter() - t0) * 1e3
+        h2d = sd_bytes // 10
+        d2h = eng.G * 5 + 2 * eng.G * eng.P * 8
+        return dt, h2d, d2h
+
+    def dominant(self, step_ms, peaks):
+        eng = self.eng
+        eng.profile(True)
+        eng.rollout(40)
+        prof = eng.profile(False)
+        rows = eng.G * eng.P
+        nets = 1 if self.args.target_precision == "uniform" else 2
+        flops = 2.0 * rows * 2048 * 1024 * nets            # one LSTM-layer launch, both networks (algorithmic: the fp32 math once)
+        ms = (prof["lstm0"][0] + prof["lstm1"][0]) / max(1, prof["lstm0"][1] + prof["lstm1"][1])
+        ach = flops / (ms * 1e-3) / 1e12
+        tick_total = sum(v[0] for v in prof.values()) / max(1, prof["tick"][1])
+        hbm_bytes = 40321.0 * eng.G                       # SURVEY 8(d): algorithmic bytes per env-step at C2
+        return {"bound": "tensor", "kernel": "hbg::gemm3_kernel<EPI_LSTM> (LSTM layer GEMM + fused cell update, online+target in one launch)",
+                "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                "peak_source": peaks["source"] + " (sustained bf16)", "algorithmic_flop_per_launch": flops, "avg_launch_ms": ms,
+                "tensor_issue_factor": 3 if True else 1,
+                "kernel_ms_per_tick": {k: v[0] / max(1, v[1]) for k, v in prof.items()}, "kernel_ms_sum_per_tick": tick_total,
+                "hbm_view": {"algorithmic_bytes_per_env_step": 40321, "achieved_gbs": hbm_bytes / (sum(step_ms) / len(step_ms) * 1e-3) / 1e9,
+                             "peak_gbs": peaks["hbm_gbs"]}}
 
 
 class EnvBench:

@@ -115,6 +115,7 @@ void hb_destroy(hb_engine* e) {
   cudaFree(e->obs.priv_s); cudaFree(e->obs.legal_move); cudaFree(e->obs.own_hand); cudaFree(e->obs.eps);
   cudaFree(e->d_reward); cudaFree(e->d_terminal); cudaFree(e->d_a); cudaFree(e->d_greedy_a); cudaFree(e->d_flags);
   cudaFreeHost(e->h_flags);
+  for (int k = 0; k < 2 * HB_PROF_N; ++k) if (e->prof_ev[k]) cudaEventDestroy(e->prof_ev[k]);
   cudaStreamDestroy(e->stream);
   delete e;
 }

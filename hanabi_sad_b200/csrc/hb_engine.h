@@ -43,6 +43,8 @@ struct HbHidPtrs {
   int rows_pad;
 };
 
+enum { HB_PROF_TICK = 0, HB_PROF_FC = 1, HB_PROF_LSTM0 = 2, HB_PROF_LSTM1 = 3, HB_PROF_HEAD = 4, HB_PROF_N = 5 };
+
 struct hb_engine {
   hb_config cfg;
   HbEnvCfg env;
@@ -51,6 +53,11 @@ struct hb_engine {
   int sm_count;
   cudaStream_t stream;
   int64_t launches;
+  // per-kernel-class device timing (hb_profile): CUDA events around every launch of a tick, off by default
+  int prof_on;
+  cudaEvent_t prof_ev[2 * HB_PROF_N];
+  double prof_ms[HB_PROF_N];
+  int64_t prof_n[HB_PROF_N];
   int pending_actions;   // d_a / d_greedy_a hold a reply the environment has not consumed yet
   int64_t num_act;       // sum of R2D2Actor::numAct_ (r2d2_actor.h:98): env-steps acted on
 
@@ -73,6 +80,14 @@ struct hb_engine {
 };
 
 void hb_set_error(const char* fmt, ...);
+
+// Brackets one kernel launch with events when profiling is on (see hb_profile in include/hanabi_b200.h).
+struct HbProfScope {
+  hb_engine* e;
+  int k;
+  HbProfScope(hb_engine* e_, int k_) : e(e_), k(k_) { if (e->prof_on) cudaEventRecord(e->prof_ev[2 * k], e->stream); }
+  ~HbProfScope() { if (e->prof_on) cudaEventRecord(e->prof_ev[2 * k + 1], e->stream); }
+};
 
 #define HB_CUDA(call)                                                                                   \
   do {                                                                                                  \

@@ -401,9 +401,12 @@ int hb_policy_forward(hb_engine* e, int greedy_only) {
   const int nets = P->have_weights[1] && e->cfg.priority_mode != 1 ? 2 : 1;
   const int mt = P->rows_pad / hbg::BM;
   const Params* base = P->d_params + (size_t)P->parity * 6;
-  hbg::gemm3_kernel<hbg::EPI_RELU><<<dim3(HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 0);
-  hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 2);
-  hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 4);
+  { HbProfScope ps(e, HB_PROF_FC);
+    hbg::gemm3_kernel<hbg::EPI_RELU><<<dim3(HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 0); }
+  { HbProfScope ps(e, HB_PROF_LSTM0);
+    hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 2); }
+  { HbProfScope ps(e, HB_PROF_LSTM1);
+    hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 4); }
   HbHeadArgs a;
   a.rows = e->rows; a.A = e->A; a.have_target = nets == 2;
   for (int n = 0; n < 2; ++n) {
@@ -411,7 +414,8 @@ int hb_policy_forward(hb_engine* e, int greedy_only) {
   }
   a.legal = e->obs.legal_move; a.eps = e->obs.eps; a.a = e->d_a; a.greedy_a = e->d_greedy_a;
   a.adv = P->adv; a.oq = P->oq; a.tq = P->tq; a.seed = e->cfg.seed; a.tick = (uint32_t)P->act_count; a.greedy_only = greedy_only;
-  hb_k_head_act<<<(e->rows + HB_HEAD_WARPS - 1) / HB_HEAD_WARPS, HB_HEAD_WARPS * 32, 0, e->stream>>>(a);
+  { HbProfScope ps(e, HB_PROF_HEAD);
+    hb_k_head_act<<<(e->rows + HB_HEAD_WARPS - 1) / HB_HEAD_WARPS, HB_HEAD_WARPS * 32, 0, e->stream>>>(a); }
   HB_CUDA(cudaGetLastError());
   e->launches += 4;
   P->parity ^= 1;

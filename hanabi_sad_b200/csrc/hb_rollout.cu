@@ -205,7 +205,8 @@ int hb_launch_tick(hb_engine* e, int do_step, int do_reset) {
   a.tq = e->policy && e->policy->have_weights[1] && e->cfg.priority_mode != 1 ? e->policy->tq : nullptr;
   if (e->replay) a.ring = hb_replay_ring(e);
   HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
-  hb_k_tick<<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a);
+  { HbProfScope ps(e, HB_PROF_TICK);
+    hb_k_tick<<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a); }
   HB_CUDA(cudaGetLastError());
   e->launches += 1;
   return 0;
@@ -225,7 +226,30 @@ int hb_rollout(hb_engine* e, int n_ticks) {
     if (rc) return rc;
     e->pending_actions = 1;
     e->num_act += e->G;
+    if (e->prof_on) {  // profiling mode: one sync per tick, accumulate the five launch durations
+      HB_CUDA(cudaStreamSynchronize(e->stream));
+      for (int k = 0; k < HB_PROF_N; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->prof_ev[2 * k], e->prof_ev[2 * k + 1]) == cudaSuccess) { e->prof_ms[k] += ms; e->prof_n[k] += 1; }
+      }
+    }
   }
+  return 0;
+}
+
+// Device time per kernel class of the fused tick, measured with CUDA events on the engine stream while `on`:
+// index 0 tick (env+replay+encode), 1 fc GEMM, 2 LSTM layer-0 GEMM, 3 LSTM layer-1 GEMM, 4 head/act.  Turning it on
+// clears the accumulators and makes hb_rollout synchronise after every tick (do not time throughput in this mode).
+int hb_profile(hb_engine* e, int on, double* ms_sum, int64_t* launches) {
+  if (!e) { hb_set_error("hb_profile: null engine"); return -1; }
+  HB_CUDA(cudaSetDevice(e->device));
+  if (ms_sum) for (int k = 0; k < HB_PROF_N; ++k) ms_sum[k] = e->prof_ms[k];
+  if (launches) for (int k = 0; k < HB_PROF_N; ++k) launches[k] = e->prof_n[k];
+  if (on && !e->prof_on) {
+    for (int k = 0; k < 2 * HB_PROF_N; ++k) if (!e->prof_ev[k]) HB_CUDA(cudaEventCreate(&e->prof_ev[k]));
+    for (int k = 0; k < HB_PROF_N; ++k) { e->prof_ms[k] = 0; e->prof_n[k] = 0; }
+  }
+  e->prof_on = on ? 1 : 0;
   return 0;
 }
 

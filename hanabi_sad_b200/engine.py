@@ -214,6 +214,13 @@ class Engine:
             p = np.ascontiguousarray(priority, dtype=np.float32)
             check(lib().hb_replay_update_priority(self._h, _ptr(p), int(p.size)))
 
+    def profile(self, on):
+        """Switch per-kernel event timing on/off; returns what was gathered so far as {name: (ms_sum, launches)}."""
+        ms = np.zeros(5, np.float64)
+        n = np.zeros(5, np.int64)
+        check(lib().hb_profile(self._h, int(bool(on)), _ptr(ms), _ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("tick", "fc", "lstm0", "lstm1", "head"))}
+
     def sync(self):
         check(lib().hb_sync(self._h))
 

@@ -189,6 +189,11 @@ int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out);
 /* PrioritizedReplay::updatePriority (rela/prioritized_replay.h:242-257): `priority` float [n], host or device. */
 int hb_replay_update_priority(hb_engine* e, const float* priority, int n);
 
+/* Measurement hook: device time per kernel class of the fused tick (CUDA events on the engine stream).  Returns the
+ * accumulated milliseconds / launch counts [5] = {tick, fc GEMM, LSTM-0 GEMM, LSTM-1 GEMM, head} gathered while
+ * profiling was on, then switches profiling on/off (switching on clears the accumulators).  NULL skips. */
+int hb_profile(hb_engine* e, int on, double* ms_sum, int64_t* launches);
+
 /* Diagnostic: run the tcgen05 GEMM template alone, C[M,N] = A[M,K] B[N,K]^T + bias on host fp32 buffers
  * (M % 128 == N % 256 == K % 64 == 0; split != 0 selects the bf16x3 fp32-class mode). */
 int hb_debug_gemm(int device, const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int split);
