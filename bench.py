@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu_seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--ref_seconds", type=float, default=6.0, help="--impl reference: wall seconds per step sample")
+    ap.add_argument("--ref_replay", type=int, default=4096, help="--impl reference: replay capacity in episodes (563 KB of host RAM each)")
+    ap.add_argument("--ref_port", action="store_true", help="--impl reference: time the C oracle port of the env path instead of the reference actors")
     return ap.parse_args()
 
 
@@ -140,31 +142,113 @@ def cpu_port_sample(args, seconds, threads):
         threads, envs, steps_per_env, total, dt)
 
 
+class ReferenceActors:
+    """The UNMODIFIED reference actor stack (oracle/_ref: rela + hanalearn pybind modules built from /root/reference by
+    oracle/build_ref.sh, its own pyhanabi/r2d2.py TorchScript agent): Context + HanabiThreadLoop threads on every host
+    core, R2D2Actor + BatchRunner("act", "compute_priority") on `device`, RNNPrioritizedReplay -- i.e. create.py's
+    ActGroup / create_threads (pyhanabi/create.py:57-145) with the C2 flags.  env-steps = sum of R2D2Actor.num_act()."""
+
+    def __init__(self, args, device):
+        import torch
+        from oracle.oracle import REF_DIR, import_ref
+
+        self.rela, self.hanalearn = import_ref()
+        sys.path.insert(0, os.path.join(REF_DIR, "pyhanabi"))
+        import r2d2  # the reference's own (generated copy with the one-token TorchScript fix, oracle/build_ref.sh)
+
+        P, H = args.players, args.hand_size
+        self.threads = os.cpu_count() or 1
+        self.gpt = max(1, args.games // self.threads)
+        self.games = []
+        for i in range(self.threads * self.gpt):
+            params = {"players": str(P), "hand_size": str(H), "seed": str(1 + i), "bomb": "0"}
+            self.games.append(self.hanalearn.HanabiEnv(params, eps_list(), 80, bool(args.sad), False, bool(args.shuffle_color), False))
+        F, A = self.games[0].feature_size(), self.games[0].num_action()
+        torch.manual_seed(1)
+        self.agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, device, F, 512, A, 2, H, False).to(device)
+        self.replay = self.rela.RNNPrioritizedReplay(args.ref_replay, 1, 0.6, 0.4, 0)
+        self.runner = self.rela.BatchRunner(self.agent.clone(device), device, 100, ["act", "compute_priority"])
+        self.actors = [self.rela.R2D2Actor(self.runner, 3, self.gpt, 0.999, 0.9, 80, P, self.replay) for _ in range(self.threads)]
+        self.context = self.rela.Context()
+        self.loops = []
+        for t in range(self.threads):
+            env = self.hanalearn.HanabiVecEnv()
+            for g in range(self.gpt):
+                env.append(self.games[t * self.gpt + g])
+            loop = self.hanalearn.HanabiThreadLoop(self.actors[t], env, False)
+            self.loops.append(loop)
+            self.context.push_env_thread(loop)
+        self.device = device
+        self.runner.start()
+        self.context.start()
+
+    def num_act(self):
+        return sum(a.num_act() for a in self.actors)
+
+    def sample(self, seconds):
+        n0, t0 = self.num_act(), time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            time.sleep(0.05)
+            # keep the replay from filling up (a full ring blocks the actors, prioritized_replay.h:52-57): do what the
+            # learner does, sample + write back, without training
+            if self.replay.size() > 256:
+                _, w = self.replay.sample(128, "cpu")
+                self.replay.update_priority(w.cpu())
+        dt = time.perf_counter() - t0
+        return (self.num_act() - n0) / dt, dt
+
+    def close(self):
+        self.context.terminate()
+        while not self.context.terminated():
+            time.sleep(0.05)
+        self.runner.stop()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    from oracle.oracle import ref_available
+
     vals = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        v, dt, sample = cpu_port_sample(args, args.ref_seconds, cores)
-        if i >= args.warmup:
-            vals.append((v, dt))
-        if sum(d for _, d in vals) > 150:
-            break
+    if ref_available() and not args.ref_port:
+        import torch
+
+        device = "cuda:0" if torch.cuda.is_available() else "cpu"
+        ra = ReferenceActors(args, device)
+        ra.sample(min(3.0, args.ref_seconds))  # let every thread finish its first ticks / TorchScript warm-up
+        for i in range(args.warmup + args.steps):
+            v, dt = ra.sample(args.ref_seconds)
+            if i >= args.warmup:
+                vals.append((v, dt))
+            if sum(d for _, d in vals) > 150:
+                break
+        kind = "reference"
+        sample = ("unmodified reference actors (oracle/_ref): %d HanabiThreadLoop threads x %d games = %d games, vdn, sad=%d, R2D2Actor + BatchRunner"
+                  "(act, compute_priority) with the TorchScript R2D2Agent on %s; each step = %.0f s of wall time, env-steps from R2D2Actor.num_act()"
+                  % (ra.threads, ra.gpt, ra.threads * ra.gpt, args.sad, device, args.ref_seconds))
+    else:
+        for i in range(args.warmup + args.steps):
+            v, dt, sample = cpu_port_sample(args, args.ref_seconds, cores)
+            if i >= args.warmup:
+                vals.append((v, dt))
+            if sum(d for _, d in vals) > 150:
+                break
+        kind = "port"
     value = sum(v * d for v, d in vals) / max(1e-9, sum(d for _, d in vals))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(d for _, d in vals) / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "games": args.games, "players": args.players, "hand_size": args.hand_size, "sad": args.sad},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
-    return 0
+    sys.stdout.flush()
+    os._exit(0)  # the reference's runner / env threads are plain C++ threads; do not wait on their destructors
 
 
 def workload_name(args):

@@ -61,6 +61,7 @@ SIGNATURES = {
     "hb_env_step_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hb_env_any_terminated": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "hb_env_query": (c_int, [c_void_p, c_int, ctypes.POINTER(HbGameInfo)]),
+    "hb_env_last_scores": (c_int, [c_void_p, c_void_p]),
     "hb_env_get_deck": (c_int, [c_void_p, c_int, c_void_p]),
     "hb_env_check_invariants": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "hb_env_get_actions": (c_int, [c_void_p, c_void_p, c_void_p]),

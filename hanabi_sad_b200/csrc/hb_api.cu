@@ -265,6 +265,20 @@ int hb_env_query(hb_engine* e, int game, hb_game_info* out) {
   return 0;
 }
 
+int hb_env_last_scores(hb_engine* e, int32_t* out) {
+  if (!e || !out) return hb_fail(-1, "hb_env_last_scores: null argument");
+  HB_CUDA(cudaSetDevice(e->device));
+  HbGame* tmp = new (std::nothrow) HbGame[e->G];
+  if (!tmp) return hb_fail(-2, "hb_env_last_scores: out of host memory");
+  cudaError_t c1 = cudaMemcpyAsync(tmp, e->d_games, (size_t)e->G * sizeof(HbGame), cudaMemcpyDeviceToHost, e->stream);
+  cudaError_t c2 = cudaStreamSynchronize(e->stream);
+  for (int g = 0; g < e->G; ++g) out[g] = tmp[g].last_score;
+  delete[] tmp;
+  HB_CUDA(c1);
+  HB_CUDA(c2);
+  return 0;
+}
+
 int hb_env_get_deck(hb_engine* e, int game, int8_t* deck50) {
   if (!e || !deck50) return hb_fail(-1, "hb_env_get_deck: null argument");
   if (game < 0 || game >= e->G) return hb_fail(-1, "hb_env_get_deck: game out of range");

@@ -100,6 +100,11 @@ class Engine:
         check(lib().hb_env_query(self._h, int(game), ctypes.byref(info)))
         return info
 
+    def last_scores(self):
+        out = np.empty((self.G,), np.int32)
+        check(lib().hb_env_last_scores(self._h, _ptr(out)))
+        return out
+
     def get_deck(self, game):
         out = np.empty((50,), np.int8)
         check(lib().hb_env_get_deck(self._h, int(game), _ptr(out)))

@@ -41,8 +41,9 @@ class HanabiEnv:
         self.eps_list = [float(x) for x in eps_list]
         self.max_len, self.sad, self.shuffle_color = int(max_len), bool(sad), bool(shuffle_color)
         self._F, self._A = _geom(self.players, self.hand_size, self.sad)
-        self._engine = None  # (engine, game index)
+        self._engine = None  # the engine holding this game's board state, and the game's index in it
         self._slot = 0
+        self._lock = None    # set when the engine is shared with a running rela.Context
         self._last_score = -1
         if verbose:
             print("Hanabi game created, with parameters:")
@@ -60,8 +61,8 @@ class HanabiEnv:
         return self.hand_size * 25
 
     # -- device state
-    def _bind(self, engine, slot):
-        self._engine, self._slot = engine, slot
+    def _bind(self, engine, slot, lock=None):
+        self._engine, self._slot, self._lock = engine, slot, lock
 
     def _eng(self):
         if self._engine is None:
@@ -95,6 +96,9 @@ class HanabiEnv:
         return self._obs(), float(r[0]), bool(t[0])
 
     def _info(self):
+        if self._lock is not None:
+            with self._lock:
+                return self._engine.query(self._slot)
         return self._eng().query(self._slot)
 
     def terminated(self):
@@ -107,6 +111,8 @@ class HanabiEnv:
         return self._info().cur_player
 
     def last_score(self):
+        if self._engine is None and self._last_score >= 0:
+            return self._last_score  # filled in bulk when an eval Context finished and released its engine
         i = self._info()
         return i.last_score
 
@@ -145,3 +151,19 @@ class HanabiVecEnv:
 
     def size(self):
         return len(self.envs)
+
+
+from . import rela as _rela  # noqa: E402
+
+
+class HanabiThreadLoop(_rela.ThreadLoop):
+    """hanalearn.HanabiThreadLoop(actor | [actors], vec_env, eval) (cpp/thread_loop.h:13-40, cpp/pybind.cc:45-55): a
+    description of one env thread; rela.Context.start() turns all of them into device rollouts."""
+
+    def __init__(self, actor, vec_env, eval_mode):
+        self.actor_arg = actor
+        self.actors = list(actor) if isinstance(actor, (list, tuple)) else [actor]
+        self.vec_env = vec_env
+        self.eval = bool(eval_mode)
+        if self.eval:
+            assert vec_env.size() == 1, "eval thread loops hold one game (cpp/thread_loop.h:20-25)"

@@ -1,0 +1,346 @@
+"""`rela` facade -- the classes of the reference's pybind module rela/pybind.cc:16-93 (Context, BatchRunner, R2D2Actor,
+RNNPrioritizedReplay, RNNTransition, aggregate_priority, ThreadLoop) with the same constructor signatures and methods,
+so that pyhanabi/create.py, selfplay.py and eval.py can run unmodified against this package.
+
+Nothing here computes: the objects are descriptions until `Context.start()`, which groups the pushed thread loops by
+act device and builds ONE CUDA engine per device (include/hanabi_b200.h) holding all their games, the device policy and
+the replay shard.  A single host thread per engine then keeps `hb_rollout` queued -- it replaces the reference's
+num_thread env threads + runner threads (cpp/thread_loop.h:42-88, rela/batch_runner.h:84-113).
+"""
+import threading
+import time
+
+import numpy as np
+import torch
+
+from .engine import Engine
+
+ROLLOUT_CHUNK = 8  # ticks queued per host iteration (pause / terminate latency = one chunk)
+
+
+class _EngineLock:
+    """Mutex around one engine (the C ABI is single-caller) that lets foreground callers -- the learner thread's sample /
+    update_priority / update_model / counters -- overtake the rollout driver thread, which would otherwise re-acquire a
+    plain Lock immediately after releasing it and starve them."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._waiting = 0
+        self._meta = threading.Lock()
+
+    def __enter__(self):
+        with self._meta:
+            self._waiting += 1
+        self._lock.acquire()
+        with self._meta:
+            self._waiting -= 1
+        return self
+
+    def __exit__(self, *exc):
+        self._lock.release()
+
+    def driver_acquire(self):
+        while True:
+            while self._waiting > 0:
+                time.sleep(0.0002)
+            self._lock.acquire()
+            if self._waiting == 0:
+                return
+            self._lock.release()
+
+    def driver_release(self):
+        self._lock.release()
+
+
+def aggregate_priority(priority, seq_len, eta):
+    """rela.aggregate_priority (rela/r2d2_actor.h:10-21; called from selfplay.py:222-224): priority [T,B], seq_len [B]."""
+    mask = torch.arange(0, priority.size(0), device=priority.device)
+    mask = (mask.unsqueeze(1) < seq_len.unsqueeze(0)).float()
+    priority = priority * mask
+    p_mean = priority.sum(0) / seq_len
+    p_max = priority.max(0)[0]
+    return (eta * p_max + (1.0 - eta) * p_mean).detach()
+
+
+class RNNTransition:
+    """rela.RNNTransition (rela/pybind.cc:25-32): obs, h0, action, reward, terminal, bootstrap, seq_len."""
+
+    def __init__(self, obs, action, reward, terminal, bootstrap, seq_len):
+        self.obs, self.h0, self.action = obs, {}, action
+        self.reward, self.terminal, self.bootstrap, self.seq_len = reward, terminal, bootstrap, seq_len
+
+    def to_device(self, device):
+        mv = lambda d: {k: v.to(device) for k, v in d.items()}
+        return RNNTransition(mv(self.obs), mv(self.action), self.reward.to(device), self.terminal.to(device), self.bootstrap.to(device),
+                             self.seq_len.to(device))
+
+
+class RNNPrioritizedReplay:
+    """rela.RNNPrioritizedReplay(capacity, seed, alpha, beta, prefetch) (rela/prioritized_replay.h:176-265).  The storage is
+    the device ring of the engine(s) created by Context.start(); `prefetch` is accepted and ignored (sampling is a
+    device kernel, there is nothing to overlap with host threads)."""
+
+    def __init__(self, capacity, seed, alpha, beta, prefetch=0):
+        self.capacity, self.seed, self.alpha, self.beta, self.prefetch = int(capacity), int(seed), float(alpha), float(beta), int(prefetch)
+        self._engines = []       # (engine, lock)
+        self._last = []          # engines sampled from (with counts) awaiting update_priority
+
+    def _attach(self, engine, lock):
+        self._engines.append((engine, lock))
+
+    def size(self):
+        n = 0
+        for e, lk in self._engines:
+            with lk:
+                n += e.counters()[0]
+        return n
+
+    def num_add(self):
+        n = 0
+        for e, lk in self._engines:
+            with lk:
+                n += e.counters()[1]
+        return n
+
+    def sample(self, batchsize, device):
+        if self._last:
+            raise RuntimeError("Error: previous samples' priority has not been updated.")  # prioritized_replay.h:209-212
+        assert self._engines, "the replay is filled by a started rela.Context"
+        n_eng = len(self._engines)
+        parts, shares = [], [batchsize // n_eng + (1 if i < batchsize % n_eng else 0) for i in range(n_eng)]
+        for (e, lk), b in zip(self._engines, shares):
+            if b == 0:
+                continue
+            with lk:
+                t = e.sample(b)
+            parts.append(t)
+            self._last.append((e, lk, b))
+        dev = torch.device(device)
+        cat = lambda k, dim: torch.cat([p[k].to(dev) for p in parts], dim) if len(parts) > 1 else parts[0][k].to(dev)
+        obs = {k: cat(k, 1) for k in ("priv_s", "legal_move", "eps", "own_hand")}
+        action = {k: cat(k, 1) for k in ("a", "greedy_a")}
+        batch = RNNTransition(obs, action, cat("reward", 1), cat("terminal", 1), cat("bootstrap", 1), cat("seq_len", 0))
+        weight = cat("weight", 0)
+        if len(parts) > 1:
+            weight = weight / weight.max()
+        return batch, weight
+
+    def update_priority(self, priority):
+        if priority.numel() == 0:
+            for e, lk, b in self._last:
+                with lk:
+                    e.update_priority(np.zeros((0,), np.float32))
+            self._last = []
+            return
+        off = 0
+        for e, lk, b in self._last:
+            with lk:
+                e.update_priority(priority[off:off + b])
+            off += b
+        assert off == priority.numel()
+        self._last = []
+
+    def get(self, idx):
+        raise NotImplementedError("RNNPrioritizedReplay.get is analysis tooling (tools/action_matrix.py); not part of the actor path")
+
+
+class BatchRunner:
+    """rela.BatchRunner(py_model, device, max_batchsize, methods) (rela/batch_runner.h:17-130): here the holder of the
+    agent whose weights the device policy uses, and of the act device name."""
+
+    def __init__(self, py_model, device, max_batchsize=100, methods=()):
+        self.agent, self.device, self.max_batchsize, self.methods = py_model, str(device), int(max_batchsize), list(methods)
+        self._engines = []
+        self._started = False
+
+    def _device_index(self):
+        d = torch.device(self.device)
+        assert d.type == "cuda", "the B200 actor path needs a CUDA act device, got %r" % self.device
+        return d.index or 0
+
+    def _attach(self, engine, lock):
+        self._engines.append((engine, lock))
+        self._push(engine, lock)
+
+    def _push(self, engine, lock):
+        with lock:
+            engine.set_weights(0, self.agent.online_net.state_dict())
+            engine.set_weights(1, self.agent.target_net.state_dict())
+
+    def start(self):
+        self._started = True
+
+    def stop(self):
+        self._started = False
+
+    def update_model(self, agent):
+        """BatchRunner::updateModel (batch_runner.h:74-77): load_state_dict of the learner's agent into the actors' copy."""
+        self.agent.load_state_dict(agent.state_dict())
+        for e, lk in self._engines:
+            self._push(e, lk)
+
+
+class R2D2Actor:
+    """rela.R2D2Actor (rela/r2d2_actor.h:23-58).  Training: (runner, multi_step, num_envs, gamma, eta, seq_len, num_player,
+    replay); eval: (runner, num_player)."""
+
+    def __init__(self, runner, *args):
+        self.runner = runner
+        if len(args) == 1:
+            self.num_player, self.replay, self.num_envs = int(args[0]), None, 1
+            self.multi_step, self.gamma, self.eta, self.seq_len = 1, 0.99, 0.0, 80
+        else:
+            multi_step, num_envs, gamma, eta, seq_len, num_player, replay = args
+            self.multi_step, self.num_envs, self.gamma, self.eta = int(multi_step), int(num_envs), float(gamma), float(eta)
+            self.seq_len, self.num_player, self.replay = int(seq_len), int(num_player), replay
+        self._engine = None  # (engine, lock, total games of the engine)
+
+    def num_act(self):
+        """R2D2Actor::numAct (r2d2_actor.h:57-59): += numEnvs per tick."""
+        if self._engine is None:
+            return 0
+        e, lk, G = self._engine
+        with lk:
+            return e.counters()[2] // G * self.num_envs
+
+
+class ThreadLoop:
+    """rela.ThreadLoop (rela/thread_loop.h:9-58): opaque base class."""
+
+
+class _DeviceGroup:
+    """All thread loops of one act device = one engine + one host driver thread."""
+
+    def __init__(self, loops):
+        from .hanalearn import HanabiEnv  # noqa: F401
+
+        self.loops = loops
+        self.lock = _EngineLock()
+        first = loops[0]
+        env0 = first.vec_env.envs[0]
+        actors = first.actors
+        self.eval = first.eval
+        self.iql = isinstance(first.actor_arg, (list, tuple)) and not self.eval and actors[0].num_player == 1 and env0.players > 1
+        self.envs = [g for lp in loops for g in lp.vec_env.envs]
+        for g in self.envs:
+            same = (g.players, g.hand_size, g.bomb, g.max_len, g.sad, g.shuffle_color, g.eps_list) == (
+                env0.players, env0.hand_size, env0.bomb, env0.max_len, env0.sad, env0.shuffle_color, env0.eps_list)
+            assert same, "all games of one act device must share the game configuration"
+        a0 = actors[0]
+        runner = a0.runner
+        if self.eval:
+            for a in actors:
+                if a.runner.agent is not runner.agent and a.runner is not runner:
+                    raise NotImplementedError("evaluating different agents per seat (cross-play) is not served by the device policy yet")
+        replay = a0.replay
+        hid = runner.agent.online_net.hid_dim
+        self.engine = Engine(
+            len(self.envs), env0.players, env0.hand_size, env0.bomb, env0.max_len, env0.sad, env0.shuffle_color, env0.eps_list,
+            seed=env0.seed, device=runner._device_index(), vdn=not self.iql, multi_step=a0.multi_step, gamma=a0.gamma, eta=a0.eta,
+            seq_len=a0.seq_len, replay_capacity=(replay.capacity if replay is not None else 0),
+            alpha=(replay.alpha if replay is not None else 0.6), beta=(replay.beta if replay is not None else 0.4), hid_dim=hid,
+            num_lstm_layer=runner.agent.online_net.num_lstm_layer, num_fc_layer=runner.agent.online_net.num_fc_layer,
+            skip_connect=runner.agent.online_net.skip_connect,
+            priority_mode=(1 if getattr(runner.agent, "uniform_priority", False) else 0))
+        for i, g in enumerate(self.envs):
+            g._bind(self.engine, i, self.lock)
+        seen = set()
+        for lp in loops:
+            for a in lp.actors:
+                a._engine = (self.engine, self.lock, len(self.envs))
+                if id(a.runner) not in seen:
+                    seen.add(id(a.runner))
+                    a.runner._attach(self.engine, self.lock)
+        if replay is not None:
+            replay._attach(self.engine, self.lock)
+        self.paused = threading.Event()
+        self.stop = threading.Event()
+        self.done = threading.Event()
+        self.thread = None
+
+    def run(self):
+        try:
+            if self.eval:
+                self._run_eval()
+            else:
+                while not self.stop.is_set():
+                    if self.paused.is_set():
+                        time.sleep(0.002)
+                        continue
+                    self.lock.driver_acquire()
+                    try:
+                        if not self.paused.is_set() and not self.stop.is_set():  # pause() may have won the race for the lock
+                            self.engine.rollout(ROLLOUT_CHUNK)
+                            self.engine.sync()
+                    finally:
+                        self.lock.driver_release()
+        finally:
+            self.done.set()
+
+    def _run_eval(self):
+        """HanabiThreadLoop(eval=True) (cpp/thread_loop.h:74-86): every game plays ONE episode, no replay, no restart."""
+        e = self.engine
+        with self.lock:
+            e.reset()
+        while not self.stop.is_set():
+            with self.lock:
+                e.policy_act()
+                e.step_dev()
+                _, term = e.result()
+            if term.all():
+                break
+        with self.lock:
+            scores = e.last_scores()
+        for g, s in zip(self.envs, scores):
+            g._last_score = int(s)
+            g._engine, g._lock = None, None
+        for lp in self.loops:   # an eval engine lives for one evaluation (eval.py:19-66 builds everything anew each time)
+            for a in lp.actors:
+                a.runner._engines = [(en, lk) for en, lk in a.runner._engines if en is not e]
+                a._engine = None
+        e.close()
+
+
+class Context:
+    """rela.Context (rela/context.h:18-80)."""
+
+    def __init__(self):
+        self.loops, self.groups, self.started = [], [], False
+
+    def push_env_thread(self, loop):
+        assert not self.started
+        self.loops.append(loop)
+        return len(self.loops) - 1
+
+    def start(self):
+        by_dev = {}
+        for lp in self.loops:
+            by_dev.setdefault(lp.actors[0].runner.device, []).append(lp)
+        self.groups = [_DeviceGroup(lps) for lps in by_dev.values()]
+        for g in self.groups:
+            g.thread = threading.Thread(target=g.run, daemon=True)
+            g.thread.start()
+        self.started = True
+
+    def pause(self):
+        for g in self.groups:
+            g.paused.set()
+            with g.lock:   # wait for the chunk in flight
+                g.engine.sync()
+
+    def resume(self):
+        for g in self.groups:
+            g.paused.clear()
+
+    def terminate(self):
+        for g in self.groups:
+            g.stop.set()
+
+    def terminated(self):
+        return all(g.done.is_set() for g in self.groups)
+
+    def __del__(self):
+        try:
+            self.terminate()
+        except Exception:
+            pass

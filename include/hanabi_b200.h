@@ -114,6 +114,9 @@ int hb_env_step_dev(hb_engine* e, const int64_t* a_dev, const int64_t* greedy_a_
 int hb_env_any_terminated(hb_engine* e, int* out);
 int hb_env_query(hb_engine* e, int game, hb_game_info* out);
 
+/* HanabiEnv::lastScore of every game (hanabi_env.h:108-110): host int32 [G], -1 before a game's first terminal. */
+int hb_env_last_scores(hb_engine* e, int32_t* out);
+
 /* The 50-card deal order of `game`'s current episode (card id colour*5+rank), whether injected or drawn from the
  * engine's Philox stream -- what ApplyRandomChance (hanabi_state.cc:285-289) would have produced one draw at a
  * time.  Together with hb_env_query's eps_idx / perm it lets a test replay the same episode on the CPU oracle. */

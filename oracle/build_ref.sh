@@ -48,6 +48,6 @@ g++ -shared -o "../rela$EXT" rela_pybind.o transition.o $LIBS
 g++ -shared -o "../hanalearn$EXT" hl_pybind.o hanabi_env.o ../libhanabi.a $LIBS
 # 3. python side (generated copy, never committed)
 cp -r "$REF/pyhanabi/common_utils" "$OUT/pyhanabi/" 2>/dev/null || true
-for f in utils.py create.py eval.py set_path.py; do cp "$REF/pyhanabi/$f" "$OUT/pyhanabi/$f"; done
+for f in utils.py create.py eval.py set_path.py selfplay.py; do cp "$REF/pyhanabi/$f" "$OUT/pyhanabi/$f"; done
 sed 's/% s\.dim()/% priv_s.dim()/' "$REF/pyhanabi/r2d2.py" > "$OUT/pyhanabi/r2d2.py"
 echo "[build_ref] done -> $OUT"

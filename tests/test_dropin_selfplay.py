@@ -1,0 +1,41 @@
+"""Drop-in check on the GPU: the reference's OWN learner script (pyhanabi/selfplay.py with its create.py, eval.py, r2d2.py,
+utils.py -- the generated copies under oracle/_ref/pyhanabi, identical to the reference except the one-token TorchScript
+fix in r2d2.py) runs UNMODIFIED on top of this package's `rela` / `hanalearn` modules (hanabi_sad_b200/compat on
+sys.path where the reference expects its build/ directory): actors fill the device replay, the PyTorch learner samples,
+trains, writes priorities back, syncs weights to the actors, pauses them for the per-epoch evaluation and resumes."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PYH = os.path.join(ROOT, "oracle", "_ref", "pyhanabi")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(PYH, "selfplay.py")), reason="oracle/_ref/pyhanabi not generated (oracle/build_ref.sh)")
+@pytest.mark.parametrize("method,extra", [("vdn", []), ("iql", ["--shuffle_color", "1", "--pred_weight", "0.25"])], ids=["vdn_sad", "iql_sad_op_aux"])
+def test_reference_selfplay_runs_on_the_device_actors(gpu_or_skip, tmp_path, method, extra):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(ROOT, "hanabi_sad_b200", "compat") + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "selfplay.py", "--save_dir", str(tmp_path / "run"), "--method", method, "--num_thread", "2", "--num_game_per_thread", "64",
+           "--sad", "1", "--act_base_eps", "0.1", "--act_eps_alpha", "7", "--lr", "6.25e-05", "--eps", "1.5e-05", "--grad_clip", "5", "--gamma", "0.999",
+           "--seed", "1", "--batchsize", "32", "--burn_in_frames", "300", "--replay_buffer_size", "4096", "--epoch_len", "25", "--num_epoch", "2",
+           "--priority_exponent", "0.9", "--priority_weight", "0.6", "--train_bomb", "0", "--eval_bomb", "0", "--num_player", "2",
+           "--rnn_hid_dim", "512", "--act_device", "cuda:0", "--train_device", "cuda:0"] + extra
+    log = tmp_path / "selfplay.out"
+    with open(log, "w") as f:
+        try:
+            p = subprocess.run(cmd, cwd=PYH, env=env, stdout=f, stderr=subprocess.STDOUT, text=True, timeout=420)
+        except subprocess.TimeoutExpired:
+            pytest.fail("selfplay.py did not finish in 420 s; tail of its output:\n" + open(log).read()[-3000:])
+    out = open(log).read()
+    assert p.returncode == 0, out[-4000:]
+    m = re.findall(r"epoch (\d+), eval score: ([0-9.]+)", out)
+    assert [int(e) for e, _ in m] == [0, 1], out[-3000:]
+    assert all(0.0 <= float(s) <= 25.0 for _, s in m)
+    # Tachometer lines (utils.py:237-240): actors produced env-steps and replay entries while the learner trained
+    rates = re.findall(r"Speed: train: ([0-9.]+), act: ([0-9.]+), buffer_add: ([0-9.]+)", out)
+    assert rates and all(float(a) > 0 and float(b) > 0 for _, a, b in rates), out[-3000:]

@@ -1,0 +1,158 @@
+"""CPU-only host-logic test of the `rela` / `hanalearn` facades: the reference's own create.py / eval.py (generated copies
+in oracle/_ref/pyhanabi) drive the facade classes exactly as selfplay.py does, with the CUDA engine replaced by a
+recording fake -- checks grouping of thread loops into one engine per act device, configuration plumbing, the
+pause / resume / terminate protocol, replay sample / update_priority alternation, weight pushes and eval scoring."""
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PYH = os.path.join(ROOT, "oracle", "_ref", "pyhanabi")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(PYH, "create.py")), reason="oracle/_ref/pyhanabi not generated")
+
+
+class FakeEngine:
+    instances = []
+
+    def __init__(self, num_games, players, hand_size, bomb, max_len, sad, shuffle_color, eps_list, **kw):
+        self.G, self.P, self.H, self.kw = num_games, players, hand_size, dict(kw, bomb=bomb, max_len=max_len, sad=sad, shuffle_color=shuffle_color, eps=list(eps_list))
+        self.F, self.A = 838 if sad else 783, 21
+        self.ticks, self.weights, self.closed, self.sampled, self.updated = 0, [], False, 0, 0
+        self.eval_ticks = 0
+        FakeEngine.instances.append(self)
+
+    def rollout(self, n):
+        self.ticks += n
+        time.sleep(0.001)
+
+    def sync(self):
+        pass
+
+    def counters(self):
+        return (min(self.ticks // 4, self.kw["replay_capacity"]), self.ticks // 4, self.ticks * self.G)
+
+    def set_weights(self, net, sd):
+        assert "lstm.weight_ih_l0" in sd
+        self.weights.append(net)
+
+    def sample(self, b):
+        assert self.sampled == self.updated
+        self.sampled += 1
+        T, pp = self.kw["seq_len"], ((self.P,) if self.kw["vdn"] else ())
+        return {"priv_s": torch.zeros((T, b) + pp + (self.F,)), "legal_move": torch.ones((T, b) + pp + (self.A,)), "own_hand": torch.zeros((T, b) + pp + (15,)),
+                "eps": torch.zeros((T, b) + pp), "a": torch.zeros((T, b) + pp, dtype=torch.long), "greedy_a": torch.zeros((T, b) + pp, dtype=torch.long),
+                "reward": torch.zeros(T, b), "bootstrap": torch.ones(T, b), "terminal": torch.zeros(T, b, dtype=torch.bool), "seq_len": torch.full((b,), 7.0),
+                "weight": torch.ones(b), "ids": torch.zeros(b, dtype=torch.int32)}
+
+    def update_priority(self, p):
+        self.updated += 1
+
+    # eval primitives
+    def reset(self):
+        pass
+
+    def policy_act(self, greedy_only=False):
+        pass
+
+    def step_dev(self):
+        self.eval_ticks += 1
+
+    def result(self):
+        return np.zeros(self.G, np.float32), np.full(self.G, self.eval_ticks >= 5)
+
+    def last_scores(self):
+        return np.arange(self.G, dtype=np.int32) % 26
+
+    def close(self):
+        self.closed = True
+
+
+@pytest.fixture()
+def ref_modules(monkeypatch):
+    monkeypatch.syspath_prepend(PYH)
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "hanabi_sad_b200", "compat"))
+    for m in ("rela", "hanalearn", "create", "eval", "r2d2", "utils"):
+        sys.modules.pop(m, None)
+    import hanabi_sad_b200.rela as hrela
+
+    monkeypatch.setattr(hrela, "Engine", FakeEngine)
+    monkeypatch.setattr(hrela.BatchRunner, "_device_index", lambda self: 0)  # no CUDA here: the act device is "cpu" in this test
+    FakeEngine.instances = []
+    import create
+    import eval as ref_eval
+    import r2d2
+    import rela
+
+    assert rela.__file__.endswith(".so") and rela.Context is hrela.Context
+    yield create, ref_eval, r2d2, rela
+    for m in ("rela", "hanalearn", "create", "eval", "r2d2", "utils"):
+        sys.modules.pop(m, None)
+
+
+@pytest.mark.parametrize("method", ["vdn", "iql"])
+def test_selfplay_call_sequence(ref_modules, method):
+    create, ref_eval, r2d2, rela = ref_modules
+    nt, gpt, P = 3, 5, 2
+    games = create.create_envs(nt * gpt, 1, P, 5, 0, [0.1, 0.2], 80, True, False, False)
+    assert games[0].feature_size() == 838 and games[0].num_action() == 21
+    agent = r2d2.R2D2Agent(method == "vdn", 3, 0.999, 0.9, "cpu", 838, 512, 21, 2, 5, False)
+    replay = rela.RNNPrioritizedReplay(1000, 1, 0.9, 0.6, 3)
+    ag = create.ActGroup(method, "cpu", agent, nt, gpt, 3, 0.999, 0.9, 80, P, replay)
+    context, threads = create.create_threads(nt, gpt, ag.actors, games)
+    ag.start()
+    context.start()
+    assert len(FakeEngine.instances) == 1
+    eng = FakeEngine.instances[0]
+    assert eng.G == nt * gpt and eng.kw["vdn"] == (method == "vdn") and eng.kw["replay_capacity"] == 1000 and eng.kw["multi_step"] == 3
+    assert eng.kw["alpha"] == pytest.approx(0.9) and eng.kw["beta"] == pytest.approx(0.6) and eng.kw["seed"] == 1 and eng.kw["eps"] == [0.1, 0.2]
+    assert eng.weights == [0, 1]
+    t0 = time.time()
+    while replay.size() < 20:
+        assert time.time() - t0 < 20, "foreground calls are starved by the rollout driver"
+        time.sleep(0.01)
+    batch, weight = replay.sample(8, "cpu")
+    assert batch.obs["priv_s"].shape == ((80, 8, 2, 838) if method == "vdn" else (80, 8, 838)) and batch.h0 == {} and weight.shape == (8,)
+    with pytest.raises(RuntimeError):
+        replay.sample(8, "cpu")
+    prio = rela.aggregate_priority(torch.rand(80, 8), batch.seq_len, 0.9)
+    replay.update_priority(prio)
+    ag.update_model(agent)
+    assert eng.weights == [0, 1, 0, 1]
+    flat = [a for x in ag.actors for a in (x if isinstance(x, list) else [x])]
+    assert len(flat) == (nt if method == "vdn" else nt * P)
+    n1 = sum(a.num_act() for a in flat)
+    assert n1 > 0 and n1 % gpt == 0
+    context.pause()
+    t = eng.ticks
+    time.sleep(0.1)
+    assert eng.ticks == t
+    # per-epoch evaluation with the training context paused (selfplay.py:254-280)
+    eval_agent = agent.clone("cpu", {"vdn": False})
+    runners = [rela.BatchRunner(eval_agent, "cpu", 1000, ["act"]) for _ in range(P)]
+    score, perfect, scores, n_perfect = ref_eval.evaluate(None, 52, 7, 0, 0, True, runners=runners)
+    assert len(FakeEngine.instances) == 2 and FakeEngine.instances[1].closed and FakeEngine.instances[1].kw["max_len"] == -1
+    assert scores == [i % 26 for i in range(52)] and n_perfect == 2
+    context.resume()
+    time.sleep(0.05)
+    assert eng.ticks > t
+    context.terminate()
+    t0 = time.time()
+    while not context.terminated():
+        assert time.time() - t0 < 5
+        time.sleep(0.01)
+
+
+def test_aggregate_priority_matches_oracle():
+    from hanabi_sad_b200.rela import aggregate_priority
+    from oracle.replay_oracle import aggregate_priority as ref
+
+    rng = np.random.default_rng(0)
+    p = rng.random((80, 16)).astype(np.float32)
+    L = rng.integers(1, 81, size=16).astype(np.float32)
+    got = aggregate_priority(torch.from_numpy(p), torch.from_numpy(L), 0.9).numpy()
+    assert np.allclose(got, ref(p, L, 0.9), rtol=1e-6)
