@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--cpu_seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--ref_seconds", type=float, default=6.0, help="--impl reference: wall seconds per step sample")
-    ap.add_argument("--ref_replay", type=int, default=4096, help="--impl reference: replay capacity in episodes (563 KB of host RAM each)")
+    ap.add_argument("--ref_replay", type=int, default=8192, help="--impl reference: replay capacity in episodes (563 KB of host RAM each)")
+    ap.add_argument("--ref_threads", type=int, default=0, help="--impl reference: HanabiThreadLoop threads (0 = one per host core)")
     ap.add_argument("--ref_port", action="store_true", help="--impl reference: time the C oracle port of the env path instead of the reference actors")
     return ap.parse_args()
 
@@ -157,7 +158,7 @@ class ReferenceActors:
         import r2d2  # the reference's own (generated copy with the one-token TorchScript fix, oracle/build_ref.sh)
 
         P, H = args.players, args.hand_size
-        self.threads = os.cpu_count() or 1
+        self.threads = getattr(args, "ref_threads", 0) or (os.cpu_count() or 1)
         self.gpt = max(1, args.games // self.threads)
         self.games = []
         for i in range(self.threads * self.gpt):
@@ -166,6 +167,7 @@ class ReferenceActors:
         F, A = self.games[0].feature_size(), self.games[0].num_action()
         torch.manual_seed(1)
         self.agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, device, F, 512, A, 2, H, False).to(device)
+        self.capacity = args.ref_replay
         self.replay = self.rela.RNNPrioritizedReplay(args.ref_replay, 1, 0.6, 0.4, 0)
         self.runner = self.rela.BatchRunner(self.agent.clone(device), device, 100, ["act", "compute_priority"])
         self.actors = [self.rela.R2D2Actor(self.runner, 3, self.gpt, 0.999, 0.9, 80, P, self.replay) for _ in range(self.threads)]
@@ -188,10 +190,10 @@ class ReferenceActors:
     def sample(self, seconds):
         n0, t0 = self.num_act(), time.perf_counter()
         while time.perf_counter() - t0 < seconds:
-            time.sleep(0.05)
+            time.sleep(0.1)
             # keep the replay from filling up (a full ring blocks the actors, prioritized_replay.h:52-57): do what the
-            # learner does, sample + write back, without training
-            if self.replay.size() > 256:
+            # learner does, sample (which evicts down to capacity, :329-332) + write back, without training
+            if self.replay.size() > self.capacity:
                 _, w = self.replay.sample(128, "cpu")
                 self.replay.update_priority(w.cpu())
         dt = time.perf_counter() - t0
