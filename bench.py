@@ -149,7 +149,7 @@ class ReferenceActors:
     core, R2D2Actor + BatchRunner("act", "compute_priority") on `device`, RNNPrioritizedReplay -- i.e. create.py's
     ActGroup / create_threads (pyhanabi/create.py:57-145) with the C2 flags.  env-steps = sum of R2D2Actor.num_act()."""
 
-    def __init__(self, args, device):
+    def __init__(self, args, device, n_devices=1):
         import torch
         from oracle.oracle import REF_DIR, import_ref
 
@@ -159,7 +159,7 @@ class ReferenceActors:
 
         P, H = args.players, args.hand_size
         self.threads = getattr(args, "ref_threads", 0) or (os.cpu_count() or 1)
-        self.gpt = max(1, args.games // self.threads)
+        self.gpt = max(1, args.games * n_devices // self.threads)
         self.games = []
         for i in range(self.threads * self.gpt):
             params = {"players": str(P), "hand_size": str(H), "seed": str(1 + i), "bomb": "0"}
@@ -169,8 +169,10 @@ class ReferenceActors:
         self.agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, device, F, 512, A, 2, H, False).to(device)
         self.capacity = args.ref_replay
         self.replay = self.rela.RNNPrioritizedReplay(args.ref_replay, 1, 0.6, 0.4, 0)
-        self.runner = self.rela.BatchRunner(self.agent.clone(device), device, 100, ["act", "compute_priority"])
-        self.actors = [self.rela.R2D2Actor(self.runner, 3, self.gpt, 0.999, 0.9, 80, P, self.replay) for _ in range(self.threads)]
+        # one BatchRunner + cloned agent per act device, threads round-robin over them (create.py:94-110)
+        devs = [device] if not device.startswith("cuda") else ["cuda:%d" % i for i in range(n_devices)]
+        self.runners = [self.rela.BatchRunner(self.agent.clone(d), d, 100, ["act", "compute_priority"]) for d in devs]
+        self.actors = [self.rela.R2D2Actor(self.runners[t % len(self.runners)], 3, self.gpt, 0.999, 0.9, 80, P, self.replay) for t in range(self.threads)]
         self.context = self.rela.Context()
         self.loops = []
         for t in range(self.threads):
@@ -180,8 +182,9 @@ class ReferenceActors:
             loop = self.hanalearn.HanabiThreadLoop(self.actors[t], env, False)
             self.loops.append(loop)
             self.context.push_env_thread(loop)
-        self.device = device
-        self.runner.start()
+        self.device = ",".join(devs)
+        for r in self.runners:
+            r.start()
         self.context.start()
 
     def num_act(self):
@@ -203,7 +206,8 @@ class ReferenceActors:
         self.context.terminate()
         while not self.context.terminated():
             time.sleep(0.05)
-        self.runner.stop()
+        for r in self.runners:
+            r.stop()
 
 
 def run_reference(args):
@@ -218,7 +222,8 @@ def run_reference(args):
         import torch
 
         device = "cuda:0" if torch.cuda.is_available() else "cpu"
-        ra = ReferenceActors(args, device)
+        n_dev = max(1, min(args.gpus, torch.cuda.device_count())) if device != "cpu" else 1
+        ra = ReferenceActors(args, device, n_dev)
         ra.sample(min(3.0, args.ref_seconds))  # let every thread finish its first ticks / TorchScript warm-up
         for i in range(args.warmup + args.steps):
             v, dt = ra.sample(args.ref_seconds)
@@ -229,7 +234,7 @@ def run_reference(args):
         kind = "reference"
         sample = ("unmodified reference actors (oracle/_ref): %d HanabiThreadLoop threads x %d games = %d games, vdn, sad=%d, R2D2Actor + BatchRunner"
                   "(act, compute_priority) with the TorchScript R2D2Agent on %s; each step = %.0f s of wall time, env-steps from R2D2Actor.num_act()"
-                  % (ra.threads, ra.gpt, ra.threads * ra.gpt, args.sad, device, args.ref_seconds))
+                  % (ra.threads, ra.gpt, ra.threads * ra.gpt, args.sad, ra.device, args.ref_seconds))
     else:
         for i in range(args.warmup + args.steps):
             v, dt, sample = cpu_port_sample(args, args.ref_seconds, cores)

@@ -160,35 +160,51 @@ __device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi_
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-// grid = (N / BN, rows_padded / BM, number of Params records).  One output tile per CTA; blockIdx.z picks the
-// problem (online / target network), so both networks' layer runs as one launch.  Params records live in global
-// memory (the tensor maps inside them are read by the TMA unit through their generic address).
+// Persistent: grid = min(#tiles, #SMs), every CTA walks the tile list  tile = blockIdx.x, += gridDim.x  with
+// tile -> (problem z, m_tile, n_tile), n fastest, so that the CTAs running at the same time share A row-blocks and
+// the whole B matrix of one network in L2.  `ps[z]` picks the problem (online / target network): both networks' layer
+// run as one launch.  Params records live in global memory (the tensor maps inside them are read by the TMA unit
+// through their generic address).
+//
+// Three concurrent pipelines per CTA:
+//   warp 0 (1 thread)  TMA producer: streams K-chunks of A/B into a STAGES-deep shared-memory ring, across tile borders;
+//   warp 1 (1 thread)  tcgen05.mma issuer: accumulates a tile into one of TWO 256-column TMEM accumulators;
+//   warps 2-5          epilogue: drain the other accumulator (tcgen05.ld), apply the layer's pointwise tail, store.
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_ALLOC_COLS = ACC_STAGES * TMEM_COLS;  // 512: the whole tensor memory of the SM
+
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restrict__ ps) {
-  const Params& p = ps[blockIdx.z];
+__global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restrict__ ps, int n_tiles_n, int n_tiles_m, int n_problems) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // barriers: full[s] at +8s, empty[s] at +16+8s, tmem_full at +32, tmem base slot at +40
-  const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * STAGES, bar_tmem = bar_base + 16 * STAGES;
-  const uint32_t tmem_slot = bar_tmem + 8;
+  // barriers (8 bytes each): full[STAGES], empty[STAGES], tmem_full[ACC_STAGES], tmem_empty[ACC_STAGES], then the TMEM base slot
+  const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 8 * ACC_STAGES, tmem_slot = bar_tempty + 8 * ACC_STAGES;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool dead = false;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
-  const int k_chunks = p.k_chunks, lo_first = p.lo_first, lo_last = p.lo_last;
-  const bool split = p.split != 0;
+  const int tiles_per_problem = n_tiles_n * n_tiles_m;
+  const int total_tiles = tiles_per_problem * n_problems;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.a_hi[0]); tma_prefetch_desc(&p.a_lo[0]); tma_prefetch_desc(&p.b_hi); tma_prefetch_desc(&p.b_lo);
+    for (int z = 0; z < n_problems; ++z) {
+      tma_prefetch_desc(&ps[z].a_hi[0]); tma_prefetch_desc(&ps[z].a_lo[0]); tma_prefetch_desc(&ps[z].a_hi[1]); tma_prefetch_desc(&ps[z].a_lo[1]);
+      tma_prefetch_desc(&ps[z].b_hi); tma_prefetch_desc(&ps[z].b_lo);
+    }
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_tmem, 1);
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_ALLOC_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -199,120 +215,147 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int seg0 = p.k_chunks_seg0;
-      for (int kc = 0; kc < k_chunks; ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, dead);  // slot free (first pass: passes immediately)
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        const bool need_lo = split && kc >= lo_first && kc < lo_last;
-        mbar_expect_tx(bar_full + 8 * s, (need_lo ? 2 : 1) * A_TILE + (split ? 2 : 1) * B_TILE);
-        const int seg = kc >= seg0 ? 1 : 0;
-        const int kx = (seg ? kc - seg0 : kc) * BK;
-        tma_load_2d(st, &p.a_hi[seg], bar_full + 8 * s, kx, m_tile * BM);
-        if (need_lo) tma_load_2d(st + A_TILE, &p.a_lo[seg], bar_full + 8 * s, kx, m_tile * BM);
-        tma_load_2d(st + 2 * A_TILE, &p.b_hi, bar_full + 8 * s, kc * BK, n_tile * BN);
-        if (split) tma_load_2d(st + 2 * A_TILE + B_TILE, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_per_problem, r = tile - z * tiles_per_problem;
+        const int m_tile = r / n_tiles_n, n_tile = r - m_tile * n_tiles_n;
+        const Params& p = ps[z];
+        const int k_chunks = p.k_chunks, lo_first = p.lo_first, lo_last = p.lo_last, seg0 = p.k_chunks_seg0;
+        const bool split = p.split != 0;
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, dead);  // slot free (first pass: passes immediately)
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const bool need_lo = split && kc >= lo_first && kc < lo_last;
+          mbar_expect_tx(bar_full + 8 * s, (need_lo ? 2 : 1) * A_TILE + (split ? 2 : 1) * B_TILE);
+          const int seg = kc >= seg0 ? 1 : 0;
+          const int kx = (seg ? kc - seg0 : kc) * BK;
+          tma_load_2d(st, &p.a_hi[seg], bar_full + 8 * s, kx, m_tile * BM);
+          if (need_lo) tma_load_2d(st + A_TILE, &p.a_lo[seg], bar_full + 8 * s, kx, m_tile * BM);
+          tma_load_2d(st + 2 * A_TILE, &p.b_hi, bar_full + 8 * s, kc * BK, n_tile * BN);
+          if (split) tma_load_2d(st + 2 * A_TILE + B_TILE, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc();
-      uint32_t acc = 0;
-      for (int kc = 0; kc < k_chunks; ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (uint32_t)(kc / STAGES) & 1u;
-        mbar_wait(bar_full + 8 * s, ph, p.error_flag, dead);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int z = tile / tiles_per_problem;
+        const Params& p = ps[z];
+        const int k_chunks = p.k_chunks, lo_first = p.lo_first, lo_last = p.lo_last;
+        const bool split = p.split != 0;
+        const uint32_t acc_stage = lt % ACC_STAGES, aph = (lt / ACC_STAGES) & 1u;
+        mbar_wait(bar_tempty + 8 * acc_stage, aph ^ 1u, p.error_flag, dead);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        const bool need_lo = split && kc >= lo_first && kc < lo_last;
-        const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
-        const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE), b_lo = make_desc_sw128(st + 2 * A_TILE + B_TILE);
+        const uint32_t d_tmem = tmem_base + acc_stage * TMEM_COLS;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+          mbar_wait(bar_full + 8 * s, ph, p.error_flag, dead);
+          tc_fence_after();
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const bool need_lo = split && kc >= lo_first && kc < lo_last;
+          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE), b_lo = make_desc_sw128(st + 2 * A_TILE + B_TILE);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance the start address inside the swizzle span
-          if (split) { umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, acc); acc = 1; }  // small terms first
-          if (need_lo) umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
-          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
-          acc = 1;
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance the start address inside the swizzle span
+            if (split) { umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, acc); acc = 1; }  // small terms first
+            if (need_lo) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(bar_empty + 8 * s);          // the smem slot is free once these MMAs have read it
         }
-        umma_commit(bar_empty + 8 * s);  // the smem slot is free once these MMAs have read it
+        umma_commit(bar_tfull + 8 * acc_stage);    // accumulator complete
       }
-      umma_commit(bar_tmem);             // accumulator complete
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> pointwise tail -> global =====================
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
-    const size_t row = (size_t)m_tile * BM + row_in_tile;
-    mbar_wait(bar_tmem, 0, p.error_flag, dead);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (EPI == EPI_F32) {
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        float* dst = p.c_f32 + row * p.ldc + (size_t)n_tile * BN + c0;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int z = tile / tiles_per_problem, r = tile - z * tiles_per_problem;
+      const int m_tile = r / n_tiles_n, n_tile = r - m_tile * n_tiles_n;
+      const Params& p = ps[z];
+      const size_t row = (size_t)m_tile * BM + row_in_tile;
+      const uint32_t acc_stage = lt % ACC_STAGES, aph = (lt / ACC_STAGES) & 1u;
+      mbar_wait(bar_tfull + 8 * acc_stage, aph, p.error_flag, dead);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * TMEM_COLS;
+      if (EPI == EPI_F32) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          float* dst = p.c_f32 + row * p.ldc + (size_t)n_tile * BN + c0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += p.bias ? __ldg(p.bias + n_tile * BN + c0 + i) : 0.f;
+          for (int i = 0; i < 16; ++i) v[i] += p.bias ? __ldg(p.bias + n_tile * BN + c0 + i) : 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      } else if (EPI == EPI_RELU) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          const int col = n_tile * BN + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + col + i), 0.f);
+          const size_t o = row * p.out_ld + p.out_col0 + col;
+          store_split16(v, p.out_hi + o, p.out_lo + o);
+        }
+      } else {
+        // tile columns: [gate i | f | g | o][64 hidden units]; hidden unit = n_tile*64 + u
+        for (int u0 = 0; u0 < 64; u0 += 16) {
+          float gi[16], gf[16], gg[16], go[16], c[16], h[16];
+          tmem_ld16(taddr + 0 * 64 + u0, gi);
+          tmem_ld16(taddr + 1 * 64 + u0, gf);
+          tmem_ld16(taddr + 2 * 64 + u0, gg);
+          tmem_ld16(taddr + 3 * 64 + u0, go);
+          const int unit = n_tile * 64 + u0;
+          const float* bias = p.bias + n_tile * BN + u0;
+          const float4* cin = reinterpret_cast<const float4*>(p.c_in + row * HID + unit);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float4 t = cin[i]; c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w; }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float ig = sigmoid_f(gi[i] + __ldg(bias + i));
+            const float fg = sigmoid_f(gf[i] + __ldg(bias + 64 + i));
+            const float g_ = tanh_f(gg[i] + __ldg(bias + 128 + i));
+            const float og = sigmoid_f(go[i] + __ldg(bias + 192 + i));
+            c[i] = fg * c[i] + ig * g_;
+            h[i] = og * tanh_f(c[i]);
+          }
+          if (p.c_out) {
+            float4* cout = reinterpret_cast<float4*>(p.c_out + row * HID + unit);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cout[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+          }
+          if (p.h_f32) {
+            float4* ho = reinterpret_cast<float4*>(p.h_f32 + row * HID + unit);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ho[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+          }
+          if (p.out_hi) {
+            const size_t o = row * p.out_ld + p.out_col0 + unit;
+            store_split16(h, p.out_hi + o, p.out_lo + o);
+          }
+        }
       }
-    } else if (EPI == EPI_RELU) {
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        const int col = n_tile * BN + c0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + col + i), 0.f);
-        const size_t o = row * p.out_ld + p.out_col0 + col;
-        store_split16(v, p.out_hi + o, p.out_lo + o);
-      }
-    } else {
-      // tile columns: [gate i | f | g | o][64 hidden units]; hidden unit = n_tile*64 + u
-      for (int u0 = 0; u0 < 64; u0 += 16) {
-        float gi[16], gf[16], gg[16], go[16], c[16], h[16];
-        tmem_ld16(taddr + 0 * 64 + u0, gi);
-        tmem_ld16(taddr + 1 * 64 + u0, gf);
-        tmem_ld16(taddr + 2 * 64 + u0, gg);
-        tmem_ld16(taddr + 3 * 64 + u0, go);
-        const int unit = n_tile * 64 + u0;
-        const float* bias = p.bias + n_tile * BN + u0;
-        const float4* cin = reinterpret_cast<const float4*>(p.c_in + row * HID + unit);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const float4 t = cin[i]; c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w; }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float ig = sigmoid_f(gi[i] + __ldg(bias + i));
-          const float fg = sigmoid_f(gf[i] + __ldg(bias + 64 + i));
-          const float g_ = tanh_f(gg[i] + __ldg(bias + 128 + i));
-          const float og = sigmoid_f(go[i] + __ldg(bias + 192 + i));
-          c[i] = fg * c[i] + ig * g_;
-          h[i] = og * tanh_f(c[i]);
-        }
-        if (p.c_out) {
-          float4* cout = reinterpret_cast<float4*>(p.c_out + row * HID + unit);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cout[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
-        }
-        if (p.h_f32) {
-          float4* ho = reinterpret_cast<float4*>(p.h_f32 + row * HID + unit);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) ho[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-        }
-        if (p.out_hi) {
-          const size_t o = row * p.out_ld + p.out_col0 + unit;
-          store_split16(h, p.out_hi + o, p.out_lo + o);
-        }
-      }
+      // all of this warp's tcgen05.ld have completed (tmem_ld16 waits): hand the accumulator back to the MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc_stage);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC_COLS) : "memory");
   }
 }
 

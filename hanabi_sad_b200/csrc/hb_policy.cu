@@ -97,94 +97,119 @@ struct HbHeadArgs {
   int greedy_only;            // eval actors: eps ignored
 };
 
-#define HB_HEAD_WARPS 8
+#define HB_HEAD_WARPS 4
+#define HB_HEAD_ROWS 4   // agents per warp: every weight vector fetched from L1 is used for 4 rows
 
 __global__ void __launch_bounds__(HB_HEAD_WARPS * 32) hb_k_head_act(HbHeadArgs p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * HB_HEAD_WARPS + warp;
-  if (row >= p.rows) return;
+  const int row0 = (blockIdx.x * HB_HEAD_WARPS + warp) * HB_HEAD_ROWS;
+  if (row0 >= p.rows) return;
   const int A = p.A;
   const unsigned FULL = 0xffffffffu;
-  // legal mask: lane holds outputs lane and lane+32
-  const float* lm = p.legal + (size_t)row * A;
-  const float l0 = lane < A ? lm[lane] : 0.f;
-  const float l1 = lane + 32 < A ? lm[lane + 32] : 0.f;
-
-  int greedy = A - 1;
-  int action = A - 1;
-  for (int net = 0; net < (p.have_target ? 2 : 1); ++net) {
-    const float4* h4 = reinterpret_cast<const float4*>(p.htop[net] + (size_t)row * HB_HID);
-    float4 h[4];
+  const int nets = p.have_target ? 2 : 1;
+  // out[net][r][0|1]: lane holds outputs `lane` and `lane + 32` of row r; vv[net][r]: the value head
+  float out[2][HB_HEAD_ROWS][2], vv[2][HB_HEAD_ROWS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = h4[j * 32 + lane];
-    float o0 = 0.f, o1 = 0.f, v = 0.f;
+  for (int net = 0; net < 2; ++net) {
+    if (net >= nets) break;
+    float4 h[HB_HEAD_ROWS][4];
+#pragma unroll
+    for (int r = 0; r < HB_HEAD_ROWS; ++r) {
+      const int row = min(row0 + r, p.rows - 1);
+      const float4* h4 = reinterpret_cast<const float4*>(p.htop[net] + (size_t)row * HB_HID);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[r][j] = h4[j * 32 + lane];
+      out[net][r][0] = out[net][r][1] = 0.f;
+      vv[net][r] = 0.f;
+    }
     for (int o = 0; o <= A; ++o) {
       const float4* w4 = reinterpret_cast<const float4*>(o < A ? p.wa[net] + (size_t)o * HB_HID : p.wv[net]);
-      float acc = 0.f;
+      float4 w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w = __ldg(w4 + j * 32 + lane);
-        acc = fmaf(h[j].x, w.x, acc); acc = fmaf(h[j].y, w.y, acc); acc = fmaf(h[j].z, w.z, acc); acc = fmaf(h[j].w, w.w, acc);
+      for (int j = 0; j < 4; ++j) w[j] = __ldg(w4 + j * 32 + lane);
+      float acc[HB_HEAD_ROWS];
+#pragma unroll
+      for (int r = 0; r < HB_HEAD_ROWS; ++r) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a = fmaf(h[r][j].x, w[j].x, a); a = fmaf(h[r][j].y, w[j].y, a); a = fmaf(h[r][j].z, w[j].z, a); a = fmaf(h[r][j].w, w[j].w, a);
+        }
+        acc[r] = a;
       }
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(FULL, acc, s);
-      if (o < A) {
-        acc += __ldg(p.ba[net] + o);
-        if (o == lane) o0 = acc;
-        if (o == lane + 32) o1 = acc;
-      } else {
-        v = acc + __ldg(p.bv[net]);
+      for (int s = 16; s > 0; s >>= 1) {
+#pragma unroll
+        for (int r = 0; r < HB_HEAD_ROWS; ++r) acc[r] += __shfl_xor_sync(FULL, acc[r], s);
+      }
+      const float b = o < A ? __ldg(p.ba[net] + o) : __ldg(p.bv[net]);
+#pragma unroll
+      for (int r = 0; r < HB_HEAD_ROWS; ++r) {
+        const float val = acc[r] + b;
+        if (o == A) vv[net][r] = val;
+        else if (o == lane) out[net][r][0] = val;
+        else if (o == lane + 32) out[net][r][1] = val;
       }
     }
+  }
+#pragma unroll
+  for (int r = 0; r < HB_HEAD_ROWS; ++r) {
+    const int row = row0 + r;
+    if (row >= p.rows) break;  // warp-uniform
+    const float* lm = p.legal + (size_t)row * A;
+    const float l0 = lane < A ? lm[lane] : 0.f;
+    const float l1 = lane + 32 < A ? lm[lane + 32] : 0.f;
+    const float o0 = out[0][r][0], o1 = out[0][r][1];
     // mean over ALL A entries of adv*legal (r2d2.py:129-130)
     float s = o0 * l0 + o1 * l1;
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(FULL, s, k);
     const float mean = s / (float)A;
-    if (net == 0) {
-
-      if (lane < A) p.adv[(size_t)row * A + lane] = o0;
-      if (lane + 32 < A) p.adv[(size_t)row * A + lane + 32] = o1;
-      // greedy = first index of the largest advantage among legal moves (r2d2.py:242-243)
-      float best = -INFINITY;
-      int bi = 0x7fffffff;
-      if (l0 != 0.f) { best = o0; bi = lane; }
-      if (l1 != 0.f && (o1 > best || bi == 0x7fffffff)) { best = o1; bi = lane + 32; }
+    if (lane < A) p.adv[(size_t)row * A + lane] = o0;
+    if (lane + 32 < A) p.adv[(size_t)row * A + lane + 32] = o1;
+    // greedy = first index of the largest advantage among legal moves (r2d2.py:242-243)
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    if (l0 != 0.f) { best = o0; bi = lane; }
+    if (l1 != 0.f && (o1 > best || bi == 0x7fffffff)) { best = o1; bi = lane + 32; }
 #pragma unroll
-      for (int k = 16; k > 0; k >>= 1) {
-        const float ob = __shfl_xor_sync(FULL, best, k);
-        const int oi = __shfl_xor_sync(FULL, bi, k);
-        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    for (int k = 16; k > 0; k >>= 1) {
+      const float ob = __shfl_xor_sync(FULL, best, k);
+      const int oi = __shfl_xor_sync(FULL, bi, k);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    }
+    const int greedy = bi == 0x7fffffff ? A - 1 : bi;
+    // eps-greedy: uniform over legal moves with probability eps (r2d2.py:273-277)
+    int action = greedy;
+    if (!p.greedy_only) {
+      const unsigned m0 = __ballot_sync(FULL, l0 != 0.f), m1 = __ballot_sync(FULL, l1 != 0.f);
+      const int n_legal = __popc(m0) + __popc(m1);
+      HbRng rng(p.seed, (uint32_t)row, p.tick, HB_RNG_ACT);
+      const float u = rng.uniform();
+      int k = n_legal > 0 ? (int)rng.below((uint32_t)n_legal) : 0;
+      if (u < p.eps[row] && n_legal > 0) {
+        if (k < __popc(m0)) { unsigned m = m0; for (int i = 0; i < k; ++i) m &= m - 1; action = __ffs(m) - 1; }
+        else { k -= __popc(m0); unsigned m = m1; for (int i = 0; i < k; ++i) m &= m - 1; action = 32 + __ffs(m) - 1; }
       }
-      greedy = bi == 0x7fffffff ? A - 1 : bi;
-      // eps-greedy: uniform over legal moves with probability eps (r2d2.py:273-277)
-      action = greedy;
-      if (!p.greedy_only) {
-        const unsigned m0 = __ballot_sync(FULL, l0 != 0.f), m1 = __ballot_sync(FULL, l1 != 0.f);
-        const int n_legal = __popc(m0) + __popc(m1);
-        HbRng rng(p.seed, (uint32_t)row, p.tick, HB_RNG_ACT);
-        const float u = rng.uniform();
-        int k = n_legal > 0 ? (int)rng.below((uint32_t)n_legal) : 0;
-        if (u < p.eps[row] && n_legal > 0) {
-          int ra;
-          if (k < __popc(m0)) { unsigned m = m0; for (int i = 0; i < k; ++i) m &= m - 1; ra = __ffs(m) - 1; }
-          else { k -= __popc(m0); unsigned m = m1; for (int i = 0; i < k; ++i) m &= m - 1; ra = 32 + __ffs(m) - 1; }
-          action = ra;
-        }
-      }
-      // Q_online(s, a) for the action actually taken
-      const float qa_src = action < 32 ? __shfl_sync(FULL, o0 * l0, action) : __shfl_sync(FULL, o1 * l1, action - 32);
-      if (lane == 0) {
-        p.a[row] = action;
-        p.greedy_a[row] = greedy;
-        p.oq[row] = v + qa_src - mean;
-      }
-    } else {
-      const float qa_src = greedy < 32 ? __shfl_sync(FULL, o0 * l0, greedy) : __shfl_sync(FULL, o1 * l1, greedy - 32);
-      if (lane == 0) p.tq[row] = v + qa_src - mean;
+    }
+    // Q_online(s, a) for the action actually taken; Q_target(s, greedy) under the target network
+    const float qa = action < 32 ? __shfl_sync(FULL, o0 * l0, action) : __shfl_sync(FULL, o1 * l1, action - 32);
+    float tq = 0.f;
+    if (nets == 2) {
+      const float t0 = out[1][r][0], t1 = out[1][r][1];
+      float ts = t0 * l0 + t1 * l1;
+#pragma unroll
+      for (int k = 16; k > 0; k >>= 1) ts += __shfl_xor_sync(FULL, ts, k);
+      const float tqa = greedy < 32 ? __shfl_sync(FULL, t0 * l0, greedy) : __shfl_sync(FULL, t1 * l1, greedy - 32);
+      tq = vv[1][r] + tqa - ts / (float)A;
+    }
+    if (lane == 0) {
+      p.a[row] = action;
+      p.greedy_a[row] = greedy;
+      p.oq[row] = vv[0][r] + qa - mean;
+      if (nets == 2) p.tq[row] = tq;
     }
   }
-
 }
 
 // ---------------------------------------------------------------------------------------- host side
@@ -401,12 +426,14 @@ int hb_policy_forward(hb_engine* e, int greedy_only) {
   const int nets = P->have_weights[1] && e->cfg.priority_mode != 1 ? 2 : 1;
   const int mt = P->rows_pad / hbg::BM;
   const Params* base = P->d_params + (size_t)P->parity * 6;
+  const int nt_fc = HB_HID / hbg::BN, nt_l = 4 * HB_HID / hbg::BN;
+  auto grid = [&](int nt) { const int t = nt * mt * nets; return t < e->sm_count ? t : e->sm_count; };  // persistent: one CTA per SM
   { HbProfScope ps(e, HB_PROF_FC);
-    hbg::gemm3_kernel<hbg::EPI_RELU><<<dim3(HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 0); }
+    hbg::gemm3_kernel<hbg::EPI_RELU><<<grid(nt_fc), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 0, nt_fc, mt, nets); }
   { HbProfScope ps(e, HB_PROF_LSTM0);
-    hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 2); }
+    hbg::gemm3_kernel<hbg::EPI_LSTM><<<grid(nt_l), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 2, nt_l, mt, nets); }
   { HbProfScope ps(e, HB_PROF_LSTM1);
-    hbg::gemm3_kernel<hbg::EPI_LSTM><<<dim3(4 * HB_HID / hbg::BN, mt, nets), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 4); }
+    hbg::gemm3_kernel<hbg::EPI_LSTM><<<grid(nt_l), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 4, nt_l, mt, nets); }
   HbHeadArgs a;
   a.rows = e->rows; a.A = e->A; a.have_target = nets == 2;
   for (int n = 0; n < 2; ++n) {
@@ -415,7 +442,7 @@ int hb_policy_forward(hb_engine* e, int greedy_only) {
   a.legal = e->obs.legal_move; a.eps = e->obs.eps; a.a = e->d_a; a.greedy_a = e->d_greedy_a;
   a.adv = P->adv; a.oq = P->oq; a.tq = P->tq; a.seed = e->cfg.seed; a.tick = (uint32_t)P->act_count; a.greedy_only = greedy_only;
   { HbProfScope ps(e, HB_PROF_HEAD);
-    hb_k_head_act<<<(e->rows + HB_HEAD_WARPS - 1) / HB_HEAD_WARPS, HB_HEAD_WARPS * 32, 0, e->stream>>>(a); }
+    hb_k_head_act<<<(e->rows + HB_HEAD_WARPS * HB_HEAD_ROWS - 1) / (HB_HEAD_WARPS * HB_HEAD_ROWS), HB_HEAD_WARPS * 32, 0, e->stream>>>(a); }
   HB_CUDA(cudaGetLastError());
   e->launches += 4;
   P->parity ^= 1;
@@ -482,7 +509,13 @@ int hb_debug_gemm(int device, const float* A, const float* B, const float* bias,
   hp.bias = dbias; hp.c_f32 = dC; hp.ldc = N; hp.error_flag = derr;
   HB_CUDA(cudaMemcpy(dp, &hp, sizeof(hp), cudaMemcpyHostToDevice));
   HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
-  hbg::gemm3_kernel<hbg::EPI_F32><<<dim3(N / hbg::BN, M / hbg::BM, 1), hbg::THREADS, hbg::SMEM_BYTES>>>(dp);
+  {
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int tiles = (N / hbg::BN) * (M / hbg::BM);
+    hbg::gemm3_kernel<hbg::EPI_F32><<<tiles < prop.multiProcessorCount ? tiles : prop.multiProcessorCount, hbg::THREADS, hbg::SMEM_BYTES>>>(
+        dp, N / hbg::BN, M / hbg::BM, 1);
+  }
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaDeviceSynchronize());
   int herr = 0;

@@ -112,6 +112,9 @@ __device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, 
   }
 }
 
+// TP / TH / TSAD > 0 bake the game geometry into the kernel (feature offsets, F, A become literals: the per-feature index
+// arithmetic is mul-shift instead of runtime division); TP == 0 is the generic fallback for unusual configurations.
+template <int TP, int TH, int TSAD>
 __global__ void __launch_bounds__(HB_TICK_THREADS) hb_k_tick(const __grid_constant__ HbTickArgs A) {
   __shared__ HbGame s;
   __shared__ HbEncTables tab;
@@ -119,7 +122,8 @@ __global__ void __launch_bounds__(HB_TICK_THREADS) hb_k_tick(const __grid_consta
   __shared__ int sh_did_step, sh_t, sh_term, sh_reset, sh_slot, sh_drop;
   __shared__ float red[2 * HB_TICK_THREADS / 32];
   const int g = blockIdx.x, tid = threadIdx.x;
-  const HbEnvCfg& cfg = A.cfg;
+  HbEnvCfg cfg = A.cfg;
+  if (TP > 0) cfg.g = hb_make_geom(TP, TH, TSAD);
   const HbGeom& geo = cfg.g;
   const HbRing& R = A.ring;
   const int P = geo.P;
@@ -205,8 +209,17 @@ int hb_launch_tick(hb_engine* e, int do_step, int do_reset) {
   a.tq = e->policy && e->policy->have_weights[1] && e->cfg.priority_mode != 1 ? e->policy->tq : nullptr;
   if (e->replay) a.ring = hb_replay_ring(e);
   HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
-  { HbProfScope ps(e, HB_PROF_TICK);
-    hb_k_tick<<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a); }
+  {
+    HbProfScope ps(e, HB_PROF_TICK);
+    const int key = e->P * 100 + e->H * 10 + (e->env.g.sad ? 1 : 0);
+#define HB_TICK_CASE(P_, H_, S_) case P_ * 100 + H_ * 10 + S_: hb_k_tick<P_, H_, S_><<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a); break
+    switch (key) {
+      HB_TICK_CASE(2, 5, 1); HB_TICK_CASE(2, 5, 0); HB_TICK_CASE(3, 5, 1); HB_TICK_CASE(3, 5, 0);
+      HB_TICK_CASE(4, 4, 1); HB_TICK_CASE(4, 4, 0); HB_TICK_CASE(5, 4, 1); HB_TICK_CASE(5, 4, 0);
+      default: hb_k_tick<0, 0, 0><<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a); break;
+    }
+#undef HB_TICK_CASE
+  }
   HB_CUDA(cudaGetLastError());
   e->launches += 1;
   return 0;
