@@ -28,7 +28,9 @@ constexpr int STAGES = 2;
 constexpr int A_TILE = BM * BK * 2;                  // 16 KB
 constexpr int B_TILE = BN * BK * 2;                  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE; // hi+lo of both operands: 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+constexpr int HEAD_MAX_OUT = 56;                     // advantage head rows + the value head, padded to a multiple of 8
+constexpr int HEAD_SMEM = HEAD_MAX_OUT * 64 * 4;     // one n-tile's slice of the head weights: [out][64 units] fp32
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + HEAD_SMEM;
 constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TMEM_COLS = 256;
 constexpr int HID = 512;
@@ -56,6 +58,14 @@ struct __align__(64) Params {
   const float* c_in;
   float* c_out;
   float* h_f32;
+  // EPI_LSTM, top layer only (null otherwise): the dueling head fused into the epilogue.  head_w = fc_a / fc_v weights
+  // re-tiled as [n_tile][head_out][64 units] fp32 (head_out = A + 1, last row = fc_v); every epilogue thread multiplies
+  // its row's 64 fresh h' values with the tile's slice and writes head_part[n_tile][row][head_out] -- the act kernel
+  // adds the 8 partial sums.  Keeps h' out of HBM and removes a 512-deep reduction kernel.
+  const float* head_w;
+  float* head_part;
+  int head_out;
+  int head_rows;                 // rows_pad (stride of the n_tile axis of head_part)
   int* error_flag;               // set to 1 if a barrier wait ran into the spin guard (never in a healthy run)
 };
 
@@ -187,6 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
   const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES;
   const uint32_t bar_tempty = bar_tfull + 8 * ACC_STAGES, tmem_slot = bar_tempty + 8 * ACC_STAGES;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* head_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 128 - smem_u32(smem_raw)));  // [head_out][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool dead = false;
@@ -309,8 +320,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
         }
       } else {
         // tile columns: [gate i | f | g | o][64 hidden units]; hidden unit = n_tile*64 + u
+        const bool do_head = p.head_w != nullptr;
+        const int head_out = p.head_out;
+        if (do_head) {
+          // stage this n-tile's slice of the head weights (the 4 epilogue warps only: named barrier 1)
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's slice
+          const float4* src = reinterpret_cast<const float4*>(p.head_w + (size_t)n_tile * head_out * 64);
+          float4* dst = reinterpret_cast<float4*>(head_smem);
+          const int et = threadIdx.x - 64;
+          for (int i = et; i < head_out * 16; i += 128) dst[i] = __ldg(src + i);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        float h_all[64];
+#pragma unroll
         for (int u0 = 0; u0 < 64; u0 += 16) {
-          float gi[16], gf[16], gg[16], go[16], c[16], h[16];
+          float gi[16], gf[16], gg[16], go[16], c[16];
+          float* h = h_all + u0;
           tmem_ld16(taddr + 0 * 64 + u0, gi);
           tmem_ld16(taddr + 1 * 64 + u0, gf);
           tmem_ld16(taddr + 2 * 64 + u0, gg);
@@ -343,6 +368,30 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
             const size_t o = row * p.out_ld + p.out_col0 + unit;
             store_split16(h, p.out_hi + o, p.out_lo + o);
           }
+        }
+        if (do_head) {
+          // the TMEM reads of this tile are done: let the MMA thread start refilling the accumulator right away
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc_stage);
+          float* part = p.head_part + ((size_t)n_tile * p.head_rows + row) * head_out;
+          for (int o0 = 0; o0 < head_out; o0 += 8) {   // 8 outputs at a time: 8 accumulators, weights broadcast from smem
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int u = 0; u < 64; u += 4) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(head_smem + (o0 + j) * 64 + u);  // rows past head_out: stale but unused
+                acc[j] = fmaf(h_all[u], w.x, acc[j]); acc[j] = fmaf(h_all[u + 1], w.y, acc[j]);
+                acc[j] = fmaf(h_all[u + 2], w.z, acc[j]); acc[j] = fmaf(h_all[u + 3], w.w, acc[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (o0 + j < head_out) part[o0 + j] = acc[j];
+          }
+          continue;  // the accumulator was already released above
         }
       }
       // all of this warp's tcgen05.ld have completed (tmem_ld16 waits): hand the accumulator back to the MMA thread

@@ -77,14 +77,22 @@ __global__ void hb_k_prep_lstm_bias(const float* __restrict__ b_ih, const float*
   out[(unit / 64) * 256 + gate * 64 + (unit % 64)] = b_ih[r] + b_hh[r];
 }
 
+// fc_a [A][512] and fc_v [512] -> [8][A+1][64]: the slice of the head every LSTM output tile needs (hb_gemm.cuh).
+__global__ void hb_k_prep_head(const float* __restrict__ wa, const float* __restrict__ wv, int A, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (A + 1) * HB_HID;
+  if (idx >= n) return;
+  const int o = idx / HB_HID, k = idx % HB_HID;
+  const float v = o < A ? wa[(size_t)o * HB_HID + k] : wv[k];
+  out[((size_t)(k / 64) * (A + 1) + o) * 64 + (k % 64)] = v;
+}
+
 // ---------------------------------------------------------------------------------------- head + action selection
 struct HbHeadArgs {
-  int rows, A, have_target;
-  const float* htop[2];       // [rows_pad][512] top-layer h' of the online / target network
-  const float* wa[2];         // [A][512]
-  const float* ba[2];
-  const float* wv[2];         // [512]
-  const float* bv[2];
+  int rows, rows_pad, A, have_target;
+  const float* part[2];       // [8][rows_pad][A+1] partial head sums of the online / target network (LSTM-1 epilogue)
+  const float* ba[2];         // fc_a bias [A]
+  const float* bv[2];         // fc_v bias [1]
   const float* legal;         // [rows][A]
   const float* eps;           // [rows]
   int64_t* a;                 // [rows]
@@ -93,122 +101,92 @@ struct HbHeadArgs {
   float* oq;                  // [rows] online dueling Q of the chosen action          (r2d2.py:344, :124-131)
   float* tq;                  // [rows] target dueling Q of the online greedy action   (r2d2.py:345-348)
   uint64_t seed;
+  const unsigned long long* tick_ctr;  // device tick counter (Philox counter of the eps-greedy draw); may be null
   uint32_t tick;
   int greedy_only;            // eval actors: eps ignored
 };
 
-#define HB_HEAD_WARPS 4
-#define HB_HEAD_ROWS 4   // agents per warp: every weight vector fetched from L1 is used for 4 rows
+#define HB_HEAD_WARPS 8
 
+// One warp per agent: finish the head (sum of the 8 per-tile partials + bias), masked first-index argmax, eps-greedy,
+// dueling Q-values.  Lane l owns outputs l and l+32.
 __global__ void __launch_bounds__(HB_HEAD_WARPS * 32) hb_k_head_act(HbHeadArgs p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * HB_HEAD_WARPS + warp) * HB_HEAD_ROWS;
-  if (row0 >= p.rows) return;
-  const int A = p.A;
+  const int row = blockIdx.x * HB_HEAD_WARPS + warp;
+  if (row >= p.rows) return;
+  const int A = p.A, HO = A + 1;
   const unsigned FULL = 0xffffffffu;
   const int nets = p.have_target ? 2 : 1;
-  // out[net][r][0|1]: lane holds outputs `lane` and `lane + 32` of row r; vv[net][r]: the value head
-  float out[2][HB_HEAD_ROWS][2], vv[2][HB_HEAD_ROWS];
+  float out[2][2], vv[2];
 #pragma unroll
   for (int net = 0; net < 2; ++net) {
-    if (net >= nets) break;
-    float4 h[HB_HEAD_ROWS][4];
+    out[net][0] = out[net][1] = vv[net] = 0.f;
+    if (net >= nets) continue;
+    float s0 = 0.f, s1 = 0.f, sv = 0.f;
 #pragma unroll
-    for (int r = 0; r < HB_HEAD_ROWS; ++r) {
-      const int row = min(row0 + r, p.rows - 1);
-      const float4* h4 = reinterpret_cast<const float4*>(p.htop[net] + (size_t)row * HB_HID);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h[r][j] = h4[j * 32 + lane];
-      out[net][r][0] = out[net][r][1] = 0.f;
-      vv[net][r] = 0.f;
+    for (int t = 0; t < 8; ++t) {
+      const float* pr = p.part[net] + ((size_t)t * p.rows_pad + row) * HO;
+      if (lane < A) s0 += pr[lane];
+      if (lane + 32 < A) s1 += pr[lane + 32];
+      sv += pr[A];  // same address for the whole warp: one broadcast load
     }
-    for (int o = 0; o <= A; ++o) {
-      const float4* w4 = reinterpret_cast<const float4*>(o < A ? p.wa[net] + (size_t)o * HB_HID : p.wv[net]);
-      float4 w[4];
+    out[net][0] = lane < A ? s0 + __ldg(p.ba[net] + lane) : 0.f;
+    out[net][1] = lane + 32 < A ? s1 + __ldg(p.ba[net] + lane + 32) : 0.f;
+    vv[net] = sv + __ldg(p.bv[net]);
+  }
+  const float* lm = p.legal + (size_t)row * A;
+  const float l0 = lane < A ? lm[lane] : 0.f;
+  const float l1 = lane + 32 < A ? lm[lane + 32] : 0.f;
+  const float o0 = out[0][0], o1 = out[0][1];
+  // mean over ALL A entries of adv*legal (r2d2.py:129-130)
+  float s = o0 * l0 + o1 * l1;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = __ldg(w4 + j * 32 + lane);
-      float acc[HB_HEAD_ROWS];
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(FULL, s, k);
+  const float mean = s / (float)A;
+  if (lane < A) p.adv[(size_t)row * A + lane] = o0;
+  if (lane + 32 < A) p.adv[(size_t)row * A + lane + 32] = o1;
+  // greedy = first index of the largest advantage among legal moves (r2d2.py:242-243)
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  if (l0 != 0.f) { best = o0; bi = lane; }
+  if (l1 != 0.f && (o1 > best || bi == 0x7fffffff)) { best = o1; bi = lane + 32; }
 #pragma unroll
-      for (int r = 0; r < HB_HEAD_ROWS; ++r) {
-        float a = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          a = fmaf(h[r][j].x, w[j].x, a); a = fmaf(h[r][j].y, w[j].y, a); a = fmaf(h[r][j].z, w[j].z, a); a = fmaf(h[r][j].w, w[j].w, a);
-        }
-        acc[r] = a;
-      }
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) {
-#pragma unroll
-        for (int r = 0; r < HB_HEAD_ROWS; ++r) acc[r] += __shfl_xor_sync(FULL, acc[r], s);
-      }
-      const float b = o < A ? __ldg(p.ba[net] + o) : __ldg(p.bv[net]);
-#pragma unroll
-      for (int r = 0; r < HB_HEAD_ROWS; ++r) {
-        const float val = acc[r] + b;
-        if (o == A) vv[net][r] = val;
-        else if (o == lane) out[net][r][0] = val;
-        else if (o == lane + 32) out[net][r][1] = val;
-      }
+  for (int k = 16; k > 0; k >>= 1) {
+    const float ob = __shfl_xor_sync(FULL, best, k);
+    const int oi = __shfl_xor_sync(FULL, bi, k);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+  }
+  const int greedy = bi == 0x7fffffff ? A - 1 : bi;
+  // eps-greedy: uniform over legal moves with probability eps (r2d2.py:273-277)
+  int action = greedy;
+  if (!p.greedy_only) {
+    const unsigned m0 = __ballot_sync(FULL, l0 != 0.f), m1 = __ballot_sync(FULL, l1 != 0.f);
+    const int n_legal = __popc(m0) + __popc(m1);
+    const uint32_t tick = p.tick_ctr ? (uint32_t)*p.tick_ctr : p.tick;
+    HbRng rng(p.seed, (uint32_t)row, tick, HB_RNG_ACT);
+    const float u = rng.uniform();
+    int k = n_legal > 0 ? (int)rng.below((uint32_t)n_legal) : 0;
+    if (u < p.eps[row] && n_legal > 0) {
+      if (k < __popc(m0)) { unsigned m = m0; for (int i = 0; i < k; ++i) m &= m - 1; action = __ffs(m) - 1; }
+      else { k -= __popc(m0); unsigned m = m1; for (int i = 0; i < k; ++i) m &= m - 1; action = 32 + __ffs(m) - 1; }
     }
   }
+  // Q_online(s, a) for the action actually taken; Q_target(s, greedy) under the target network
+  const float qa = action < 32 ? __shfl_sync(FULL, o0 * l0, action) : __shfl_sync(FULL, o1 * l1, action - 32);
+  float tq = 0.f;
+  if (nets == 2) {
+    const float t0 = out[1][0], t1 = out[1][1];
+    float ts = t0 * l0 + t1 * l1;
 #pragma unroll
-  for (int r = 0; r < HB_HEAD_ROWS; ++r) {
-    const int row = row0 + r;
-    if (row >= p.rows) break;  // warp-uniform
-    const float* lm = p.legal + (size_t)row * A;
-    const float l0 = lane < A ? lm[lane] : 0.f;
-    const float l1 = lane + 32 < A ? lm[lane + 32] : 0.f;
-    const float o0 = out[0][r][0], o1 = out[0][r][1];
-    // mean over ALL A entries of adv*legal (r2d2.py:129-130)
-    float s = o0 * l0 + o1 * l1;
-#pragma unroll
-    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(FULL, s, k);
-    const float mean = s / (float)A;
-    if (lane < A) p.adv[(size_t)row * A + lane] = o0;
-    if (lane + 32 < A) p.adv[(size_t)row * A + lane + 32] = o1;
-    // greedy = first index of the largest advantage among legal moves (r2d2.py:242-243)
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    if (l0 != 0.f) { best = o0; bi = lane; }
-    if (l1 != 0.f && (o1 > best || bi == 0x7fffffff)) { best = o1; bi = lane + 32; }
-#pragma unroll
-    for (int k = 16; k > 0; k >>= 1) {
-      const float ob = __shfl_xor_sync(FULL, best, k);
-      const int oi = __shfl_xor_sync(FULL, bi, k);
-      if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
-    }
-    const int greedy = bi == 0x7fffffff ? A - 1 : bi;
-    // eps-greedy: uniform over legal moves with probability eps (r2d2.py:273-277)
-    int action = greedy;
-    if (!p.greedy_only) {
-      const unsigned m0 = __ballot_sync(FULL, l0 != 0.f), m1 = __ballot_sync(FULL, l1 != 0.f);
-      const int n_legal = __popc(m0) + __popc(m1);
-      HbRng rng(p.seed, (uint32_t)row, p.tick, HB_RNG_ACT);
-      const float u = rng.uniform();
-      int k = n_legal > 0 ? (int)rng.below((uint32_t)n_legal) : 0;
-      if (u < p.eps[row] && n_legal > 0) {
-        if (k < __popc(m0)) { unsigned m = m0; for (int i = 0; i < k; ++i) m &= m - 1; action = __ffs(m) - 1; }
-        else { k -= __popc(m0); unsigned m = m1; for (int i = 0; i < k; ++i) m &= m - 1; action = 32 + __ffs(m) - 1; }
-      }
-    }
-    // Q_online(s, a) for the action actually taken; Q_target(s, greedy) under the target network
-    const float qa = action < 32 ? __shfl_sync(FULL, o0 * l0, action) : __shfl_sync(FULL, o1 * l1, action - 32);
-    float tq = 0.f;
-    if (nets == 2) {
-      const float t0 = out[1][r][0], t1 = out[1][r][1];
-      float ts = t0 * l0 + t1 * l1;
-#pragma unroll
-      for (int k = 16; k > 0; k >>= 1) ts += __shfl_xor_sync(FULL, ts, k);
-      const float tqa = greedy < 32 ? __shfl_sync(FULL, t0 * l0, greedy) : __shfl_sync(FULL, t1 * l1, greedy - 32);
-      tq = vv[1][r] + tqa - ts / (float)A;
-    }
-    if (lane == 0) {
-      p.a[row] = action;
-      p.greedy_a[row] = greedy;
-      p.oq[row] = vv[0][r] + qa - mean;
-      if (nets == 2) p.tq[row] = tq;
-    }
+    for (int k = 16; k > 0; k >>= 1) ts += __shfl_xor_sync(FULL, ts, k);
+    const float tqa = greedy < 32 ? __shfl_sync(FULL, t0 * l0, greedy) : __shfl_sync(FULL, t1 * l1, greedy - 32);
+    tq = vv[1] + tqa - ts / (float)A;
+  }
+  if (lane == 0) {
+    p.a[row] = action;
+    p.greedy_a[row] = greedy;
+    p.oq[row] = vv[0] + qa - mean;
+    if (nets == 2) p.tq[row] = tq;
   }
 }
 
@@ -279,7 +257,8 @@ static int hb_build_params(hb_engine* e) {
       l1.c_in = P->c[cur] + lsz;
       if (net == 0) { l1.c_out = P->c[nxt] + lsz; l1.out_hi = P->h_hi[nxt] + lsz; l1.out_lo = P->h_lo[nxt] + lsz; }
       else { l1.c_out = nullptr; l1.out_hi = nullptr; l1.out_lo = nullptr; }
-      l1.out_ld = HB_HID; l1.out_col0 = 0; l1.h_f32 = P->htop[net];
+      l1.out_ld = HB_HID; l1.out_col0 = 0; l1.h_f32 = nullptr;
+      l1.head_w = W.head_tiles; l1.head_part = P->head_part[net]; l1.head_out = e->A + 1; l1.head_rows = rp;
       if (rc) return -2;
       for (Params* q : {&f, &l0, &l1}) {
         q->split = (net == 0 || P->target_split) ? 1 : 0;
@@ -317,7 +296,7 @@ int hb_policy_create(hb_engine* e) {
   for (int n = 0; n < 2; ++n) {
     HB_ALLOC(P->x_hi[n], rp * HB_HID * bf);
     HB_ALLOC(P->x_lo[n], rp * HB_HID * bf);
-    HB_ALLOC(P->htop[n], rp * HB_HID * sizeof(float));
+    HB_ALLOC(P->head_part[n], (size_t)8 * rp * (e->A + 1) * sizeof(float));
     HB_ALLOC(P->h_hi[n], HB_LAYERS * rp * HB_HID * bf);
     HB_ALLOC(P->h_lo[n], HB_LAYERS * rp * HB_HID * bf);
     HB_ALLOC(P->c[n], HB_LAYERS * rp * HB_HID * sizeof(float));
@@ -333,6 +312,7 @@ int hb_policy_create(hb_engine* e) {
     HB_ALLOC(W.wa, (size_t)e->A * HB_HID * sizeof(float));
     HB_ALLOC(W.ba, e->A * sizeof(float));
     HB_ALLOC(W.wv, HB_HID * sizeof(float));
+    HB_ALLOC(W.head_tiles, (size_t)8 * (e->A + 1) * 64 * sizeof(float));
     HB_ALLOC(W.bv, sizeof(float));
     size_t raw = (size_t)HB_HID * e->F;
     if (raw < (size_t)4 * HB_HID * HB_HID) raw = (size_t)4 * HB_HID * HB_HID;
@@ -358,11 +338,11 @@ void hb_policy_destroy(hb_engine* e) {
   if (!P) return;
   cudaFree(P->s_hi); cudaFree(P->s_lo); cudaFree(P->th_hi); cudaFree(P->th_lo);
   for (int n = 0; n < 2; ++n) {
-    cudaFree(P->x_hi[n]); cudaFree(P->x_lo[n]); cudaFree(P->htop[n]); cudaFree(P->h_hi[n]); cudaFree(P->h_lo[n]); cudaFree(P->c[n]);
+    cudaFree(P->x_hi[n]); cudaFree(P->x_lo[n]); cudaFree(P->head_part[n]); cudaFree(P->h_hi[n]); cudaFree(P->h_lo[n]); cudaFree(P->c[n]);
     HbNetWeights& W = P->net[n];
     cudaFree(W.w0_hi); cudaFree(W.w0_lo); cudaFree(W.b0);
     for (int l = 0; l < HB_LAYERS; ++l) { cudaFree(W.wl_hi[l]); cudaFree(W.wl_lo[l]); cudaFree(W.bl[l]); }
-    cudaFree(W.wa); cudaFree(W.ba); cudaFree(W.wv); cudaFree(W.bv); cudaFree(W.raw); cudaFree(W.raw2);
+    cudaFree(W.wa); cudaFree(W.ba); cudaFree(W.wv); cudaFree(W.bv); cudaFree(W.head_tiles); cudaFree(W.raw); cudaFree(W.raw2);
   }
   cudaFree(P->adv); cudaFree(P->oq); cudaFree(P->tq); cudaFree(P->d_error); cudaFree(P->d_params);
   delete P;
@@ -404,6 +384,8 @@ int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w) {
   HB_CUDA(cudaMemcpyAsync(W.ba, w->fc_a_b, A * sizeof(float), cudaMemcpyDefault, st));
   HB_CUDA(cudaMemcpyAsync(W.wv, w->fc_v_w, HB_HID * sizeof(float), cudaMemcpyDefault, st));
   HB_CUDA(cudaMemcpyAsync(W.bv, w->fc_v_b, sizeof(float), cudaMemcpyDefault, st));
+  hb_k_prep_head<<<blocks((size_t)(A + 1) * HB_HID), 256, 0, st>>>(W.wa, W.wv, A, W.head_tiles);
+  e->launches += 1;
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaStreamSynchronize(st));  // the caller may free / overwrite its tensors once this returns
   P->have_weights[net] = 1;
@@ -435,14 +417,13 @@ int hb_policy_forward(hb_engine* e, int greedy_only) {
   { HbProfScope ps(e, HB_PROF_LSTM1);
     hbg::gemm3_kernel<hbg::EPI_LSTM><<<grid(nt_l), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 4, nt_l, mt, nets); }
   HbHeadArgs a;
-  a.rows = e->rows; a.A = e->A; a.have_target = nets == 2;
-  for (int n = 0; n < 2; ++n) {
-    a.htop[n] = P->htop[n]; a.wa[n] = P->net[n].wa; a.ba[n] = P->net[n].ba; a.wv[n] = P->net[n].wv; a.bv[n] = P->net[n].bv;
-  }
+  a.rows = e->rows; a.rows_pad = P->rows_pad; a.A = e->A; a.have_target = nets == 2;
+  for (int n = 0; n < 2; ++n) { a.part[n] = P->head_part[n]; a.ba[n] = P->net[n].ba; a.bv[n] = P->net[n].bv; }
   a.legal = e->obs.legal_move; a.eps = e->obs.eps; a.a = e->d_a; a.greedy_a = e->d_greedy_a;
-  a.adv = P->adv; a.oq = P->oq; a.tq = P->tq; a.seed = e->cfg.seed; a.tick = (uint32_t)P->act_count; a.greedy_only = greedy_only;
+  a.adv = P->adv; a.oq = P->oq; a.tq = P->tq; a.seed = e->cfg.seed; a.tick = (uint32_t)P->act_count; a.tick_ctr = nullptr;
+  a.greedy_only = greedy_only;
   { HbProfScope ps(e, HB_PROF_HEAD);
-    hb_k_head_act<<<(e->rows + HB_HEAD_WARPS * HB_HEAD_ROWS - 1) / (HB_HEAD_WARPS * HB_HEAD_ROWS), HB_HEAD_WARPS * 32, 0, e->stream>>>(a); }
+    hb_k_head_act<<<(e->rows + HB_HEAD_WARPS - 1) / HB_HEAD_WARPS, HB_HEAD_WARPS * 32, 0, e->stream>>>(a); }
   HB_CUDA(cudaGetLastError());
   e->launches += 4;
   P->parity ^= 1;
