@@ -106,6 +106,47 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Multicast variant: the box lands at the same shared-memory offset of every CTA in `mask` and completes bytes on the
+// mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// cta_group::2 variant: issued by either CTA of a pair, the bytes complete on the mbarrier of the pair's LEADER (the
+// address has the CTA-rank bit cleared by the caller).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
 }
@@ -119,6 +160,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Arrives on the mbarrier at the same offset in every CTA of `mask` once the MMAs issued so far have completed.
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -148,8 +194,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 }
 
 // Instruction descriptor for kind::f16: D fp32, A and B bf16, both K-major, M=128, N=BN.
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ constexpr uint32_t make_idesc(int m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -188,38 +234,65 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_ALLOC_COLS = ACC_STAGES * TMEM_COLS;  // 512: the whole tensor memory of the SM
 
-template <int EPI>
+//
+// CL = 2: the grid is launched as clusters of two CTAs that work on vertically adjacent tiles (same n_tile, m_tile =
+// 2*pair + rank) and therefore need the SAME weight tile: each CTA fetches one half of it (128 of the 256 rows) and
+// TMA-multicasts it into both shared memories, halving the L2 -> SMEM traffic of the B operand (which dominates: the
+// tile is 128 x 256).  A slot is refilled only after BOTH CTAs' MMAs have released it (empty barriers count 2, the
+// release is a multicast tcgen05.commit).  Accumulators, MMAs and epilogues stay per-CTA (cta_group::1).
+//
+// CL = 3: the same pairs as ONE tcgen05 CTA pair (cta_group::2): the leader CTA issues M = 256 MMAs for both, each CTA
+// holds its own 128 rows of A and HALF of the weight tile (the tensor core reads the other half from the peer), its own
+// 128 x 256 accumulator in its own TMEM and runs its own epilogue.  Per MMA a CTA's shared memory supplies 8 KB instead
+// of 12 KB and receives 64 KB instead of 96 KB per K-chunk (3-deep ring), which lifts the shared-memory bandwidth bound
+// of the single-CTA form (TMA fill 62 B/clk + operand reads 96 B/clk > 128 B/clk).
+template <int EPI, int CL>
 __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restrict__ ps, int n_tiles_n, int n_tiles_m, int n_problems) {
+  constexpr bool PAIR = CL == 3;
+  constexpr int CW = CL == 1 ? 1 : 2;                       // CTAs per cluster
+  constexpr int NST = PAIR ? 3 : STAGES;                    // ring depth
+  constexpr int STB = PAIR ? 2 * A_TILE + B_TILE : STAGE_BYTES;  // bytes per ring slot (PAIR: half weight tiles)
+  constexpr int OFF_BLO = PAIR ? 2 * A_TILE + B_TILE / 2 : 2 * A_TILE + B_TILE;
+  static_assert(NST * STB <= STAGES * STAGE_BYTES, "ring must fit the shared-memory budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // barriers (8 bytes each): full[STAGES], empty[STAGES], tmem_full[ACC_STAGES], tmem_empty[ACC_STAGES], then the TMEM base slot
-  const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES;
+  // barriers (8 bytes each): full[NST], empty[NST], tmem_full[ACC_STAGES], tmem_empty[ACC_STAGES], then the TMEM base slot
+  const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * NST, bar_tfull = bar_empty + 8 * NST;
   const uint32_t bar_tempty = bar_tfull + 8 * ACC_STAGES, tmem_slot = bar_tempty + 8 * ACC_STAGES;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* head_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 128 - smem_u32(smem_raw)));  // [head_out][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool dead = false;
-  const int tiles_per_problem = n_tiles_n * n_tiles_m;
+  // work items: single tiles (CL = 1) or vertical tile pairs (CL = 2), walked with stride = number of CTAs / clusters
+  const int rank = CW == 2 ? (int)cluster_ctarank() : 0;
+  const int tiles_per_problem = n_tiles_n * (n_tiles_m / CW);
   const int total_tiles = tiles_per_problem * n_problems;
+  const int first_tile = blockIdx.x / CW, tile_stride = gridDim.x / CW;
 
   if (warp == 0 && lane == 0) {
     for (int z = 0; z < n_problems; ++z) {
       tma_prefetch_desc(&ps[z].a_hi[0]); tma_prefetch_desc(&ps[z].a_lo[0]); tma_prefetch_desc(&ps[z].a_hi[1]); tma_prefetch_desc(&ps[z].a_lo[1]);
       tma_prefetch_desc(&ps[z].b_hi); tma_prefetch_desc(&ps[z].b_lo);
     }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL == 2 ? 2 : 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_ALLOC_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_ALLOC_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_ALLOC_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CW == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -227,33 +300,50 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int z = tile / tiles_per_problem, r = tile - z * tiles_per_problem;
-        const int m_tile = r / n_tiles_n, n_tile = r - m_tile * n_tiles_n;
+        const int m_tile = (r / n_tiles_n) * CW + rank, n_tile = r % n_tiles_n;
         const Params& p = ps[z];
         const int k_chunks = p.k_chunks, lo_first = p.lo_first, lo_last = p.lo_last, seg0 = p.k_chunks_seg0;
         const bool split = p.split != 0;
         for (int kc = 0; kc < k_chunks; ++kc, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+          const uint32_t s = it % NST, ph = (it / NST) & 1u;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, p.error_flag, dead);  // slot free (first pass: passes immediately)
-          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const uint32_t st = smem_base + s * STB;
           const bool need_lo = split && kc >= lo_first && kc < lo_last;
-          mbar_expect_tx(bar_full + 8 * s, (need_lo ? 2 : 1) * A_TILE + (split ? 2 : 1) * B_TILE);
           const int seg = kc >= seg0 ? 1 : 0;
           const int kx = (seg ? kc - seg0 : kc) * BK;
+          if (PAIR) {
+            // the leader's barrier collects the bytes of BOTH CTAs; only the leader arms it
+            const uint32_t fb = (bar_full + 8 * s) & PEER_MASK;
+            const uint32_t bytes = (need_lo ? 2 : 1) * A_TILE + (split ? 2 : 1) * (B_TILE / 2);
+            if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * bytes);
+            tma_load_2d_pair(st, &p.a_hi[seg], fb, kx, m_tile * BM);
+            if (need_lo) tma_load_2d_pair(st + A_TILE, &p.a_lo[seg], fb, kx, m_tile * BM);
+            tma_load_2d_pair(st + 2 * A_TILE, &p.b_hi, fb, kc * BK, n_tile * BN + rank * (BN / 2));
+            if (split) tma_load_2d_pair(st + OFF_BLO, &p.b_lo, fb, kc * BK, n_tile * BN + rank * (BN / 2));
+            continue;
+          }
+          mbar_expect_tx(bar_full + 8 * s, (need_lo ? 2 : 1) * A_TILE + (split ? 2 : 1) * B_TILE);
           tma_load_2d(st, &p.a_hi[seg], bar_full + 8 * s, kx, m_tile * BM);
           if (need_lo) tma_load_2d(st + A_TILE, &p.a_lo[seg], bar_full + 8 * s, kx, m_tile * BM);
-          tma_load_2d(st + 2 * A_TILE, &p.b_hi, bar_full + 8 * s, kc * BK, n_tile * BN);
-          if (split) tma_load_2d(st + 2 * A_TILE + B_TILE, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN);
+          if (CL == 1) {
+            tma_load_2d(st + 2 * A_TILE, &p.b_hi, bar_full + 8 * s, kc * BK, n_tile * BN);
+            if (split) tma_load_2d(st + 2 * A_TILE + B_TILE, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN);
+          } else {  // this CTA's half of the weight tile, delivered to both CTAs of the pair
+            const uint32_t half = (uint32_t)rank * (B_TILE / 2);
+            tma_load_2d_mc(st + 2 * A_TILE + half, &p.b_hi, bar_full + 8 * s, kc * BK, n_tile * BN + rank * (BN / 2), 3);
+            if (split) tma_load_2d_mc(st + 2 * A_TILE + B_TILE + half, &p.b_lo, bar_full + 8 * s, kc * BK, n_tile * BN + rank * (BN / 2), 3);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc();
+    if (lane == 0 && (!PAIR || rank == 0)) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM);
       uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++lt) {
         const int z = tile / tiles_per_problem;
         const Params& p = ps[z];
         const int k_chunks = p.k_chunks, lo_first = p.lo_first, lo_last = p.lo_last;
@@ -264,24 +354,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
         const uint32_t d_tmem = tmem_base + acc_stage * TMEM_COLS;
         uint32_t acc = 0;
         for (int kc = 0; kc < k_chunks; ++kc, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+          const uint32_t s = it % NST, ph = (it / NST) & 1u;
           mbar_wait(bar_full + 8 * s, ph, p.error_flag, dead);
           tc_fence_after();
-          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const uint32_t st = smem_base + s * STB;
           const bool need_lo = split && kc >= lo_first && kc < lo_last;
           const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
-          const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE), b_lo = make_desc_sw128(st + 2 * A_TILE + B_TILE);
+          const uint64_t b_hi = make_desc_sw128(st + 2 * A_TILE), b_lo = make_desc_sw128(st + OFF_BLO);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // advance the start address inside the swizzle span
-            if (split) { umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, acc); acc = 1; }  // small terms first
-            if (need_lo) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
-            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, acc);
+            if (PAIR) {
+              if (split) { umma_bf16_pair(d_tmem, a_hi + adv, b_lo + adv, idesc, acc); acc = 1; }
+              if (need_lo) umma_bf16_pair(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+              umma_bf16_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, acc);
+            } else {
+              if (split) { umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, acc); acc = 1; }  // small terms first
+              if (need_lo) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1);
+              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, acc);
+            }
             acc = 1;
           }
-          umma_commit(bar_empty + 8 * s);          // the smem slot is free once these MMAs have read it
+          if (CL == 1) umma_commit(bar_empty + 8 * s);  // the smem slot is free once these MMAs have read it
+          else if (CL == 2) umma_commit_mc(bar_empty + 8 * s, 3);  // ... in BOTH CTAs: the peer's multicast writes into this slot too
+          else umma_commit_pair(bar_empty + 8 * s, 3);
         }
-        umma_commit(bar_tfull + 8 * acc_stage);    // accumulator complete
+        if (PAIR) umma_commit_pair(bar_tfull + 8 * acc_stage, 3);  // both CTAs' accumulators are complete
+        else umma_commit(bar_tfull + 8 * acc_stage);               // accumulator complete
       }
     }
   } else {
@@ -289,9 +388,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++lt) {
       const int z = tile / tiles_per_problem, r = tile - z * tiles_per_problem;
-      const int m_tile = r / n_tiles_n, n_tile = r - m_tile * n_tiles_n;
+      const int m_tile = (r / n_tiles_n) * CW + rank, n_tile = r % n_tiles_n;
       const Params& p = ps[z];
       const size_t row = (size_t)m_tile * BM + row_in_tile;
       const uint32_t acc_stage = lt % ACC_STAGES, aph = (lt / ACC_STAGES) & 1u;
@@ -373,7 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           // the TMEM reads of this tile are done: let the MMA thread start refilling the accumulator right away
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc_stage);
+          if (lane == 0) { if (PAIR) mbar_arrive_cluster((bar_tempty + 8 * acc_stage) & PEER_MASK); else mbar_arrive(bar_tempty + 8 * acc_stage); }
           float* part = p.head_part + ((size_t)n_tile * p.head_rows + row) * head_out;
           for (int o0 = 0; o0 < head_out; o0 += 8) {   // 8 outputs at a time: 8 accumulators, weights broadcast from smem
             float acc[8];
@@ -397,14 +496,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
       // all of this warp's tcgen05.ld have completed (tmem_ld16 waits): hand the accumulator back to the MMA thread
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc_stage);
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster((bar_tempty + 8 * acc_stage) & PEER_MASK); else mbar_arrive(bar_tempty + 8 * acc_stage); }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CW == 2) cluster_sync_all();  // the peer may still be arriving on this CTA's barriers / reading its shared memory
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC_COLS) : "memory");
   }
 }
 

@@ -20,6 +20,10 @@
 
 using hbg::Params;
 
+// GEMM variant used by the policy forward (hb_gemm.cuh): 1 = one CTA per tile, 2 = CTA pairs with TMA multicast of the
+// weight tile, 3 = tcgen05 CTA pairs (cta_group::2, M = 256).
+#define HB_GEMM_MODE 3
+
 // ---------------------------------------------------------------------------------------- tensor maps
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -218,8 +222,8 @@ static int hb_build_params(hb_engine* e) {
       rc |= hb_make_tmap(&f.a_hi[0], P->s_hi, rp, KS, hbg::BM);
       rc |= hb_make_tmap(&f.a_lo[0], P->s_lo, rp, KS, hbg::BM);
       f.a_hi[1] = f.a_hi[0]; f.a_lo[1] = f.a_lo[0];
-      rc |= hb_make_tmap(&f.b_hi, W.w0_hi, HB_HID, KS, hbg::BN);
-      rc |= hb_make_tmap(&f.b_lo, W.w0_lo, HB_HID, KS, hbg::BN);
+      rc |= hb_make_tmap(&f.b_hi, W.w0_hi, HB_HID, KS, hbg::BN / 2);
+      rc |= hb_make_tmap(&f.b_lo, W.w0_lo, HB_HID, KS, hbg::BN / 2);
       f.k_chunks = KS / hbg::BK; f.k_chunks_seg0 = f.k_chunks;
       f.lo_first = e->env.g.off_belief / hbg::BK;
       f.lo_last = (e->env.g.off_sad + hbg::BK - 1) / hbg::BK;
@@ -231,8 +235,8 @@ static int hb_build_params(hb_engine* e) {
       rc |= hb_make_tmap(&l0.a_lo[0], P->x_lo[net], rp, HB_HID, hbg::BM);
       rc |= hb_make_tmap(&l0.a_hi[1], P->h_hi[cur], rp, HB_HID, hbg::BM);
       rc |= hb_make_tmap(&l0.a_lo[1], P->h_lo[cur], rp, HB_HID, hbg::BM);
-      rc |= hb_make_tmap(&l0.b_hi, W.wl_hi[0], 4 * HB_HID, 2 * HB_HID, hbg::BN);
-      rc |= hb_make_tmap(&l0.b_lo, W.wl_lo[0], 4 * HB_HID, 2 * HB_HID, hbg::BN);
+      rc |= hb_make_tmap(&l0.b_hi, W.wl_hi[0], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
+      rc |= hb_make_tmap(&l0.b_lo, W.wl_lo[0], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
       l0.k_chunks = 2 * HB_HID / hbg::BK; l0.k_chunks_seg0 = HB_HID / hbg::BK; l0.lo_first = 0; l0.lo_last = l0.k_chunks;
       l0.bias = W.bl[0];
       l0.c_in = P->c[cur];
@@ -250,8 +254,8 @@ static int hb_build_params(hb_engine* e) {
       }
       rc |= hb_make_tmap(&l1.a_hi[1], P->h_hi[cur] + lsz, rp, HB_HID, hbg::BM);
       rc |= hb_make_tmap(&l1.a_lo[1], P->h_lo[cur] + lsz, rp, HB_HID, hbg::BM);
-      rc |= hb_make_tmap(&l1.b_hi, W.wl_hi[1], 4 * HB_HID, 2 * HB_HID, hbg::BN);
-      rc |= hb_make_tmap(&l1.b_lo, W.wl_lo[1], 4 * HB_HID, 2 * HB_HID, hbg::BN);
+      rc |= hb_make_tmap(&l1.b_hi, W.wl_hi[1], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
+      rc |= hb_make_tmap(&l1.b_lo, W.wl_lo[1], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
       l1.k_chunks = 2 * HB_HID / hbg::BK; l1.k_chunks_seg0 = HB_HID / hbg::BK; l1.lo_first = 0; l1.lo_last = l1.k_chunks;
       l1.bias = W.bl[1];
       l1.c_in = P->c[cur] + lsz;
@@ -287,7 +291,7 @@ int hb_policy_create(hb_engine* e) {
   memset(P, 0, sizeof(*P));
   e->policy = P;
   P->rows = e->rows;
-  P->rows_pad = (e->rows + hbg::BM - 1) / hbg::BM * hbg::BM;
+  P->rows_pad = (e->rows + 2 * hbg::BM - 1) / (2 * hbg::BM) * (2 * hbg::BM);  // CTA pairs work on two vertically adjacent tiles
   P->KS = (e->F + hbg::BK - 1) / hbg::BK * hbg::BK;
   P->target_split = c.priority_mode == 2 ? 0 : 1;
   const size_t rp = P->rows_pad, KS = P->KS, bf = sizeof(__nv_bfloat16);
@@ -327,9 +331,8 @@ int hb_policy_create(hb_engine* e) {
   HB_ALLOC(P->d_error, sizeof(int));
   HB_ALLOC(P->d_params, 12 * sizeof(Params));
   e->obs.s_hi = P->s_hi; e->obs.s_lo = P->s_lo; e->obs.KS = P->KS;
-  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
-  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
-  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
+  HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_RELU, HB_GEMM_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
+  HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
   return hb_build_params(e);
 }
 
@@ -394,6 +397,25 @@ int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w) {
 
 }  // extern "C"
 
+// Persistent launch: one CTA per SM (as many as there are work items if fewer), in clusters of `cl` CTAs.
+typedef void (*HbGemmKernel)(const Params*, int, int, int);
+static int hb_launch_gemm(HbGemmKernel k, int cl, int sm_count, cudaStream_t st, const Params* ps, int nt, int mt, int nprob) {
+  const int items = nt * (mt / cl) * nprob;
+  int clusters = sm_count / cl;
+  if (items < clusters) clusters = items;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * cl), 1, 1);
+  cfg.blockDim = dim3(hbg::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = hbg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  HB_CUDA(cudaLaunchKernelEx(&cfg, k, ps, nt, mt, nprob));
+  return 0;
+}
+
 HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e) {
   HbHidPtrs h = {nullptr, nullptr, nullptr, 0};
   if (e->policy) { HbPolicy* P = e->policy; h.h_hi = P->h_hi[P->parity]; h.h_lo = P->h_lo[P->parity]; h.c = P->c[P->parity]; h.rows_pad = P->rows_pad; }
@@ -409,13 +431,16 @@ int hb_policy_forward(hb_engine* e, int greedy_only) {
   const int mt = P->rows_pad / hbg::BM;
   const Params* base = P->d_params + (size_t)P->parity * 6;
   const int nt_fc = HB_HID / hbg::BN, nt_l = 4 * HB_HID / hbg::BN;
-  auto grid = [&](int nt) { const int t = nt * mt * nets; return t < e->sm_count ? t : e->sm_count; };  // persistent: one CTA per SM
+  int rc;
   { HbProfScope ps(e, HB_PROF_FC);
-    hbg::gemm3_kernel<hbg::EPI_RELU><<<grid(nt_fc), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 0, nt_fc, mt, nets); }
+    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_RELU, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + 0, nt_fc, mt, nets); }
+  if (rc) return rc;
   { HbProfScope ps(e, HB_PROF_LSTM0);
-    hbg::gemm3_kernel<hbg::EPI_LSTM><<<grid(nt_l), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 2, nt_l, mt, nets); }
+    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + 2, nt_l, mt, nets); }
+  if (rc) return rc;
   { HbProfScope ps(e, HB_PROF_LSTM1);
-    hbg::gemm3_kernel<hbg::EPI_LSTM><<<grid(nt_l), hbg::THREADS, hbg::SMEM_BYTES, e->stream>>>(base + 4, nt_l, mt, nets); }
+    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + 4, nt_l, mt, nets); }
+  if (rc) return rc;
   HbHeadArgs a;
   a.rows = e->rows; a.rows_pad = P->rows_pad; a.A = e->A; a.have_target = nets == 2;
   for (int n = 0; n < 2; ++n) { a.part[n] = P->head_part[n]; a.ba[n] = P->net[n].ba; a.bv[n] = P->net[n].bv; }
@@ -484,18 +509,24 @@ int hb_debug_gemm(int device, const float* A, const float* B, const float* bias,
   int rc = 0;
   rc |= hb_make_tmap(&hp.a_hi[0], ah, M, K, hbg::BM); rc |= hb_make_tmap(&hp.a_lo[0], al, M, K, hbg::BM);
   hp.a_hi[1] = hp.a_hi[0]; hp.a_lo[1] = hp.a_lo[0];
-  rc |= hb_make_tmap(&hp.b_hi, bh, N, K, hbg::BN); rc |= hb_make_tmap(&hp.b_lo, bl, N, K, hbg::BN);
+  // exercises all three variants: M % 512 == 0 -> cta_group::2 pairs, M % 256 == 0 -> multicast pairs, else single CTAs
+  const int mode = (M % (4 * hbg::BM) == 0) ? 3 : ((M % (2 * hbg::BM) == 0) ? 2 : 1);
+  const int cl = mode == 1 ? 1 : 2;
+  rc |= hb_make_tmap(&hp.b_hi, bh, N, K, hbg::BN / cl); rc |= hb_make_tmap(&hp.b_lo, bl, N, K, hbg::BN / cl);
   if (rc) return rc;
   hp.k_chunks = K / hbg::BK; hp.k_chunks_seg0 = hp.k_chunks; hp.lo_first = 0; hp.lo_last = hp.k_chunks; hp.split = split;
   hp.bias = dbias; hp.c_f32 = dC; hp.ldc = N; hp.error_flag = derr;
   HB_CUDA(cudaMemcpy(dp, &hp, sizeof(hp), cudaMemcpyHostToDevice));
-  HB_CUDA(cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES));
+  HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
+  HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
+  HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
   {
     cudaDeviceProp prop;
     HB_CUDA(cudaGetDeviceProperties(&prop, device));
-    const int tiles = (N / hbg::BN) * (M / hbg::BM);
-    hbg::gemm3_kernel<hbg::EPI_F32><<<tiles < prop.multiProcessorCount ? tiles : prop.multiProcessorCount, hbg::THREADS, hbg::SMEM_BYTES>>>(
-        dp, N / hbg::BN, M / hbg::BM, 1);
+    rc = hb_launch_gemm(mode == 3 ? hbg::gemm3_kernel<hbg::EPI_F32, 3> : (mode == 2 ? hbg::gemm3_kernel<hbg::EPI_F32, 2> : hbg::gemm3_kernel<hbg::EPI_F32, 1>), cl,
+                        prop.multiProcessorCount, 0, dp,
+                        N / hbg::BN, M / hbg::BM, 1);
+    if (rc) return rc;
   }
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaDeviceSynchronize());

@@ -22,7 +22,7 @@ def hb(gpu_or_skip):
     return hanabi_sad_b200
 
 
-@pytest.mark.parametrize("shape", [(128, 256, 64), (256, 512, 896), (384, 2048, 1024)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (256, 512, 896), (384, 2048, 1024), (512, 256, 128), (1024, 2048, 1024)])
 def test_gemm_template_bf16x3(hb, shape):
     M, N, K = shape
     rng = np.random.default_rng(M + N + K)
