@@ -30,8 +30,9 @@ def _key(priv_s_first, actions):
     return hashlib.sha1(np.ascontiguousarray(priv_s_first).tobytes() + np.ascontiguousarray(actions).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("cfg", [(2, 5, 1, True, 3, 0), (2, 5, 1, False, 3, 0), (3, 5, 0, True, 1, 0), (2, 5, 1, True, 3, 1)],
-                         ids=["vdn_2p_n3", "iql_2p_n3", "vdn_3p_n1", "vdn_uniform_priority"])
+@pytest.mark.parametrize("cfg", [(2, 5, 1, True, 3, 0), (2, 5, 1, False, 3, 0), (3, 5, 0, True, 1, 0), (2, 5, 1, True, 3, 1), (5, 4, 1, True, 3, 0),
+                                 (4, 4, 0, False, 2, 0)],
+                         ids=["vdn_2p_n3", "iql_2p_n3", "vdn_3p_n1", "vdn_uniform_priority", "vdn_5p_n3", "iql_4p_n2"])
 def test_rollout_fills_replay_like_the_reference(hb, cfg):
     P, H, sad, vdn, n_step, prio_mode = cfg
     G, T, gamma, eta, alpha, beta = 40, 80, 0.999, 0.9, 0.6, 0.4

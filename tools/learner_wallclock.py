@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Secondary metric of BASELINE.json ("learner-wallclock speedup over the reference CPU actors on the same box"):
+runs the reference's OWN selfplay.py (generated copy under oracle/_ref/pyhanabi) twice with identical dev.sh-style flags,
+once on the reference's C++ actors (oracle/_ref rela/hanalearn modules) and once on this repo's device actors
+(hanabi_sad_b200/compat), and compares what its Tachometer / wall clock report.  GPU box only; test/measurement tooling
+(it drives oracle/_ref), not part of the product.
+
+    python tools/learner_wallclock.py [--epoch_len 200] [--num_epoch 2] > gpurun_out/learner_wallclock.json
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PYH = os.path.join(ROOT, "oracle", "_ref", "pyhanabi")
+
+
+def run(arm, a, out_dir):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = (os.path.join(ROOT, "hanabi_sad_b200", "compat") if arm == "b200" else os.path.join(ROOT, "oracle", "_ref")) + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "selfplay.py", "--save_dir", os.path.join(out_dir, arm), "--method", "iql", "--num_thread", str(a.num_thread),
+           "--num_game_per_thread", str(a.num_game_per_thread), "--sad", "1", "--act_base_eps", "0.1", "--act_eps_alpha", "7", "--lr", "6.25e-05",
+           "--eps", "1.5e-05", "--grad_clip", "5", "--gamma", "0.999", "--seed", "1", "--batchsize", "128", "--burn_in_frames", str(a.burn_in),
+           "--replay_buffer_size", str(a.replay), "--epoch_len", str(a.epoch_len), "--num_epoch", str(a.num_epoch), "--priority_exponent", "0.9",
+           "--priority_weight", "0.6", "--train_bomb", "0", "--eval_bomb", "0", "--num_player", "2", "--rnn_hid_dim", "512", "--act_device", "cuda:0",
+           "--shuffle_color", "1"]
+    t0 = time.time()
+    log = os.path.join(out_dir, arm + ".log")
+    with open(log, "w") as f:
+        p = subprocess.run(cmd, cwd=PYH, env=env, stdout=f, stderr=subprocess.STDOUT, text=True, timeout=a.timeout)
+    wall = time.time() - t0
+    out = open(log).read()
+    speeds = [tuple(float(x) for x in m) for m in re.findall(r"Speed: train: ([0-9.]+), act: ([0-9.]+), buffer_add: ([0-9.]+)", out)]
+    scores = [float(x) for x in re.findall(r"eval score: ([0-9.]+)", out)]
+    burn = out.count("warming up replay buffer")
+    return {"arm": arm, "returncode": p.returncode, "wall_s": wall, "burn_in_wait_s": burn, "epochs": len(speeds),
+            "train_samples_per_s": [s[0] for s in speeds], "act_per_s": [s[1] for s in speeds], "buffer_add_per_s": [s[2] for s in speeds],
+            "eval_scores": scores, "tail": out[-600:] if p.returncode else ""}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--epoch_len", type=int, default=200)
+    ap.add_argument("--num_epoch", type=int, default=2)
+    ap.add_argument("--num_thread", type=int, default=10)
+    ap.add_argument("--num_game_per_thread", type=int, default=80)
+    ap.add_argument("--burn_in", type=int, default=5000)
+    ap.add_argument("--replay", type=int, default=32768)
+    ap.add_argument("--timeout", type=int, default=900)
+    a = ap.parse_args()
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for arm in ("reference", "b200"):
+            res[arm] = run(arm, a, d)
+    r, b = res["reference"], res["b200"]
+    if r["train_samples_per_s"] and b["train_samples_per_s"]:
+        res["summary"] = {
+            "flags": "tools/dev.sh (iql, sad 1, shuffle_color 1, %d x %d games, batchsize 128, burn_in %d), epoch_len %d x %d epochs, actors and learner on cuda:0"
+                     % (a.num_thread, a.num_game_per_thread, a.burn_in, a.epoch_len, a.num_epoch),
+            "learner_updates_per_s": {"reference": r["train_samples_per_s"][-1] / 128, "b200": b["train_samples_per_s"][-1] / 128},
+            "learner_wallclock_speedup_last_epoch": b["train_samples_per_s"][-1] / r["train_samples_per_s"][-1],
+            "actor_rate_ratio_last_epoch": b["act_per_s"][-1] / max(r["act_per_s"][-1], 1e-9),
+            "total_wall_speedup": r["wall_s"] / b["wall_s"],
+        }
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
