@@ -61,6 +61,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
 
 
+def load_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/traffic.json, written from the .ncu-rep by profiles/summarize.py); None if no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(p))[key]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -338,6 +348,7 @@ def run_b200(args):
     t_e2e, h2d, d2h = runner.e2e(e2e_steps, stream)
     barrier()
     assert eng.check_invariants() == 0, "board-state audit failed after the timed region"
+    rsize, radd, ract = eng.counters()
 
     t = torch.tensor([total_ms, b2b_ms, t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -352,7 +363,8 @@ def run_b200(args):
         "dtype": runner.dtype, "data": "synthetic",
         "config": {"workload": workload_name(args), "mode": mode, "games_per_gpu": G, "players": P, "hand_size": H, "sad": args.sad,
                    "shuffle_color": args.shuffle_color, "feature_size": F, "num_action": A, "policy": runner.policy,
-                   "l2": runner.l2_note, "back_to_back_env_steps_per_s": units / (b2b_ms * 1e-3)},
+                   "l2": runner.l2_note, "back_to_back_env_steps_per_s": units / (b2b_ms * 1e-3),
+                   "mean_episode_len": (ract / radd if radd else None), "replay_episodes": rsize},
         "clocks": clocks,
         "e2e": {"value": float(G) * world * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": runner.e2e_note},
@@ -440,12 +452,14 @@ class RolloutBench:
         flops = 2.0 * rows * 2048 * 1024 * nets            # one LSTM-layer launch, both networks (algorithmic: the fp32 math once)
         ms = (prof["lstm0"][0] + prof["lstm1"][0]) / max(1, prof["lstm0"][1] + prof["lstm1"][1])
         ach = flops / (ms * 1e-3) / 1e12
+        issue = {"x3": 3.0, "x1": 2.0, "uniform": 3.0}[self.args.target_precision]  # MMAs issued per algorithmic MAC, averaged over both nets
         tick_total = sum(v[0] for v in prof.values()) / max(1, prof["tick"][1])
         hbm_bytes = 40321.0 * eng.G                       # algorithmic bytes per env-step at C2
         return {"bound": "tensor", "kernel": "hbg::gemm3_kernel<EPI_LSTM> (LSTM layer GEMM + fused cell update, online+target in one launch)",
-                "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": load_traffic("lstm"),
                 "peak_source": peaks["source"] + " (sustained bf16)", "algorithmic_flop_per_launch": flops, "avg_launch_ms": ms,
-                "tensor_issue_factor": 3 if True else 1,
+                "issued_tflops": ach * issue, "issued_frac": ach * issue / peaks["bf16_tflops"],
+                "note": "achieved counts the fp32 math once; the tensor cores issue %.1fx that (bf16x3 split accumulate for the 1e-4-vs-fp32 contract)" % issue,
                 "kernel_ms_per_tick": {k: v[0] / max(1, v[1]) for k, v in prof.items()}, "kernel_ms_sum_per_tick": tick_total,
                 "hbm_view": {"algorithmic_bytes_per_env_step": 40321, "achieved_gbs": hbm_bytes / (sum(step_ms) / len(step_ms) * 1e-3) / 1e9,
                              "peak_gbs": peaks["hbm_gbs"]}}

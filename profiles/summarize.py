@@ -45,5 +45,28 @@ def full(path, pat=None):
                 print("  %-70s %s %s" % (w, r[hdr.index(w)], units[hdr.index(w)]))
 
 
+def traffic(path, out_json):
+    """profiles/traffic.json: DRAM bytes per launch of the kernels bench.py reports a roofline for."""
+    import json
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+
+    def val(r, name):
+        v, u = float(r[hdr.index(name)].replace(",", "")), units[hdr.index(name)]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+
+    acc = {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        key = "lstm" if "gemm3_kernel<2" in name or "gemm3_kernel<(int)2" in name else ("fc" if "gemm3_kernel" in name else ("tick" if "hb_k_tick" in name else ("head" if "head" in name else None)))
+        if key:
+            acc.setdefault(key, []).append(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"))
+    res = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v), "source": path.split("/")[-1]} for k, v in acc.items()}
+    json.dump(res, open(out_json, "w"), indent=1)
+    print(res)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
