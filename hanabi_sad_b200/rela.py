@@ -229,9 +229,17 @@ class _DeviceGroup:
         a0 = actors[0]
         runner = a0.runner
         if self.eval:
+            # self-play evaluation: every seat must run the same network (eval.py builds one runner per seat; utils.load_sad_model
+            # even builds one agent object per seat from the same weight file) -- identical tensors are accepted
+            ref_sd = runner.agent.online_net.state_dict()
             for a in actors:
-                if a.runner.agent is not runner.agent and a.runner is not runner:
-                    raise NotImplementedError("evaluating different agents per seat (cross-play) is not served by the device policy yet")
+                if a.runner.agent is runner.agent:
+                    continue
+                sd = a.runner.agent.online_net.state_dict()
+                same = sd.keys() == ref_sd.keys() and all(torch.equal(sd[k].cpu(), ref_sd[k].cpu()) for k in ref_sd)
+                if not same:
+                    raise NotImplementedError("evaluating DIFFERENT agents per seat (cross-play, tools/eval_model.py --paper op) is not "
+                                              "served by the device policy yet (SURVEY 8f-1)")
         replay = a0.replay
         hid = runner.agent.online_net.hid_dim
         self.engine = Engine(
