@@ -19,7 +19,7 @@ class HbConfig(ctypes.Structure):
         ("vdn", c_i32), ("multi_step", c_i32), ("gamma", c_float), ("eta", c_float), ("seq_len", c_i32),
         ("replay_capacity", c_i32), ("alpha", c_float), ("beta", c_float), ("hid_dim", c_i32),
         ("num_lstm_layer", c_i32), ("num_fc_layer", c_i32), ("skip_connect", c_i32), ("priority_mode", c_i32),
-        ("reserved", c_i32 * 7),
+        ("eval_seats", c_i32), ("reserved", c_i32 * 6),
     ]
 
 
@@ -36,6 +36,7 @@ class HbWeights(ctypes.Structure):
     _fields_ = [
         ("fc_w", c_void_p), ("fc_b", c_void_p), ("w_ih", c_void_p * 2), ("w_hh", c_void_p * 2), ("b_ih", c_void_p * 2),
         ("b_hh", c_void_p * 2), ("fc_a_w", c_void_p), ("fc_a_b", c_void_p), ("fc_v_w", c_void_p), ("fc_v_b", c_void_p),
+        ("fc2_w", c_void_p), ("fc2_b", c_void_p), ("skip_connect", c_i32),
     ]
 
 

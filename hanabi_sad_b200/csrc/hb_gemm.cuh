@@ -66,6 +66,14 @@ struct __align__(64) Params {
   float* head_part;
   int head_out;
   int head_rows;                 // rows_pad (stride of the n_tile axis of head_part)
+  // Row mapping of this problem: tile row r (0 .. tiles*128) is row  r*row_mul + row_add  of the caller's buffers and is
+  // real only if r < valid_rows.  (1, 0, rows_pad) for a problem over all agents; (P, seat, G) when the problem is ONE
+  // seat's network over that seat's agents (evaluation with a different network per seat: the A operands are strided
+  // TMA views, everything the epilogue touches goes through this mapping).
+  int row_mul, row_add, valid_rows;
+  // EPI_LSTM top layer with skip_connect (r2d2.py:74-75): the head consumes h' + x; x as bf16 hi/lo [rows][512]
+  const __nv_bfloat16* skip_hi;
+  const __nv_bfloat16* skip_lo;
   int* error_flag;               // set to 1 if a barrier wait ran into the spin guard (never in a healthy run)
 };
 
@@ -392,7 +400,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
       const int z = tile / tiles_per_problem, r = tile - z * tiles_per_problem;
       const int m_tile = (r / n_tiles_n) * CW + rank, n_tile = r % n_tiles_n;
       const Params& p = ps[z];
-      const size_t row = (size_t)m_tile * BM + row_in_tile;
+      const int row_local = m_tile * BM + row_in_tile;
+      const bool valid = row_local < p.valid_rows;
+      const size_t row = (size_t)row_local * p.row_mul + p.row_add;
       const uint32_t acc_stage = lt % ACC_STAGES, aph = (lt / ACC_STAGES) & 1u;
       mbar_wait(bar_tfull + 8 * acc_stage, aph, p.error_flag, dead);
       tc_fence_after();
@@ -404,8 +414,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           float* dst = p.c_f32 + row * p.ldc + (size_t)n_tile * BN + c0;
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += p.bias ? __ldg(p.bias + n_tile * BN + c0 + i) : 0.f;
+          if (valid)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
       } else if (EPI == EPI_RELU) {
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -415,7 +426,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + col + i), 0.f);
           const size_t o = row * p.out_ld + p.out_col0 + col;
-          store_split16(v, p.out_hi + o, p.out_lo + o);
+          if (valid) store_split16(v, p.out_hi + o, p.out_lo + o);
         }
       } else {
         // tile columns: [gate i | f | g | o][64 hidden units]; hidden unit = n_tile*64 + u
@@ -443,7 +454,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           const float* bias = p.bias + n_tile * BN + u0;
           const float4* cin = reinterpret_cast<const float4*>(p.c_in + row * HID + unit);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { const float4 t = cin[i]; c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w; }
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = valid ? cin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w;
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float ig = sigmoid_f(gi[i] + __ldg(bias + i));
@@ -453,17 +467,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
             c[i] = fg * c[i] + ig * g_;
             h[i] = og * tanh_f(c[i]);
           }
-          if (p.c_out) {
+          if (p.c_out && valid) {
             float4* cout = reinterpret_cast<float4*>(p.c_out + row * HID + unit);
 #pragma unroll
             for (int i = 0; i < 4; ++i) cout[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
           }
-          if (p.h_f32) {
+          if (p.h_f32 && valid) {
             float4* ho = reinterpret_cast<float4*>(p.h_f32 + row * HID + unit);
 #pragma unroll
             for (int i = 0; i < 4; ++i) ho[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
           }
-          if (p.out_hi) {
+          if (p.out_hi && valid) {
             const size_t o = row * p.out_ld + p.out_col0 + unit;
             store_split16(h, p.out_hi + o, p.out_lo + o);
           }
@@ -473,6 +487,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (PAIR) mbar_arrive_cluster((bar_tempty + 8 * acc_stage) & PEER_MASK); else mbar_arrive(bar_tempty + 8 * acc_stage); }
+          if (p.skip_hi != nullptr && valid) {  // skip_connect: the head sees h' + x
+            const __nv_bfloat16* xh = p.skip_hi + row * HID + n_tile * 64;
+            const __nv_bfloat16* xl = p.skip_lo + row * HID + n_tile * 64;
+#pragma unroll
+            for (int u = 0; u < 64; u += 8) {
+              const uint4 a = *reinterpret_cast<const uint4*>(xh + u), b = *reinterpret_cast<const uint4*>(xl + u);
+              const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&a);
+              const __nv_bfloat16* bl = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h_all[u + i] += __bfloat162float(ah[i]) + __bfloat162float(bl[i]);
+            }
+          }
           float* part = p.head_part + ((size_t)n_tile * p.head_rows + row) * head_out;
           for (int o0 = 0; o0 < head_out; o0 += 8) {   // 8 outputs at a time: 8 accumulators, weights broadcast from smem
             float acc[8];
@@ -488,7 +514,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
               }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (o0 + j < head_out) part[o0 + j] = acc[j];
+            for (int j = 0; j < 8; ++j) if (o0 + j < head_out && valid) part[o0 + j] = acc[j];
           }
           continue;  // the accumulator was already released above
         }

@@ -41,11 +41,12 @@ static PFN_tmapEncodeTiled hb_get_encode() {
 }
 
 // [rows][cols] bf16, cols contiguous; box = 64 columns (128 bytes, one swizzle span) x box_rows rows.
-static int hb_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// `row_stride` (elements, 0 = cols) lets a map describe every P-th row of a buffer: one seat's agents.
+static int hb_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t row_stride = 0) {
   PFN_tmapEncodeTiled enc = hb_get_encode();
   if (!enc) { hb_set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
+  cuuint64_t gstride[1] = {(row_stride ? row_stride : cols) * 2};
   cuuint32_t box[2] = {(cuuint32_t)hbg::BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -94,9 +95,10 @@ __global__ void hb_k_prep_head(const float* __restrict__ wa, const float* __rest
 // ---------------------------------------------------------------------------------------- head + action selection
 struct HbHeadArgs {
   int rows, rows_pad, A, have_target;
+  int seat_mode, P;           // seat mode: the network of row r is net r % P (no target network)
   const float* part[2];       // [8][rows_pad][A+1] partial head sums of the online / target network (LSTM-1 epilogue)
-  const float* ba[2];         // fc_a bias [A]
-  const float* bv[2];         // fc_v bias [1]
+  const float* ba[HB_MAX_P];  // fc_a bias [A] per network (training: 0 online, 1 target)
+  const float* bv[HB_MAX_P];  // fc_v bias [1]
   const float* legal;         // [rows][A]
   const float* eps;           // [rows]
   int64_t* a;                 // [rows]
@@ -134,9 +136,10 @@ __global__ void __launch_bounds__(HB_HEAD_WARPS * 32) hb_k_head_act(HbHeadArgs p
       if (lane + 32 < A) s1 += pr[lane + 32];
       sv += pr[A];  // same address for the whole warp: one broadcast load
     }
-    out[net][0] = lane < A ? s0 + __ldg(p.ba[net] + lane) : 0.f;
-    out[net][1] = lane + 32 < A ? s1 + __ldg(p.ba[net] + lane + 32) : 0.f;
-    vv[net] = sv + __ldg(p.bv[net]);
+    const int wn = p.seat_mode ? row % p.P : net;  // whose biases
+    out[net][0] = lane < A ? s0 + __ldg(p.ba[wn] + lane) : 0.f;
+    out[net][1] = lane + 32 < A ? s1 + __ldg(p.ba[wn] + lane + 32) : 0.f;
+    vv[net] = sv + __ldg(p.bv[wn]);
   }
   const float* lm = p.legal + (size_t)row * A;
   const float l0 = lane < A ? lm[lane] : 0.f;
@@ -206,21 +209,39 @@ static int hb_alloc_zero(void** p, size_t bytes, cudaStream_t st) {
     if (_rc) return _rc;                                                       \
   } while (0)
 
+#define HB_PARAMS_PER_PARITY (4 * HB_MAX_P)  // launches fc, fc2, lstm0, lstm1 x up to HB_MAX_P problems
+enum { HB_L_FC = 0, HB_L_FC2 = 1, HB_L_LSTM0 = 2, HB_L_LSTM1 = 3 };
+
+// (Re)builds the Params records of every launch for both state parities.  Training engines: problems = {online, target}
+// over all agents.  eval_seats engines: problems = seats, each a strided view (every P-th row) of the same buffers.
 static int hb_build_params(hb_engine* e) {
   HbPolicy* P = e->policy;
   const int rp = P->rows_pad, KS = P->KS;
-  std::vector<Params> hp(2 * 3 * 2);
+  const bool seat = P->seat_mode != 0;
+  const int np = seat ? e->P : 2;
+  const int mul = seat ? e->P : 1;
+  const uint64_t vrows = seat ? (uint64_t)e->G : (uint64_t)rp;  // rows of one problem's operand view
+  std::vector<Params> hp(2 * HB_PARAMS_PER_PARITY);
   memset(hp.data(), 0, hp.size() * sizeof(Params));
+  const size_t lsz = (size_t)rp * HB_HID;  // one layer of one state half
+  int n_fc2 = 0;
   for (int par = 0; par < 2; ++par) {
     const int cur = par, nxt = par ^ 1;
-    for (int net = 0; net < 2; ++net) {
-      const HbNetWeights& W = P->net[net];
-      const size_t lsz = (size_t)rp * HB_HID;  // one layer of one state half
+    n_fc2 = 0;
+    for (int z = 0; z < np; ++z) {
+      const HbNetWeights& W = P->net[z];
+      const int add = seat ? z : 0;
       int rc = 0;
+      auto amap = [&](CUtensorMap* m, const __nv_bfloat16* base, int ld) {  // A-operand view of a [rows_pad][ld] buffer
+        return hb_make_tmap(m, base + (size_t)add * ld, vrows, ld, hbg::BM, (uint64_t)mul * ld);
+      };
+      __nv_bfloat16 *xh = seat ? P->x_hi[0] : P->x_hi[z], *xl = seat ? P->x_lo[0] : P->x_lo[z];
+      const bool fc2 = seat && W.has_fc2;
+      __nv_bfloat16 *lin_h = fc2 ? P->x_hi[1] : xh, *lin_l = fc2 ? P->x_lo[1] : xl;  // what the LSTM (and a skip connection) consumes
+      Params* base = hp.data() + (size_t)par * HB_PARAMS_PER_PARITY;
       // ---- fc
-      Params& f = hp[(par * 3 + 0) * 2 + net];
-      rc |= hb_make_tmap(&f.a_hi[0], P->s_hi, rp, KS, hbg::BM);
-      rc |= hb_make_tmap(&f.a_lo[0], P->s_lo, rp, KS, hbg::BM);
+      Params& f = base[HB_L_FC * HB_MAX_P + z];
+      rc |= amap(&f.a_hi[0], P->s_hi, KS); rc |= amap(&f.a_lo[0], P->s_lo, KS);
       f.a_hi[1] = f.a_hi[0]; f.a_lo[1] = f.a_lo[0];
       rc |= hb_make_tmap(&f.b_hi, W.w0_hi, HB_HID, KS, hbg::BN / 2);
       rc |= hb_make_tmap(&f.b_lo, W.w0_lo, HB_HID, KS, hbg::BN / 2);
@@ -228,48 +249,57 @@ static int hb_build_params(hb_engine* e) {
       f.lo_first = e->env.g.off_belief / hbg::BK;
       f.lo_last = (e->env.g.off_sad + hbg::BK - 1) / hbg::BK;
       f.bias = W.b0;
-      f.out_hi = P->x_hi[net]; f.out_lo = P->x_lo[net]; f.out_ld = HB_HID; f.out_col0 = 0;
+      f.out_hi = xh; f.out_lo = xl; f.out_ld = HB_HID; f.out_col0 = 0;
+      // ---- second fc layer (r2d2.py:42-46), compact list: only the seats that have one
+      Params* f2 = nullptr;
+      if (fc2) {
+        f2 = &base[HB_L_FC2 * HB_MAX_P + n_fc2++];
+        rc |= amap(&f2->a_hi[0], xh, HB_HID); rc |= amap(&f2->a_lo[0], xl, HB_HID);
+        f2->a_hi[1] = f2->a_hi[0]; f2->a_lo[1] = f2->a_lo[0];
+        rc |= hb_make_tmap(&f2->b_hi, W.w1_hi, HB_HID, HB_HID, hbg::BN / 2);
+        rc |= hb_make_tmap(&f2->b_lo, W.w1_lo, HB_HID, HB_HID, hbg::BN / 2);
+        f2->k_chunks = HB_HID / hbg::BK; f2->k_chunks_seg0 = f2->k_chunks; f2->lo_first = 0; f2->lo_last = f2->k_chunks;
+        f2->bias = W.b1;
+        f2->out_hi = P->x_hi[1]; f2->out_lo = P->x_lo[1]; f2->out_ld = HB_HID; f2->out_col0 = 0;
+      }
+      const bool owner = seat || z == 0;  // this problem advances the recurrent state (the target network only reads it)
       // ---- lstm layer 0
-      Params& l0 = hp[(par * 3 + 1) * 2 + net];
-      rc |= hb_make_tmap(&l0.a_hi[0], P->x_hi[net], rp, HB_HID, hbg::BM);
-      rc |= hb_make_tmap(&l0.a_lo[0], P->x_lo[net], rp, HB_HID, hbg::BM);
-      rc |= hb_make_tmap(&l0.a_hi[1], P->h_hi[cur], rp, HB_HID, hbg::BM);
-      rc |= hb_make_tmap(&l0.a_lo[1], P->h_lo[cur], rp, HB_HID, hbg::BM);
+      Params& l0 = base[HB_L_LSTM0 * HB_MAX_P + z];
+      rc |= amap(&l0.a_hi[0], lin_h, HB_HID); rc |= amap(&l0.a_lo[0], lin_l, HB_HID);
+      rc |= amap(&l0.a_hi[1], P->h_hi[cur], HB_HID); rc |= amap(&l0.a_lo[1], P->h_lo[cur], HB_HID);
       rc |= hb_make_tmap(&l0.b_hi, W.wl_hi[0], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
       rc |= hb_make_tmap(&l0.b_lo, W.wl_lo[0], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
       l0.k_chunks = 2 * HB_HID / hbg::BK; l0.k_chunks_seg0 = HB_HID / hbg::BK; l0.lo_first = 0; l0.lo_last = l0.k_chunks;
       l0.bias = W.bl[0];
       l0.c_in = P->c[cur];
-      if (net == 0) { l0.c_out = P->c[nxt]; l0.out_hi = P->h_hi[nxt]; l0.out_lo = P->h_lo[nxt]; }
+      if (owner) { l0.c_out = P->c[nxt]; l0.out_hi = P->h_hi[nxt]; l0.out_lo = P->h_lo[nxt]; }
       else { l0.c_out = nullptr; l0.out_hi = P->th_hi; l0.out_lo = P->th_lo; }
       l0.out_ld = HB_HID; l0.out_col0 = 0; l0.h_f32 = nullptr;
-      // ---- lstm layer 1
-      Params& l1 = hp[(par * 3 + 2) * 2 + net];
-      if (net == 0) {
-        rc |= hb_make_tmap(&l1.a_hi[0], P->h_hi[nxt], rp, HB_HID, hbg::BM);
-        rc |= hb_make_tmap(&l1.a_lo[0], P->h_lo[nxt], rp, HB_HID, hbg::BM);
-      } else {
-        rc |= hb_make_tmap(&l1.a_hi[0], P->th_hi, rp, HB_HID, hbg::BM);
-        rc |= hb_make_tmap(&l1.a_lo[0], P->th_lo, rp, HB_HID, hbg::BM);
-      }
-      rc |= hb_make_tmap(&l1.a_hi[1], P->h_hi[cur] + lsz, rp, HB_HID, hbg::BM);
-      rc |= hb_make_tmap(&l1.a_lo[1], P->h_lo[cur] + lsz, rp, HB_HID, hbg::BM);
+      // ---- lstm layer 1 (+ fused dueling head)
+      Params& l1 = base[HB_L_LSTM1 * HB_MAX_P + z];
+      if (owner) { rc |= amap(&l1.a_hi[0], P->h_hi[nxt], HB_HID); rc |= amap(&l1.a_lo[0], P->h_lo[nxt], HB_HID); }
+      else { rc |= amap(&l1.a_hi[0], P->th_hi, HB_HID); rc |= amap(&l1.a_lo[0], P->th_lo, HB_HID); }
+      rc |= amap(&l1.a_hi[1], P->h_hi[cur] + lsz, HB_HID); rc |= amap(&l1.a_lo[1], P->h_lo[cur] + lsz, HB_HID);
       rc |= hb_make_tmap(&l1.b_hi, W.wl_hi[1], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
       rc |= hb_make_tmap(&l1.b_lo, W.wl_lo[1], 4 * HB_HID, 2 * HB_HID, hbg::BN / 2);
       l1.k_chunks = 2 * HB_HID / hbg::BK; l1.k_chunks_seg0 = HB_HID / hbg::BK; l1.lo_first = 0; l1.lo_last = l1.k_chunks;
       l1.bias = W.bl[1];
       l1.c_in = P->c[cur] + lsz;
-      if (net == 0) { l1.c_out = P->c[nxt] + lsz; l1.out_hi = P->h_hi[nxt] + lsz; l1.out_lo = P->h_lo[nxt] + lsz; }
+      if (owner) { l1.c_out = P->c[nxt] + lsz; l1.out_hi = P->h_hi[nxt] + lsz; l1.out_lo = P->h_lo[nxt] + lsz; }
       else { l1.c_out = nullptr; l1.out_hi = nullptr; l1.out_lo = nullptr; }
       l1.out_ld = HB_HID; l1.out_col0 = 0; l1.h_f32 = nullptr;
-      l1.head_w = W.head_tiles; l1.head_part = P->head_part[net]; l1.head_out = e->A + 1; l1.head_rows = rp;
+      l1.head_w = W.head_tiles; l1.head_part = seat ? P->head_part[0] : P->head_part[z]; l1.head_out = e->A + 1; l1.head_rows = rp;
+      if (seat && W.skip) { l1.skip_hi = lin_h; l1.skip_lo = lin_l; }
       if (rc) return -2;
-      for (Params* q : {&f, &l0, &l1}) {
-        q->split = (net == 0 || P->target_split) ? 1 : 0;
+      for (Params* q : {&f, f2, &l0, &l1}) {
+        if (!q) continue;
+        q->split = (seat || z == 0 || P->target_split) ? 1 : 0;
+        q->row_mul = mul; q->row_add = add; q->valid_rows = (int)vrows;
         q->error_flag = P->d_error;
       }
     }
   }
+  P->n_fc2 = n_fc2;
   HB_CUDA(cudaMemcpyAsync(P->d_params, hp.data(), hp.size() * sizeof(Params), cudaMemcpyHostToDevice, e->stream));
   HB_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
@@ -281,11 +311,15 @@ int hb_policy_create(hb_engine* e) {
   e->policy = nullptr;
   const hb_config& c = e->cfg;
   if (c.hid_dim == 0) return 0;  // environment-only engine
-  if (c.hid_dim != HB_HID || c.num_lstm_layer != HB_LAYERS || c.num_fc_layer != 1 || c.skip_connect != 0) {
-    hb_set_error("hb_create: the device policy serves hid_dim=512, num_lstm_layer=2, num_fc_layer=1, skip_connect=0 (got %d, %d, %d, %d)",
-                 c.hid_dim, c.num_lstm_layer, c.num_fc_layer, c.skip_connect);
+  if (c.hid_dim != HB_HID || c.num_lstm_layer != HB_LAYERS) {
+    hb_set_error("hb_create: the device policy serves hid_dim=512, num_lstm_layer=2 (got %d, %d)", c.hid_dim, c.num_lstm_layer);
     return -1;
   }
+  if (!c.eval_seats && (c.num_fc_layer != 1 || c.skip_connect != 0)) {
+    hb_set_error("hb_create: num_fc_layer=2 / skip_connect are served by eval_seats engines only (selfplay.py never trains them)");
+    return -1;
+  }
+  if (c.eval_seats && c.replay_capacity > 0) { hb_set_error("hb_create: an eval_seats engine has no replay"); return -1; }
   if (e->A > 63) { hb_set_error("hb_create: num_action > 63 is not supported by the head kernel"); return -1; }
   HbPolicy* P = new HbPolicy();
   memset(P, 0, sizeof(*P));
@@ -294,9 +328,11 @@ int hb_policy_create(hb_engine* e) {
   P->rows_pad = (e->rows + 2 * hbg::BM - 1) / (2 * hbg::BM) * (2 * hbg::BM);  // CTA pairs work on two vertically adjacent tiles
   P->KS = (e->F + hbg::BK - 1) / hbg::BK * hbg::BK;
   P->target_split = c.priority_mode == 2 ? 0 : 1;
+  P->seat_mode = c.eval_seats ? 1 : 0;
   const size_t rp = P->rows_pad, KS = P->KS, bf = sizeof(__nv_bfloat16);
   HB_ALLOC(P->s_hi, rp * KS * bf);
   HB_ALLOC(P->s_lo, rp * KS * bf);
+  const int n_nets = P->seat_mode ? e->P : 2;
   for (int n = 0; n < 2; ++n) {
     HB_ALLOC(P->x_hi[n], rp * HB_HID * bf);
     HB_ALLOC(P->x_lo[n], rp * HB_HID * bf);
@@ -304,6 +340,8 @@ int hb_policy_create(hb_engine* e) {
     HB_ALLOC(P->h_hi[n], HB_LAYERS * rp * HB_HID * bf);
     HB_ALLOC(P->h_lo[n], HB_LAYERS * rp * HB_HID * bf);
     HB_ALLOC(P->c[n], HB_LAYERS * rp * HB_HID * sizeof(float));
+  }
+  for (int n = 0; n < n_nets; ++n) {
     HbNetWeights& W = P->net[n];
     HB_ALLOC(W.w0_hi, (size_t)HB_HID * KS * bf);
     HB_ALLOC(W.w0_lo, (size_t)HB_HID * KS * bf);
@@ -322,6 +360,11 @@ int hb_policy_create(hb_engine* e) {
     if (raw < (size_t)4 * HB_HID * HB_HID) raw = (size_t)4 * HB_HID * HB_HID;
     HB_ALLOC(W.raw, raw * sizeof(float));
     HB_ALLOC(W.raw2, (size_t)4 * HB_HID * sizeof(float) * 2);
+    if (P->seat_mode) {
+      HB_ALLOC(W.w1_hi, (size_t)HB_HID * HB_HID * bf);
+      HB_ALLOC(W.w1_lo, (size_t)HB_HID * HB_HID * bf);
+      HB_ALLOC(W.b1, HB_HID * sizeof(float));
+    }
   }
   HB_ALLOC(P->th_hi, rp * HB_HID * bf);
   HB_ALLOC(P->th_lo, rp * HB_HID * bf);
@@ -329,7 +372,7 @@ int hb_policy_create(hb_engine* e) {
   HB_ALLOC(P->oq, e->rows * sizeof(float));
   HB_ALLOC(P->tq, e->rows * sizeof(float));
   HB_ALLOC(P->d_error, sizeof(int));
-  HB_ALLOC(P->d_params, 12 * sizeof(Params));
+  HB_ALLOC(P->d_params, 2 * HB_PARAMS_PER_PARITY * sizeof(Params));
   e->obs.s_hi = P->s_hi; e->obs.s_lo = P->s_lo; e->obs.KS = P->KS;
   HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_RELU, HB_GEMM_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
   HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
@@ -342,7 +385,10 @@ void hb_policy_destroy(hb_engine* e) {
   cudaFree(P->s_hi); cudaFree(P->s_lo); cudaFree(P->th_hi); cudaFree(P->th_lo);
   for (int n = 0; n < 2; ++n) {
     cudaFree(P->x_hi[n]); cudaFree(P->x_lo[n]); cudaFree(P->head_part[n]); cudaFree(P->h_hi[n]); cudaFree(P->h_lo[n]); cudaFree(P->c[n]);
+  }
+  for (int n = 0; n < HB_MAX_P; ++n) {
     HbNetWeights& W = P->net[n];
+    cudaFree(W.w1_hi); cudaFree(W.w1_lo); cudaFree(W.b1);
     cudaFree(W.w0_hi); cudaFree(W.w0_lo); cudaFree(W.b0);
     for (int l = 0; l < HB_LAYERS; ++l) { cudaFree(W.wl_hi[l]); cudaFree(W.wl_lo[l]); cudaFree(W.bl[l]); }
     cudaFree(W.wa); cudaFree(W.ba); cudaFree(W.wv); cudaFree(W.bv); cudaFree(W.head_tiles); cudaFree(W.raw); cudaFree(W.raw2);
@@ -358,7 +404,16 @@ int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w) {
   if (!e || !w) { hb_set_error("hb_policy_set_weights: null argument"); return -1; }
   HbPolicy* P = e->policy;
   if (!P) { hb_set_error("hb_policy_set_weights: this engine was created without a policy (hid_dim = 0)"); return -1; }
-  if (net < 0 || net > 1) { hb_set_error("hb_policy_set_weights: net must be 0 (online) or 1 (target)"); return -1; }
+  const int n_nets = P->seat_mode ? e->P : 2;
+  if (net < 0 || net >= n_nets) {
+    hb_set_error(P->seat_mode ? "hb_policy_set_weights: net must be a seat index 0..%d" : "hb_policy_set_weights: net must be 0 (online) or 1 (target), max %d", n_nets - 1);
+    return -1;
+  }
+  if (!P->seat_mode && (w->fc2_w != nullptr || w->skip_connect != 0)) {
+    hb_set_error("hb_policy_set_weights: num_fc_layer=2 / skip_connect need an eval_seats engine");
+    return -1;
+  }
+  if (w->fc2_w != nullptr && w->fc2_b == nullptr) { hb_set_error("hb_policy_set_weights: fc2_b is null"); return -1; }
   const void* need[] = {w->fc_w, w->fc_b, w->w_ih[0], w->w_hh[0], w->b_ih[0], w->b_hh[0], w->w_ih[1], w->w_hh[1], w->b_ih[1], w->b_hh[1],
                         w->fc_a_w, w->fc_a_b, w->fc_v_w, w->fc_v_b};
   for (const void* p : need)
@@ -371,6 +426,14 @@ int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w) {
   HB_CUDA(cudaMemcpyAsync(W.raw, w->fc_w, (size_t)HB_HID * F * sizeof(float), cudaMemcpyDefault, st));
   hb_k_prep_weight<<<blocks((size_t)HB_HID * F), 256, 0, st>>>(W.raw, HB_HID, F, 0, W.w0_hi, W.w0_lo, KS, 0);
   HB_CUDA(cudaMemcpyAsync(W.b0, w->fc_b, HB_HID * sizeof(float), cudaMemcpyDefault, st));
+  W.has_fc2 = w->fc2_w != nullptr;
+  W.skip = w->skip_connect != 0;
+  if (W.has_fc2) {
+    HB_CUDA(cudaMemcpyAsync(W.raw, w->fc2_w, (size_t)HB_HID * HB_HID * sizeof(float), cudaMemcpyDefault, st));
+    hb_k_prep_weight<<<blocks((size_t)HB_HID * HB_HID), 256, 0, st>>>(W.raw, HB_HID, HB_HID, 0, W.w1_hi, W.w1_lo, HB_HID, 0);
+    HB_CUDA(cudaMemcpyAsync(W.b1, w->fc2_b, HB_HID * sizeof(float), cudaMemcpyDefault, st));
+    e->launches += 1;
+  }
   for (int l = 0; l < HB_LAYERS; ++l) {
     const size_t n = (size_t)4 * HB_HID * HB_HID;
     HB_CUDA(cudaMemcpyAsync(W.raw, w->w_ih[l], n * sizeof(float), cudaMemcpyDefault, st));
@@ -392,6 +455,7 @@ int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w) {
   HB_CUDA(cudaGetLastError());
   HB_CUDA(cudaStreamSynchronize(st));  // the caller may free / overwrite its tensors once this returns
   P->have_weights[net] = 1;
+  if (P->seat_mode) return hb_build_params(e);  // the launch lists depend on each seat's architecture variant
   return 0;
 }
 
@@ -427,23 +491,37 @@ HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e) {
 int hb_policy_forward(hb_engine* e, int greedy_only) {
   HbPolicy* P = e->policy;
   if (!P || !P->have_weights[0]) { hb_set_error("policy forward without online weights (call hb_policy_set_weights first)"); return -1; }
-  const int nets = P->have_weights[1] && e->cfg.priority_mode != 1 ? 2 : 1;
-  const int mt = P->rows_pad / hbg::BM;
-  const Params* base = P->d_params + (size_t)P->parity * 6;
+  int nets;
+  if (P->seat_mode) {
+    nets = e->P;
+    for (int n = 0; n < nets; ++n)
+      if (!P->have_weights[n]) { hb_set_error("policy forward: seat %d has no weights (hb_policy_set_weights)", n); return -1; }
+  } else {
+    nets = P->have_weights[1] && e->cfg.priority_mode != 1 ? 2 : 1;
+  }
+  const int view_rows = P->seat_mode ? (e->G + 2 * hbg::BM - 1) / (2 * hbg::BM) * (2 * hbg::BM) : P->rows_pad;
+  const int mt = view_rows / hbg::BM;
+  const Params* base = P->d_params + (size_t)P->parity * HB_PARAMS_PER_PARITY;
   const int nt_fc = HB_HID / hbg::BN, nt_l = 4 * HB_HID / hbg::BN;
   int rc;
   { HbProfScope ps(e, HB_PROF_FC);
-    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_RELU, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + 0, nt_fc, mt, nets); }
+    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_RELU, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + HB_L_FC * HB_MAX_P, nt_fc, mt, nets);
+    if (!rc && P->seat_mode && P->n_fc2 > 0) {
+      rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_RELU, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + HB_L_FC2 * HB_MAX_P, nt_fc, mt, P->n_fc2);
+      e->launches += 1;
+    } }
   if (rc) return rc;
   { HbProfScope ps(e, HB_PROF_LSTM0);
-    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + 2, nt_l, mt, nets); }
+    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + HB_L_LSTM0 * HB_MAX_P, nt_l, mt, nets); }
   if (rc) return rc;
   { HbProfScope ps(e, HB_PROF_LSTM1);
-    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + 4, nt_l, mt, nets); }
+    rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_LSTM, HB_GEMM_MODE>, 2, e->sm_count, e->stream, base + HB_L_LSTM1 * HB_MAX_P, nt_l, mt, nets); }
   if (rc) return rc;
   HbHeadArgs a;
-  a.rows = e->rows; a.rows_pad = P->rows_pad; a.A = e->A; a.have_target = nets == 2;
-  for (int n = 0; n < 2; ++n) { a.part[n] = P->head_part[n]; a.ba[n] = P->net[n].ba; a.bv[n] = P->net[n].bv; }
+  a.rows = e->rows; a.rows_pad = P->rows_pad; a.A = e->A; a.have_target = !P->seat_mode && nets == 2;
+  a.seat_mode = P->seat_mode; a.P = e->P;
+  for (int n = 0; n < 2; ++n) a.part[n] = P->head_part[n];
+  for (int n = 0; n < HB_MAX_P; ++n) { a.ba[n] = P->net[n].ba; a.bv[n] = P->net[n].bv; }
   a.legal = e->obs.legal_move; a.eps = e->obs.eps; a.a = e->d_a; a.greedy_a = e->d_greedy_a;
   a.adv = P->adv; a.oq = P->oq; a.tq = P->tq; a.seed = e->cfg.seed; a.tick = (uint32_t)P->act_count; a.tick_ctr = nullptr;
   a.greedy_only = greedy_only;
@@ -516,6 +594,7 @@ int hb_debug_gemm(int device, const float* A, const float* B, const float* bias,
   if (rc) return rc;
   hp.k_chunks = K / hbg::BK; hp.k_chunks_seg0 = hp.k_chunks; hp.lo_first = 0; hp.lo_last = hp.k_chunks; hp.split = split;
   hp.bias = dbias; hp.c_f32 = dC; hp.ldc = N; hp.error_flag = derr;
+  hp.row_mul = 1; hp.row_add = 0; hp.valid_rows = M;
   HB_CUDA(cudaMemcpy(dp, &hp, sizeof(hp), cudaMemcpyHostToDevice));
   HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
   HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));

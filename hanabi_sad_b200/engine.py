@@ -15,7 +15,7 @@ class Engine:
     def __init__(self, num_games, players=2, hand_size=5, bomb=0, max_len=80, sad=True, shuffle_color=False,
                  eps_list=(0.0,), seed=1, device=0, vdn=True, multi_step=3, gamma=0.999, eta=0.9, seq_len=80,
                  replay_capacity=0, alpha=0.6, beta=0.4, hid_dim=512, num_lstm_layer=2, num_fc_layer=1,
-                 skip_connect=False, priority_mode=0):
+                 skip_connect=False, priority_mode=0, eval_seats=False):
         L = lib()
         self._eps = np.ascontiguousarray(eps_list, dtype=np.float32)
         cfg = HbConfig()
@@ -28,6 +28,7 @@ class Engine:
         cfg.seq_len, cfg.replay_capacity, cfg.alpha, cfg.beta = int(seq_len), int(replay_capacity), float(alpha), float(beta)
         cfg.hid_dim, cfg.num_lstm_layer, cfg.num_fc_layer = int(hid_dim), int(num_lstm_layer), int(num_fc_layer)
         cfg.skip_connect, cfg.priority_mode = int(bool(skip_connect)), int(priority_mode)
+        cfg.eval_seats = int(bool(eval_seats))
         self.cfg = cfg
         h = ctypes.c_void_p()
         check(L.hb_create(ctypes.byref(cfg), ctypes.byref(h)))
@@ -133,10 +134,12 @@ class Engine:
                    "lstm.weight_ih_l1", "lstm.weight_hh_l1", "lstm.bias_ih_l1", "lstm.bias_hh_l1", "fc_a.weight", "fc_a.bias",
                    "fc_v.weight", "fc_v.bias")
 
-    def set_weights(self, net, state_dict):
-        """`state_dict` = R2D2Net.state_dict() (torch tensors on any device, or numpy arrays); net 0 online, 1 target."""
+    def set_weights(self, net, state_dict, skip_connect=False):
+        """`state_dict` = R2D2Net.state_dict() (torch tensors on any device, or numpy arrays); net 0 online, 1 target -- or,
+        on an eval_seats engine, the seat index; there a second fc layer (`net.2.*`) and `skip_connect` are honoured."""
         keep, ptr = [], {}
-        for k in self.WEIGHT_KEYS:
+        keys = self.WEIGHT_KEYS + (("net.2.weight", "net.2.bias") if "net.2.weight" in state_dict else ())
+        for k in keys:
             v = state_dict[k]
             if hasattr(v, "data_ptr"):
                 v = v.detach().float().contiguous()
@@ -155,6 +158,10 @@ class Engine:
             w.w_ih[l], w.w_hh[l] = ptr["lstm.weight_ih_l%d" % l], ptr["lstm.weight_hh_l%d" % l]
             w.b_ih[l], w.b_hh[l] = ptr["lstm.bias_ih_l%d" % l], ptr["lstm.bias_hh_l%d" % l]
         w.fc_a_w, w.fc_a_b, w.fc_v_w, w.fc_v_b = ptr["fc_a.weight"], ptr["fc_a.bias"], ptr["fc_v.weight"], ptr["fc_v.bias"]
+        if "net.2.weight" in ptr:
+            assert tuple(state_dict["net.2.weight"].shape) == (512, 512)
+            w.fc2_w, w.fc2_b = ptr["net.2.weight"], ptr["net.2.bias"]
+        w.skip_connect = int(bool(skip_connect))
         check(lib().hb_policy_set_weights(self._h, int(net), ctypes.byref(w)))
         del keep
 

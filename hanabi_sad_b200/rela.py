@@ -158,14 +158,18 @@ class BatchRunner:
         assert d.type == "cuda", "the B200 actor path needs a CUDA act device, got %r" % self.device
         return d.index or 0
 
-    def _attach(self, engine, lock):
-        self._engines.append((engine, lock))
-        self._push(engine, lock)
+    def _attach(self, engine, lock, seat=None):
+        self._engines.append((engine, lock, seat))
+        self._push(engine, lock, seat)
 
-    def _push(self, engine, lock):
+    def _push(self, engine, lock, seat=None):
+        net = self.agent.online_net
         with lock:
-            engine.set_weights(0, self.agent.online_net.state_dict())
-            engine.set_weights(1, self.agent.target_net.state_dict())
+            if seat is None:   # training engine: online + target network for every agent
+                engine.set_weights(0, net.state_dict())
+                engine.set_weights(1, self.agent.target_net.state_dict())
+            else:              # evaluation engine: this runner's agent plays seat `seat`
+                engine.set_weights(seat, net.state_dict(), skip_connect=bool(getattr(net, "skip_connect", False)))
 
     def start(self):
         self._started = True
@@ -176,8 +180,8 @@ class BatchRunner:
     def update_model(self, agent):
         """BatchRunner::updateModel (batch_runner.h:74-77): load_state_dict of the learner's agent into the actors' copy."""
         self.agent.load_state_dict(agent.state_dict())
-        for e, lk in self._engines:
-            self._push(e, lk)
+        for e, lk, seat in self._engines:
+            self._push(e, lk, seat)
 
 
 class R2D2Actor:
@@ -229,17 +233,9 @@ class _DeviceGroup:
         a0 = actors[0]
         runner = a0.runner
         if self.eval:
-            # self-play evaluation: every seat must run the same network (eval.py builds one runner per seat; utils.load_sad_model
-            # even builds one agent object per seat from the same weight file) -- identical tensors are accepted
-            ref_sd = runner.agent.online_net.state_dict()
-            for a in actors:
-                if a.runner.agent is runner.agent:
-                    continue
-                sd = a.runner.agent.online_net.state_dict()
-                same = sd.keys() == ref_sd.keys() and all(torch.equal(sd[k].cpu(), ref_sd[k].cpu()) for k in ref_sd)
-                if not same:
-                    raise NotImplementedError("evaluating DIFFERENT agents per seat (cross-play, tools/eval_model.py --paper op) is not "
-                                              "served by the device policy yet (SURVEY 8f-1)")
+            # one actor (and runner / agent) per seat (eval.py:43-48): the engine keeps one network per seat, so the seats may
+            # run different agents, incl. the num_fc_layer=2 / skip_connect variants of utils.load_op_model (cross-play)
+            assert len(actors) == env0.players, "eval thread loops carry one actor per player"
         replay = a0.replay
         hid = runner.agent.online_net.hid_dim
         self.engine = Engine(
@@ -247,18 +243,20 @@ class _DeviceGroup:
             seed=env0.seed, device=runner._device_index(), vdn=not self.iql, multi_step=a0.multi_step, gamma=a0.gamma, eta=a0.eta,
             seq_len=a0.seq_len, replay_capacity=(replay.capacity if replay is not None else 0),
             alpha=(replay.alpha if replay is not None else 0.6), beta=(replay.beta if replay is not None else 0.4), hid_dim=hid,
-            num_lstm_layer=runner.agent.online_net.num_lstm_layer, num_fc_layer=runner.agent.online_net.num_fc_layer,
-            skip_connect=runner.agent.online_net.skip_connect,
-            priority_mode=(1 if getattr(runner.agent, "uniform_priority", False) else 0))
+            num_lstm_layer=runner.agent.online_net.num_lstm_layer,
+            num_fc_layer=(1 if self.eval else runner.agent.online_net.num_fc_layer),
+            skip_connect=(False if self.eval else runner.agent.online_net.skip_connect),
+            priority_mode=(1 if getattr(runner.agent, "uniform_priority", False) else 0), eval_seats=self.eval)
         for i, g in enumerate(self.envs):
             g._bind(self.engine, i, self.lock)
         seen = set()
         for lp in loops:
-            for a in lp.actors:
+            for seat, a in enumerate(lp.actors):
                 a._engine = (self.engine, self.lock, len(self.envs))
-                if id(a.runner) not in seen:
-                    seen.add(id(a.runner))
-                    a.runner._attach(self.engine, self.lock)
+                key = (id(a.runner), seat if self.eval else -1)
+                if key not in seen:
+                    seen.add(key)
+                    a.runner._attach(self.engine, self.lock, seat if self.eval else None)
         if replay is not None:
             replay._attach(self.engine, self.lock)
         self.paused = threading.Event()
@@ -304,7 +302,7 @@ class _DeviceGroup:
             g._engine, g._lock = None, None
         for lp in self.loops:   # an eval engine lives for one evaluation (eval.py:19-66 builds everything anew each time)
             for a in lp.actors:
-                a.runner._engines = [(en, lk) for en, lk in a.runner._engines if en is not e]
+                a.runner._engines = [t for t in a.runner._engines if t[0] is not e]
                 a._engine = None
         e.close()
 

@@ -58,7 +58,10 @@ typedef struct hb_config {
   int32_t priority_mode;   /* 0: reference semantics (online + target forward every tick, both fp32-class);
                             * 1: uniform priority (R2D2Agent uniform_priority, r2d2.py:310-311: no target forward);
                             * 2: as 0 but the target forward runs in plain bf16 (priorities are heuristics) */
-  int32_t reserved[7];
+  int32_t eval_seats;      /* 1: evaluation engine -- one network PER SEAT (hb_policy_set_weights net = seat index), which may
+                            * differ in weights and in architecture variant (num_fc_layer 1|2, skip_connect): tools/eval_model.py
+                            * cross-play (utils.load_op_model, utils.py:35-84).  No target network, no replay. */
+  int32_t reserved[6];
 } hb_config;
 
 /* Snapshot of one game, for tests / eval (HanabiEnv getters, cpp/pybind.cc:23-38). */
@@ -146,6 +149,9 @@ typedef struct hb_weights {
   const float* w_ih[2]; const float* w_hh[2]; const float* b_ih[2]; const float* b_hh[2];
   const float* fc_a_w; const float* fc_a_b;
   const float* fc_v_w; const float* fc_v_b;
+  /* architecture variants of the OP-paper models (r2d2.py:42-46, 74-75); honoured by eval_seats engines only */
+  const float* fc2_w; const float* fc2_b;   /* net.2.{weight [512,512], bias}: second fc layer, NULL if num_fc_layer == 1 */
+  int32_t skip_connect;                      /* the head consumes lstm_out + fc_out */
 } hb_weights;
 
 /* BatchRunner::updateModel (rela/batch_runner.h:74-77) / R2D2Agent.sync_target_with_online: net 0 = online_net,

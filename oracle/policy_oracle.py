@@ -18,19 +18,23 @@ def _t(x):
 class PolicyOracle:
     """One R2D2Net (r2d2.py:24-57) as plain tensors taken from its state_dict."""
 
-    def __init__(self, state_dict, num_lstm_layer=2):
+    def __init__(self, state_dict, num_lstm_layer=2, skip_connect=False):
         sd = {k: _t(v).detach().float().cpu() for k, v in state_dict.items()}
         self.sd = sd
         self.L = num_lstm_layer
         self.hid = sd["lstm.weight_hh_l0"].shape[1]
+        self.num_fc_layer = 2 if "net.2.weight" in sd else 1  # nn.Sequential(Linear, ReLU[, Linear, ReLU]) (r2d2.py:42-46)
+        self.skip_connect = bool(skip_connect)                  # o = o + x (r2d2.py:74-75)
 
     def get_h0(self, rows):  # r2d2.py:59-63
         return {"h0": torch.zeros(self.L, rows, self.hid), "c0": torch.zeros(self.L, rows, self.hid)}
 
     def act(self, priv_s, hid):
-        """R2D2Net.act (r2d2.py:65-78), skip_connect=False, num_fc_layer=1: returns (adv, v, new_hid)."""
+        """R2D2Net.act (r2d2.py:65-78): returns (adv, v, new_hid)."""
         sd = self.sd
         x = torch.relu(_t(priv_s).float() @ sd["net.0.weight"].t() + sd["net.0.bias"])
+        if self.num_fc_layer == 2:
+            x = torch.relu(x @ sd["net.2.weight"].t() + sd["net.2.bias"])
         hs, cs = [], []
         inp = x
         for l in range(self.L):
@@ -42,6 +46,8 @@ class PolicyOracle:
             hs.append(h)
             cs.append(c)
             inp = h
+        if self.skip_connect:
+            inp = inp + x
         adv = inp @ sd["fc_a.weight"].t() + sd["fc_a.bias"]
         v = inp @ sd["fc_v.weight"].t() + sd["fc_v.bias"]
         return adv, v, {"h0": torch.stack(hs), "c0": torch.stack(cs)}
@@ -84,7 +90,7 @@ class AgentOracle:
         return out
 
 
-def random_state_dict(in_dim, hid, num_action, seed, hand_size=5):
+def random_state_dict(in_dim, hid, num_action, seed, hand_size=5, num_fc_layer=1):
     """Weights with nn.Linear / nn.LSTM default-init ranges (uniform(-1/sqrt(fan), 1/sqrt(fan))), numpy-seeded so the
     values do not depend on the torch version."""
     rng = np.random.default_rng(seed)
@@ -94,6 +100,9 @@ def random_state_dict(in_dim, hid, num_action, seed, hand_size=5):
         return torch.from_numpy(rng.uniform(-b, b, size=shape).astype(np.float32))
 
     sd = {"net.0.weight": u((hid, in_dim), in_dim), "net.0.bias": u((hid,), in_dim)}
+    if num_fc_layer == 2:
+        sd["net.2.weight"] = u((hid, hid), hid)
+        sd["net.2.bias"] = u((hid,), hid)
     for l in range(2):
         sd["lstm.weight_ih_l%d" % l] = u((4 * hid, hid), hid)
         sd["lstm.weight_hh_l%d" % l] = u((4 * hid, hid), hid)

@@ -63,5 +63,18 @@ with torch.no_grad():
         }
         prios.append(agent.compute_priority(inp)["priority"].numpy()[0])
     out["actions"], out["reward"], out["bootstrap"], out["priority"] = actions, reward, bootstrap, np.stack(prios)
+# a second network with the OP-paper variants (utils.py:47-58): num_fc_layer=2 and skip_connect=True
+agent2 = r2d2.R2D2Agent(False, 3, 0.999, 0.9, "cpu", IN, HID, A, 2, 5, False, num_fc_layer=2, skip_connect=True)
+v2 = random_state_dict(IN, HID, A, 13, num_fc_layer=2)
+agent2.online_net.load_state_dict(v2)
+out.update({"variant." + k: v.numpy() for k, v in v2.items()})
+hid = agent2.online_net.get_h0(ROWS)
+advs = []
+with torch.no_grad():
+    for t in range(4):
+        adv, hid = agent2.online_net.act(torch.from_numpy(priv_s[t]), hid)
+        advs.append(adv.numpy())
+out["variant_adv"] = np.stack(advs)
+out["variant_h"] = hid["h0"].numpy()
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "policy_small.npz"), **out)
 print("wrote policy_small.npz", {k: v.shape for k, v in out.items() if not k.startswith(("online", "target"))})

@@ -36,7 +36,7 @@ class FakeEngine:
     def counters(self):
         return (min(self.ticks // 4, self.kw["replay_capacity"]), self.ticks // 4, self.ticks * self.G)
 
-    def set_weights(self, net, sd):
+    def set_weights(self, net, sd, skip_connect=False):
         assert "lstm.weight_ih_l0" in sd
         self.weights.append(net)
 
@@ -136,6 +136,7 @@ def test_selfplay_call_sequence(ref_modules, method):
     runners = [rela.BatchRunner(eval_agent, "cpu", 1000, ["act"]) for _ in range(P)]
     score, perfect, scores, n_perfect = ref_eval.evaluate(None, 52, 7, 0, 0, True, runners=runners)
     assert len(FakeEngine.instances) == 2 and FakeEngine.instances[1].closed and FakeEngine.instances[1].kw["max_len"] == -1
+    assert FakeEngine.instances[1].kw["eval_seats"] and FakeEngine.instances[1].weights == [0, 1]  # one network per seat
     assert scores == [i % 26 for i in range(52)] and n_perfect == 2
     context.resume()
     time.sleep(0.05)

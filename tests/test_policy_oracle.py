@@ -46,3 +46,16 @@ def test_priority_terms_match_reference_compute_priority():
     for t in range(T):
         prio = np.abs(z["reward"][t] + z["bootstrap"][t] * np.float32(0.999 ** 3) * tq[t + 3] - oq[t])
         assert np.abs(prio - z["priority"][t]).max() < 5e-6
+
+
+def test_fc2_skip_variant_matches_reference_fixture():
+    """num_fc_layer=2 + skip_connect=True (the OP-paper model variants, utils.py:47-58)."""
+    z = np.load(GOLD)
+    sd = {k[len("variant."):]: z[k] for k in z.files if k.startswith("variant.")}
+    net = PolicyOracle(sd, skip_connect=True)
+    assert net.num_fc_layer == 2
+    hid = net.get_h0(z["priv_s"].shape[1])
+    for t in range(z["variant_adv"].shape[0]):
+        adv, v, hid = net.act(z["priv_s"][t], hid)
+        assert np.abs(adv.numpy() - z["variant_adv"][t]).max() < 2e-6
+    assert np.abs(hid["h0"].numpy() - z["variant_h"]).max() < 2e-6

@@ -116,3 +116,45 @@ def test_eps_greedy_statistics(hb):
     frac = n_diff / n
     assert 0.19 < frac < 0.26, frac
     eng.close()
+
+
+@pytest.mark.parametrize("cfg", [(2, 5, 70), (3, 5, 33)], ids=["2p_crossplay_variants", "3p_three_agents"])
+def test_eval_seats_one_network_per_seat(hb, cfg):
+    """Evaluation engines (tools/eval_model.py cross-play): every seat runs its OWN network, incl. the OP-paper architecture
+    variants num_fc_layer=2 / skip_connect (utils.py:47-58); each seat is checked against its own fp32 oracle."""
+    from oracle.policy_oracle import PolicyOracle, greedy_action
+
+    P, H, G = cfg
+    eng = hb.Engine(G, P, H, 0, -1, True, False, [0.0], seed=6, eval_seats=True)
+    F, A, rows = eng.F, eng.A, G * P
+    variants = [(1, False), (2, True), (2, False)][:P]
+    sds = [random_state_dict(F, 512, A, 40 + s, H, num_fc_layer=nf) for s, (nf, _) in enumerate(variants)]
+    for s, (sd, (nf, skip)) in enumerate(zip(sds, variants)):
+        eng.set_weights(s, sd, skip_connect=skip)
+    orcs = [PolicyOracle(sd, skip_connect=skip) for sd, (_, skip) in zip(sds, variants)]
+    hids = [o.get_h0(G) for o in orcs]
+    eng.reset()
+    worst = 0.0
+    alive = np.ones(G, bool)
+    for tick in range(45):
+        obs = eng.observe()
+        eng.policy_act()
+        a, ga = eng.actions()
+        got = eng.policy_get(hidden=True)
+        for s in range(P):
+            adv, v, hids[s] = orcs[s].act(obs["priv_s"][:, s], hids[s])
+            worst = max(worst, float(np.abs(got["adv"][:, s] - adv.numpy()).max()),
+                        float(np.abs(got["h"][:, s::P] - hids[s]["h0"].numpy()).max()))
+            g_ref = greedy_action(adv, obs["legal_move"][:, s]).numpy()
+            diff = g_ref != ga[:, s]
+            if diff.any():  # only near-ties may flip
+                advn = adv.numpy()
+                idx = np.nonzero(diff)[0]
+                assert np.abs(advn[idx, ga[idx, s]] - advn[idx, g_ref[idx]]).max() < 2 * TOL
+        assert (a == ga).all()  # eps = 0: greedy play
+        eng.step_dev()
+        _, term = eng.result()
+        alive &= ~term
+    assert worst < TOL, worst
+    assert not alive.all()  # some games finished (no auto-restart in eval: they stay frozen)
+    eng.close()
