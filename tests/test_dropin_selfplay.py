@@ -39,3 +39,35 @@ def test_reference_selfplay_runs_on_the_device_actors(gpu_or_skip, tmp_path, met
     # Tachometer lines (utils.py:237-240): actors produced env-steps and replay entries while the learner trained
     rates = re.findall(r"Speed: train: ([0-9.]+), act: ([0-9.]+), buffer_add: ([0-9.]+)", out)
     assert rates and all(float(a) > 0 and float(b) > 0 for _, a, b in rates), out[-3000:]
+
+
+CROSSPLAY = r"""
+import sys, torch
+import set_path
+set_path.append_sys_path()
+import r2d2, utils
+from eval import evaluate
+torch.manual_seed(3)
+mk = lambda nf, skip: r2d2.R2D2Agent(False, 3, 0.999, 0.9, "cuda:0", 838, 512, 21, 2, 5, False, num_fc_layer=nf, skip_connect=skip).to("cuda:0")
+agents = [mk(1, False), mk(2, True)]           # utils.load_op_model builds exactly such pairs (utils.py:47-84)
+mean, perfect, scores, n_perfect = evaluate(agents, 300, 1, 0, 0, True, device="cuda:0")
+print("CROSSPLAY mean %.4f games %d" % (mean, len(scores)))
+mean2, _, scores2, _ = evaluate([agents[0], agents[0]], 300, 1, 0, 0, True, device="cuda:0")
+print("SELFPLAY mean %.4f games %d" % (mean2, len(scores2)))
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(PYH, "eval.py")), reason="oracle/_ref/pyhanabi not generated (oracle/build_ref.sh)")
+def test_reference_eval_crossplay_runs_on_the_device_actors(gpu_or_skip, tmp_path):
+    """tools/eval_model.py's core -- eval.evaluate(agents, ...) with a DIFFERENT agent (and architecture variant) per seat --
+    through the reference's own eval.py / create.py on this package's modules."""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(ROOT, "hanabi_sad_b200", "compat") + os.pathsep + env.get("PYTHONPATH", "")
+    p = subprocess.run([sys.executable, "-c", CROSSPLAY], cwd=PYH, env=env, capture_output=True, text=True, timeout=420)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    m = re.search(r"CROSSPLAY mean ([0-9.]+) games (\d+)", out)
+    m2 = re.search(r"SELFPLAY mean ([0-9.]+) games (\d+)", out)
+    assert m and m2, out[-2000:]
+    assert int(m.group(2)) == 300 and 0.0 <= float(m.group(1)) <= 25.0
+    assert int(m2.group(2)) == 300 and 0.0 <= float(m2.group(1)) <= 25.0
