@@ -63,15 +63,24 @@ def aggregate_priority(priority, seq_len, eta):
 
 
 class RNNTransition:
-    """rela.RNNTransition (rela/pybind.cc:25-32): obs, h0, action, reward, terminal, bootstrap, seq_len."""
+    """rela.RNNTransition (rela/pybind.cc:25-32): obs, h0, action, reward, terminal, bootstrap, seq_len.
+
+    pybind converts the C++ TensorDict members to a NEW Python dict on every attribute read, and the reference relies on
+    it: R2D2Agent.td_error re-views `batch.obs` in place for VDN (r2d2.py:386-389 flat_4d) and later reads
+    `batch.obs["own_hand"]` expecting the original 4-d tensor (r2d2.py:481-488).  The dict attributes are therefore
+    properties that hand out shallow copies."""
 
     def __init__(self, obs, action, reward, terminal, bootstrap, seq_len):
-        self.obs, self.h0, self.action = obs, {}, action
+        self._obs, self._h0, self._action = dict(obs), {}, dict(action)
         self.reward, self.terminal, self.bootstrap, self.seq_len = reward, terminal, bootstrap, seq_len
+
+    obs = property(lambda self: dict(self._obs), lambda self, v: setattr(self, "_obs", dict(v)))
+    action = property(lambda self: dict(self._action), lambda self, v: setattr(self, "_action", dict(v)))
+    h0 = property(lambda self: dict(self._h0), lambda self, v: setattr(self, "_h0", dict(v)))
 
     def to_device(self, device):
         mv = lambda d: {k: v.to(device) for k, v in d.items()}
-        return RNNTransition(mv(self.obs), mv(self.action), self.reward.to(device), self.terminal.to(device), self.bootstrap.to(device),
+        return RNNTransition(mv(self._obs), mv(self._action), self.reward.to(device), self.terminal.to(device), self.bootstrap.to(device),
                              self.seq_len.to(device))
 
 

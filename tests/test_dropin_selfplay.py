@@ -71,3 +71,16 @@ def test_reference_eval_crossplay_runs_on_the_device_actors(gpu_or_skip, tmp_pat
     assert m and m2, out[-2000:]
     assert int(m.group(2)) == 300 and 0.0 <= float(m.group(1)) <= 25.0
     assert int(m2.group(2)) == 300 and 0.0 <= float(m2.group(1)) <= 25.0
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(PYH, "r2d2.py")), reason="oracle/_ref/pyhanabi not generated (oracle/build_ref.sh)")
+def test_data_parallel_learner_script_single_rank(gpu_or_skip):
+    """tools/train_multi_gpu.py (games sharded per GPU, reference loss, flat gradient all-reduce) with world size 1; the
+    2-GPU NCCL run is recorded in profiles/r01_train_multi_gpu.txt, the all-reduce itself is covered by tests/test_dist_gloo.py."""
+    import json
+
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "train_multi_gpu.py"), "--pyhanabi", PYH, "--games", "512", "--updates", "6",
+                        "--burn_in", "200", "--pred_weight", "0.25", "--batchsize", "16"], capture_output=True, text=True, timeout=420)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["finite"] and d["replica_weight_drift"] == 0.0 and d["env_steps_total"] > 0

@@ -117,6 +117,9 @@ def test_selfplay_call_sequence(ref_modules, method):
         time.sleep(0.01)
     batch, weight = replay.sample(8, "cpu")
     assert batch.obs["priv_s"].shape == ((80, 8, 2, 838) if method == "vdn" else (80, 8, 838)) and batch.h0 == {} and weight.shape == (8,)
+    o1 = batch.obs
+    o1["priv_s"] = None  # pybind semantics: every read of .obs is a fresh dict (r2d2.py flat_4d mutates its copy)
+    assert batch.obs["priv_s"] is not None
     with pytest.raises(RuntimeError):
         replay.sample(8, "cpu")
     prio = rela.aggregate_priority(torch.rand(80, 8), batch.seq_len, 0.9)
