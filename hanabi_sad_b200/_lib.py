@@ -74,6 +74,7 @@ SIGNATURES = {
     "hb_rollout": (c_int, [c_void_p, c_int]),
     "hb_counters": (c_int, [c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "hb_replay_sample": (c_int, [c_void_p, c_int, ctypes.POINTER(HbBatch)]),
+    "hb_replay_get": (c_int, [c_void_p, c_i64, ctypes.POINTER(HbBatch)]),
     "hb_replay_update_priority": (c_int, [c_void_p, c_void_p, c_int]),
     "hb_profile": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "hb_debug_gemm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),

@@ -96,7 +96,9 @@ struct HbBatchPtrs {
 // length are the reference's padding (zeros, terminal = 1).
 __global__ void __launch_bounds__(128) hb_k_replay_gather(HbRing R, const int* __restrict__ idx, int B, HbBatchPtrs out) {
   const int b = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
-  const int entry = idx[b], slot = entry / R.NE, e = entry % R.NE;
+  const int entry = idx[b];
+  if (entry < 0) return;                       // hb_replay_get: lookup failed, reported by the host
+  const int slot = entry / R.NE, e = entry % R.NE;
   const int PP = R.NE == 1 ? R.P : 1;          // players kept in one entry
   const int p0 = R.NE == 1 ? 0 : e;
   const int len = R.seq_len[slot];
@@ -125,6 +127,16 @@ __global__ void hb_k_replay_update(HbRing R, const int* __restrict__ idx, const 
   if (i >= n) return;
   const int entry = idx[i], slot = entry / R.NE;
   if (R.state[slot] == HB_SLOT_COMMITTED && R.commit_seq[slot] == seq[i]) R.weight[entry] = powf(prio[i], R.alpha);
+}
+
+// ConcurrentQueue::get (prioritized_replay.h:125-128): the idx-th oldest entry still held = arrival number
+// `oldest + idx / NE`; one thread per slot looks for it (arrival numbers are unique).
+__global__ void hb_k_replay_find(HbRing R, long long idx, int* __restrict__ entry_out) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= R.phys_slots) return;
+  const long long commits = (long long)R.counters[HB_CNT_COMMIT];
+  const long long oldest = commits > R.cap_slots ? commits - R.cap_slots : 0;
+  if (R.state[slot] == HB_SLOT_COMMITTED && R.commit_seq[slot] == oldest + idx / R.NE) entry_out[0] = slot * R.NE + (int)(idx % R.NE);
 }
 
 HbRing hb_replay_ring(hb_engine* e) { return e->replay->ring; }
@@ -183,7 +195,7 @@ int hb_replay_create(hb_engine* e) {
   HB_RALLOC(R.counters, HB_CNT_N * sizeof(unsigned long long));
   Q->max_batch = 1024;
   HB_RALLOC(Q->prefix, (S * R.NE + 2) * sizeof(double));
-  HB_RALLOC(Q->sampled_idx, Q->max_batch * sizeof(int));
+  HB_RALLOC(Q->sampled_idx, (Q->max_batch + 1) * sizeof(int));
   HB_RALLOC(Q->sampled_seq, Q->max_batch * sizeof(long long));
   HB_RALLOC(Q->sampled_w, Q->max_batch * sizeof(float));
   HB_RALLOC(Q->d_prio, Q->max_batch * sizeof(float));
@@ -248,6 +260,30 @@ int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) {
   e->launches += 3;
   Q->sample_count += 1;
   Q->n_sampled = batchsize;
+  return 0;
+}
+
+int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out) {
+  if (!e || !out) { hb_set_error("hb_replay_get: null argument"); return -1; }
+  HbReplay* Q = e->replay;
+  if (!Q) { hb_set_error("hb_replay_get: this engine has no replay (replay_capacity = 0)"); return -1; }
+  int64_t size = 0;
+  int rc = hb_counters(e, &size, nullptr, nullptr);
+  if (rc) return rc;
+  if (idx < 0 || idx >= size) { hb_set_error("hb_replay_get: index %lld out of range, the replay holds %lld entries", (long long)idx, (long long)size); return -3; }
+  HbRing& R = Q->ring;
+  int* d_entry = Q->sampled_idx + Q->max_batch;  // one spare element behind the sampling scratch
+  HB_CUDA(cudaMemsetAsync(d_entry, 0xFF, sizeof(int), e->stream));
+  hb_k_replay_find<<<(R.phys_slots + 255) / 256, 256, 0, e->stream>>>(R, (long long)idx, d_entry);
+  HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
+  hb_k_replay_gather<<<dim3(1, R.T), 128, 0, e->stream>>>(R, d_entry, 1, bp);
+  HB_CUDA(cudaGetLastError());
+  int h_entry = -1;
+  HB_CUDA(cudaMemcpyAsync(&h_entry, d_entry, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  e->launches += 2;
+  if (h_entry < 0) { hb_set_error("hb_replay_get: entry %lld not found (ring bookkeeping corrupt)", (long long)idx); return -2; }
+  if (out->ids) HB_CUDA(cudaMemcpy(out->ids, &h_entry, sizeof(int), cudaMemcpyHostToDevice));
   return 0;
 }
 

@@ -213,6 +213,30 @@ class Engine:
         t["terminal"] = t["terminal"].bool()
         return t
 
+    def get(self, idx):
+        """PrioritizedReplay::get: the idx-th oldest entry held, UNBATCHED torch tensors on the engine's GPU."""
+        import torch
+
+        dev = torch.device("cuda", self.cfg.device)
+        T = self.cfg.seq_len
+        pp = (self.P,) if self.cfg.vdn else ()
+        f32 = dict(dtype=torch.float32, device=dev)
+        t = {
+            "priv_s": torch.empty((T,) + pp + (self.F,), **f32), "legal_move": torch.empty((T,) + pp + (self.A,), **f32),
+            "own_hand": torch.empty((T,) + pp + (3 * self.H,), **f32), "eps": torch.empty((T,) + pp, **f32),
+            "a": torch.empty((T,) + pp, dtype=torch.int64, device=dev), "greedy_a": torch.empty((T,) + pp, dtype=torch.int64, device=dev),
+            "reward": torch.empty((T,), **f32), "bootstrap": torch.empty((T,), **f32),
+            "terminal": torch.empty((T,), dtype=torch.uint8, device=dev), "seq_len": torch.empty((1,), **f32),
+        }
+        hb = HbBatch()
+        for k, v in t.items():
+            setattr(hb, k, v.data_ptr())
+        torch.cuda.current_stream(dev).synchronize()
+        check(lib().hb_replay_get(self._h, int(idx), ctypes.byref(hb)))
+        t["terminal"] = t["terminal"].bool()
+        t["seq_len"] = t["seq_len"].reshape(())   # RNNTransition.seq_len of a single episode is 0-dim (transition.cc:74-97)
+        return t
+
     def update_priority(self, priority):
         """PrioritizedReplay::updatePriority: `priority` = torch tensor (any device) or numpy array, float32 [B]."""
         if hasattr(priority, "data_ptr"):

@@ -150,7 +150,22 @@ class RNNPrioritizedReplay:
         self._last = []
 
     def get(self, idx):
-        raise NotImplementedError("RNNPrioritizedReplay.get is analysis tooling (tools/action_matrix.py); not part of the actor path")
+        """PrioritizedReplay::get (prioritized_replay.h:259-261; pyhanabi/tools/action_matrix.py:90-107): the idx-th oldest
+        episode held, unbatched, on the CPU like the reference's storage.  With several engines (act devices) the index runs
+        through the engines in attach order."""
+        idx = int(idx)
+        for e, lk in self._engines:
+            with lk:
+                n = e.counters()[0]
+                if idx < n:
+                    t = e.get(idx)
+                    break
+            idx -= n
+        else:
+            raise IndexError("RNNPrioritizedReplay.get: index out of range")
+        cpu = lambda k: t[k].cpu()
+        return RNNTransition({k: cpu(k) for k in ("priv_s", "legal_move", "eps", "own_hand")}, {k: cpu(k) for k in ("a", "greedy_a")},
+                             cpu("reward"), cpu("terminal"), cpu("bootstrap"), cpu("seq_len"))
 
 
 class BatchRunner:

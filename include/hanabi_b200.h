@@ -195,6 +195,12 @@ typedef struct hb_batch {
  * `batchsize` entries or the previous batch's priorities were not written back. */
 int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out);
 
+/* PrioritizedReplay::get (rela/prioritized_replay.h:259-261 -> ConcurrentQueue::get, :125-128; used by
+ * pyhanabi/tools/action_matrix.py:90-107): the idx-th OLDEST entry still held (0 <= idx < size), written UNBATCHED into
+ * `out` (device pointers; layouts of hb_batch with B = 1, i.e. priv_s [T,(P,)F], ..., reward [T], seq_len [1]).
+ * out->weight is not written; out->ids (or NULL) receives the physical entry index.  Does not touch the sampling state. */
+int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out);
+
 /* PrioritizedReplay::updatePriority (rela/prioritized_replay.h:242-257): `priority` float [n], host or device. */
 int hb_replay_update_priority(hb_engine* e, const float* priority, int n);
 

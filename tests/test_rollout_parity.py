@@ -178,6 +178,46 @@ def test_ring_evicts_oldest_and_respects_capacity(hb):
     eng.close()
 
 
+@pytest.mark.parametrize("vdn", [True, False], ids=["vdn", "iql"])
+def test_replay_get_walks_the_ring_in_arrival_order(hb, vdn):
+    """RNNPrioritizedReplay.get(idx) (prioritized_replay.h:259-261, ConcurrentQueue::get :125-128): idx-th oldest entry held,
+    unbatched; every sampled entry is one of them; capacity eviction moves the window."""
+    G, P, cap = 48, 2, 120
+    eng = hb.Engine(G, P, 5, 0, 80, True, False, [1.0], seed=9, vdn=vdn, replay_capacity=cap, priority_mode=1)
+    eng.set_weights(0, random_state_dict(eng.F, 512, eng.A, 1))
+    eng.set_weights(1, random_state_dict(eng.F, 512, eng.A, 2))
+    eng.rollout(200)
+    size, num_add, _ = eng.counters()
+    assert size == cap and num_add > 2 * cap
+    held = {}
+    for i in range(size):
+        t = {k: v.cpu().numpy() for k, v in eng.get(i).items()}
+        L = int(t["seq_len"])
+        assert t["seq_len"].shape == () and 1 <= L <= 80
+        assert t["priv_s"].shape == ((80, P, eng.F) if vdn else (80, eng.F)) and t["a"].shape == ((80, P) if vdn else (80,))
+        assert not t["terminal"][: L - 1].any() and t["terminal"][L - 1:].all()
+        assert not t["priv_s"][L:].any() and t["priv_s"][:L].any()
+        held[_key(t["priv_s"][:L], t["a"][:L])] = i
+    assert len(held) == size
+    if not vdn:   # the P entries of one game episode are adjacent and share reward / length
+        t0, t1 = eng.get(0), eng.get(1)
+        assert float(t0["seq_len"]) == float(t1["seq_len"]) and bool((t0["reward"] == t1["reward"]).all())
+        assert not bool((t0["priv_s"] == t1["priv_s"]).all())
+    b = {k: v.cpu().numpy() for k, v in eng.sample(64).items()}
+    for j in range(64):
+        L = int(b["seq_len"][j])
+        assert _key(b["priv_s"][:L, j], b["a"][:L, j]) in held
+    eng.update_priority(np.ones(64, np.float32))
+    with pytest.raises(hb.HbError, match="out of range"):
+        eng.get(size)
+    with pytest.raises(hb.HbError, match="out of range"):
+        eng.get(-1)
+    first = eng.get(0)["priv_s"].cpu().numpy().copy()
+    eng.rollout(60)   # new arrivals push the oldest out
+    assert not np.array_equal(eng.get(0)["priv_s"].cpu().numpy(), first)
+    eng.close()
+
+
 def test_rollout_env_obs_match_oracle(hb):
     """During a fused rollout the observation stream is still bit-exact against the C oracle (same checks as the env tests,
     but through hb_k_tick)."""
