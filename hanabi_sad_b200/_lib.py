@@ -45,6 +45,14 @@ class HbBatch(ctypes.Structure):
                                         "seq_len", "weight", "ids")]
 
 
+class HbLstmWeights(ctypes.Structure):
+    _fields_ = [("w_ih", c_void_p * 2), ("w_hh", c_void_p * 2), ("b_ih", c_void_p * 2), ("b_hh", c_void_p * 2)]
+
+
+class HbLstmGrads(ctypes.Structure):
+    _fields_ = [("dw_ih", c_void_p * 2), ("dw_hh", c_void_p * 2), ("db_ih", c_void_p * 2), ("db_hh", c_void_p * 2)]
+
+
 # name -> (restype, argtypes); the list tests/test_abi.py checks against include/hanabi_b200.h
 SIGNATURES = {
     "hb_last_error": (ctypes.c_char_p, []),
@@ -78,6 +86,12 @@ SIGNATURES = {
     "hb_replay_update_priority": (c_int, [c_void_p, c_void_p, c_int]),
     "hb_profile": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "hb_debug_gemm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "hb_lstm_create": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "hb_lstm_destroy": (None, [c_void_p]),
+    "hb_lstm_forward": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(HbLstmWeights), ctypes.POINTER(c_void_p),
+                                c_int, c_void_p]),
+    "hb_lstm_backward": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(HbLstmGrads), c_void_p]),
+    "hb_lstm_launches": (c_i64, [c_void_p]),
     "hb_sync": (c_int, [c_void_p]),
     "hb_stream": (c_void_p, [c_void_p]),
     "hb_kernel_launches": (c_i64, [c_void_p]),

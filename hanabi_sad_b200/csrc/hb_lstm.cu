@@ -1,0 +1,868 @@
+// hb_lstm.cu -- learner side: the T-step, 2-layer, hid=512 LSTM of R2D2Net.forward (pyhanabi/r2d2.py:99-105,
+// nn.LSTM over the padded [T, rows, 512] sequence with zero initial state, r2d2.py:383-401) and its backward, as
+// sm_100a kernels.  cuDNN runs this as ~1000 small launches per update (one GEMM + one pointwise kernel per step, layer
+// and direction); here each layer is
+//
+//   input projection   GX = X W_ih^T + (b_ih + b_hh) over ALL steps at once      tcgen05 GEMM template (hb_gemm.cuh, EPI_F32)
+//   recurrence         ONE persistent kernel per layer (lstm_fwd_kernel): every CTA keeps a 64-column slice
+//                      ([i|f|g|o] x 16 hidden units) of W_hh resident in shared memory as bf16 hi/lo, per step pulls
+//                      h_{t-1} (bf16 hi/lo, TMA) of its 128-row block, runs 96 tcgen05.mma (bf16x3, fp32 accumulate in
+//                      TMEM), applies the cell update with c kept in registers across all T steps, and publishes its
+//                      slice of h_t; the 32 CTAs of a row block meet at a global-memory step counter.  Online and target
+//                      network run in the same launch.
+//   backward           lstm_bwd_kernel, same residency idea with the contraction split over K: a CTA turns dh_t of its 16
+//                      units into its 64 dgate columns, multiplies them (as the A operand, written to swizzled shared
+//                      memory) with its resident 64 x 512 slice of W_hh and writes a [128 x 512] partial of dh_{t-1};
+//                      the partials of the 32 CTAs are summed by their consumers after the step barrier.
+//   dX, dW, db         dX = dG W_ih and the four weight gradients dG^T X / dG^T H_{t-1} as GEMM-template launches over
+//                      operands the recurrence kernels already wrote in both orientations (bf16 hi/lo); db by a reduction.
+//
+// Arithmetic: fp32-class everywhere (bf16x3 products accumulated in fp32, pointwise math in fp32); parity target: CPU fp32
+// torch.nn.LSTM forward / autograd within 1e-4 (tests/test_lstm_train_parity.py).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+#include <vector>
+
+#include "hb_engine.h"
+#include "hb_gemm.cuh"
+#include "hb_gemm_host.h"
+
+using hbg::Params;
+using namespace hbg;
+
+namespace hbl {
+
+constexpr int HIDN = 512;
+constexpr int G4 = 4 * HIDN;          // 2048 gate columns
+constexpr int UPC = 16;               // hidden units per CTA
+constexpr int NC = 4 * UPC;           // gate columns per CTA: [i|f|g|o][16 units]
+constexpr int SLICES = HIDN / UPC;    // 32 CTAs share one 128-row block ("domain")
+constexpr int KCH = HIDN / BK;        // 8 K-chunks of 64
+constexpr int W_HALF = NC * BK * 2;   // 8 KB: one [64 x 64] bf16 tile
+constexpr int W_BYTES = KCH * 2 * W_HALF;   // 128 KB: the CTA's W_hh slice, hi + lo
+constexpr int FWD_NST = 3;
+constexpr int FWD_STAGE = 2 * A_TILE;       // h hi + lo chunk: 32 KB
+constexpr int FWD_SMEM = W_BYTES + FWD_NST * FWD_STAGE + 1024 + 256;
+constexpr int BWD_WT_HALF = 256 * BK * 2;   // 32 KB: [256 x 64] bf16 tile
+constexpr int BWD_WT_BYTES = 4 * BWD_WT_HALF;  // 128 KB: [512 x 64] hi + lo
+constexpr int BWD_SMEM = BWD_WT_BYTES + 2 * A_TILE + 1024 + 256;
+constexpr int CTR_STRIDE = 32;        // unsigned ints between two domains' step counters (128 bytes)
+
+struct FwdNet {
+  CUtensorMap w_hi, w_lo;             // W_hh in CTA-slice row order [2048][512], box 64 x 64
+  CUtensorMap h_hi, h_lo;             // h sequence [(T+1)*R_pad][512], block 0 = h_{-1} = 0; box 128 x 64
+  const float* gx;                    // [T*R_pad][2048] input projection + bias, CTA-slice column order
+  __nv_bfloat16 *hs_hi, *hs_lo;       // same buffer as h_hi / h_lo
+  __nv_bfloat16 *hsT_hi, *hsT_lo;     // [512][ldT] transposed copy (operand of the weight-gradient GEMMs) or null
+  float* y;                           // fp32 output [T][rows][512] (the caller's tensor) or null
+  float* act;                         // [T*R_pad][2048] gate activations i,f,g,o (saved for backward) or null
+  float* cs;                          // [T*R_pad][512] cell states (saved for backward) or null
+};
+struct __align__(64) FwdParams {
+  FwdNet net[2];
+  int T, rows, R_pad, MB;
+  long long ldT;
+  unsigned* ctr;
+  int* error_flag;
+};
+struct __align__(64) BwdParams {
+  CUtensorMap wt_hi, wt_lo;           // W_hh^T [512][2048 slice-order columns], box 256 x 64
+  const float* dh_ext;                // [T][dh_rows][512] gradient w.r.t. this layer's output sequence
+  int dh_rows;
+  const float* act;
+  const float* cs;
+  __nv_bfloat16 *dg_hi, *dg_lo;       // [T*R_pad][2048] dgates, slice column order
+  __nv_bfloat16 *dgT_hi, *dgT_lo;     // [2048][T*R_pad]
+  float* part;                        // [2][MB*32][128][512] split-K partials of dh_{t-1}
+  int T, rows, R_pad, MB;
+  unsigned* ctr;
+  int* error_flag;
+};
+
+__device__ __forceinline__ constexpr uint32_t idesc_mn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Bounded waits: a protocol bug must not hang the (shared) GPU.  Once any thread of the grid gives up it raises
+// *error_flag, and every other wait in the grid sees the flag within ~1000 polls and gives up too.
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* error_flag, bool& dead) {
+  if (dead) return;
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 1023u) == 1023u) {
+      if (*(volatile int*)error_flag != 0) { dead = true; return; }
+      if (spin > (1u << 22)) { atomicExch(error_flag, 1); dead = true; return; }
+    }
+  }
+}
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, int* error_flag, bool& dead) {
+  if (dead) return;
+  for (uint32_t spin = 0; ld_acquire(ctr) < target; ++spin) {
+    if ((spin & 255u) == 255u) {
+      if (*(volatile int*)error_flag != 0) { dead = true; return; }
+      if (spin > (1u << 20)) { atomicExch(error_flag, 2); dead = true; return; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward recurrence
+// grid = nets * MB * 32 CTAs (all co-resident: one per SM), 192 threads: warp 0 TMA producer + step-barrier poller,
+// warp 1 MMA issuer / TMEM owner, warps 2-5 cell update (thread = one sequence row of the block).
+__global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __restrict__ pp) {
+  extern __shared__ uint8_t smem_raw[];
+  const FwdParams& P = *pp;
+  const int slice = blockIdx.x % SLICES, dom = blockIdx.x / SLICES, mb = dom % P.MB, net = dom / P.MB;
+  const FwdNet& N = P.net[net];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base, ring = base + W_BYTES, bar_base = ring + FWD_NST * FWD_STAGE;
+  const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * FWD_NST, bar_w = bar_empty + 8 * FWD_NST;
+  const uint32_t bar_tfull = bar_w + 8, bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = P.T, R_pad = P.R_pad;
+  unsigned* ctr = P.ctr + (size_t)dom * CTR_STRIDE;
+  int* ef = P.error_flag;
+  bool dead = false;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&N.w_hi); tma_prefetch_desc(&N.w_lo); tma_prefetch_desc(&N.h_hi); tma_prefetch_desc(&N.h_lo);
+    for (int s = 0; s < FWD_NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_w, 1); mbar_init(bar_tfull, 1); mbar_init(bar_tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, W_BYTES);
+      for (int kc = 0; kc < KCH; ++kc) {
+        tma_load_2d(w_base + kc * 2 * W_HALF, &N.w_hi, bar_w, kc * BK, slice * NC);
+        tma_load_2d(w_base + kc * 2 * W_HALF + W_HALF, &N.w_lo, bar_w, kc * BK, slice * NC);
+      }
+      uint32_t it = 0;
+      for (int t = 1; t < T; ++t) {
+        wait_counter(ctr, (unsigned)(SLICES * t), ef, dead);   // h_{t-1} of this row block is complete
+        fence_async_global();
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
+          wait_bar(bar_empty + 8 * s, ph ^ 1u, ef, dead);
+          if (dead) break;
+          const uint32_t st = ring + s * FWD_STAGE;
+          mbar_expect_tx(bar_full + 8 * s, FWD_STAGE);
+          tma_load_2d(st, &N.h_hi, bar_full + 8 * s, kc * BK, t * R_pad + mb * BM);   // block t = h_{t-1}
+          tma_load_2d(st + A_TILE, &N.h_lo, bar_full + 8 * s, kc * BK, t * R_pad + mb * BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_mn(BM, NC);
+      wait_bar(bar_w, 0, ef, dead);
+      uint32_t it = 0;
+      for (int t = 1; t < T; ++t) {
+        wait_bar(bar_tempty, (uint32_t)(t - 1) & 1u, ef, dead);   // the cell update of step t-1 has drained the accumulator
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
+          wait_bar(bar_full + 8 * s, ph, ef, dead);
+          if (dead) break;
+          tc_fence_after();
+          const uint32_t st = ring + s * FWD_STAGE;
+          const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
+          const uint64_t b_hi = make_desc_sw128(w_base + kc * 2 * W_HALF), b_lo = make_desc_sw128(w_base + kc * 2 * W_HALF + W_HALF);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+            umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, acc);
+            umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+            umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+            acc = 1;
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        if (dead) break;
+        umma_commit(bar_tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane, row = mb * BM + r;
+    const bool valid = row < P.rows;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float c[UPC];
+#pragma unroll
+    for (int i = 0; i < UPC; ++i) c[i] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const size_t grow = (size_t)t * R_pad + row;
+      float g[NC];
+      {
+        const float4* src = reinterpret_cast<const float4*>(N.gx + grow * G4 + slice * NC);
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) {
+          const float4 v = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          g[4 * i] = v.x; g[4 * i + 1] = v.y; g[4 * i + 2] = v.z; g[4 * i + 3] = v.w;
+        }
+      }
+      if (t > 0) {
+        wait_bar(bar_tfull, (uint32_t)(t - 1) & 1u, ef, dead);
+        tc_fence_after();
+        if (!dead) {
+#pragma unroll
+          for (int gate = 0; gate < 4; ++gate) {
+            float v[16];
+            tmem_ld16(taddr + gate * UPC, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g[gate * UPC + i] += v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty);
+      float h[UPC];
+#pragma unroll
+      for (int i = 0; i < UPC; ++i) {
+        const float ig = sigmoid_f(g[i]), fg = sigmoid_f(g[UPC + i]), gg = tanh_f(g[2 * UPC + i]), og = sigmoid_f(g[3 * UPC + i]);
+        c[i] = fg * c[i] + ig * gg;
+        h[i] = og * tanh_f(c[i]);
+        g[i] = ig; g[UPC + i] = fg; g[2 * UPC + i] = gg; g[3 * UPC + i] = og;
+      }
+      if (valid && !dead) {
+        const int unit = slice * UPC;
+        const size_t o = ((size_t)(t + 1) * R_pad + row) * HIDN + unit;
+        store_split16(h, N.hs_hi + o, N.hs_lo + o);
+        if (N.y) {
+          float4* dst = reinterpret_cast<float4*>(N.y + ((size_t)t * P.rows + row) * HIDN + unit);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        }
+        if (N.act) {
+          float4* dst = reinterpret_cast<float4*>(N.act + grow * G4 + slice * NC);
+#pragma unroll
+          for (int i = 0; i < NC / 4; ++i) dst[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+          float4* dc = reinterpret_cast<float4*>(N.cs + grow * HIDN + unit);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dc[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+        }
+        if (N.hsT_hi) {
+          const size_t col = (size_t)(t + 1) * R_pad + row;
+#pragma unroll
+          for (int i = 0; i < UPC; ++i) {
+            __nv_bfloat16 hh, ll;
+            split_bf16(h[i], hh, ll);
+            N.hsT_hi[(size_t)(unit + i) * P.ldT + col] = hh;
+            N.hsT_lo[(size_t)(unit + i) * P.ldT + col] = ll;
+          }
+        }
+      }
+      // publish: generic-proxy stores -> visible to the other CTAs' TMA (async proxy) reads after the counter bump
+      __threadfence();
+      fence_async_global();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) red_release_add(ctr, 1u);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward recurrence
+// grid = MB * 32 CTAs.  Warp 0: loads the CTA's slice of W_hh^T; warp 1: MMA issuer; warps 2-5: pointwise backward,
+// A-operand staging, partial drain.  Steps run t = T-1 .. 0; the partial of step t is consumed at step t-1.
+__global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __restrict__ pp) {
+  extern __shared__ uint8_t smem_raw[];
+  const BwdParams& P = *pp;
+  const int slice = blockIdx.x % SLICES, dom = blockIdx.x / SLICES, mb = dom;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t wt_base = base, a_base = base + BWD_WT_BYTES, bar_base = a_base + 2 * A_TILE;
+  const uint32_t bar_w = bar_base, bar_a = bar_w + 8, bar_tfull = bar_a + 8, tmem_slot = bar_tfull + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* a_ptr = smem_raw + (a_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = P.T, R_pad = P.R_pad;
+  unsigned* ctr = P.ctr + (size_t)dom * CTR_STRIDE;
+  int* ef = P.error_flag;
+  bool dead = false;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.wt_hi); tma_prefetch_desc(&P.wt_lo);
+    mbar_init(bar_w, 1); mbar_init(bar_a, 1); mbar_init(bar_tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, BWD_WT_BYTES);
+      // B operand [N = 512 outputs][K = this CTA's 64 gate columns]: hi rows 0-255, hi rows 256-511, lo likewise
+      tma_load_2d(wt_base + 0 * BWD_WT_HALF, &P.wt_hi, bar_w, slice * NC, 0);
+      tma_load_2d(wt_base + 1 * BWD_WT_HALF, &P.wt_hi, bar_w, slice * NC, 256);
+      tma_load_2d(wt_base + 2 * BWD_WT_HALF, &P.wt_lo, bar_w, slice * NC, 0);
+      tma_load_2d(wt_base + 3 * BWD_WT_HALF, &P.wt_lo, bar_w, slice * NC, 256);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_mn(BM, 256);
+      wait_bar(bar_w, 0, ef, dead);
+      for (int t = T - 1; t >= 1; --t) {
+        wait_bar(bar_a, (uint32_t)(T - 1 - t) & 1u, ef, dead);   // A tile of step t staged, accumulator of step t+1 drained
+        if (dead) break;
+        tc_fence_after();
+        const uint64_t a_hi = make_desc_sw128(a_base), a_lo = make_desc_sw128(a_base + A_TILE);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t b_hi = make_desc_sw128(wt_base + half * BWD_WT_HALF), b_lo = make_desc_sw128(wt_base + (2 + half) * BWD_WT_HALF);
+          const uint32_t d = tmem_base + half * 256;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+            umma_bf16(d, a_hi + adv, b_lo + adv, idesc, k > 0 ? 1u : 0u);
+            umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1);
+            umma_bf16(d, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+        }
+        umma_commit(bar_tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane, row = mb * BM + r;
+    const bool valid = row < P.rows;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int unit = slice * UPC;
+    const size_t part_dom = (size_t)P.MB * SLICES;   // partial blocks per buffer
+    float dc[UPC];
+#pragma unroll
+    for (int i = 0; i < UPC; ++i) dc[i] = 0.f;
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t grow = (size_t)t * R_pad + row;
+      float dh[UPC], a[NC], ct[UPC], cp[UPC];
+      {
+        const float4* s0 = reinterpret_cast<const float4*>(P.dh_ext + ((size_t)t * P.dh_rows + row) * HIDN + unit);
+        const float4* s1 = reinterpret_cast<const float4*>(P.act + grow * G4 + slice * NC);
+        const float4* s2 = reinterpret_cast<const float4*>(P.cs + grow * HIDN + unit);
+        const float4* s3 = reinterpret_cast<const float4*>(P.cs + (grow - (size_t)R_pad) * HIDN + unit);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v0 = valid ? __ldg(s0 + i) : z, v2 = valid ? __ldg(s2 + i) : z, v3 = (valid && t > 0) ? __ldg(s3 + i) : z;
+          dh[4 * i] = v0.x; dh[4 * i + 1] = v0.y; dh[4 * i + 2] = v0.z; dh[4 * i + 3] = v0.w;
+          ct[4 * i] = v2.x; ct[4 * i + 1] = v2.y; ct[4 * i + 2] = v2.z; ct[4 * i + 3] = v2.w;
+          cp[4 * i] = v3.x; cp[4 * i + 1] = v3.y; cp[4 * i + 2] = v3.z; cp[4 * i + 3] = v3.w;
+        }
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) {
+          const float4 v = valid ? __ldg(s1 + i) : z;
+          a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+        }
+      }
+      if (t < T - 1) {
+        // dh_t += sum over the 32 CTAs' partials written at step t+1 (buffer (t+1)&1)
+        if (lane == 0) wait_counter(ctr, (unsigned)(SLICES * (T - 1 - t)), ef, dead);
+        dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
+        if (!dead) {
+          const float* pb = P.part + ((((size_t)((t + 1) & 1) * part_dom + (size_t)dom * SLICES) * BM + r) * HIDN + unit);
+#pragma unroll 4
+          for (int j = 0; j < SLICES; ++j) {
+            const float4* src = reinterpret_cast<const float4*>(pb + (size_t)j * BM * HIDN);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 v = __ldcg(src + i);
+              dh[4 * i] += v.x; dh[4 * i + 1] += v.y; dh[4 * i + 2] += v.z; dh[4 * i + 3] += v.w;
+            }
+          }
+        }
+      }
+      // pointwise backward of the cell (gate activations saved by the forward kernel)
+      __align__(16) __nv_bfloat16 ghi[NC], glo[NC];
+#pragma unroll
+      for (int u = 0; u < UPC; ++u) {
+        const float ig = a[u], fg = a[UPC + u], gg = a[2 * UPC + u], og = a[3 * UPC + u];
+        const float tc = tanh_f(ct[u]);
+        const float dct = dc[u] + dh[u] * og * (1.f - tc * tc);
+        float d_i = dct * gg * ig * (1.f - ig);
+        float d_f = dct * cp[u] * fg * (1.f - fg);
+        float d_g = dct * ig * (1.f - gg * gg);
+        float d_o = dh[u] * tc * og * (1.f - og);
+        dc[u] = dct * fg;
+        if (!valid) { d_i = d_f = d_g = d_o = 0.f; dc[u] = 0.f; }
+        split_bf16(d_i, ghi[u], glo[u]);
+        split_bf16(d_f, ghi[UPC + u], glo[UPC + u]);
+        split_bf16(d_g, ghi[2 * UPC + u], glo[2 * UPC + u]);
+        split_bf16(d_o, ghi[3 * UPC + u], glo[3 * UPC + u]);
+      }
+      if (valid && !dead) {
+        uint4* d0 = reinterpret_cast<uint4*>(P.dg_hi + grow * G4 + slice * NC);
+        uint4* d1 = reinterpret_cast<uint4*>(P.dg_lo + grow * G4 + slice * NC);
+#pragma unroll
+        for (int i = 0; i < NC / 8; ++i) { d0[i] = reinterpret_cast<const uint4*>(ghi)[i]; d1[i] = reinterpret_cast<const uint4*>(glo)[i]; }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          P.dgT_hi[(size_t)(slice * NC + k) * ((size_t)T * R_pad) + grow] = ghi[k];
+          P.dgT_lo[(size_t)(slice * NC + k) * ((size_t)T * R_pad) + grow] = glo[k];
+        }
+      }
+      if (t == 0) break;
+      // stage this CTA's dgate slice as the A operand [128 rows][64 K] (128-byte swizzle, what TMA would have written)
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(a_ptr + off) = reinterpret_cast<const uint4*>(ghi)[ch];
+        *reinterpret_cast<uint4*>(a_ptr + A_TILE + off) = reinterpret_cast<const uint4*>(glo)[ch];
+      }
+      fence_async_smem();
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) mbar_arrive(bar_a);
+      wait_bar(bar_tfull, (uint32_t)(T - 1 - t) & 1u, ef, dead);
+      tc_fence_after();
+      if (!dead) {
+        float* dst = P.part + ((((size_t)(t & 1) * part_dom + (size_t)dom * SLICES + slice) * BM + r) * HIDN);
+        for (int c0 = 0; c0 < HIDN; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) __stcg(reinterpret_cast<float4*>(dst + c0) + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) red_release_add(ctr, 1u);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+// CTA-slice order of the 2048 gate rows / columns: p = slice*64 + gate*16 + u  <->  nn.LSTM row gate*512 + slice*16 + u.
+__device__ __forceinline__ int perm_to_orig(int p) { return ((p >> 4) & 3) * HIDN + (p >> 6) * UPC + (p & 15); }
+
+// W [2048][512] fp32 (nn.LSTM layout) -> Wp hi/lo [2048 slice order][512]  and (optional) WT hi/lo [512][2048 slice order]
+__global__ void lstm_prep_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo,
+                                 __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.y * 32, k0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;  // block (32, 8)
+  for (int j = ty; j < 32; j += 8) {
+    const float v = w[(size_t)perm_to_orig(p0 + j) * HIDN + k0 + tx];
+    tile[j][tx] = v;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    p_hi[(size_t)(p0 + j) * HIDN + k0 + tx] = h;
+    p_lo[(size_t)(p0 + j) * HIDN + k0 + tx] = l;
+  }
+  if (!t_hi) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    __nv_bfloat16 h, l;
+    split_bf16(tile[tx][j], h, l);
+    t_hi[(size_t)(k0 + j) * G4 + p0 + tx] = h;
+    t_lo[(size_t)(k0 + j) * G4 + p0 + tx] = l;
+  }
+}
+__global__ void lstm_prep_bias(const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < G4) { const int o = perm_to_orig(p); out[p] = b_ih[o] + b_hh[o]; }
+}
+
+// x [T][rows][512] fp32 -> xs hi/lo [T*R_pad][512] and (optional) xT hi/lo [512][ldT] at column t*R_pad + row
+__global__ void lstm_prep_x(const float* __restrict__ x, int T, int rows, int R_pad, __nv_bfloat16* __restrict__ s_hi,
+                            __nv_bfloat16* __restrict__ s_lo, __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo, long long ldT) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z, r0 = blockIdx.y * 32, k0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 32; j += 8) {
+    const int row = r0 + j;
+    const float v = row < rows ? x[((size_t)t * rows + row) * HIDN + k0 + tx] : 0.f;
+    tile[j][tx] = v;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    if (row < R_pad) {
+      s_hi[((size_t)t * R_pad + row) * HIDN + k0 + tx] = h;
+      s_lo[((size_t)t * R_pad + row) * HIDN + k0 + tx] = l;
+    }
+  }
+  if (!t_hi) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int row = r0 + tx;
+    if (row >= R_pad) continue;
+    __nv_bfloat16 h, l;
+    split_bf16(tile[tx][j], h, l);
+    t_hi[(size_t)(k0 + j) * ldT + (size_t)t * R_pad + row] = h;
+    t_lo[(size_t)(k0 + j) * ldT + (size_t)t * R_pad + row] = l;
+  }
+}
+
+// db[orig row] = sum over all (t, row) of dgate column p: one block per slice-order column, reading the transposed copy
+__global__ void lstm_bias_grad(const __nv_bfloat16* __restrict__ t_hi, const __nv_bfloat16* __restrict__ t_lo, long long n,
+                               float* __restrict__ db_ih, float* __restrict__ db_hh) {
+  __shared__ float red[8];
+  const int p = blockIdx.x;
+  const __nv_bfloat16 *a = t_hi + (size_t)p * n, *b = t_lo + (size_t)p * n;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += __bfloat162float(a[i]) + __bfloat162float(b[i]);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    const int o = perm_to_orig(p);
+    db_ih[o] = tot;
+    db_hh[o] = tot;
+  }
+}
+
+// dWp [2048 slice order][512] -> dW [2048][512] (nn.LSTM row order)
+__global__ void lstm_unperm_rows(const float* __restrict__ src, float* __restrict__ dst) {
+  const int p = blockIdx.x;
+  const int o = perm_to_orig(p);
+  reinterpret_cast<float4*>(dst + (size_t)o * HIDN)[threadIdx.x] = reinterpret_cast<const float4*>(src + (size_t)p * HIDN)[threadIdx.x];  // 128 threads
+}
+
+// padded [T*R_pad][512] -> caller's [T][rows][512]
+__global__ void lstm_unpad(const float* __restrict__ src, float* __restrict__ dst, int rows, int R_pad) {
+  const int t = blockIdx.y, row = blockIdx.x;
+  reinterpret_cast<float4*>(dst + ((size_t)t * rows + row) * HIDN)[threadIdx.x] =
+      reinterpret_cast<const float4*>(src + ((size_t)t * R_pad + row) * HIDN)[threadIdx.x];
+}
+
+}  // namespace hbl
+
+// ---------------------------------------------------------------------------------------------------- host side
+struct HbLstmNetBuf {                       // per network (0: the one that may be saved for backward, 1: forward only)
+  __nv_bfloat16 *wih_hi[2], *wih_lo[2], *whh_hi[2], *whh_lo[2];     // [2048p][512]
+  __nv_bfloat16 *wihT_hi[2], *wihT_lo[2], *whhT_hi[2], *whhT_lo[2]; // [512][2048p] (net 0 only)
+  float* bias[2];                           // [2048p]
+  __nv_bfloat16 *xs_hi, *xs_lo;             // [N][512]
+  __nv_bfloat16 *hs_hi[2], *hs_lo[2];       // [(T+1)*R_pad][512] per layer
+  float* gx;                                // [N][2048] (reused by both layers)
+};
+
+struct hb_lstm {
+  int device, sm_count, max_T, max_rows, max_rpad;
+  int T, rows, R_pad, MB;                   // geometry of the last forward
+  int saved;                                // 1: net 0's activations of the last forward are valid for backward
+  HbLstmNetBuf nb[2];
+  // saved for backward (net 0)
+  __nv_bfloat16 *xT_hi, *xT_lo;             // [512][ldT]
+  __nv_bfloat16 *hsT_hi[2], *hsT_lo[2];     // [512][ldT]
+  float *act[2], *cs[2];
+  // backward scratch
+  __nv_bfloat16 *dg_hi[2], *dg_lo[2], *dgT_hi[2], *dgT_lo[2];
+  float* dh0;                               // [N][512] gradient w.r.t. layer 0's output
+  float* dx_pad;                            // [N][512]
+  float* part;                              // [2][MB*32][128][512]
+  float* dwp;                               // [4][2048][512]
+  unsigned* ctr;
+  int* d_error;
+  hbl::FwdParams* d_fwd;                    // [2 layers]
+  hbl::BwdParams* d_bwd;                    // [2 layers]
+  Params* d_gemm;                           // [16]
+  int64_t launches;
+};
+
+#define HBL_ALLOC(ptr, bytes)                                             \
+  do {                                                                    \
+    HB_CUDA(cudaMalloc((void**)&(ptr), (bytes)));                         \
+    HB_CUDA(cudaMemset((ptr), 0, (bytes)));                               \
+  } while (0)
+
+static void hbl_gemm_problem(Params& p, int& rc, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, uint64_t m, uint64_t lda,
+                             const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, uint64_t n, uint64_t ldb, uint64_t k, int cl,
+                             const float* bias, float* c, int ldc, int* err) {
+  memset(&p, 0, sizeof(p));
+  rc |= hb_make_tmap(&p.a_hi[0], a_hi, m, k, BM, lda);
+  rc |= hb_make_tmap(&p.a_lo[0], a_lo, m, k, BM, lda);
+  p.a_hi[1] = p.a_hi[0]; p.a_lo[1] = p.a_lo[0];
+  rc |= hb_make_tmap(&p.b_hi, b_hi, n, k, BN / cl, ldb);
+  rc |= hb_make_tmap(&p.b_lo, b_lo, n, k, BN / cl, ldb);
+  p.k_chunks = (int)(k / BK); p.k_chunks_seg0 = p.k_chunks; p.lo_first = 0; p.lo_last = p.k_chunks; p.split = 1;
+  p.bias = bias; p.c_f32 = c; p.ldc = ldc; p.error_flag = err;
+  p.row_mul = 1; p.row_add = 0; p.valid_rows = (int)m;
+}
+
+static int hbl_run_gemm(hb_lstm* L, cudaStream_t st, const Params* hp, int nprob, int mt, int nt, int slot) {
+  HB_CUDA(cudaMemcpyAsync(L->d_gemm + slot, hp, nprob * sizeof(Params), cudaMemcpyHostToDevice, st));
+  const bool pair = (mt % 2) == 0;
+  L->launches += 1;
+  if (pair) return hb_launch_gemm(gemm3_kernel<EPI_F32, 3>, 2, L->sm_count, st, L->d_gemm + slot, nt, mt, nprob);
+  return hb_launch_gemm(gemm3_kernel<EPI_F32, 1>, 1, L->sm_count, st, L->d_gemm + slot, nt, mt, nprob);
+}
+
+extern "C" {
+
+int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
+  if (!out) { hb_set_error("hb_lstm_create: null argument"); return -1; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { hb_set_error("hb_lstm_create: no CUDA device -- libhanabi_b200 has no CPU path"); return -2; }
+  if (device < 0 || device >= ndev) { hb_set_error("hb_lstm_create: bad device ordinal"); return -1; }
+  if (max_T < 1 || max_T > 4096 || max_rows < 1 || max_rows > 512) { hb_set_error("hb_lstm_create: need 1 <= max_T <= 4096, 1 <= max_rows <= 512"); return -1; }
+  HB_CUDA(cudaSetDevice(device));
+  hb_lstm* L = new hb_lstm();
+  memset(L, 0, sizeof(*L));
+  L->device = device; L->max_T = max_T; L->max_rows = max_rows;
+  L->max_rpad = (max_rows + BM - 1) / BM * BM;
+  cudaDeviceProp prop;
+  HB_CUDA(cudaGetDeviceProperties(&prop, device));
+  L->sm_count = prop.multiProcessorCount;
+  const size_t bf = sizeof(__nv_bfloat16), N = (size_t)max_T * L->max_rpad, N1 = (size_t)(max_T + 1) * L->max_rpad, WN = (size_t)hbl::G4 * hbl::HIDN;
+  for (int n = 0; n < 2; ++n) {
+    HbLstmNetBuf& B = L->nb[n];
+    for (int l = 0; l < 2; ++l) {
+      HBL_ALLOC(B.wih_hi[l], WN * bf); HBL_ALLOC(B.wih_lo[l], WN * bf); HBL_ALLOC(B.whh_hi[l], WN * bf); HBL_ALLOC(B.whh_lo[l], WN * bf);
+      if (n == 0) { HBL_ALLOC(B.wihT_hi[l], WN * bf); HBL_ALLOC(B.wihT_lo[l], WN * bf); HBL_ALLOC(B.whhT_hi[l], WN * bf); HBL_ALLOC(B.whhT_lo[l], WN * bf); }
+      HBL_ALLOC(B.bias[l], hbl::G4 * sizeof(float));
+      HBL_ALLOC(B.hs_hi[l], N1 * hbl::HIDN * bf); HBL_ALLOC(B.hs_lo[l], N1 * hbl::HIDN * bf);
+    }
+    HBL_ALLOC(B.xs_hi, N * hbl::HIDN * bf); HBL_ALLOC(B.xs_lo, N * hbl::HIDN * bf);
+    HBL_ALLOC(B.gx, N * hbl::G4 * sizeof(float));
+  }
+  HBL_ALLOC(L->xT_hi, N1 * hbl::HIDN * bf); HBL_ALLOC(L->xT_lo, N1 * hbl::HIDN * bf);
+  for (int l = 0; l < 2; ++l) {
+    HBL_ALLOC(L->hsT_hi[l], N1 * hbl::HIDN * bf); HBL_ALLOC(L->hsT_lo[l], N1 * hbl::HIDN * bf);
+    HBL_ALLOC(L->act[l], N * hbl::G4 * sizeof(float)); HBL_ALLOC(L->cs[l], N * hbl::HIDN * sizeof(float));
+    HBL_ALLOC(L->dg_hi[l], N * hbl::G4 * bf); HBL_ALLOC(L->dg_lo[l], N * hbl::G4 * bf);
+    HBL_ALLOC(L->dgT_hi[l], N * hbl::G4 * bf); HBL_ALLOC(L->dgT_lo[l], N * hbl::G4 * bf);
+  }
+  HBL_ALLOC(L->dh0, N * hbl::HIDN * sizeof(float));
+  HBL_ALLOC(L->dx_pad, N * hbl::HIDN * sizeof(float));
+  HBL_ALLOC(L->part, (size_t)2 * (L->max_rpad / BM) * hbl::SLICES * BM * hbl::HIDN * sizeof(float));
+  HBL_ALLOC(L->dwp, 4 * WN * sizeof(float));
+  HBL_ALLOC(L->ctr, 16 * hbl::CTR_STRIDE * sizeof(unsigned));
+  HBL_ALLOC(L->d_error, sizeof(int));
+  HBL_ALLOC(L->d_fwd, 2 * sizeof(hbl::FwdParams));
+  HBL_ALLOC(L->d_bwd, 2 * sizeof(hbl::BwdParams));
+  HBL_ALLOC(L->d_gemm, 16 * sizeof(Params));
+  HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
+  HB_CUDA((cudaFuncSetAttribute(hbl::lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::BWD_SMEM)));
+  HB_CUDA((cudaFuncSetAttribute(gemm3_kernel<EPI_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+  HB_CUDA((cudaFuncSetAttribute(gemm3_kernel<EPI_F32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+  *out = L;
+  return 0;
+}
+
+void hb_lstm_destroy(hb_lstm* L) {
+  if (!L) return;
+  cudaSetDevice(L->device);
+  for (int n = 0; n < 2; ++n) {
+    HbLstmNetBuf& B = L->nb[n];
+    for (int l = 0; l < 2; ++l) {
+      cudaFree(B.wih_hi[l]); cudaFree(B.wih_lo[l]); cudaFree(B.whh_hi[l]); cudaFree(B.whh_lo[l]);
+      cudaFree(B.wihT_hi[l]); cudaFree(B.wihT_lo[l]); cudaFree(B.whhT_hi[l]); cudaFree(B.whhT_lo[l]);
+      cudaFree(B.bias[l]); cudaFree(B.hs_hi[l]); cudaFree(B.hs_lo[l]);
+    }
+    cudaFree(B.xs_hi); cudaFree(B.xs_lo); cudaFree(B.gx);
+  }
+  cudaFree(L->xT_hi); cudaFree(L->xT_lo);
+  for (int l = 0; l < 2; ++l) {
+    cudaFree(L->hsT_hi[l]); cudaFree(L->hsT_lo[l]); cudaFree(L->act[l]); cudaFree(L->cs[l]);
+    cudaFree(L->dg_hi[l]); cudaFree(L->dg_lo[l]); cudaFree(L->dgT_hi[l]); cudaFree(L->dgT_lo[l]);
+  }
+  cudaFree(L->dh0); cudaFree(L->dx_pad); cudaFree(L->part); cudaFree(L->dwp); cudaFree(L->ctr); cudaFree(L->d_error);
+  cudaFree(L->d_fwd); cudaFree(L->d_bwd); cudaFree(L->d_gemm);
+  delete L;
+}
+
+static int hbl_check_error(hb_lstm* L, cudaStream_t st, const char* what) {
+  int herr = 0;
+  HB_CUDA(cudaMemcpyAsync(&herr, L->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HB_CUDA(cudaStreamSynchronize(st));
+  if (herr) {
+    cudaMemsetAsync(L->d_error, 0, sizeof(int), st);
+    hb_set_error("%s: a pipeline / step barrier timed out (spin guard, code %d)", what, herr);
+    return -4;
+  }
+  return 0;
+}
+
+int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x, const hb_lstm_weights* w, float* const* y, int save,
+                    void* stream) {
+  if (!L || !x || !w || !y) { hb_set_error("hb_lstm_forward: null argument"); return -1; }
+  if (T < 1 || T > L->max_T || rows < 1 || rows > L->max_rows) { hb_set_error("hb_lstm_forward: T=%d rows=%d exceed the handle's (%d, %d)", T, rows, L->max_T, L->max_rows); return -1; }
+  if (nets < 1 || nets > 2) { hb_set_error("hb_lstm_forward: nets must be 1 or 2"); return -1; }
+  for (int n = 0; n < nets; ++n) {
+    if (!x[n] || !y[n]) { hb_set_error("hb_lstm_forward: null sequence pointer"); return -1; }
+    for (int l = 0; l < 2; ++l)
+      if (!w[n].w_ih[l] || !w[n].w_hh[l] || !w[n].b_ih[l] || !w[n].b_hh[l]) { hb_set_error("hb_lstm_forward: null weight pointer"); return -1; }
+  }
+  HB_CUDA(cudaSetDevice(L->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R_pad = (rows + BM - 1) / BM * BM, MB = R_pad / BM;
+  const size_t N = (size_t)T * R_pad;
+  const long long ldT = (long long)(T + 1) * R_pad;
+  const size_t bf = sizeof(__nv_bfloat16);
+  L->T = T; L->rows = rows; L->R_pad = R_pad; L->MB = MB; L->saved = 0;
+  if (nets * MB * hbl::SLICES > L->sm_count) { hb_set_error("hb_lstm_forward: %d networks x %d rows need %d co-resident CTAs, the device has %d SMs", nets, rows, nets * MB * hbl::SLICES, L->sm_count); return -1; }
+  // ---- operands
+  for (int n = 0; n < nets; ++n) {
+    HbLstmNetBuf& B = L->nb[n];
+    const bool sv = save && n == 0;
+    for (int l = 0; l < 2; ++l) {
+      hbl::lstm_prep_weight<<<dim3(hbl::HIDN / 32, hbl::G4 / 32), dim3(32, 8), 0, st>>>(w[n].w_ih[l], B.wih_hi[l], B.wih_lo[l], sv ? B.wihT_hi[l] : nullptr, sv ? B.wihT_lo[l] : nullptr);
+      hbl::lstm_prep_weight<<<dim3(hbl::HIDN / 32, hbl::G4 / 32), dim3(32, 8), 0, st>>>(w[n].w_hh[l], B.whh_hi[l], B.whh_lo[l], sv ? B.whhT_hi[l] : nullptr, sv ? B.whhT_lo[l] : nullptr);
+      hbl::lstm_prep_bias<<<hbl::G4 / 256, 256, 0, st>>>(w[n].b_ih[l], w[n].b_hh[l], B.bias[l]);
+      // block 0 of the h sequence is h_{-1} = 0 (and stays 0: the kernels never write it); padded rows stay 0 as well
+    }
+    hbl::lstm_prep_x<<<dim3(hbl::HIDN / 32, R_pad / 32, T), dim3(32, 8), 0, st>>>(x[n], T, rows, R_pad, B.xs_hi, B.xs_lo, sv ? L->xT_hi : nullptr, sv ? L->xT_lo : nullptr, ldT);
+    L->launches += 7;
+  }
+  if (save) {  // column block 0 of the transposed h copies = h_{-1} = 0 for THIS geometry
+    for (int l = 0; l < 2; ++l) {
+      HB_CUDA(cudaMemset2DAsync(L->hsT_hi[l], (size_t)ldT * bf, 0, (size_t)R_pad * bf, hbl::HIDN, st));
+      HB_CUDA(cudaMemset2DAsync(L->hsT_lo[l], (size_t)ldT * bf, 0, (size_t)R_pad * bf, hbl::HIDN, st));
+    }
+  }
+  for (int n = 0; n < nets; ++n)
+    for (int l = 0; l < 2; ++l) {  // block 0 and the padded rows of a previous, differently shaped call
+      HB_CUDA(cudaMemsetAsync(L->nb[n].hs_hi[l], 0, (size_t)(T + 1) * R_pad * hbl::HIDN * bf, st));
+      HB_CUDA(cudaMemsetAsync(L->nb[n].hs_lo[l], 0, (size_t)(T + 1) * R_pad * hbl::HIDN * bf, st));
+    }
+  HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
+  std::vector<hbl::FwdParams> fp(2);
+  memset(fp.data(), 0, 2 * sizeof(hbl::FwdParams));
+  int rc = 0;
+  const int mt = (int)(N / BM), cl = (mt % 2 == 0) ? 2 : 1;
+  for (int l = 0; l < 2; ++l) {
+    // ---- input projection of layer l for all steps (both networks as two problems of one launch)
+    Params gp[2];
+    for (int n = 0; n < nets; ++n) {
+      HbLstmNetBuf& B = L->nb[n];
+      const __nv_bfloat16* a_hi = l == 0 ? B.xs_hi : B.hs_hi[0] + (size_t)R_pad * hbl::HIDN;   // layer 1 consumes h^0_t = block t+1
+      const __nv_bfloat16* a_lo = l == 0 ? B.xs_lo : B.hs_lo[0] + (size_t)R_pad * hbl::HIDN;
+      hbl_gemm_problem(gp[n], rc, a_hi, a_lo, N, hbl::HIDN, B.wih_hi[l], B.wih_lo[l], hbl::G4, hbl::HIDN, hbl::HIDN, cl, B.bias[l], B.gx, hbl::G4, L->d_error);
+    }
+    if (rc) return -2;
+    rc = hbl_run_gemm(L, st, gp, nets, mt, hbl::G4 / BN, l * 2);
+    if (rc) return rc;
+    // ---- recurrence of layer l
+    hbl::FwdParams& F = fp[l];
+    F.T = T; F.rows = rows; F.R_pad = R_pad; F.MB = MB; F.ldT = ldT; F.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; F.error_flag = L->d_error;
+    for (int n = 0; n < nets; ++n) {
+      HbLstmNetBuf& B = L->nb[n];
+      hbl::FwdNet& Q = F.net[n];
+      const bool sv = save && n == 0;
+      rc |= hb_make_tmap(&Q.w_hi, B.whh_hi[l], hbl::G4, hbl::HIDN, hbl::NC);
+      rc |= hb_make_tmap(&Q.w_lo, B.whh_lo[l], hbl::G4, hbl::HIDN, hbl::NC);
+      rc |= hb_make_tmap(&Q.h_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
+      rc |= hb_make_tmap(&Q.h_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
+      Q.gx = B.gx; Q.hs_hi = B.hs_hi[l]; Q.hs_lo = B.hs_lo[l];
+      Q.hsT_hi = sv ? L->hsT_hi[l] : nullptr; Q.hsT_lo = sv ? L->hsT_lo[l] : nullptr;
+      Q.y = l == 1 ? y[n] : nullptr;
+      Q.act = sv ? L->act[l] : nullptr; Q.cs = sv ? L->cs[l] : nullptr;
+    }
+    if (rc) return -2;
+    HB_CUDA(cudaMemcpyAsync(L->d_fwd + l, &F, sizeof(F), cudaMemcpyHostToDevice, st));
+    hbl::lstm_fwd_kernel<<<nets * MB * hbl::SLICES, 192, hbl::FWD_SMEM, st>>>(L->d_fwd + l);
+    HB_CUDA(cudaGetLastError());
+    L->launches += 1;
+  }
+  rc = hbl_check_error(L, st, "hb_lstm_forward");   // also makes the host-side Params / vectors safe to drop
+  if (rc) return rc;
+  L->saved = save ? 1 : 0;
+  return 0;
+}
+
+int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads* g, void* stream) {
+  if (!L || !dy || !g) { hb_set_error("hb_lstm_backward: null argument"); return -1; }
+  if (!L->saved) { hb_set_error("hb_lstm_backward: no saved forward (call hb_lstm_forward with save != 0 first)"); return -1; }
+  for (int l = 0; l < 2; ++l)
+    if (!g->dw_ih[l] || !g->dw_hh[l] || !g->db_ih[l] || !g->db_hh[l]) { hb_set_error("hb_lstm_backward: null gradient pointer"); return -1; }
+  HB_CUDA(cudaSetDevice(L->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = L->T, rows = L->rows, R_pad = L->R_pad, MB = L->MB;
+  const size_t N = (size_t)T * R_pad;
+  const long long ldT = (long long)(T + 1) * R_pad;
+  const int mt = (int)(N / BM), cl = (mt % 2 == 0) ? 2 : 1;
+  HbLstmNetBuf& B = L->nb[0];
+  HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
+  int rc = 0;
+  std::vector<hbl::BwdParams> bp(2);
+  memset(bp.data(), 0, 2 * sizeof(hbl::BwdParams));
+  for (int l = 1; l >= 0; --l) {
+    hbl::BwdParams& Q = bp[l];
+    rc |= hb_make_tmap(&Q.wt_hi, B.whhT_hi[l], hbl::HIDN, hbl::G4, 256);
+    rc |= hb_make_tmap(&Q.wt_lo, B.whhT_lo[l], hbl::HIDN, hbl::G4, 256);
+    if (rc) return -2;
+    Q.dh_ext = l == 1 ? dy : L->dh0; Q.dh_rows = l == 1 ? rows : R_pad;
+    Q.act = L->act[l]; Q.cs = L->cs[l];
+    Q.dg_hi = L->dg_hi[l]; Q.dg_lo = L->dg_lo[l]; Q.dgT_hi = L->dgT_hi[l]; Q.dgT_lo = L->dgT_lo[l];
+    Q.part = L->part; Q.T = T; Q.rows = rows; Q.R_pad = R_pad; Q.MB = MB;
+    Q.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; Q.error_flag = L->d_error;
+    if (R_pad != rows) {  // padded rows of the dgate operands must read as zero in the GEMMs below
+      const size_t bf = sizeof(__nv_bfloat16);
+      HB_CUDA(cudaMemsetAsync(L->dg_hi[l], 0, N * hbl::G4 * bf, st)); HB_CUDA(cudaMemsetAsync(L->dg_lo[l], 0, N * hbl::G4 * bf, st));
+      HB_CUDA(cudaMemsetAsync(L->dgT_hi[l], 0, N * hbl::G4 * bf, st)); HB_CUDA(cudaMemsetAsync(L->dgT_lo[l], 0, N * hbl::G4 * bf, st));
+    }
+    HB_CUDA(cudaMemcpyAsync(L->d_bwd + l, &Q, sizeof(Q), cudaMemcpyHostToDevice, st));
+    hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, st>>>(L->d_bwd + l);
+    HB_CUDA(cudaGetLastError());
+    L->launches += 1;
+    // gradient w.r.t. this layer's input sequence: dX = dG W_ih  ([N, 2048] x [2048, 512])
+    Params gp;
+    float* dst = l == 1 ? L->dh0 : ((dx && R_pad == rows) ? dx : L->dx_pad);
+    if (l == 1 || dx) {
+      hbl_gemm_problem(gp, rc, L->dg_hi[l], L->dg_lo[l], N, hbl::G4, B.wihT_hi[l], B.wihT_lo[l], hbl::HIDN, hbl::G4, hbl::G4, cl, nullptr, dst, hbl::HIDN, L->d_error);
+      if (rc) return -2;
+      rc = hbl_run_gemm(L, st, &gp, 1, mt, hbl::HIDN / BN, 4 + l);
+      if (rc) return rc;
+      if (l == 0 && dst != dx) { hbl::lstm_unpad<<<dim3(rows, T), 128, 0, st>>>(L->dx_pad, dx, rows, R_pad); L->launches += 1; }
+    }
+  }
+  // ---- weight gradients: four [2048, 512] = dG^T [2048, N] x (operand^T [512, N])^T problems in one launch
+  Params wp[4];
+  const size_t WN = (size_t)hbl::G4 * hbl::HIDN;
+  hbl_gemm_problem(wp[0], rc, L->dgT_hi[0], L->dgT_lo[0], hbl::G4, N, L->xT_hi, L->xT_lo, hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 0 * WN, hbl::HIDN, L->d_error);
+  hbl_gemm_problem(wp[1], rc, L->dgT_hi[0], L->dgT_lo[0], hbl::G4, N, L->hsT_hi[0], L->hsT_lo[0], hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 1 * WN, hbl::HIDN, L->d_error);
+  hbl_gemm_problem(wp[2], rc, L->dgT_hi[1], L->dgT_lo[1], hbl::G4, N, L->hsT_hi[0] + R_pad, L->hsT_lo[0] + R_pad, hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 2 * WN, hbl::HIDN, L->d_error);
+  hbl_gemm_problem(wp[3], rc, L->dgT_hi[1], L->dgT_lo[1], hbl::G4, N, L->hsT_hi[1], L->hsT_lo[1], hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 3 * WN, hbl::HIDN, L->d_error);
+  if (rc) return -2;
+  rc = hbl_run_gemm(L, st, wp, 4, hbl::G4 / BM, hbl::HIDN / BN, 8);
+  if (rc) return rc;
+  float* dsts[4] = {g->dw_ih[0], g->dw_hh[0], g->dw_ih[1], g->dw_hh[1]};
+  for (int i = 0; i < 4; ++i) hbl::lstm_unperm_rows<<<hbl::G4, 128, 0, st>>>(L->dwp + i * WN, dsts[i]);
+  for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, st>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
+  HB_CUDA(cudaGetLastError());
+  L->launches += 6;
+  return hbl_check_error(L, st, "hb_lstm_backward");
+}
+
+int64_t hb_lstm_launches(const hb_lstm* L) { return L ? L->launches : 0; }
+
+}  // extern "C"

@@ -16,6 +16,7 @@
 #include "hb_engine.h"
 #include "hb_env_cta.cuh"
 #include "hb_gemm.cuh"
+#include "hb_gemm_host.h"
 #include "hb_policy.h"
 
 using hbg::Params;
@@ -42,7 +43,7 @@ static PFN_tmapEncodeTiled hb_get_encode() {
 
 // [rows][cols] bf16, cols contiguous; box = 64 columns (128 bytes, one swizzle span) x box_rows rows.
 // `row_stride` (elements, 0 = cols) lets a map describe every P-th row of a buffer: one seat's agents.
-static int hb_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t row_stride = 0) {
+int hb_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t row_stride) {
   PFN_tmapEncodeTiled enc = hb_get_encode();
   if (!enc) { hb_set_error("cuTensorMapEncodeTiled is not available from the driver"); return -2; }
   cuuint64_t gdim[2] = {cols, rows};
@@ -462,8 +463,7 @@ int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w) {
 }  // extern "C"
 
 // Persistent launch: one CTA per SM (as many as there are work items if fewer), in clusters of `cl` CTAs.
-typedef void (*HbGemmKernel)(const Params*, int, int, int);
-static int hb_launch_gemm(HbGemmKernel k, int cl, int sm_count, cudaStream_t st, const Params* ps, int nt, int mt, int nprob) {
+int hb_launch_gemm(HbGemmKernel k, int cl, int sm_count, cudaStream_t st, const Params* ps, int nt, int mt, int nprob) {
   const int items = nt * (mt / cl) * nprob;
   int clusters = sm_count / cl;
   if (items < clusters) clusters = items;

@@ -1,0 +1,132 @@
+"""Learner-side LSTM on the device kernels of csrc/hb_lstm.cu (C ABI: hb_lstm_* in include/hanabi_b200.h): the
+`nn.LSTM(512, 512, num_layers=2)` of the reference's R2D2Net (pyhanabi/r2d2.py:48-52) as R2D2Net.forward uses it in the
+learner (r2d2.py:99-105: whole padded sequences [T, rows, 512], zero initial state), with a matching autograd backward.
+
+`DeviceLSTM` has the parameters of nn.LSTM under the same names (weight_ih_l0, ... bias_hh_l1), so a reference
+state_dict loads into it unchanged.  There is no fallback: without the CUDA library / a GPU every call raises."""
+import ctypes
+
+import torch
+from torch import nn
+
+from ._lib import HbLstmGrads, HbLstmWeights, check, lib
+
+HID = 512
+PARAM_NAMES = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0", "weight_ih_l1", "weight_hh_l1", "bias_ih_l1", "bias_hh_l1")
+
+
+class LstmWorkspace:
+    """Owner of one hb_lstm handle (device buffers for sequences up to max_T x max_rows)."""
+
+    def __init__(self, device, max_T=80, max_rows=256):
+        self.device = torch.device(device)
+        assert self.device.type == "cuda", "the LSTM training kernels need a CUDA device, got %r" % (device,)
+        self.max_T, self.max_rows = int(max_T), int(max_rows)
+        h = ctypes.c_void_p()
+        check(lib().hb_lstm_create(self.device.index or 0, self.max_T, self.max_rows, ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hb_lstm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launches(self):
+        return int(lib().hb_lstm_launches(self._h))
+
+    @staticmethod
+    def _weights(params):
+        w = HbLstmWeights()
+        for l in range(2):
+            w.w_ih[l], w.w_hh[l], w.b_ih[l], w.b_hh[l] = (params[4 * l + i].data_ptr() for i in range(4))
+        return w
+
+    def forward(self, xs, params, save):
+        """xs: list of 1 or 2 float32 CUDA tensors [T, rows, 512]; params: per network the 8 nn.LSTM tensors in PARAM_NAMES
+        order.  Returns the top-layer output sequences.  save=True keeps network 0's activations for backward()."""
+        nets = len(xs)
+        T, rows, hid = xs[0].shape
+        assert hid == HID and nets in (1, 2) and len(params) == nets
+        xs = [x.contiguous() for x in xs]
+        keep = [[p.detach().contiguous() for p in ps] for ps in params]
+        for x in xs:
+            assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape) == (T, rows, HID)
+        for ps in keep:
+            assert len(ps) == 8 and all(p.is_cuda and p.dtype == torch.float32 for p in ps)
+            assert tuple(ps[0].shape) == (4 * HID, HID) and tuple(ps[2].shape) == (4 * HID,)
+        ys = [torch.empty_like(x) for x in xs]
+        xp = (ctypes.c_void_p * 2)(*[x.data_ptr() for x in xs])
+        yp = (ctypes.c_void_p * 2)(*[y.data_ptr() for y in ys])
+        ws = (HbLstmWeights * 2)(*[self._weights(ps) for ps in keep])
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib().hb_lstm_forward(self._h, int(T), int(rows), nets, xp, ws, yp, int(bool(save)), ctypes.c_void_p(stream)))
+        return ys
+
+    def backward(self, dy, need_dx=True):
+        """Gradients of the last saving forward: returns (dx or None, [8 parameter gradients in PARAM_NAMES order])."""
+        dy = dy.contiguous()
+        assert dy.is_cuda and dy.dtype == torch.float32
+        dx = torch.empty_like(dy) if need_dx else None
+        f32 = dict(dtype=torch.float32, device=dy.device)
+        grads = []
+        g = HbLstmGrads()
+        for l in range(2):
+            gw_ih, gw_hh = torch.empty((4 * HID, HID), **f32), torch.empty((4 * HID, HID), **f32)
+            gb_ih, gb_hh = torch.empty((4 * HID,), **f32), torch.empty((4 * HID,), **f32)
+            g.dw_ih[l], g.dw_hh[l], g.db_ih[l], g.db_hh[l] = gw_ih.data_ptr(), gw_hh.data_ptr(), gb_ih.data_ptr(), gb_hh.data_ptr()
+            grads += [gw_ih, gw_hh, gb_ih, gb_hh]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib().hb_lstm_backward(self._h, dy.data_ptr(), dx.data_ptr() if need_dx else None, ctypes.byref(g), ctypes.c_void_p(stream)))
+        return dx, grads
+
+
+class _LstmFn(torch.autograd.Function):
+    """y = LSTM(x; 8 parameters), optionally with a second, gradient-free network run in the same kernels."""
+
+    @staticmethod
+    def forward(ctx, ws, x, x2, params2, *params):
+        ctx.ws = ws
+        ctx.need_dx = x.requires_grad
+        xs, ps = [x.detach()], [list(params)]
+        if x2 is not None:
+            xs.append(x2.detach())
+            ps.append(list(params2))
+        ys = ws.forward(xs, ps, save=True)
+        ctx.mark_non_differentiable(*ys[1:])
+        return tuple(ys) if x2 is not None else ys[0]
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        dx, grads = ctx.ws.backward(dy, need_dx=ctx.need_dx)
+        return (None, dx, None, None) + tuple(grads)
+
+
+class DeviceLSTM(nn.Module):
+    """nn.LSTM(512, 512, num_layers=2) replacement for the learner.  forward(x) -> output sequence [T, rows, 512]."""
+
+    def __init__(self, device, max_T=80, max_rows=256, workspace=None):
+        super().__init__()
+        k = 1.0 / HID ** 0.5
+        for name in PARAM_NAMES:
+            shape = (4 * HID, HID) if name.startswith("weight") else (4 * HID,)
+            self.register_parameter(name, nn.Parameter(torch.empty(shape, device=device).uniform_(-k, k)))   # nn.LSTM's init
+        self._ws = workspace if workspace is not None else LstmWorkspace(device, max_T, max_rows)
+
+    def _params(self):
+        return [getattr(self, n) for n in PARAM_NAMES]
+
+    def forward(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params())):
+            return _LstmFn.apply(self._ws, x, None, None, *self._params())
+        return self._ws.forward([x], [self._params()], save=False)[0]
+
+    def forward_pair(self, x, other, x_other):
+        """This network on `x` (differentiable) and `other` (a second DeviceLSTM, no gradient) on `x_other` in one pass --
+        the online / target pair of R2D2Agent.td_error (r2d2.py:398-401)."""
+        return _LstmFn.apply(self._ws, x, x_other, [p.detach() for p in other._params()], *self._params())

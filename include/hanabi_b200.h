@@ -213,6 +213,40 @@ int hb_profile(hb_engine* e, int on, double* ms_sum, int64_t* launches);
  * (M % 128 == N % 256 == K % 64 == 0; split != 0 selects the bf16x3 fp32-class mode). */
 int hb_debug_gemm(int device, const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int split);
 
+/* ---- learner side: the T-step LSTM of R2D2Net.forward and its backward ------------------------ */
+
+/* torch.nn.LSTM(512, 512, num_layers=2) as the reference learner runs it (pyhanabi/r2d2.py:48-52 construction,
+ * :99-105 call from R2D2Net.forward, :383-401 td_error: padded [T, rows, 512] sequences, EMPTY hid = zero initial
+ * state) -- forward over whole sequences and the matching backward, on device buffers of the caller (fp32, e.g. torch
+ * CUDA tensors).  Independent of hb_engine: one hb_lstm per learner process / GPU. */
+typedef struct hb_lstm hb_lstm;
+
+/* Parameters in nn.LSTM's own layout: weight_ih_l{k}, weight_hh_l{k} [2048, 512] (gate order i,f,g,o), bias_ih_l{k},
+ * bias_hh_l{k} [2048]; DEVICE pointers. */
+typedef struct hb_lstm_weights {
+  const float* w_ih[2]; const float* w_hh[2]; const float* b_ih[2]; const float* b_hh[2];
+} hb_lstm_weights;
+typedef struct hb_lstm_grads {
+  float* dw_ih[2]; float* dw_hh[2]; float* db_ih[2]; float* db_hh[2];   /* overwritten, not accumulated */
+} hb_lstm_grads;
+
+/* Workspace for sequences up to max_T steps x max_rows rows (rows = batch, or batch * num_player for VDN). */
+int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out);
+void hb_lstm_destroy(hb_lstm* l);
+
+/* nn.LSTM.forward for `nets` (1 or 2) independent networks in one pass -- the reference calls online_net and target_net
+ * on the same batch back to back (r2d2.py:398-401).  x[n], y[n]: device float [T, rows, 512] (input / top-layer output
+ * sequence of network n), w[n] its parameters.  save != 0 keeps network 0's activations for hb_lstm_backward.
+ * `stream`: cudaStream_t the work is queued on (e.g. torch's current stream); returns after it completed. */
+int hb_lstm_forward(hb_lstm* l, int T, int rows, int nets, const float* const* x, const hb_lstm_weights* w, float* const* y,
+                    int save, void* stream);
+
+/* Backward of network 0 of the last saving forward: dy = dLoss/dy [T, rows, 512] -> dx = dLoss/dx [T, rows, 512] (may be
+ * NULL) and the parameter gradients. */
+int hb_lstm_backward(hb_lstm* l, const float* dy, float* dx, const hb_lstm_grads* g, void* stream);
+
+int64_t hb_lstm_launches(const hb_lstm* l); /* kernels launched through this handle so far */
+
 int hb_sync(hb_engine* e); /* cudaStreamSynchronize on the engine stream */
 void* hb_stream(hb_engine* e); /* cudaStream_t the engine launches on (for CUDA-event timing) */
 int64_t hb_kernel_launches(const hb_engine* e); /* kernels launched by this engine so far */

@@ -1,0 +1,95 @@
+"""GPU parity of the learner-side LSTM kernels (csrc/hb_lstm.cu, C ABI hb_lstm_*) against CPU fp32 torch.nn.LSTM -- the
+module R2D2Net.forward runs over the padded training sequences (pyhanabi/r2d2.py:48-52, 99-105), zero initial state --
+forward outputs and every gradient autograd produces (dx, weight_ih/hh, bias_ih/hh of both layers).
+
+Tolerance: 1e-4 (north_star's fp32 bound for the LSTM), relative to the largest magnitude of the compared tensor for the
+gradients (they are sums over T*rows terms)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hbl(gpu_or_skip):
+    from hanabi_sad_b200 import lstm
+
+    return lstm
+
+
+def _reference(T, rows, seed, scale=1.0):
+    torch.manual_seed(seed)
+    ref = torch.nn.LSTM(512, 512, num_layers=2)
+    x = (torch.randn(T, rows, 512) * scale).requires_grad_(True)
+    gy = torch.randn(T, rows, 512) / (T * rows) ** 0.5
+    y, _ = ref(x)
+    (y * gy).sum().backward()
+    return ref, x, gy, y
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
+
+
+@pytest.mark.parametrize("T,rows", [(6, 128), (80, 256), (9, 40), (5, 130), (33, 128)], ids=["T6_r128", "T80_r256", "T9_r40_padded", "T5_r130_two_blocks", "T33_odd"])
+def test_lstm_forward_backward_match_torch_cpu(hbl, T, rows):
+    ref, x, gy, y = _reference(T, rows, seed=T * 1000 + rows)
+    dev = torch.device("cuda", 0)
+    mod = hbl.DeviceLSTM(dev, max_T=T, max_rows=rows)
+    mod.load_state_dict(ref.state_dict())
+    xd = x.detach().to(dev).requires_grad_(True)
+    yd = mod(xd)
+    assert yd.shape == (T, rows, 512)
+    err_y = float((yd.detach().cpu() - y.detach()).abs().max())
+    assert err_y < 1e-4, err_y
+    (yd * gy.to(dev)).sum().backward()
+    assert _rel(xd.grad.cpu(), x.grad) < 1e-4, ("dx", _rel(xd.grad.cpu(), x.grad))
+    for name in hbl.PARAM_NAMES:
+        got, want = getattr(mod, name).grad.cpu(), getattr(ref, name).grad
+        assert got.shape == want.shape
+        assert _rel(got, want) < 1e-4, (name, _rel(got, want))
+    # a second call on the same workspace (buffers reused, different data) stays exact
+    ref2, x2, gy2, y2 = _reference(T, rows, seed=7, scale=0.3)
+    mod.load_state_dict(ref2.state_dict())
+    with torch.no_grad():
+        y2d = mod(x2.detach().to(dev))
+    assert float((y2d.cpu() - y2.detach()).abs().max()) < 1e-4
+
+
+def test_lstm_pair_runs_online_and_target_in_one_pass(hbl):
+    T, rows = 20, 128
+    ref_a, xa, gya, ya = _reference(T, rows, seed=1)
+    ref_b, xb, _, yb = _reference(T, rows, seed=2, scale=0.5)
+    dev = torch.device("cuda", 0)
+    ws = hbl.LstmWorkspace(dev, T, rows)
+    a, b = hbl.DeviceLSTM(dev, workspace=ws), hbl.DeviceLSTM(dev, workspace=ws)
+    a.load_state_dict(ref_a.state_dict())
+    b.load_state_dict(ref_b.state_dict())
+    xad = xa.detach().to(dev).requires_grad_(True)
+    n0 = ws.launches()
+    yad, ybd = a.forward_pair(xad, b, xb.detach().to(dev))
+    assert not ybd.requires_grad
+    assert float((yad.detach().cpu() - ya.detach()).abs().max()) < 1e-4
+    assert float((ybd.cpu() - yb.detach()).abs().max()) < 1e-4
+    (yad * gya.to(dev)).sum().backward()
+    assert _rel(xad.grad.cpu(), xa.grad) < 1e-4
+    assert _rel(a.weight_hh_l0.grad.cpu(), ref_a.weight_hh_l0.grad) < 1e-4
+    assert all(p.grad is None for p in b.parameters())
+    assert ws.launches() - n0 < 60   # whole sequences per launch, not one launch per step
+    ws.close()
+
+
+def test_lstm_rejects_what_it_cannot_serve(hbl):
+    from hanabi_sad_b200._lib import HbError
+
+    dev = torch.device("cuda", 0)
+    ws = hbl.LstmWorkspace(dev, 8, 128)
+    mod = hbl.DeviceLSTM(dev, workspace=ws)
+    with pytest.raises(HbError, match="exceed"):
+        mod(torch.zeros(9, 128, 512, device=dev))
+    with pytest.raises(HbError, match="saved forward"):
+        ws.backward(torch.zeros(8, 128, 512, device=dev))
+    with pytest.raises(AssertionError):
+        hbl.LstmWorkspace("cpu")
+    ws.close()
