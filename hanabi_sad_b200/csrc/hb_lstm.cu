@@ -21,6 +21,7 @@
 // torch.nn.LSTM forward / autograd within 1e-4 (tests/test_lstm_train_parity.py).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -52,9 +53,9 @@ constexpr int CTR_STRIDE = 32;        // unsigned ints between two domains' step
 struct FwdNet {
   CUtensorMap w_hi, w_lo;             // W_hh in CTA-slice row order [2048][512], box 64 x 64
   CUtensorMap h_hi, h_lo;             // h sequence [(T+1)*R_pad][512], block 0 = h_{-1} = 0; box 128 x 64
+  CUtensorMap hq_hi, hq_lo;           // the same with box 32 x 64 (cluster multicast: each CTA fetches a quarter)
   const float* gx;                    // [T*R_pad][2048] input projection + bias, CTA-slice column order
   __nv_bfloat16 *hs_hi, *hs_lo;       // same buffer as h_hi / h_lo
-  __nv_bfloat16 *hsT_hi, *hsT_lo;     // [512][ldT] transposed copy (operand of the weight-gradient GEMMs) or null
   float* y;                           // fp32 output [T][rows][512] (the caller's tensor) or null
   float* act;                         // [T*R_pad][2048] gate activations i,f,g,o (saved for backward) or null
   float* cs;                          // [T*R_pad][512] cell states (saved for backward) or null
@@ -73,7 +74,6 @@ struct __align__(64) BwdParams {
   const float* act;
   const float* cs;
   __nv_bfloat16 *dg_hi, *dg_lo;       // [T*R_pad][2048] dgates, slice column order
-  __nv_bfloat16 *dgT_hi, *dgT_lo;     // [2048][T*R_pad]
   float* part;                        // [2][MB*32][128][512] split-K partials of dh_{t-1}
   int T, rows, R_pad, MB;
   unsigned* ctr;
@@ -83,16 +83,29 @@ struct __align__(64) BwdParams {
 __device__ __forceinline__ constexpr uint32_t idesc_mn(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Bounded waits: a protocol bug must not hang the (shared) GPU.  Once any thread of the grid gives up it raises
 // *error_flag, and every other wait in the grid sees the flag within ~1000 polls and gives up too.
@@ -107,17 +120,31 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err
 }
 __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, int* error_flag, bool& dead) {
   if (dead) return;
-  for (uint32_t spin = 0; ld_acquire(ctr) < target; ++spin) {
+  for (uint32_t spin = 0; ld_relaxed(ctr) < target; ++spin) {
     if ((spin & 255u) == 255u) {
       if (*(volatile int*)error_flag != 0) { dead = true; return; }
       if (spin > (1u << 20)) { atomicExch(error_flag, 2); dead = true; return; }
     }
   }
+  fence_acq_rel_gpu();
+}
+// Step publication (the grid.sync idiom): every thread's stores are ordered before the CTA barrier, ONE thread then
+// fences at GPU scope (cumulative over what the barrier ordered) and bumps the domain's step counter.
+__device__ __forceinline__ void publish_step(unsigned* ctr) {
+  fence_async_global();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (threadIdx.x == 64) { fence_acq_rel_gpu(); fence_async_global(); red_release_add(ctr, 1u); }
 }
 
 // ------------------------------------------------------------------------------------------------ forward recurrence
 // grid = nets * MB * 32 CTAs (all co-resident: one per SM), 192 threads: warp 0 TMA producer + step-barrier poller,
 // warp 1 MMA issuer / TMEM owner, warps 2-5 cell update (thread = one sequence row of the block).
+//
+// CL = 4: the grid is launched as clusters of four CTAs of the same row block.  All of them need the same h_{t-1}
+// chunks, so each CTA fetches a quarter (32 rows) of every chunk and TMA-multicasts it into the four shared memories:
+// L2 -> SM traffic of the recurrence drops 4x.  A ring slot is refilled only after all four CTAs' MMAs released it
+// (empty barriers count 4, released by a multicast tcgen05.commit).
+template <int CL>
 __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __restrict__ pp) {
   extern __shared__ uint8_t smem_raw[];
   const FwdParams& P = *pp;
@@ -130,13 +157,15 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = P.T, R_pad = P.R_pad;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
   unsigned* ctr = P.ctr + (size_t)dom * CTR_STRIDE;
   int* ef = P.error_flag;
   bool dead = false;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&N.w_hi); tma_prefetch_desc(&N.w_lo); tma_prefetch_desc(&N.h_hi); tma_prefetch_desc(&N.h_lo);
-    for (int s = 0; s < FWD_NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < FWD_NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
     mbar_init(bar_w, 1); mbar_init(bar_tfull, 1); mbar_init(bar_tempty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
@@ -147,6 +176,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peers' barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -167,8 +197,15 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
           if (dead) break;
           const uint32_t st = ring + s * FWD_STAGE;
           mbar_expect_tx(bar_full + 8 * s, FWD_STAGE);
-          tma_load_2d(st, &N.h_hi, bar_full + 8 * s, kc * BK, t * R_pad + mb * BM);   // block t = h_{t-1}
-          tma_load_2d(st + A_TILE, &N.h_lo, bar_full + 8 * s, kc * BK, t * R_pad + mb * BM);
+          const int row0 = t * R_pad + mb * BM;                // block t of the h sequence = h_{t-1}
+          if (CL == 1) {
+            tma_load_2d(st, &N.h_hi, bar_full + 8 * s, kc * BK, row0);
+            tma_load_2d(st + A_TILE, &N.h_lo, bar_full + 8 * s, kc * BK, row0);
+          } else {                                             // this CTA's quarter of the rows, delivered to all four CTAs
+            const uint32_t q = (uint32_t)rank * (A_TILE / CL);
+            tma_load_2d_mc(st + q, &N.hq_hi, bar_full + 8 * s, kc * BK, row0 + rank * (BM / CL), CMASK);
+            tma_load_2d_mc(st + A_TILE + q, &N.hq_lo, bar_full + 8 * s, kc * BK, row0 + rank * (BM / CL), CMASK);
+          }
         }
       }
     }
@@ -197,7 +234,8 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
             umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
             acc = 1;
           }
-          umma_commit(bar_empty + 8 * s);
+          if (CL == 1) umma_commit(bar_empty + 8 * s);
+          else umma_commit_mc(bar_empty + 8 * s, CMASK);        // the slot is free in ALL CTAs of the cluster only when all have read it
         }
         if (dead) break;
         umma_commit(bar_tfull);
@@ -207,6 +245,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
     const int q = warp & 3, r = q * 32 + lane, row = mb * BM + r;
     const bool valid = row < P.rows;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int unit = slice * UPC;
     float c[UPC];
 #pragma unroll
     for (int i = 0; i < UPC; ++i) c[i] = 0.f;
@@ -245,10 +284,14 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
         h[i] = og * tanh_f(c[i]);
         g[i] = ig; g[UPC + i] = fg; g[2 * UPC + i] = gg; g[3 * UPC + i] = og;
       }
+      // critical path first: the slice of h_t the other CTAs are waiting for, then the step counter
       if (valid && !dead) {
-        const int unit = slice * UPC;
         const size_t o = ((size_t)(t + 1) * R_pad + row) * HIDN + unit;
         store_split16(h, N.hs_hi + o, N.hs_lo + o);
+      }
+      publish_step(ctr);
+      // everything only later kernels read overlaps with the other CTAs' next step
+      if (valid && !dead) {
         if (N.y) {
           float4* dst = reinterpret_cast<float4*>(N.y + ((size_t)t * P.rows + row) * HIDN + unit);
 #pragma unroll
@@ -262,26 +305,12 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
 #pragma unroll
           for (int i = 0; i < 4; ++i) dc[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
         }
-        if (N.hsT_hi) {
-          const size_t col = (size_t)(t + 1) * R_pad + row;
-#pragma unroll
-          for (int i = 0; i < UPC; ++i) {
-            __nv_bfloat16 hh, ll;
-            split_bf16(h[i], hh, ll);
-            N.hsT_hi[(size_t)(unit + i) * P.ldT + col] = hh;
-            N.hsT_lo[(size_t)(unit + i) * P.ldT + col] = ll;
-          }
-        }
       }
-      // publish: generic-proxy stores -> visible to the other CTAs' TMA (async proxy) reads after the counter bump
-      __threadfence();
-      fence_async_global();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) red_release_add(ctr, 1u);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers may still be multicasting into / arriving on this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
@@ -297,7 +326,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
   const int slice = blockIdx.x % SLICES, dom = blockIdx.x / SLICES, mb = dom;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t wt_base = base, a_base = base + BWD_WT_BYTES, bar_base = a_base + 2 * A_TILE;
-  const uint32_t bar_w = bar_base, bar_a = bar_w + 8, bar_tfull = bar_a + 8, tmem_slot = bar_tfull + 8;
+  const uint32_t bar_w = bar_base, bar_a = bar_w + 8, bar_tfull = bar_a + 8, tmem_slot = bar_tfull + 16;   // bar_tfull: one per accumulator half
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* a_ptr = smem_raw + (a_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,7 +337,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.wt_hi); tma_prefetch_desc(&P.wt_lo);
-    mbar_init(bar_w, 1); mbar_init(bar_a, 1); mbar_init(bar_tfull, 1);
+    mbar_init(bar_w, 1); mbar_init(bar_a, 1); mbar_init(bar_tfull, 1); mbar_init(bar_tfull + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -350,8 +379,8 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
             umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1);
             umma_bf16(d, a_hi + adv, b_hi + adv, idesc, 1);
           }
+          umma_commit(bar_tfull + 8 * half);   // the drain of this half overlaps the MMAs of the other
         }
-        umma_commit(bar_tfull);
       }
     }
   } else {
@@ -391,14 +420,19 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
         if (!dead) {
           const float* pb = P.part + ((((size_t)((t + 1) & 1) * part_dom + (size_t)dom * SLICES) * BM + r) * HIDN + unit);
-#pragma unroll 4
-          for (int j = 0; j < SLICES; ++j) {
-            const float4* src = reinterpret_cast<const float4*>(pb + (size_t)j * BM * HIDN);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 v = __ldcg(src + i);
-              dh[4 * i] += v.x; dh[4 * i + 1] += v.y; dh[4 * i + 2] += v.z; dh[4 * i + 3] += v.w;
+          for (int j0 = 0; j0 < SLICES; j0 += 8) {   // 32 independent 16-byte loads in flight per thread
+            float4 v[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4* src = reinterpret_cast<const float4*>(pb + (size_t)(j0 + j) * BM * HIDN);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[j][i] = __ldcg(src + i);
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { dh[4 * i] += v[j][i].x; dh[4 * i + 1] += v[j][i].y; dh[4 * i + 2] += v[j][i].z; dh[4 * i + 3] += v[j][i].w; }
           }
         }
       }
@@ -420,44 +454,48 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         split_bf16(d_g, ghi[2 * UPC + u], glo[2 * UPC + u]);
         split_bf16(d_o, ghi[3 * UPC + u], glo[3 * UPC + u]);
       }
+      if (t > 0) {
+        // stage this CTA's dgate slice as the A operand [128 rows][64 K] (128-byte swizzle, what TMA would have written)
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(a_ptr + off) = reinterpret_cast<const uint4*>(ghi)[ch];
+          *reinterpret_cast<uint4*>(a_ptr + A_TILE + off) = reinterpret_cast<const uint4*>(glo)[ch];
+        }
+        fence_async_smem();
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) mbar_arrive(bar_a);
+      }
+      // while the tensor core works: the row-major dgate copy the dX / dW GEMMs read after this kernel
       if (valid && !dead) {
         uint4* d0 = reinterpret_cast<uint4*>(P.dg_hi + grow * G4 + slice * NC);
         uint4* d1 = reinterpret_cast<uint4*>(P.dg_lo + grow * G4 + slice * NC);
 #pragma unroll
         for (int i = 0; i < NC / 8; ++i) { d0[i] = reinterpret_cast<const uint4*>(ghi)[i]; d1[i] = reinterpret_cast<const uint4*>(glo)[i]; }
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          P.dgT_hi[(size_t)(slice * NC + k) * ((size_t)T * R_pad) + grow] = ghi[k];
-          P.dgT_lo[(size_t)(slice * NC + k) * ((size_t)T * R_pad) + grow] = glo[k];
-        }
       }
       if (t == 0) break;
-      // stage this CTA's dgate slice as the A operand [128 rows][64 K] (128-byte swizzle, what TMA would have written)
+      float* dst = P.part + ((((size_t)(t & 1) * part_dom + (size_t)dom * SLICES + slice) * BM + r) * HIDN);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        wait_bar(bar_tfull + 8 * half, (uint32_t)(T - 1 - t) & 1u, ef, dead);
+        tc_fence_after();
+        if (dead) continue;
+#pragma unroll 1
+        for (int c0 = half * 256; c0 < half * 256 + 256; c0 += 64) {   // two 32-column TMEM loads in flight, then 16 stores
+          uint32_t v[64];
+          tmem_ld32_nowait(taddr + c0, v);
+          tmem_ld32_nowait(taddr + c0 + 32, v + 32);
+          tmem_wait_ld();
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(a_ptr + off) = reinterpret_cast<const uint4*>(ghi)[ch];
-        *reinterpret_cast<uint4*>(a_ptr + A_TILE + off) = reinterpret_cast<const uint4*>(glo)[ch];
-      }
-      fence_async_smem();
-      tc_fence_before();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) mbar_arrive(bar_a);
-      wait_bar(bar_tfull, (uint32_t)(T - 1 - t) & 1u, ef, dead);
-      tc_fence_after();
-      if (!dead) {
-        float* dst = P.part + ((((size_t)(t & 1) * part_dom + (size_t)dom * SLICES + slice) * BM + r) * HIDN);
-        for (int c0 = 0; c0 < HIDN; c0 += 16) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) __stcg(reinterpret_cast<float4*>(dst + c0) + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+          for (int i = 0; i < 16; ++i)
+            __stcg(reinterpret_cast<float4*>(dst + c0) + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                                                         __uint_as_float(v[4 * i + 3])));
         }
       }
       tc_fence_before();
-      __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) red_release_add(ctr, 1u);
+      if (threadIdx.x == 64) { fence_acq_rel_gpu(); red_release_add(ctr, 1u); }
     }
   }
   tc_fence_before();
@@ -465,6 +503,23 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// [rows][cols] bf16 pair -> [cols][ld_dst] (column r of the destination = row r of the source); 64 x 64 tiles
+__global__ void __launch_bounds__(256) lstm_transpose_pair(const __nv_bfloat16* __restrict__ s_hi, const __nv_bfloat16* __restrict__ s_lo, int cols,
+                                                           __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, long long ld_dst) {
+  __shared__ __nv_bfloat16 th[64][66], tl[64][66];
+  const size_t r0 = (size_t)blockIdx.y * 64;
+  const int c0 = blockIdx.x * 64, tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int j = ty; j < 64; j += 4) {
+    th[j][tx] = s_hi[(r0 + j) * cols + c0 + tx];
+    tl[j][tx] = s_lo[(r0 + j) * cols + c0 + tx];
+  }
+  __syncthreads();
+  for (int j = ty; j < 64; j += 4) {
+    d_hi[(size_t)(c0 + j) * ld_dst + r0 + tx] = th[tx][j];
+    d_lo[(size_t)(c0 + j) * ld_dst + r0 + tx] = tl[tx][j];
   }
 }
 
@@ -578,6 +633,7 @@ struct hb_lstm {
   int device, sm_count, max_T, max_rows, max_rpad;
   int T, rows, R_pad, MB;                   // geometry of the last forward
   int saved;                                // 1: net 0's activations of the last forward are valid for backward
+  int use_clusters, last_cluster;           // forward recurrence as 4-CTA multicast clusters when they all fit on the device
   HbLstmNetBuf nb[2];
   // saved for backward (net 0)
   __nv_bfloat16 *xT_hi, *xT_lo;             // [512][ldT]
@@ -670,7 +726,9 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   HBL_ALLOC(L->d_fwd, 2 * sizeof(hbl::FwdParams));
   HBL_ALLOC(L->d_bwd, 2 * sizeof(hbl::BwdParams));
   HBL_ALLOC(L->d_gemm, 16 * sizeof(Params));
-  HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
+  HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
+  HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
+  L->use_clusters = getenv("HB_LSTM_NO_CLUSTER") ? 0 : 1;   // diagnostic switch: plain (non-multicast) forward recurrence
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::BWD_SMEM)));
   HB_CUDA((cudaFuncSetAttribute(gemm3_kernel<EPI_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   HB_CUDA((cudaFuncSetAttribute(gemm3_kernel<EPI_F32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
@@ -743,12 +801,6 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     hbl::lstm_prep_x<<<dim3(hbl::HIDN / 32, R_pad / 32, T), dim3(32, 8), 0, st>>>(x[n], T, rows, R_pad, B.xs_hi, B.xs_lo, sv ? L->xT_hi : nullptr, sv ? L->xT_lo : nullptr, ldT);
     L->launches += 7;
   }
-  if (save) {  // column block 0 of the transposed h copies = h_{-1} = 0 for THIS geometry
-    for (int l = 0; l < 2; ++l) {
-      HB_CUDA(cudaMemset2DAsync(L->hsT_hi[l], (size_t)ldT * bf, 0, (size_t)R_pad * bf, hbl::HIDN, st));
-      HB_CUDA(cudaMemset2DAsync(L->hsT_lo[l], (size_t)ldT * bf, 0, (size_t)R_pad * bf, hbl::HIDN, st));
-    }
-  }
   for (int n = 0; n < nets; ++n)
     for (int l = 0; l < 2; ++l) {  // block 0 and the padded rows of a previous, differently shaped call
       HB_CUDA(cudaMemsetAsync(L->nb[n].hs_hi[l], 0, (size_t)(T + 1) * R_pad * hbl::HIDN * bf, st));
@@ -783,15 +835,42 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
       rc |= hb_make_tmap(&Q.h_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
       rc |= hb_make_tmap(&Q.h_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
       Q.gx = B.gx; Q.hs_hi = B.hs_hi[l]; Q.hs_lo = B.hs_lo[l];
-      Q.hsT_hi = sv ? L->hsT_hi[l] : nullptr; Q.hsT_lo = sv ? L->hsT_lo[l] : nullptr;
+      rc |= hb_make_tmap(&Q.hq_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / 4);
+      rc |= hb_make_tmap(&Q.hq_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / 4);
       Q.y = l == 1 ? y[n] : nullptr;
       Q.act = sv ? L->act[l] : nullptr; Q.cs = sv ? L->cs[l] : nullptr;
     }
     if (rc) return -2;
     HB_CUDA(cudaMemcpyAsync(L->d_fwd + l, &F, sizeof(F), cudaMemcpyHostToDevice, st));
-    hbl::lstm_fwd_kernel<<<nets * MB * hbl::SLICES, 192, hbl::FWD_SMEM, st>>>(L->d_fwd + l);
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(nets * MB * hbl::SLICES), 1, 1);
+      cfg.blockDim = dim3(192, 1, 1);
+      cfg.dynamicSmemBytes = hbl::FWD_SMEM;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int max_clusters = 0;   // every CTA must be resident at once (step barrier): use clusters only if they all fit
+      const bool cl4 = L->use_clusters && cudaOccupancyMaxActiveClusters(&max_clusters, hbl::lstm_fwd_kernel<4>, &cfg) == cudaSuccess &&
+                       max_clusters * 4 >= nets * MB * hbl::SLICES;
+      const hbl::FwdParams* dp = L->d_fwd + l;
+      if (cl4) {
+        HB_CUDA(cudaLaunchKernelEx(&cfg, hbl::lstm_fwd_kernel<4>, dp));
+      } else {
+        (void)cudaGetLastError();
+        hbl::lstm_fwd_kernel<1><<<nets * MB * hbl::SLICES, 192, hbl::FWD_SMEM, st>>>(dp);
+      }
+      L->last_cluster = cl4 ? 4 : 1;
+    }
     HB_CUDA(cudaGetLastError());
     L->launches += 1;
+    if (save) {  // transposed copy of net 0's h sequence (block 0 = zeros included): operand of the weight-gradient GEMMs
+      hbl::lstm_transpose_pair<<<dim3(hbl::HIDN / 64, (unsigned)((size_t)(T + 1) * R_pad / 64)), 256, 0, st>>>(L->nb[0].hs_hi[l], L->nb[0].hs_lo[l], hbl::HIDN,
+                                                                                                          L->hsT_hi[l], L->hsT_lo[l], ldT);
+      L->launches += 1;
+    }
   }
   rc = hbl_check_error(L, st, "hb_lstm_forward");   // also makes the host-side Params / vectors safe to drop
   if (rc) return rc;
@@ -822,18 +901,18 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     if (rc) return -2;
     Q.dh_ext = l == 1 ? dy : L->dh0; Q.dh_rows = l == 1 ? rows : R_pad;
     Q.act = L->act[l]; Q.cs = L->cs[l];
-    Q.dg_hi = L->dg_hi[l]; Q.dg_lo = L->dg_lo[l]; Q.dgT_hi = L->dgT_hi[l]; Q.dgT_lo = L->dgT_lo[l];
+    Q.dg_hi = L->dg_hi[l]; Q.dg_lo = L->dg_lo[l];
     Q.part = L->part; Q.T = T; Q.rows = rows; Q.R_pad = R_pad; Q.MB = MB;
     Q.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; Q.error_flag = L->d_error;
     if (R_pad != rows) {  // padded rows of the dgate operands must read as zero in the GEMMs below
       const size_t bf = sizeof(__nv_bfloat16);
       HB_CUDA(cudaMemsetAsync(L->dg_hi[l], 0, N * hbl::G4 * bf, st)); HB_CUDA(cudaMemsetAsync(L->dg_lo[l], 0, N * hbl::G4 * bf, st));
-      HB_CUDA(cudaMemsetAsync(L->dgT_hi[l], 0, N * hbl::G4 * bf, st)); HB_CUDA(cudaMemsetAsync(L->dgT_lo[l], 0, N * hbl::G4 * bf, st));
     }
     HB_CUDA(cudaMemcpyAsync(L->d_bwd + l, &Q, sizeof(Q), cudaMemcpyHostToDevice, st));
     hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, st>>>(L->d_bwd + l);
+    hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(N / 64)), 256, 0, st>>>(L->dg_hi[l], L->dg_lo[l], hbl::G4, L->dgT_hi[l], L->dgT_lo[l], (long long)N);
     HB_CUDA(cudaGetLastError());
-    L->launches += 1;
+    L->launches += 2;
     // gradient w.r.t. this layer's input sequence: dX = dG W_ih  ([N, 2048] x [2048, 512])
     Params gp;
     float* dst = l == 1 ? L->dh0 : ((dx && R_pad == rows) ? dx : L->dx_pad);

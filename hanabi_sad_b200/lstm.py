@@ -20,11 +20,23 @@ class LstmWorkspace:
 
     def __init__(self, device, max_T=80, max_rows=256):
         self.device = torch.device(device)
-        assert self.device.type == "cuda", "the LSTM training kernels need a CUDA device, got %r" % (device,)
         self.max_T, self.max_rows = int(max_T), int(max_rows)
-        h = ctypes.c_void_p()
-        check(lib().hb_lstm_create(self.device.index or 0, self.max_T, self.max_rows, ctypes.byref(h)))
-        self._h = h
+        self._h = None   # created at first use, so that modules can be built (and state_dicts moved around) on any host
+
+    def _handle(self, device=None):
+        if device is not None and self._h is None:
+            self.device = torch.device(device)   # the module may have been moved (.to) since it was built: follow the data
+        if device is not None and self._h is not None and torch.device(device) != self.device:
+            raise RuntimeError("this LSTM workspace lives on %s, the tensors are on %s" % (self.device, device))
+        if self._h is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("the LSTM training kernels need a CUDA device, got %r -- there is no CPU path" % (self.device,))
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
+            h = ctypes.c_void_p()
+            check(lib().hb_lstm_create(self.device.index or 0, self.max_T, self.max_rows, ctypes.byref(h)))
+            self._h = h
+        return self._h
 
     def close(self):
         if getattr(self, "_h", None):
@@ -38,7 +50,7 @@ class LstmWorkspace:
             pass
 
     def launches(self):
-        return int(lib().hb_lstm_launches(self._h))
+        return int(lib().hb_lstm_launches(self._handle()))
 
     @staticmethod
     def _weights(params):
@@ -50,6 +62,7 @@ class LstmWorkspace:
     def forward(self, xs, params, save):
         """xs: list of 1 or 2 float32 CUDA tensors [T, rows, 512]; params: per network the 8 nn.LSTM tensors in PARAM_NAMES
         order.  Returns the top-layer output sequences.  save=True keeps network 0's activations for backward()."""
+        self._handle(xs[0].device)
         nets = len(xs)
         T, rows, hid = xs[0].shape
         assert hid == HID and nets in (1, 2) and len(params) == nets
@@ -65,11 +78,12 @@ class LstmWorkspace:
         yp = (ctypes.c_void_p * 2)(*[y.data_ptr() for y in ys])
         ws = (HbLstmWeights * 2)(*[self._weights(ps) for ps in keep])
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        check(lib().hb_lstm_forward(self._h, int(T), int(rows), nets, xp, ws, yp, int(bool(save)), ctypes.c_void_p(stream)))
+        check(lib().hb_lstm_forward(self._handle(), int(T), int(rows), nets, xp, ws, yp, int(bool(save)), ctypes.c_void_p(stream)))
         return ys
 
     def backward(self, dy, need_dx=True):
         """Gradients of the last saving forward: returns (dx or None, [8 parameter gradients in PARAM_NAMES order])."""
+        self._handle(dy.device)
         dy = dy.contiguous()
         assert dy.is_cuda and dy.dtype == torch.float32
         dx = torch.empty_like(dy) if need_dx else None
@@ -82,7 +96,7 @@ class LstmWorkspace:
             g.dw_ih[l], g.dw_hh[l], g.db_ih[l], g.db_hh[l] = gw_ih.data_ptr(), gw_hh.data_ptr(), gb_ih.data_ptr(), gb_hh.data_ptr()
             grads += [gw_ih, gw_hh, gb_ih, gb_hh]
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        check(lib().hb_lstm_backward(self._h, dy.data_ptr(), dx.data_ptr() if need_dx else None, ctypes.byref(g), ctypes.c_void_p(stream)))
+        check(lib().hb_lstm_backward(self._handle(), dy.data_ptr(), dx.data_ptr() if need_dx else None, ctypes.byref(g), ctypes.c_void_p(stream)))
         return dx, grads
 
 

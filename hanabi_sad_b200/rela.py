@@ -15,7 +15,21 @@ import torch
 
 from .engine import Engine
 
+import os
+
 ROLLOUT_CHUNK = 8  # ticks queued per host iteration (pause / terminate latency = one chunk)
+
+# Share of the time the device actors may keep their GPU busy (0 < duty <= 1).  The reference's CPU actors leave the act GPU
+# almost idle, so a learner on the same device runs undisturbed; the device actors saturate it (8-9 M env-steps/s) and
+# would otherwise compete with the learner's kernels for every SM while producing far more experience than the learner
+# samples.  1.0 = free-running (throughput measurements); e.g. 0.1 still yields ~1 M env-steps/s.  Also: HB_ACTOR_DUTY.
+_actor_duty = float(os.environ.get("HB_ACTOR_DUTY", "1.0"))
+
+
+def set_actor_duty(duty):
+    global _actor_duty
+    assert 0.0 < duty <= 1.0
+    _actor_duty = float(duty)
 
 
 class _EngineLock:
@@ -298,12 +312,15 @@ class _DeviceGroup:
                         time.sleep(0.002)
                         continue
                     self.lock.driver_acquire()
+                    t0 = time.perf_counter()
                     try:
                         if not self.paused.is_set() and not self.stop.is_set():  # pause() may have won the race for the lock
                             self.engine.rollout(ROLLOUT_CHUNK)
                             self.engine.sync()
                     finally:
                         self.lock.driver_release()
+                    if _actor_duty < 1.0:
+                        time.sleep((time.perf_counter() - t0) * (1.0 / _actor_duty - 1.0))
         finally:
             self.done.set()
 

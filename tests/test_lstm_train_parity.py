@@ -90,6 +90,6 @@ def test_lstm_rejects_what_it_cannot_serve(hbl):
         mod(torch.zeros(9, 128, 512, device=dev))
     with pytest.raises(HbError, match="saved forward"):
         ws.backward(torch.zeros(8, 128, 512, device=dev))
-    with pytest.raises(AssertionError):
-        hbl.LstmWorkspace("cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hbl.DeviceLSTM("cpu")(torch.zeros(2, 4, 512))
     ws.close()

@@ -22,6 +22,8 @@ PYH = os.path.join(ROOT, "oracle", "_ref", "pyhanabi")
 
 def run(arm, a, out_dir):
     env = dict(os.environ)
+    if arm == "b200":
+        env["HB_ACTOR_DUTY"] = str(a.actor_duty)
     env["PYTHONPATH"] = (os.path.join(ROOT, "hanabi_sad_b200", "compat") if arm == "b200" else os.path.join(ROOT, "oracle", "_ref")) + os.pathsep + env.get("PYTHONPATH", "")
     cmd = [sys.executable, "selfplay.py", "--save_dir", os.path.join(out_dir, arm), "--method", "iql", "--num_thread", str(a.num_thread),
            "--num_game_per_thread", str(a.num_game_per_thread), "--sad", "1", "--act_base_eps", "0.1", "--act_eps_alpha", "7", "--lr", "6.25e-05",
@@ -52,6 +54,7 @@ def main():
     ap.add_argument("--burn_in", type=int, default=5000)
     ap.add_argument("--replay", type=int, default=32768)
     ap.add_argument("--timeout", type=int, default=900)
+    ap.add_argument("--actor_duty", type=float, default=1.0, help="share of the time the device actors keep the GPU busy (hanabi_sad_b200.rela.set_actor_duty)")
     a = ap.parse_args()
     res = {}
     with tempfile.TemporaryDirectory() as d:
@@ -60,6 +63,7 @@ def main():
     r, b = res["reference"], res["b200"]
     if r["train_samples_per_s"] and b["train_samples_per_s"]:
         res["summary"] = {
+            "actor_duty_b200": a.actor_duty,
             "flags": "tools/dev.sh (iql, sad 1, shuffle_color 1, %d x %d games, batchsize 128, burn_in %d), epoch_len %d x %d epochs, actors and learner on cuda:0"
                      % (a.num_thread, a.num_game_per_thread, a.burn_in, a.epoch_len, a.num_epoch),
             "learner_updates_per_s": {"reference": r["train_samples_per_s"][-1] / 128, "b200": b["train_samples_per_s"][-1] / 128},

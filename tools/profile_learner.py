@@ -45,6 +45,8 @@ def main():
     ap.add_argument("--batchsize", type=int, default=128)
     ap.add_argument("--pred_weight", type=float, default=0.0)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--impl", default="reference", choices=["reference", "device"],
+                    help="reference: r2d2.R2D2Agent as is (cuDNN LSTM); device: hanabi_sad_b200.learner.DeviceLearner (LSTM on csrc/hb_lstm.cu)")
     a = ap.parse_args()
     import r2d2
     from hanabi_sad_b200.rela import RNNTransition
@@ -55,6 +57,10 @@ def main():
     torch.manual_seed(1)
     agent = r2d2.R2D2Agent(vdn, 3, 0.999, 0.9, dev, F, 512, A, 2, H, False).to(dev)
     agent.sync_target_with_online()
+    if a.impl == "device":
+        from hanabi_sad_b200.learner import DeviceLearner
+
+        agent = DeviceLearner.from_agent(agent, max_T=T, max_rows=a.batchsize * (P if vdn else 1))
     optim = torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
     obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, a.batchsize, P, F, A, H, vdn, dev)
     weight = torch.ones(a.batchsize, device=dev)
@@ -103,7 +109,7 @@ def main():
             total += dt / a.iters / 1e3
             launches += ev.count / a.iters
     rows.sort(reverse=True)
-    print(json.dumps({"method": a.method, "batchsize": a.batchsize, "pred_weight": a.pred_weight, "cudnn_allow_tf32": torch.backends.cudnn.allow_tf32,
+    print(json.dumps({"impl": a.impl, "method": a.method, "batchsize": a.batchsize, "pred_weight": a.pred_weight, "cudnn_allow_tf32": torch.backends.cudnn.allow_tf32,
                       "matmul_allow_tf32": torch.backends.cuda.matmul.allow_tf32, "wall_ms_per_update": wall_ms,
                       "cuda_kernel_ms_per_update": total, "kernel_launches_per_update": launches,
                       "top": [{"ms": round(r[0], 4), "n": r[1], "name": r[2]} for r in rows[:30]]}, indent=1))
