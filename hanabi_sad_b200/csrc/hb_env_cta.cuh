@@ -95,45 +95,33 @@ __device__ __forceinline__ void hb_cta_build_totals(const HbGame& s, HbEncTables
   }
 }
 
-// All threads of the CTA write the obs dict of one game (hanabi_env.cc:115-205) with coalesced stores.
+// All threads of the CTA write the obs dict of one game (hanabi_env.cc:115-205) with coalesced stores: observers
+// [p0, p0 + np) into buffers whose first row is observer p0 (np = P for the actors and VDN batches, 1 for an IQL entry).
 __device__ __forceinline__ void hb_cta_write_obs(const HbGame& s, const HbEncTables& t, const HbEnvCfg& cfg,
                                                  float* __restrict__ priv_s, float* __restrict__ legal,
                                                  float* __restrict__ own, float* __restrict__ eps,
                                                  const float* __restrict__ eps_list,
                                                  __nv_bfloat16* __restrict__ s_hi = nullptr, __nv_bfloat16* __restrict__ s_lo = nullptr,
-                                                 int KS = 0, float* __restrict__ r_priv_s = nullptr, float* __restrict__ r_legal = nullptr,
-                                                 float* __restrict__ r_own = nullptr, float* __restrict__ r_eps = nullptr) {
+                                                 int KS = 0, int p0 = 0, int np = -1) {
   const HbGeom& g = cfg.g;
+  if (np < 0) np = g.P;
   const int nt = blockDim.x, tid = threadIdx.x;
-  const int PF = g.P * g.F;
+  const int PF = np * g.F;
   for (int i = tid; i < PF; i += nt) {
     const int o = i / g.F, f = i - o * g.F;
-    const float v = hb_feature(s, t, cfg, o, f);
+    const float v = hb_feature(s, t, cfg, p0 + o, f);
     priv_s[i] = v;
-    if (r_priv_s != nullptr) r_priv_s[i] = v;  // replay slot, same [P][F] layout
     if (s_hi != nullptr) {  // GEMM operand: everything outside the belief block is 0/1, i.e. exact in bf16 (lo stays 0)
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       s_hi[o * KS + f] = hi;
       if (f >= g.off_belief && f < g.off_sad) s_lo[o * KS + f] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
   }
-  const int PA = g.P * g.A;
-  for (int i = tid; i < PA; i += nt) {
-    const float v = hb_legal_elem(s, cfg, i / g.A, i % g.A);
-    legal[i] = v;
-    if (r_legal != nullptr) r_legal[i] = v;
-  }
-  const int PO = g.P * 3 * g.H;
-  for (int i = tid; i < PO; i += nt) {
-    const float v = hb_own_hand_elem(s, i / (3 * g.H), i % (3 * g.H));
-    own[i] = v;
-    if (r_own != nullptr) r_own[i] = v;
-  }
-  if (tid < g.P) {
-    const float v = eps_list[s.eps_idx[tid]];
-    eps[tid] = v;
-    if (r_eps != nullptr) r_eps[tid] = v;
-  }
+  const int PA = np * g.A;
+  for (int i = tid; i < PA; i += nt) legal[i] = hb_legal_elem(s, cfg, p0 + i / g.A, i % g.A);
+  const int PO = np * 3 * g.H;
+  for (int i = tid; i < PO; i += nt) own[i] = hb_own_hand_elem(s, p0 + i / (3 * g.H), i % (3 * g.H));
+  if (tid < np) eps[tid] = eps_list[s.eps_idx[p0 + tid]];
 }
 
 // Zero the recurrent state of one game's agents (rows g*P .. g*P+P-1, every layer) -- all threads of the CTA.

@@ -1,5 +1,5 @@
 // hb_replay.cu -- host side and learner-facing kernels of the device replay (hb_replay.h): allocation of the
-// episode ring, stratified priority sampling + importance weights (PrioritizedReplay::sample_,
+// episode ring (board records, not observations: hb_replay.h), stratified priority sampling + importance weights (PrioritizedReplay::sample_,
 // rela/prioritized_replay.h:274-345), batch assembly in the learner's [T, B, ...] layout with terminal padding
 // (RNNTransition::makeBatch, rela/transition.cc:160-202; FFTransition::padLike, :29-40) and priority write-back
 // (ConcurrentQueue::update, prioritized_replay.h:106-120).  The producer side (append / finalize / commit) is part of
@@ -92,9 +92,13 @@ struct HbBatchPtrs {
   float* reward; float* bootstrap; uint8_t* terminal; float* seq_len;
 };
 
-// grid (B, T): one CTA copies step t of sampled entry b into the [T, B, (P,) ...] batch; steps at or beyond the episode
-// length are the reference's padding (zeros, terminal = 1).
-__global__ void __launch_bounds__(128) hb_k_replay_gather(HbRing R, const int* __restrict__ idx, int B, HbBatchPtrs out) {
+// grid (B, T): one CTA re-encodes step t of sampled entry b from its stored board record into the [T, B, (P,) ...]
+// batch (the same hb_feature code the actors' observations came from: bit-exact); steps at or beyond the episode length
+// are the reference's padding (zeros, terminal = 1).
+__global__ void __launch_bounds__(128) hb_k_replay_gather(HbRing R, const int* __restrict__ idx, int B, HbBatchPtrs out, HbEnvCfg cfg,
+                                                          const float* __restrict__ eps_list) {
+  __shared__ HbGame s;
+  __shared__ HbEncTables tab;
   const int b = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
   const int entry = idx[b];
   if (entry < 0) return;                       // hb_replay_get: lookup failed, reported by the host
@@ -106,11 +110,22 @@ __global__ void __launch_bounds__(128) hb_k_replay_gather(HbRing R, const int* _
   const size_t src = ((size_t)slot * R.T + t) * R.P + p0;   // (slot, t, p0) in units of one player's row
   const size_t dst = ((size_t)t * B + b) * PP;
   const int nF = PP * R.F, nA = PP * R.A, nO = PP * R.OH;
-  for (int i = tid; i < nF; i += blockDim.x) out.priv_s[dst * R.F + i] = live ? R.priv_s[src * R.F + i] : 0.f;
-  for (int i = tid; i < nA; i += blockDim.x) out.legal[dst * R.A + i] = live ? R.legal[src * R.A + i] : 0.f;
-  for (int i = tid; i < nO; i += blockDim.x) out.own_hand[dst * R.OH + i] = live ? R.own_hand[src * R.OH + i] : 0.f;
+  if (live) {
+    if (tid < 16) reinterpret_cast<uint4*>(&s)[tid] = reinterpret_cast<const uint4*>(R.states + (size_t)slot * R.T + t)[tid];
+    __syncthreads();
+    hb_cta_build_tables(s, tab, cfg.g);
+    __syncthreads();
+    hb_cta_build_totals(s, tab, cfg.g);
+    __syncthreads();
+    hb_cta_write_obs(s, tab, cfg, out.priv_s + dst * R.F, out.legal + dst * R.A, out.own_hand + dst * R.OH, out.eps + dst, eps_list, nullptr, nullptr, 0,
+                     p0, PP);
+  } else {
+    for (int i = tid; i < nF; i += blockDim.x) out.priv_s[dst * R.F + i] = 0.f;
+    for (int i = tid; i < nA; i += blockDim.x) out.legal[dst * R.A + i] = 0.f;
+    for (int i = tid; i < nO; i += blockDim.x) out.own_hand[dst * R.OH + i] = 0.f;
+    if (tid < PP) out.eps[dst + tid] = 0.f;
+  }
   if (tid < PP) {
-    out.eps[dst + tid] = live ? R.eps[src + tid] : 0.f;
     out.a[dst + tid] = live ? R.a[src + tid] : 0;
     out.greedy_a[dst + tid] = live ? R.greedy_a[src + tid] : 0;
   }
@@ -175,10 +190,7 @@ int hb_replay_create(hb_engine* e) {
   R.uniform_priority = c.priority_mode == 1;
   Q->beta = c.beta; Q->seed = c.seed ^ 0x5851F42D4C957F2DULL;
   const size_t S = R.phys_slots, T = R.T, P = R.P, G = e->G;
-  HB_RALLOC(R.priv_s, S * T * P * R.F * sizeof(float));
-  HB_RALLOC(R.legal, S * T * P * R.A * sizeof(float));
-  HB_RALLOC(R.own_hand, S * T * P * R.OH * sizeof(float));
-  HB_RALLOC(R.eps, S * T * P * sizeof(float));
+  HB_RALLOC(R.states, S * T * sizeof(HbGame));
   HB_RALLOC(R.a, S * T * P * sizeof(int64_t));
   HB_RALLOC(R.greedy_a, S * T * P * sizeof(int64_t));
   HB_RALLOC(R.reward, S * T * sizeof(float));
@@ -207,7 +219,7 @@ void hb_replay_destroy(hb_engine* e) {
   HbReplay* Q = e->replay;
   if (!Q) return;
   HbRing& R = Q->ring;
-  cudaFree(R.priv_s); cudaFree(R.legal); cudaFree(R.own_hand); cudaFree(R.eps); cudaFree(R.a); cudaFree(R.greedy_a); cudaFree(R.reward);
+  cudaFree(R.states); cudaFree(R.a); cudaFree(R.greedy_a); cudaFree(R.reward);
   cudaFree(R.bootstrap); cudaFree(R.seq_len); cudaFree(R.weight); cudaFree(R.commit_seq); cudaFree(R.state); cudaFree(R.game_slot);
   cudaFree(R.sc_reward); cudaFree(R.sc_oq); cudaFree(R.sc_tq); cudaFree(R.counters);
   cudaFree(Q->prefix); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio);
@@ -253,7 +265,7 @@ int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) {
   hb_k_replay_draw<<<1, threads, 0, e->stream>>>(R, Q->prefix, tot, batchsize, Q->beta, Q->seed, Q->sample_count, Q->sampled_idx, Q->sampled_seq,
                                                  Q->sampled_w, out->weight);
   HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
-  hb_k_replay_gather<<<dim3(batchsize, R.T), 128, 0, e->stream>>>(R, Q->sampled_idx, batchsize, bp);
+  hb_k_replay_gather<<<dim3(batchsize, R.T), 128, 0, e->stream>>>(R, Q->sampled_idx, batchsize, bp, e->env, e->d_eps_list);
   HB_CUDA(cudaGetLastError());
   if (out->ids) HB_CUDA(cudaMemcpyAsync(out->ids, Q->sampled_idx, batchsize * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
   HB_CUDA(cudaStreamSynchronize(e->stream));  // the batch tensors are consumed on the caller's own stream
@@ -276,7 +288,7 @@ int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out) {
   HB_CUDA(cudaMemsetAsync(d_entry, 0xFF, sizeof(int), e->stream));
   hb_k_replay_find<<<(R.phys_slots + 255) / 256, 256, 0, e->stream>>>(R, (long long)idx, d_entry);
   HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
-  hb_k_replay_gather<<<dim3(1, R.T), 128, 0, e->stream>>>(R, d_entry, 1, bp);
+  hb_k_replay_gather<<<dim3(1, R.T), 128, 0, e->stream>>>(R, d_entry, 1, bp, e->env, e->d_eps_list);
   HB_CUDA(cudaGetLastError());
   int h_entry = -1;
   HB_CUDA(cudaMemcpyAsync(&h_entry, d_entry, sizeof(int), cudaMemcpyDeviceToHost, e->stream));

@@ -1,7 +1,10 @@
 // hb_replay.h -- device-resident prioritized episode replay: what rela/transition_buffer.h (MultiStepBuffer,
 // R2D2Buffer), rela/r2d2_actor.h postAct and rela/prioritized_replay.h keep in host deques of tensor dicts lives here
-// as one ring of fixed-size episode slots in HBM.  A game writes its observations straight into the slot it claimed
-// when its episode began; at the terminal step its CTA turns the raw rewards into n-step returns, computes the
+// as one ring of fixed-size episode slots in HBM.  A slot does NOT hold observations: it holds, per step, the 256-byte
+// board record the observation was encoded from ("replay compression": 256 B instead of P*(F+A+3H+1)*4 =
+// 7 KB per step at 2 players).  Every feature is a pure function of that record (hb_env.cuh), so the sampling kernel
+// re-expands the reference's padded fp32 episode bit-exactly with the very code that produced the actors' observations.
+// A game writes the record straight into the slot it claimed when its episode began; at the terminal step its CTA turns the raw rewards into n-step returns, computes the
 // per-step priorities from the Q-values the policy kernel left behind, aggregates them and commits the slot.
 #pragma once
 #include <stdint.h>
@@ -18,10 +21,7 @@ struct HbRing {                 // device pointers + geometry, passed by value t
   int n_step;
   float gamma, gamma_n, eta, alpha;
   int uniform_priority;
-  float* priv_s;                // [phys][T][P][F]
-  float* legal;                 // [phys][T][P][A]
-  float* own_hand;              // [phys][T][P][OH]
-  float* eps;                   // [phys][T][P]
+  HbGame* states;               // [phys][T]   board record behind the observation of step t (re-encoded when sampled)
   int64_t* a;                   // [phys][T][P]
   int64_t* greedy_a;            // [phys][T][P]
   float* reward;                // [phys][T]   n-step return (transition_buffer.h:83-90)

@@ -8,8 +8,9 @@
 //      (r2d2.py:344-358), eta-aggregate (r2d2_actor.h:10-21), weight = priority^alpha, commit the slot
 //      (prioritized_replay.h:192-197); zero the agents' LSTM state (r2d2_actor.h:113-126); start the next episode
 //      (HanabiEnv::reset, hanabi_env.cc:9-47) in a freshly claimed slot;
-//   4. encode the observation (hanabi_env.cc:115-205) ONCE into three places: the obs dict buffers, the replay slot
-//      at step index ep_len, and the bf16 hi/lo operand of the policy's first GEMM.
+//   4. encode the observation (hanabi_env.cc:115-205) ONCE into the obs dict buffers and the bf16 hi/lo operand of the
+//      policy's first GEMM; the replay slot receives the 256-byte board record the observation is a function of
+//      (hb_replay.h), at step index ep_len.
 //
 // The policy forward (hb_policy.cu: 3 tcgen05 GEMM launches + head/act kernel) follows on the same stream; nothing
 // returns to the host between ticks.
@@ -187,11 +188,11 @@ __global__ void __launch_bounds__(HB_TICK_THREADS) hb_k_tick(const __grid_consta
   const HbObsPtrs& O = A.obs;
   const int t_obs = s.ep_len;
   const bool to_ring = slot >= 0 && !s.terminated && t_obs < R.T;
-  const size_t ro = ((size_t)(to_ring ? slot : 0) * R.T + (to_ring ? t_obs : 0)) * P;
   hb_cta_write_obs(s, tab, cfg, O.priv_s + (size_t)g * P * geo.F, O.legal_move + (size_t)g * P * geo.A, O.own_hand + (size_t)g * P * 3 * geo.H,
                    O.eps + (size_t)g * P, A.eps_list, O.s_hi ? O.s_hi + (size_t)g * P * O.KS : nullptr,
-                   O.s_lo ? O.s_lo + (size_t)g * P * O.KS : nullptr, O.KS, to_ring ? R.priv_s + ro * geo.F : nullptr,
-                   to_ring ? R.legal + ro * geo.A : nullptr, to_ring ? R.own_hand + ro * 3 * geo.H : nullptr, to_ring ? R.eps + ro : nullptr);
+                   O.s_lo ? O.s_lo + (size_t)g * P * O.KS : nullptr, O.KS);
+  if (tid >= 32 && tid < 48 && to_ring)   // the replay keeps the record, not the observation (re-encoded by hb_k_replay_gather)
+    reinterpret_cast<uint4*>(R.states + (size_t)slot * R.T + t_obs)[tid - 32] = reinterpret_cast<const uint4*>(&s)[tid - 32];
   if (tid < 16) reinterpret_cast<uint4*>(A.games + g)[tid] = reinterpret_cast<const uint4*>(&s)[tid];
   else if (tid < 20) reinterpret_cast<uint4*>(A.decks + (size_t)g * HB_DECK_STRIDE)[tid - 16] = reinterpret_cast<const uint4*>(deck)[tid - 16];
 }
