@@ -213,6 +213,7 @@ int hb_env_step(hb_engine* e, const int64_t* a, const int64_t* greedy_a, float* 
 int hb_env_observe(hb_engine* e, float* priv_s, float* legal_move, float* own_hand, float* eps) {
   if (!e) return hb_fail(-1, "hb_env_observe: null engine");
   HB_CUDA(cudaSetDevice(e->device));
+  if (priv_s || own_hand) { const int rc = hb_refresh_obs(e); if (rc) return rc; }
   const size_t R = (size_t)e->rows;
   if (priv_s) HB_CUDA(cudaMemcpyAsync(priv_s, e->obs.priv_s, R * e->F * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   if (legal_move) HB_CUDA(cudaMemcpyAsync(legal_move, e->obs.legal_move, R * e->A * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -225,6 +226,7 @@ int hb_env_observe(hb_engine* e, float* priv_s, float* legal_move, float* own_ha
 int hb_env_observe_dev(hb_engine* e, const float** priv_s, const float** legal_move, const float** own_hand,
                        const float** eps, const float** reward, const uint8_t** terminal) {
   if (!e) return hb_fail(-1, "hb_env_observe_dev: null engine");
+  if (priv_s || own_hand) { HB_CUDA(cudaSetDevice(e->device)); const int rc = hb_refresh_obs(e); if (rc) return rc; }
   if (priv_s) *priv_s = e->obs.priv_s;
   if (legal_move) *legal_move = e->obs.legal_move;
   if (own_hand) *own_hand = e->obs.own_hand;

@@ -59,6 +59,7 @@ struct hb_engine {
   double prof_ms[HB_PROF_N];
   int64_t prof_n[HB_PROF_N];
   int pending_actions;   // d_a / d_greedy_a hold a reply the environment has not consumed yet
+  int obs_stale;         // obs.priv_s / obs.own_hand are older than the board records (the fused tick does not write them)
   int64_t num_act;       // sum of R2D2Actor::numAct_ (r2d2_actor.h:98): env-steps acted on
 
   // ---- environment
@@ -104,3 +105,4 @@ int hb_launch_tick(hb_engine* e, int do_step, int do_reset);  // hb_rollout.cu
 int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev);
 int hb_launch_random_actions(hb_engine* e, uint64_t counter);
 int hb_launch_check_invariants(hb_engine* e);
+int hb_refresh_obs(hb_engine* e);  // re-encode obs.priv_s / obs.own_hand from the board records if the fused tick left them stale

@@ -110,7 +110,7 @@ __device__ __forceinline__ void hb_cta_write_obs(const HbGame& s, const HbEncTab
   for (int i = tid; i < PF; i += nt) {
     const int o = i / g.F, f = i - o * g.F;
     const float v = hb_feature(s, t, cfg, p0 + o, f);
-    priv_s[i] = v;
+    if (priv_s != nullptr) priv_s[i] = v;   // null: only the GEMM operand is wanted (fused rollout, see hb_refresh_obs)
     if (s_hi != nullptr) {  // GEMM operand: everything outside the belief block is 0/1, i.e. exact in bf16 (lo stays 0)
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       s_hi[o * KS + f] = hi;
@@ -120,7 +120,8 @@ __device__ __forceinline__ void hb_cta_write_obs(const HbGame& s, const HbEncTab
   const int PA = np * g.A;
   for (int i = tid; i < PA; i += nt) legal[i] = hb_legal_elem(s, cfg, p0 + i / g.A, i % g.A);
   const int PO = np * 3 * g.H;
-  for (int i = tid; i < PO; i += nt) own[i] = hb_own_hand_elem(s, p0 + i / (3 * g.H), i % (3 * g.H));
+  if (own != nullptr)
+    for (int i = tid; i < PO; i += nt) own[i] = hb_own_hand_elem(s, p0 + i / (3 * g.H), i % (3 * g.H));
   if (tid < np) eps[tid] = eps_list[s.eps_idx[p0 + tid]];
 }
 

@@ -52,6 +52,32 @@ hb_k_env(HbGame* __restrict__ games, uint8_t* __restrict__ decks, HbInject* __re
   else if (tid < 20) reinterpret_cast<uint4*>(decks + (size_t)g * HB_DECK_STRIDE)[tid - 16] = reinterpret_cast<const uint4*>(deck)[tid - 16];
 }
 
+// Encode-only pass: the fp32 obs dict of every game from its current board record (same device code as hb_k_env / the
+// fused tick, so the values are the ones those kernels would have written).
+__global__ void __launch_bounds__(HB_ENV_THREADS) hb_k_encode(const HbGame* __restrict__ games, HbEnvCfg cfg, HbObsPtrs obs, const float* __restrict__ eps_list) {
+  __shared__ HbGame s;
+  __shared__ HbEncTables tab;
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const HbGeom& geo = cfg.g;
+  if (tid < 16) reinterpret_cast<uint4*>(&s)[tid] = reinterpret_cast<const uint4*>(games + g)[tid];
+  __syncthreads();
+  hb_cta_build_tables(s, tab, geo);
+  __syncthreads();
+  hb_cta_build_totals(s, tab, geo);
+  __syncthreads();
+  hb_cta_write_obs(s, tab, cfg, obs.priv_s + (size_t)g * geo.P * geo.F, obs.legal_move + (size_t)g * geo.P * geo.A,
+                   obs.own_hand + (size_t)g * geo.P * 3 * geo.H, obs.eps + (size_t)g * geo.P, eps_list);
+}
+
+int hb_refresh_obs(hb_engine* e) {
+  if (!e->obs_stale) return 0;
+  hb_k_encode<<<e->G, HB_ENV_THREADS, 0, e->stream>>>(e->d_games, e->env, e->obs, e->d_eps_list);
+  HB_CUDA(cudaGetLastError());
+  e->launches += 1;
+  e->obs_stale = 0;
+  return 0;
+}
+
 // Uniform-random legal action per agent (the role of `legal_move.multinomial(1)` in r2d2.py:273), one thread
 // per (game, player).  greedy_a gets an independent draw so the SAD block is exercised.
 __global__ void hb_k_random_actions(const float* __restrict__ legal, int rows, int A, uint64_t seed, uint64_t counter,
@@ -123,6 +149,7 @@ int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev,
                                                    e->d_flags, hb_policy_hidden_ptrs(e));
   HB_CUDA(cudaGetLastError());
   e->launches += 1;
+  e->obs_stale = 0;   // hb_k_env writes the whole obs dict
   return 0;
 }
 

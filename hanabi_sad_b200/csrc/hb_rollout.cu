@@ -8,8 +8,8 @@
 //      (r2d2.py:344-358), eta-aggregate (r2d2_actor.h:10-21), weight = priority^alpha, commit the slot
 //      (prioritized_replay.h:192-197); zero the agents' LSTM state (r2d2_actor.h:113-126); start the next episode
 //      (HanabiEnv::reset, hanabi_env.cc:9-47) in a freshly claimed slot;
-//   4. encode the observation (hanabi_env.cc:115-205) ONCE into the obs dict buffers and the bf16 hi/lo operand of the
-//      policy's first GEMM; the replay slot receives the 256-byte board record the observation is a function of
+//   4. encode the observation (hanabi_env.cc:115-205) ONCE into the bf16 hi/lo operand of the policy's first GEMM (plus
+//      legal_move / eps for the act kernel; the fp32 priv_s / own_hand of the obs dict only on demand, hb_refresh_obs); the replay slot receives the 256-byte board record the observation is a function of
 //      (hb_replay.h), at step index ep_len.
 //
 // The policy forward (hb_policy.cu: 3 tcgen05 GEMM launches + head/act kernel) follows on the same stream; nothing
@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(HB_TICK_THREADS) hb_k_tick(const __grid_consta
   const HbObsPtrs& O = A.obs;
   const int t_obs = s.ep_len;
   const bool to_ring = slot >= 0 && !s.terminated && t_obs < R.T;
-  hb_cta_write_obs(s, tab, cfg, O.priv_s + (size_t)g * P * geo.F, O.legal_move + (size_t)g * P * geo.A, O.own_hand + (size_t)g * P * 3 * geo.H,
-                   O.eps + (size_t)g * P, A.eps_list, O.s_hi ? O.s_hi + (size_t)g * P * O.KS : nullptr,
+  // the fp32 obs dict (priv_s, own_hand) has no reader inside the rollout: the policy consumes the bf16 operand, the replay
+  // the board record.  It is materialised on demand by hb_refresh_obs when the host asks for it (hb_env_observe*).
+  hb_cta_write_obs(s, tab, cfg, nullptr, O.legal_move + (size_t)g * P * geo.A, nullptr, O.eps + (size_t)g * P, A.eps_list, O.s_hi ? O.s_hi + (size_t)g * P * O.KS : nullptr,
                    O.s_lo ? O.s_lo + (size_t)g * P * O.KS : nullptr, O.KS);
   if (tid >= 32 && tid < 48 && to_ring)   // the replay keeps the record, not the observation (re-encoded by hb_k_replay_gather)
     reinterpret_cast<uint4*>(R.states + (size_t)slot * R.T + t_obs)[tid - 32] = reinterpret_cast<const uint4*>(&s)[tid - 32];
@@ -239,6 +240,7 @@ int hb_rollout(hb_engine* e, int n_ticks) {
     rc = hb_policy_forward(e, 0);
     if (rc) return rc;
     e->pending_actions = 1;
+    e->obs_stale = 1;
     e->num_act += e->G;
     if (e->prof_on) {  // profiling mode: one sync per tick, accumulate the five launch durations
       HB_CUDA(cudaStreamSynchronize(e->stream));

@@ -106,7 +106,10 @@ int hb_env_step(hb_engine* e, const int64_t* a, const int64_t* greedy_a, float* 
  * own_hand [G,P,3H], eps [G,P].  Any pointer may be NULL. */
 int hb_env_observe(hb_engine* e, float* priv_s, float* legal_move, float* own_hand, float* eps);
 
-/* Same data without the host copy: device pointers valid until hb_destroy (layouts as above). */
+/* Same data without the host copy: device pointers valid until hb_destroy (layouts as above).  The fused hb_rollout
+ * does not keep the fp32 priv_s / own_hand up to date (nothing on the device reads them: the policy consumes a bf16
+ * operand, the replay the board record); asking for them here (or in hb_env_observe) re-encodes them from the current
+ * board records first, so call this again after a rollout rather than caching the contents. */
 int hb_env_observe_dev(hb_engine* e, const float** priv_s, const float** legal_move, const float** own_hand,
                        const float** eps, const float** reward, const uint8_t** terminal);
 
