@@ -647,6 +647,9 @@ struct hb_lstm {
   float* dwp;                               // [4][2048][512]
   unsigned* ctr;
   int* d_error;
+  int* h_error;                             // pinned mirror of d_error, filled asynchronously at the end of every call
+  cudaEvent_t ev_done;
+  int check_pending;
   hbl::FwdParams* d_fwd;                    // [2 layers]
   hbl::BwdParams* d_bwd;                    // [2 layers]
   Params* d_gemm;                           // [16]
@@ -723,6 +726,9 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   HBL_ALLOC(L->dwp, 4 * WN * sizeof(float));
   HBL_ALLOC(L->ctr, 16 * hbl::CTR_STRIDE * sizeof(unsigned));
   HBL_ALLOC(L->d_error, sizeof(int));
+  HB_CUDA(cudaMallocHost((void**)&L->h_error, sizeof(int)));
+  *L->h_error = 0;
+  HB_CUDA(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
   HBL_ALLOC(L->d_fwd, 2 * sizeof(hbl::FwdParams));
   HBL_ALLOC(L->d_bwd, 2 * sizeof(hbl::BwdParams));
   HBL_ALLOC(L->d_gemm, 16 * sizeof(Params));
@@ -755,16 +761,28 @@ void hb_lstm_destroy(hb_lstm* L) {
   }
   cudaFree(L->dh0); cudaFree(L->dx_pad); cudaFree(L->part); cudaFree(L->dwp); cudaFree(L->ctr); cudaFree(L->d_error);
   cudaFree(L->d_fwd); cudaFree(L->d_bwd); cudaFree(L->d_gemm);
+  cudaFreeHost(L->h_error); cudaEventDestroy(L->ev_done);
   delete L;
 }
 
-static int hbl_check_error(hb_lstm* L, cudaStream_t st, const char* what) {
-  int herr = 0;
-  HB_CUDA(cudaMemcpyAsync(&herr, L->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
-  HB_CUDA(cudaStreamSynchronize(st));
-  if (herr) {
-    cudaMemsetAsync(L->d_error, 0, sizeof(int), st);
-    hb_set_error("%s: a pipeline / step barrier timed out (spin guard, code %d)", what, herr);
+// The calls are asynchronous (work is queued on the caller's stream).  The kernels' spin guards raise d_error; its value
+// travels to a pinned mirror at the end of every call and is examined at the START of the next one (or by hb_lstm_sync).
+static int hbl_finish_call(hb_lstm* L, cudaStream_t st) {
+  HB_CUDA(cudaMemcpyAsync(L->h_error, L->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HB_CUDA(cudaEventRecord(L->ev_done, st));
+  L->check_pending = 1;
+  return 0;
+}
+static int hbl_check_previous(hb_lstm* L, bool wait) {
+  if (!L->check_pending) return 0;
+  if (wait) HB_CUDA(cudaEventSynchronize(L->ev_done));
+  else if (cudaEventQuery(L->ev_done) != cudaSuccess) { (void)cudaGetLastError(); return 0; }   // still running: examined later
+  L->check_pending = 0;
+  if (*L->h_error) {
+    const int code = *L->h_error;
+    *L->h_error = 0;
+    cudaMemset(L->d_error, 0, sizeof(int));
+    hb_set_error("hb_lstm: a pipeline / step barrier of an earlier call timed out (spin guard, code %d)", code);
     return -4;
   }
   return 0;
@@ -781,6 +799,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
       if (!w[n].w_ih[l] || !w[n].w_hh[l] || !w[n].b_ih[l] || !w[n].b_hh[l]) { hb_set_error("hb_lstm_forward: null weight pointer"); return -1; }
   }
   HB_CUDA(cudaSetDevice(L->device));
+  { const int prc = hbl_check_previous(L, false); if (prc) return prc; }
   cudaStream_t st = (cudaStream_t)stream;
   const int R_pad = (rows + BM - 1) / BM * BM, MB = R_pad / BM;
   const size_t N = (size_t)T * R_pad;
@@ -872,10 +891,8 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
       L->launches += 1;
     }
   }
-  rc = hbl_check_error(L, st, "hb_lstm_forward");   // also makes the host-side Params / vectors safe to drop
-  if (rc) return rc;
   L->saved = save ? 1 : 0;
-  return 0;
+  return hbl_finish_call(L, st);
 }
 
 int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads* g, void* stream) {
@@ -884,6 +901,7 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
   for (int l = 0; l < 2; ++l)
     if (!g->dw_ih[l] || !g->dw_hh[l] || !g->db_ih[l] || !g->db_hh[l]) { hb_set_error("hb_lstm_backward: null gradient pointer"); return -1; }
   HB_CUDA(cudaSetDevice(L->device));
+  { const int prc = hbl_check_previous(L, false); if (prc) return prc; }
   cudaStream_t st = (cudaStream_t)stream;
   const int T = L->T, rows = L->rows, R_pad = L->R_pad, MB = L->MB;
   const size_t N = (size_t)T * R_pad;
@@ -939,7 +957,13 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
   for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, st>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
   HB_CUDA(cudaGetLastError());
   L->launches += 6;
-  return hbl_check_error(L, st, "hb_lstm_backward");
+  return hbl_finish_call(L, st);
+}
+
+int hb_lstm_sync(hb_lstm* L) {
+  if (!L) { hb_set_error("hb_lstm_sync: null handle"); return -1; }
+  HB_CUDA(cudaSetDevice(L->device));
+  return hbl_check_previous(L, true);
 }
 
 int64_t hb_lstm_launches(const hb_lstm* L) { return L ? L->launches : 0; }

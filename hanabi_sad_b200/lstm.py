@@ -49,6 +49,11 @@ class LstmWorkspace:
         except Exception:
             pass
 
+    def sync(self):
+        """Wait for the queued kernels and raise if a device-side guard fired (the calls themselves are asynchronous)."""
+        if self._h is not None:
+            check(lib().hb_lstm_sync(self._h))
+
     def launches(self):
         return int(lib().hb_lstm_launches(self._handle()))
 

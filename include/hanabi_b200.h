@@ -240,13 +240,18 @@ void hb_lstm_destroy(hb_lstm* l);
 /* nn.LSTM.forward for `nets` (1 or 2) independent networks in one pass -- the reference calls online_net and target_net
  * on the same batch back to back (r2d2.py:398-401).  x[n], y[n]: device float [T, rows, 512] (input / top-layer output
  * sequence of network n), w[n] its parameters.  save != 0 keeps network 0's activations for hb_lstm_backward.
- * `stream`: cudaStream_t the work is queued on (e.g. torch's current stream); returns after it completed. */
+ * `stream`: cudaStream_t the work is queued on (e.g. torch's current stream).  Asynchronous: returns once everything is
+ * queued; buffers must stay valid until the stream reaches that point (stream-ordered allocators do that by themselves).
+ * A device-side failure (a spin guard of the persistent kernels) is reported by the NEXT hb_lstm_* call or hb_lstm_sync. */
 int hb_lstm_forward(hb_lstm* l, int T, int rows, int nets, const float* const* x, const hb_lstm_weights* w, float* const* y,
                     int save, void* stream);
 
 /* Backward of network 0 of the last saving forward: dy = dLoss/dy [T, rows, 512] -> dx = dLoss/dx [T, rows, 512] (may be
  * NULL) and the parameter gradients. */
 int hb_lstm_backward(hb_lstm* l, const float* dy, float* dx, const hb_lstm_grads* g, void* stream);
+
+/* Waits for the last hb_lstm_forward / hb_lstm_backward and reports its device-side status. */
+int hb_lstm_sync(hb_lstm* l);
 
 int64_t hb_lstm_launches(const hb_lstm* l); /* kernels launched through this handle so far */
 

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--target_sync_freq", type=int, default=2500)
     ap.add_argument("--ticks_per_update", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--device_learner", type=int, default=0, help="1: run the reference loss on hanabi_sad_b200.learner.DeviceLearner (LSTM on csrc/hb_lstm.cu)")
     a = ap.parse_args()
 
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -54,6 +55,10 @@ def main():
     torch.manual_seed(a.seed)  # same initial weights on every rank
     agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, dev, eng.F, 512, eng.A, 2, 5, False).to(dev)
     agent.sync_target_with_online()
+    if a.device_learner:
+        from hanabi_sad_b200.learner import DeviceLearner
+
+        agent = DeviceLearner.from_agent(agent, max_T=80, max_rows=max(1, a.batchsize // world) * 2)
     optim = torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
 
     def push_weights():
@@ -109,7 +114,7 @@ def main():
     if rank == 0:
         print(json.dumps({"world": world, "games_per_gpu": a.games, "updates": a.updates, "updates_per_s": a.updates / dt, "loss_first": losses[0],
                           "loss_last": losses[-1], "finite": all(x == x and abs(x) < 1e9 for x in losses), "replica_weight_drift": drift,
-                          "env_steps_total": float(acts[0]), "replay_size_rank0": size}))
+                          "env_steps_total": float(acts[0]), "replay_size_rank0": size, "device_learner": bool(a.device_learner)}))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
