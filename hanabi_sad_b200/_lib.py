@@ -93,6 +93,7 @@ SIGNATURES = {
     "hb_lstm_backward": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(HbLstmGrads), c_void_p]),
     "hb_lstm_sync": (c_int, [c_void_p]),
     "hb_lstm_launches": (c_i64, [c_void_p]),
+    "hb_debug_operand": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int)]),
     "hb_sync": (c_int, [c_void_p]),
     "hb_stream": (c_void_p, [c_void_p]),
     "hb_kernel_launches": (c_i64, [c_void_p]),

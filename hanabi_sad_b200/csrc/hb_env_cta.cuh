@@ -106,7 +106,7 @@ __device__ __forceinline__ void hb_cta_write_obs(const HbGame& s, const HbEncTab
   const HbGeom& g = cfg.g;
   if (np < 0) np = g.P;
   const int nt = blockDim.x, tid = threadIdx.x;
-  const int PF = np * g.F;
+  const int PF = (priv_s != nullptr || s_hi != nullptr) ? np * g.F : 0;
   for (int i = tid; i < PF; i += nt) {
     const int o = i / g.F, f = i - o * g.F;
     const float v = hb_feature(s, t, cfg, p0 + o, f);
@@ -123,6 +123,165 @@ __device__ __forceinline__ void hb_cta_write_obs(const HbGame& s, const HbEncTab
   if (own != nullptr)
     for (int i = tid; i < PO; i += nt) own[i] = hb_own_hand_elem(s, p0 + i / (3 * g.H), i % (3 * g.H));
   if (tid < np) eps[tid] = eps_list[s.eps_idx[p0 + tid]];
+}
+
+// ---------------------------------------------------------------------------------------- fast operand encoder
+// The fused tick only needs priv_s as the bf16 hi/lo operand of the fc GEMM.  Evaluating every feature with hb_feature
+// costs ~118 warp instructions per 32 features (section cascade, index decomposition, an IEEE division per belief entry,
+// P-fold recomputation of observer-independent values).  This writer produces the SAME values (asserted against
+// hb_feature on the device in tests/test_rollout_parity.py::test_fast_operand_equals_feature_encoder) differently:
+//   1. every 0/1 feature of an observer's row is a bit of a shared-memory mask that starts as zero and receives the few
+//      ones by scatter (one-hot cards, thermometers as bit ranges, the <= 9 ones of a last-action block, hint one-hots);
+//   2. the belief fractions plausible * count / total (canonical_encoders.cc:553-563) are computed ONCE per game and card
+//      slot in real colour space, already split into bf16 hi/lo -- observers only differ by rotation and colour permutation;
+//   3. one coalesced pass writes the rows: a mask bit -> 0x3F80 / 0, a belief position -> the table entry.
+#define HB_MASK_WORDS 46          // ceil(max F / 32): 5 players, hand 4, sad -> F = 1439
+#define HB_BEL_ENTRIES (HB_MAX_P * HB_MAX_H * HB_NCARD)
+
+struct HbFastEnc {
+  uint32_t mask[HB_MAX_P][HB_MASK_WORDS];
+  uint32_t bel[HB_BEL_ENTRIES];   // (lo << 16) | hi for (player, slot, real card type)
+};
+
+__device__ __forceinline__ void hb_mask_set(uint32_t* row, int bit) { atomicOr(&row[bit >> 5], 1u << (bit & 31)); }
+__device__ __forceinline__ void hb_mask_range(uint32_t* row, int bit, int n) {  // bits [bit, bit + n), n <= 64
+  while (n > 0) {
+    const int w = bit >> 5, b = bit & 31, take = min(n, 32 - b);
+    atomicOr(&row[w], (take == 32 ? 0xFFFFFFFFu : ((1u << take) - 1u)) << b);
+    bit += take; n -= take;
+  }
+}
+// the ones of one last-action block (canonical_encoders.cc:293-422) for `observer`, block starting at bit `base`
+__device__ __forceinline__ void hb_mask_last_action(uint32_t* row, int base, const HbLastMove& lm, const HbGeom& g, int observer,
+                                                    uint16_t perm, bool shuffle) {
+  if (!lm.valid) return;
+  const int P = g.P, H = g.H;
+  const int rel = (lm.player - observer + P) % P;
+  const bool hint = lm.type == HB_MV_REVEAL_COLOR || lm.type == HB_MV_REVEAL_RANK;
+  const bool card_move = lm.type == HB_MV_PLAY || lm.type == HB_MV_DISCARD;
+  int o = base;
+  hb_mask_set(row, o + rel); o += P;
+  if (lm.type >= 1 && lm.type <= 4) hb_mask_set(row, o + lm.type - 1);
+  o += 4;
+  if (hint) hb_mask_set(row, o + (rel + lm.target_offset) % P);
+  o += P;
+  if (lm.type == HB_MV_REVEAL_COLOR) hb_mask_set(row, o + (shuffle ? hb_perm_get(perm, lm.color) : lm.color));
+  o += HB_NC;
+  if (lm.type == HB_MV_REVEAL_RANK && lm.rank < HB_NR) hb_mask_set(row, o + lm.rank);
+  o += HB_NR;
+  if (hint) for (int j = 0; j < H; ++j) if ((lm.reveal_mask >> j) & 1) hb_mask_set(row, o + j);
+  o += H;
+  if (card_move && lm.card_index < H) hb_mask_set(row, o + lm.card_index);
+  o += H;
+  if (card_move) {
+    const int shown = shuffle ? hb_perm_get(perm, lm.card_color) : lm.card_color;
+    const int k = shown * HB_NR + lm.card_rank;
+    if (k >= 0 && k < HB_NCARD) hb_mask_set(row, o + k);
+  }
+  o += HB_NCARD;
+  if (lm.type == HB_MV_PLAY) { if (lm.scored) hb_mask_set(row, o); if (lm.info_token) hb_mask_set(row, o + 1); }
+}
+
+// All threads of the CTA; `t` must hold pub_count and belief_total (hb_cta_build_tables / _totals + sync).  Writes the rows
+// of all P observers: hi for every feature, lo for the belief block (elsewhere lo stays 0 from allocation, as before).
+__device__ __forceinline__ void hb_cta_write_operand_fast(const HbGame& s, const HbEncTables& t, const HbEnvCfg& cfg, HbFastEnc& E,
+                                                          __nv_bfloat16* __restrict__ s_hi, __nv_bfloat16* __restrict__ s_lo, int KS) {
+  const HbGeom& g = cfg.g;
+  const int P = g.P, H = g.H, F = g.F, nt = blockDim.x, tid = threadIdx.x;
+  const bool shuffle = cfg.shuffle_color != 0;
+  const int MW = (F + 31) >> 5;
+  for (int i = tid; i < P * HB_MASK_WORDS; i += nt) E.mask[i / HB_MASK_WORDS][i % HB_MASK_WORDS] = 0u;
+  // belief fractions per (player, slot, real card type)
+  for (int i = tid; i < P * H * HB_NCARD; i += nt) {
+    const int ps = i / HB_NCARD, k = i - ps * HB_NCARD, p = ps / H, slot = ps - p * H;
+    float v = 0.f;
+    if (slot < s.hand_len[p]) {
+      const unsigned kn = s.know[p][slot];
+      const int c = k / HB_NR, r = k - c * HB_NR;
+      if (((kn >> c) & 1u) && ((kn >> (5 + r)) & 1u)) {
+        const float total = t.belief_total[p][slot];
+        v = total > 0.f ? HB_FDIV((float)t.pub_count[k], total) : 0.f;
+      }
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    E.bel[i] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+  }
+  __syncthreads();
+  // ---- scatter the ones.  Task list per observer o (tasks are independent; atomicOr on shared memory):
+  //   [0, P*H)            card slots of the hands block + the belief hint one-hots of the same (rel, slot)
+  //   [P*H, P*H + P)      "hand shorter than H" bits
+  //   P*H + P + {0,1,2,3} deck / fireworks / info / life
+  //   then 25 discard thermometers, then the last-action block and the SAD block
+  const int n_task = P * H + P + 4 + HB_NCARD + 2;
+  for (int i = tid; i < P * n_task; i += nt) {
+    const int o = i / n_task;
+    int k = i - o * n_task;
+    uint32_t* row = E.mask[o];
+    const uint16_t perm = s.perm[o], inv = s.inv_perm[o];
+    if (k < P * H) {
+      const int rel = k / H, slot = k - rel * H, p = (o + rel) % P;
+      if (slot < s.hand_len[p]) {
+        if (rel != 0) {  // own cards are hidden (canonical_encoders.cc:88-95)
+          const int card = s.hand_card[p][slot], c = card / HB_NR, r = card - c * HB_NR;
+          hb_mask_set(row, k * HB_NCARD + (shuffle ? hb_perm_get(perm, c) : c) * HB_NR + r);
+        }
+        const unsigned kn = s.know[p][slot];
+        const int hc = (kn >> 10) & 7, hr = (kn >> 13) & 7;
+        const int b0 = g.off_belief + k * 35 + HB_NCARD;
+        if (hc != 7) hb_mask_set(row, b0 + (shuffle ? hb_perm_get(perm, hc) : hc));
+        if (hr != 7) hb_mask_set(row, b0 + HB_NC + hr);
+      }
+      continue;
+    }
+    k -= P * H;
+    if (k < P) { if (s.hand_len[(o + k) % P] < H) hb_mask_set(row, P * H * HB_NCARD + k); continue; }
+    k -= P;
+    if (k == 0) { hb_mask_range(row, g.off_board, min(g.deck_bits, HB_DECK - (int)s.deck_pos)); continue; }
+    if (k == 1) {
+      for (int sc = 0; sc < HB_NC; ++sc) {
+        const int fw = s.fireworks[shuffle ? hb_perm_get(inv, sc) : sc];
+        if (fw > 0) hb_mask_set(row, g.off_board + g.deck_bits + sc * HB_NR + fw - 1);
+      }
+      continue;
+    }
+    if (k == 2) { hb_mask_range(row, g.off_board + g.deck_bits + HB_NCARD, min((int)s.info, HB_MAX_INFO)); continue; }
+    if (k == 3) { hb_mask_range(row, g.off_board + g.deck_bits + HB_NCARD + HB_MAX_INFO, min((int)s.life, HB_MAX_LIFE)); continue; }
+    k -= 4;
+    if (k < HB_NCARD) {  // discard thermometer of shown colour sc, rank r: widths 3,2,2,2,1 (canonical_encoders.cc:252-280)
+      const int sc = k / HB_NR, r = k - sc * HB_NR;
+      const int real_c = shuffle ? hb_perm_get(inv, sc) : sc;
+      const int n = min((int)s.discard_count[real_c * HB_NR + r], hb_card_mult(r));
+      hb_mask_range(row, g.off_discard + sc * 10 + (r == 0 ? 0 : 2 * r + 1), n);
+      continue;
+    }
+    k -= HB_NCARD;
+    if (k == 0) hb_mask_last_action(row, g.off_last, s.last, g, o, perm, shuffle);
+    else if (g.sad) hb_mask_last_action(row, g.off_sad, s.greedy_valid ? s.greedy : s.last, g, o, perm, shuffle);
+  }
+  __syncthreads();
+  // ---- one coalesced pass over the rows
+  const int bel_len = P * H * 35;
+  for (int i = tid; i < P * F; i += nt) {
+    const int o = i / F, f = i - o * F;
+    const int j = f - g.off_belief;
+    uint32_t hi = ((E.mask[o][f >> 5] >> (f & 31)) & 1u) ? 0x3F80u : 0u;
+    if (j >= 0 && j < bel_len) {
+      const int rs = j / 35, kk = j - rs * 35;
+      if (kk < HB_NCARD) {
+        const int rel = rs / H, slot = rs - rel * H, p = (o + rel) % P;
+        const int sc = kk / HB_NR, r = kk - sc * HB_NR;
+        const int real_c = shuffle ? hb_perm_get(s.inv_perm[o], sc) : sc;
+        const uint32_t e = E.bel[(p * H + slot) * HB_NCARD + real_c * HB_NR + r];
+        hi = e & 0xFFFFu;
+        s_lo[o * KS + f] = __ushort_as_bfloat16((unsigned short)(e >> 16));
+      } else {
+        s_lo[o * KS + f] = __ushort_as_bfloat16((unsigned short)0);
+      }
+    }
+    s_hi[o * KS + f] = __ushort_as_bfloat16((unsigned short)hi);
+  }
+  (void)MW;
 }
 
 // Zero the recurrent state of one game's agents (rows g*P .. g*P+P-1, every layer) -- all threads of the CTA.

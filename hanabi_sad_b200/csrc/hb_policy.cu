@@ -617,6 +617,19 @@ int hb_debug_gemm(int device, const float* A, const float* B, const float* bias,
   return 0;
 }
 
+// Diagnostic: the fc GEMM's A operand as the encoder left it -- bf16 bit patterns [rows][KS] (hi and lo halves).
+int hb_debug_operand(hb_engine* e, uint16_t* hi, uint16_t* lo, int* ks) {
+  if (!e || !e->policy) { hb_set_error("hb_debug_operand: no policy"); return -1; }
+  HbPolicy* P = e->policy;
+  HB_CUDA(cudaSetDevice(e->device));
+  if (ks) *ks = P->KS;
+  const size_t n = (size_t)e->rows * P->KS * sizeof(uint16_t);
+  if (hi) HB_CUDA(cudaMemcpyAsync(hi, P->s_hi, n, cudaMemcpyDeviceToHost, e->stream));
+  if (lo) HB_CUDA(cudaMemcpyAsync(lo, P->s_lo, n, cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 // R2D2Actor::act without the environment (r2d2_actor.h:61-100): one policy forward on the engine's current
 // observation; the reply (a, greedy_a) lands in the engine's action buffers, the hidden state advances.
 int hb_policy_act(hb_engine* e, int greedy_only) {

@@ -121,6 +121,7 @@ template <int TP, int TH, int TSAD>
 __global__ void __launch_bounds__(HB_TICK_THREADS, 12) hb_k_tick(const __grid_constant__ HbTickArgs A) {
   __shared__ HbGame s;
   __shared__ HbEncTables tab;
+  __shared__ HbFastEnc enc;
   __shared__ __align__(16) uint8_t deck[HB_DECK_STRIDE];
   __shared__ int sh_did_step, sh_t, sh_term, sh_reset, sh_slot, sh_drop;
   __shared__ float red[2 * HB_TICK_THREADS / 32];
@@ -192,8 +193,8 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 12) hb_k_tick(const __grid_co
   const bool to_ring = slot >= 0 && !s.terminated && t_obs < R.T;
   // the fp32 obs dict (priv_s, own_hand) has no reader inside the rollout: the policy consumes the bf16 operand, the replay
   // the board record.  It is materialised on demand by hb_refresh_obs when the host asks for it (hb_env_observe*).
-  hb_cta_write_obs(s, tab, cfg, nullptr, O.legal_move + (size_t)g * P * geo.A, nullptr, O.eps + (size_t)g * P, A.eps_list, O.s_hi ? O.s_hi + (size_t)g * P * O.KS : nullptr,
-                   O.s_lo ? O.s_lo + (size_t)g * P * O.KS : nullptr, O.KS);
+  hb_cta_write_obs(s, tab, cfg, nullptr, O.legal_move + (size_t)g * P * geo.A, nullptr, O.eps + (size_t)g * P, A.eps_list);
+  if (O.s_hi != nullptr) hb_cta_write_operand_fast(s, tab, cfg, enc, O.s_hi + (size_t)g * P * O.KS, O.s_lo + (size_t)g * P * O.KS, O.KS);
   if (tid >= 32 && tid < 48 && to_ring)   // the replay keeps the record, not the observation (re-encoded by hb_k_replay_gather)
     reinterpret_cast<uint4*>(R.states + (size_t)slot * R.T + t_obs)[tid - 32] = reinterpret_cast<const uint4*>(&s)[tid - 32];
   if (tid < 16) reinterpret_cast<uint4*>(A.games + g)[tid] = reinterpret_cast<const uint4*>(&s)[tid];

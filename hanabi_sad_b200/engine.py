@@ -179,6 +179,15 @@ class Engine:
         check(lib().hb_policy_get(self._h, _ptr(out["adv"]), _ptr(out["online_q"]), _ptr(out["target_q"]), _ptr(h), _ptr(c)))
         return out
 
+    def debug_operand(self):
+        """The fc GEMM operand the encoder wrote: (hi, lo) uint16 bf16 bit patterns [G*P, KS]."""
+        ks = ctypes.c_int()
+        check(lib().hb_debug_operand(self._h, None, None, ctypes.byref(ks)))
+        hi = np.empty((self.rows, ks.value), np.uint16)
+        lo = np.empty((self.rows, ks.value), np.uint16)
+        check(lib().hb_debug_operand(self._h, _ptr(hi), _ptr(lo), ctypes.byref(ks)))
+        return hi, lo
+
     # ---- fused actor loop + replay ------------------------------------------------------------------------
     def rollout(self, n_ticks):
         check(lib().hb_rollout(self._h, int(n_ticks)))

@@ -255,6 +255,10 @@ int hb_lstm_sync(hb_lstm* l);
 
 int64_t hb_lstm_launches(const hb_lstm* l); /* kernels launched through this handle so far */
 
+/* Diagnostic: the observation as the policy consumes it -- the bf16 hi / lo operand of the first GEMM written by the fused
+ * tick's encoder, as bit patterns [G*P][*ks] (host; hi or lo may be NULL; *ks = row length, F rounded up to 64). */
+int hb_debug_operand(hb_engine* e, uint16_t* hi, uint16_t* lo, int* ks);
+
 int hb_sync(hb_engine* e); /* cudaStreamSynchronize on the engine stream */
 void* hb_stream(hb_engine* e); /* cudaStream_t the engine launches on (for CUDA-event timing) */
 int64_t hb_kernel_launches(const hb_engine* e); /* kernels launched by this engine so far */

@@ -218,6 +218,39 @@ def test_replay_get_walks_the_ring_in_arrival_order(hb, vdn):
     eng.close()
 
 
+def _bf16_rne(x):
+    """float32 array -> bf16 bit patterns, round to nearest even (what __float2bfloat16_rn does for finite values)."""
+    b = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return ((b + 0x7FFF + ((b >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+@pytest.mark.parametrize("cfg", [(2, 5, 1, 0), (2, 5, 1, 1), (2, 5, 0, 1), (3, 5, 1, 1), (5, 4, 1, 1), (4, 4, 0, 0)],
+                         ids=["2p_sad", "2p_sad_shuffle", "2p_shuffle", "3p_sad_shuffle", "5p_sad_shuffle", "4p"])
+def test_fast_operand_equals_feature_encoder(hb, cfg):
+    """The tick's fast encoder (bit masks + per-game belief table, hb_cta_write_operand_fast) must produce exactly the bf16 hi/lo
+    split of the per-feature encoder's priv_s (hb_feature, itself bit-exact vs the oracle) -- every game, every tick."""
+    P, H, sad, shuffle = cfg
+    G = 96
+    eng = hb.Engine(G, P, H, 0, 80, bool(sad), bool(shuffle), [0.1, 0.6, 1.0], seed=41, replay_capacity=256)
+    eng.set_weights(0, random_state_dict(eng.F, 512, eng.A, 5, H))
+    eng.set_weights(1, random_state_dict(eng.F, 512, eng.A, 6, H))
+    F = eng.F
+    seen_nonbinary = 0
+    for tick in range(70):
+        eng.rollout(1)
+        hi, lo = eng.debug_operand()
+        v = eng.observe()["priv_s"].reshape(G * P, F)      # re-encoded from the same board records by hb_feature
+        want_hi = _bf16_rne(v)
+        back = (want_hi.astype(np.uint32) << 16).view(np.float32)
+        want_lo = _bf16_rne(v - back)
+        assert np.array_equal(hi[:, :F], want_hi), (tick, np.argwhere(hi[:, :F] != want_hi)[:5])
+        assert np.array_equal(lo[:, :F], want_lo), (tick, np.argwhere(lo[:, :F] != want_lo)[:5])
+        assert not hi[:, F:].any() and not lo[:, F:].any()
+        seen_nonbinary += int(((v != 0) & (v != 1)).sum())
+    assert seen_nonbinary > 1000
+    eng.close()
+
+
 def test_rollout_env_obs_match_oracle(hb):
     """During a fused rollout the observation stream is still bit-exact against the C oracle (same checks as the env tests,
     but through hb_k_tick)."""
