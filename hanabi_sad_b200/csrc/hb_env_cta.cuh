@@ -187,9 +187,8 @@ __device__ __forceinline__ void hb_mask_last_action(uint32_t* row, int base, con
 __device__ __forceinline__ void hb_cta_write_operand_fast(const HbGame& s, const HbEncTables& t, const HbEnvCfg& cfg, HbFastEnc& E,
                                                           __nv_bfloat16* __restrict__ s_hi, __nv_bfloat16* __restrict__ s_lo, int KS) {
   const HbGeom& g = cfg.g;
-  const int P = g.P, H = g.H, F = g.F, nt = blockDim.x, tid = threadIdx.x;
+  const int P = g.P, H = g.H, nt = blockDim.x, tid = threadIdx.x;
   const bool shuffle = cfg.shuffle_color != 0;
-  const int MW = (F + 31) >> 5;
   for (int i = tid; i < P * HB_MASK_WORDS; i += nt) E.mask[i / HB_MASK_WORDS][i % HB_MASK_WORDS] = 0u;
   // belief fractions per (player, slot, real card type)
   for (int i = tid; i < P * H * HB_NCARD; i += nt) {
@@ -208,80 +207,91 @@ __device__ __forceinline__ void hb_cta_write_operand_fast(const HbGame& s, const
     E.bel[i] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
   }
   __syncthreads();
-  // ---- scatter the ones.  Task list per observer o (tasks are independent; atomicOr on shared memory):
-  //   [0, P*H)            card slots of the hands block + the belief hint one-hots of the same (rel, slot)
-  //   [P*H, P*H + P)      "hand shorter than H" bits
-  //   P*H + P + {0,1,2,3} deck / fireworks / info / life
-  //   then 25 discard thermometers, then the last-action block and the SAD block
-  const int n_task = P * H + P + 4 + HB_NCARD + 2;
-  for (int i = tid; i < P * n_task; i += nt) {
-    const int o = i / n_task;
-    int k = i - o * n_task;
-    uint32_t* row = E.mask[o];
-    const uint16_t perm = s.perm[o], inv = s.inv_perm[o];
-    if (k < P * H) {
-      const int rel = k / H, slot = k - rel * H, p = (o + rel) % P;
-      if (slot < s.hand_len[p]) {
-        if (rel != 0) {  // own cards are hidden (canonical_encoders.cc:88-95)
-          const int card = s.hand_card[p][slot], c = card / HB_NR, r = card - c * HB_NR;
-          hb_mask_set(row, k * HB_NCARD + (shuffle ? hb_perm_get(perm, c) : c) * HB_NR + r);
-        }
-        const unsigned kn = s.know[p][slot];
-        const int hc = (kn >> 10) & 7, hr = (kn >> 13) & 7;
-        const int b0 = g.off_belief + k * 35 + HB_NCARD;
-        if (hc != 7) hb_mask_set(row, b0 + (shuffle ? hb_perm_get(perm, hc) : hc));
-        if (hr != 7) hb_mask_set(row, b0 + HB_NC + hr);
+  // ---- scatter the ones (atomicOr on shared memory).  One KIND of task per warp, so that no warp walks through the other
+  // kinds' branches: warp 0 card slots (hands block + belief hint one-hots), warp 1 discard thermometers, warp 2 the
+  // "hand short" bits and the board block, warp 3 the last-action and SAD blocks.
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  if (warp == 0 % nw) {
+    for (int i = lane; i < P * P * H; i += 32) {
+      const int o = i / (P * H), k = i - o * (P * H), rel = k / H, slot = k - rel * H, p = (o + rel) % P;
+      if (slot >= s.hand_len[p]) continue;
+      uint32_t* row = E.mask[o];
+      const uint16_t perm = s.perm[o];
+      if (rel != 0) {  // own cards are hidden (canonical_encoders.cc:88-95)
+        const int card = s.hand_card[p][slot], c = card / HB_NR, r = card - c * HB_NR;
+        hb_mask_set(row, k * HB_NCARD + (shuffle ? hb_perm_get(perm, c) : c) * HB_NR + r);
       }
-      continue;
+      const unsigned kn = s.know[p][slot];
+      const int hc = (kn >> 10) & 7, hr = (kn >> 13) & 7;
+      const int b0 = g.off_belief + k * 35 + HB_NCARD;
+      if (hc != 7) hb_mask_set(row, b0 + (shuffle ? hb_perm_get(perm, hc) : hc));
+      if (hr != 7) hb_mask_set(row, b0 + HB_NC + hr);
     }
-    k -= P * H;
-    if (k < P) { if (s.hand_len[(o + k) % P] < H) hb_mask_set(row, P * H * HB_NCARD + k); continue; }
-    k -= P;
-    if (k == 0) { hb_mask_range(row, g.off_board, min(g.deck_bits, HB_DECK - (int)s.deck_pos)); continue; }
-    if (k == 1) {
-      for (int sc = 0; sc < HB_NC; ++sc) {
-        const int fw = s.fireworks[shuffle ? hb_perm_get(inv, sc) : sc];
-        if (fw > 0) hb_mask_set(row, g.off_board + g.deck_bits + sc * HB_NR + fw - 1);
-      }
-      continue;
-    }
-    if (k == 2) { hb_mask_range(row, g.off_board + g.deck_bits + HB_NCARD, min((int)s.info, HB_MAX_INFO)); continue; }
-    if (k == 3) { hb_mask_range(row, g.off_board + g.deck_bits + HB_NCARD + HB_MAX_INFO, min((int)s.life, HB_MAX_LIFE)); continue; }
-    k -= 4;
-    if (k < HB_NCARD) {  // discard thermometer of shown colour sc, rank r: widths 3,2,2,2,1 (canonical_encoders.cc:252-280)
-      const int sc = k / HB_NR, r = k - sc * HB_NR;
-      const int real_c = shuffle ? hb_perm_get(inv, sc) : sc;
+  }
+  if (warp == 1 % nw) {
+    for (int i = lane; i < P * HB_NCARD; i += 32) {  // discard thermometer of shown colour sc, rank r: widths 3,2,2,2,1 (:252-280)
+      const int o = i / HB_NCARD, k = i - o * HB_NCARD, sc = k / HB_NR, r = k - sc * HB_NR;
+      const int real_c = shuffle ? hb_perm_get(s.inv_perm[o], sc) : sc;
       const int n = min((int)s.discard_count[real_c * HB_NR + r], hb_card_mult(r));
-      hb_mask_range(row, g.off_discard + sc * 10 + (r == 0 ? 0 : 2 * r + 1), n);
-      continue;
+      hb_mask_range(E.mask[o], g.off_discard + sc * 10 + (r == 0 ? 0 : 2 * r + 1), n);
     }
-    k -= HB_NCARD;
-    if (k == 0) hb_mask_last_action(row, g.off_last, s.last, g, o, perm, shuffle);
-    else if (g.sad) hb_mask_last_action(row, g.off_sad, s.greedy_valid ? s.greedy : s.last, g, o, perm, shuffle);
+  }
+  if (warp == 2 % nw) {
+    for (int i = lane; i < P * P; i += 32) {
+      const int o = i / P, k = i - o * P;
+      if (s.hand_len[(o + k) % P] < H) hb_mask_set(E.mask[o], P * H * HB_NCARD + k);
+    }
+    for (int i = lane; i < P * HB_NC; i += 32) {
+      const int o = i / HB_NC, sc = i - o * HB_NC;
+      const int fw = s.fireworks[shuffle ? hb_perm_get(s.inv_perm[o], sc) : sc];
+      if (fw > 0) hb_mask_set(E.mask[o], g.off_board + g.deck_bits + sc * HB_NR + fw - 1);
+    }
+    for (int i = lane; i < 3 * P; i += 32) {
+      const int o = i / 3, k = i - o * 3;
+      const int bit = k == 0 ? g.off_board : (k == 1 ? g.off_board + g.deck_bits + HB_NCARD : g.off_board + g.deck_bits + HB_NCARD + HB_MAX_INFO);
+      const int n = k == 0 ? min(g.deck_bits, HB_DECK - (int)s.deck_pos) : (k == 1 ? min((int)s.info, HB_MAX_INFO) : min((int)s.life, HB_MAX_LIFE));
+      hb_mask_range(E.mask[o], bit, n);
+    }
+  }
+  if (warp == 3 % nw) {
+    if (lane < 2 * P && (lane < P || g.sad)) {
+      const int o = lane < P ? lane : lane - P;
+      const bool sad_block = lane >= P;
+      hb_mask_last_action(E.mask[o], sad_block ? g.off_sad : g.off_last, (sad_block && s.greedy_valid) ? s.greedy : s.last, g, o, s.perm[o], shuffle);
+    }
   }
   __syncthreads();
-  // ---- one coalesced pass over the rows
-  const int bel_len = P * H * 35;
-  for (int i = tid; i < P * F; i += nt) {
-    const int o = i / F, f = i - o * F;
-    const int j = f - g.off_belief;
-    uint32_t hi = ((E.mask[o][f >> 5] >> (f & 31)) & 1u) ? 0x3F80u : 0u;
-    if (j >= 0 && j < bel_len) {
-      const int rs = j / 35, kk = j - rs * 35;
-      if (kk < HB_NCARD) {
-        const int rel = rs / H, slot = rs - rel * H, p = (o + rel) % P;
-        const int sc = kk / HB_NR, r = kk - sc * HB_NR;
-        const int real_c = shuffle ? hb_perm_get(s.inv_perm[o], sc) : sc;
-        const uint32_t e = E.bel[(p * H + slot) * HB_NCARD + real_c * HB_NR + r];
-        hi = e & 0xFFFFu;
-        s_lo[o * KS + f] = __ushort_as_bfloat16((unsigned short)(e >> 16));
-      } else {
-        s_lo[o * KS + f] = __ushort_as_bfloat16((unsigned short)0);
-      }
+  // ---- rows out.  Pass 1: every 32-bit mask word becomes 32 bf16 (0x3F80 / 0) = four 16-byte stores; KS is a multiple of
+  // 64, so a row is exactly KS/32 words (bits at and beyond F are zero).  Pass 2 (after the barrier, which orders the two
+  // writes of the same CTA to the same addresses) overwrites the belief fractions and writes their lo halves.
+  const int words = KS >> 5;
+  for (int i = tid; i < P * words; i += nt) {
+    const int o = i / words, w = i - o * words;
+    const uint32_t m = w < HB_MASK_WORDS ? E.mask[o][w] : 0u;
+    uint4* dst = reinterpret_cast<uint4*>(s_hi + (size_t)o * KS + w * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t b8 = (m >> (8 * q)) & 0xFFu;
+      uint4 v;
+      v.x = ((b8 & 1u) ? 0x3F80u : 0u) | ((b8 & 2u) ? 0x3F800000u : 0u);
+      v.y = ((b8 & 4u) ? 0x3F80u : 0u) | ((b8 & 8u) ? 0x3F800000u : 0u);
+      v.z = ((b8 & 16u) ? 0x3F80u : 0u) | ((b8 & 32u) ? 0x3F800000u : 0u);
+      v.w = ((b8 & 64u) ? 0x3F80u : 0u) | ((b8 & 128u) ? 0x3F800000u : 0u);
+      dst[q] = v;
     }
-    s_hi[o * KS + f] = __ushort_as_bfloat16((unsigned short)hi);
   }
-  (void)MW;
+  __syncthreads();
+  for (int i = tid; i < P * P * H * HB_NCARD; i += nt) {
+    const int o = i / (P * H * HB_NCARD), r1 = i - o * (P * H * HB_NCARD);
+    const int rs = r1 / HB_NCARD, kk = r1 - rs * HB_NCARD;     // rs = rel * H + slot, kk = shown card type
+    const int rel = rs / H, slot = rs - rel * H, p = (o + rel) % P;
+    const int sc = kk / HB_NR, r = kk - sc * HB_NR;
+    const int real_c = shuffle ? hb_perm_get(s.inv_perm[o], sc) : sc;
+    const uint32_t e = E.bel[(p * H + slot) * HB_NCARD + real_c * HB_NR + r];
+    const size_t at = (size_t)o * KS + g.off_belief + rs * 35 + kk;
+    s_hi[at] = __ushort_as_bfloat16((unsigned short)(e & 0xFFFFu));
+    s_lo[at] = __ushort_as_bfloat16((unsigned short)(e >> 16));
+  }
 }
 
 // Zero the recurrent state of one game's agents (rows g*P .. g*P+P-1, every layer) -- all threads of the CTA.
