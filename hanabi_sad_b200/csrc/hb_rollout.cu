@@ -19,7 +19,7 @@
 #include "hb_policy.h"
 #include "hb_replay.h"
 
-#define HB_TICK_THREADS 128
+#define HB_TICK_THREADS 96
 
 struct HbTickArgs {
   HbGame* games;
@@ -115,10 +115,11 @@ __device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, 
 
 // TP / TH / TSAD > 0 bake the game geometry into the kernel (feature offsets, F, A become literals: the per-feature index
 // arithmetic is mul-shift instead of runtime division); TP == 0 is the generic fallback for unusual configurations.
-// 12 resident CTAs / SM (40 registers): the kernel is latency bound (issue slots ~40 % busy at 7 CTAs / SM), more warps
-// in flight took it from 82 to 71 us at 4096 games; beyond 12 the spills outweigh the occupancy.
+// 96 threads, 16 resident CTAs / SM (40 registers): the kernel is latency bound -- all threads wait at barriers while
+// thread 0 applies the move / starts an episode -- so what helps is more CTAs in flight per SM, not more threads per CTA
+// (7 CTAs of 128 threads: 82 us per 4096-game tick; 12: 71 us; with the fast encoder 58 us, as 16 x 96 threads 54 us).
 template <int TP, int TH, int TSAD>
-__global__ void __launch_bounds__(HB_TICK_THREADS, 12) hb_k_tick(const __grid_constant__ HbTickArgs A) {
+__global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_constant__ HbTickArgs A) {
   __shared__ HbGame s;
   __shared__ HbEncTables tab;
   __shared__ HbFastEnc enc;
