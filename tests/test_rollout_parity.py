@@ -31,13 +31,15 @@ def _key(priv_s_first, actions):
 
 
 @pytest.mark.parametrize("cfg", [(2, 5, 1, True, 3, 0), (2, 5, 1, False, 3, 0), (3, 5, 0, True, 1, 0), (2, 5, 1, True, 3, 1), (5, 4, 1, True, 3, 0),
-                                 (4, 4, 0, False, 2, 0)],
-                         ids=["vdn_2p_n3", "iql_2p_n3", "vdn_3p_n1", "vdn_uniform_priority", "vdn_5p_n3", "iql_4p_n2"])
+                                 (4, 4, 0, False, 2, 0), (2, 5, 1, True, 3, 0, 1), (3, 5, 1, False, 3, 0, 1)],
+                         ids=["vdn_2p_n3", "iql_2p_n3", "vdn_3p_n1", "vdn_uniform_priority", "vdn_5p_n3", "iql_4p_n2", "vdn_2p_shuffle_color",
+                              "iql_3p_shuffle_color"])
 def test_rollout_fills_replay_like_the_reference(hb, cfg):
-    P, H, sad, vdn, n_step, prio_mode = cfg
+    shuffle = len(cfg) > 6 and bool(cfg[6])   # Other-Play colour permutations: the replay re-encodes them from the stored record
+    P, H, sad, vdn, n_step, prio_mode = cfg[:6]
     G, T, gamma, eta, alpha, beta = 40, 80, 0.999, 0.9, 0.6, 0.4
     eps_list = [0.05, 0.3, 0.8]  # plenty of exploration: short and long episodes
-    eng = hb.Engine(G, P, H, 0, T, bool(sad), False, eps_list, seed=17, vdn=vdn, multi_step=n_step, gamma=gamma, eta=eta, seq_len=T,
+    eng = hb.Engine(G, P, H, 0, T, bool(sad), shuffle, eps_list, seed=17, vdn=vdn, multi_step=n_step, gamma=gamma, eta=eta, seq_len=T,
                     replay_capacity=4096, alpha=alpha, beta=beta, priority_mode=prio_mode)
     F, A = eng.F, eng.A
     eng.set_weights(0, random_state_dict(F, 512, A, 31, H))
