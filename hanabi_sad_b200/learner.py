@@ -36,6 +36,7 @@ class DeviceR2D2Net(nn.Module):
         self._ref_cross_entropy = ref_net_cls.cross_entropy
         self._partner = None      # the network whose LSTM rides along with this one's forward (target net)
         self._ride = None         # (input tensor, lstm output) left by the partner's forward
+        self._t_eff = None        # longest episode of the batch in flight (set by DeviceLearner.loss): later steps are padding
 
     def cross_entropy(self, net, lstm_o, target_p, hand_slot_mask, seq_len):
         return self._ref_cross_entropy(self, net, lstm_o, target_p, hand_slot_mask, seq_len)
@@ -43,32 +44,40 @@ class DeviceR2D2Net(nn.Module):
     def pred_loss_1st(self, lstm_o, target, hand_slot_mask, seq_len):
         return self.cross_entropy(self.pred, lstm_o, target, hand_slot_mask, seq_len)
 
-    def _lstm_out(self, priv_s, x):
-        if self._ride is not None and self._ride[0] is priv_s:   # computed during the online network's forward
+    def _lstm_out(self, key, ps):
+        """LSTM output for the (already truncated) input `ps`; `key` identifies the batch (the caller's full priv_s tensor)."""
+        if self._ride is not None and self._ride[0] is key:   # computed during the online network's forward
             o, self._ride = self._ride[1], None
             return o
+        x = self.net(ps)
         p = self._partner
         if p is not None and torch.is_grad_enabled():
             with torch.no_grad():
-                xp = p.net(priv_s)
+                xp = p.net(ps)
             o, op = self.lstm.forward_pair(x, p.lstm, xp)
-            p._ride = (priv_s, op)
+            p._ride = (key, op)
             return o
         return self.lstm(x)
 
     def forward(self, priv_s, legal_move, action, hid):
         """R2D2Net.forward (r2d2.py:80-128) for [seq_len, batch, dim] inputs with an empty `hid` (zero initial state), which is
-        how the learner calls it (r2d2.py:392-401)."""
+        how the learner calls it (r2d2.py:392-401).  With `_t_eff` set (DeviceLearner.loss) only the first t_eff steps are
+        computed -- every later step is padding in all rows -- and the outputs are zero-padded back to seq_len."""
         assert priv_s.dim() == 3 and len(hid) == 0, "the learner path passes whole sequences and no initial hidden state"
-        x = self.net(priv_s)
-        o = self._lstm_out(priv_s, x)
+        T = priv_s.size(0)
+        te = T if self._t_eff is None else max(1, min(int(self._t_eff), T))
+        ps, lm, ac = priv_s[:te], legal_move[:te], action[:te]
+        o = self._lstm_out(priv_s, ps)
         a = self.fc_a(o)
         v = self.fc_v(o)
-        legal_a = a * legal_move
+        legal_a = a * lm
         q = v + legal_a - legal_a.mean(2, keepdim=True)
-        qa = q.gather(2, action.unsqueeze(2)).squeeze(2)
-        legal_q = (1 + q - q.min()) * legal_move
+        qa = q.gather(2, ac.unsqueeze(2)).squeeze(2)
+        legal_q = (1 + q - q.min()) * lm
         greedy_action = legal_q.argmax(2).detach()
+        if te < T:
+            pad = lambda t: torch.cat([t, t.new_zeros((T - te,) + tuple(t.shape[1:]))], 0)
+            qa, greedy_action, q, o = pad(qa), pad(greedy_action), pad(q), pad(o)
         return qa, greedy_action, q, o
 
 
@@ -84,8 +93,22 @@ class DeviceLearner(nn.Module):
         self.vdn, self.multi_step, self.gamma, self.eta, self.uniform_priority = vdn, multi_step, gamma, eta, uniform_priority
         self.workspace = ws
         # R2D2Agent's python-only functions (r2d2.py:363-497), bound to this object
-        for name in ("flat_4d", "td_error", "aux_task_iql", "aux_task_vdn", "loss"):
+        for name in ("flat_4d", "td_error", "aux_task_iql", "aux_task_vdn"):
             setattr(self, name, getattr(ref_agent_cls, name).__get__(self))
+        self._ref_loss = getattr(ref_agent_cls, "loss").__get__(self)
+        self.skip_padding = True
+
+    def loss(self, batch, pred_weight, stat):
+        """R2D2Agent.loss (r2d2.py:464-497), unchanged.  The replay pads every episode to seq_len steps (transition_buffer.h:
+        134-211); steps at or beyond the longest episode of the batch are padding in EVERY row: their TD errors are masked
+        (r2d2.py:425-427), their aux targets are empty, and no unmasked step reads them (bootstrap = 0 within n steps of an
+        episode's end), so the LSTM recurrences stop there (outputs beyond are zeros) -- same loss, priorities and gradients."""
+        t_eff = int(batch.seq_len.max().item()) if self.skip_padding else None
+        self.online_net._t_eff = self.target_net._t_eff = t_eff
+        try:
+            return self._ref_loss(batch, pred_weight, stat)
+        finally:
+            self.online_net._t_eff = self.target_net._t_eff = None
 
     @classmethod
     def from_agent(cls, agent, max_T=80, max_rows=256):

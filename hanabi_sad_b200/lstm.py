@@ -64,12 +64,16 @@ class LstmWorkspace:
             w.w_ih[l], w.w_hh[l], w.b_ih[l], w.b_hh[l] = (params[4 * l + i].data_ptr() for i in range(4))
         return w
 
-    def forward(self, xs, params, save):
+    def forward(self, xs, params, save, t_eff=None):
         """xs: list of 1 or 2 float32 CUDA tensors [T, rows, 512]; params: per network the 8 nn.LSTM tensors in PARAM_NAMES
-        order.  Returns the top-layer output sequences.  save=True keeps network 0's activations for backward()."""
+        order.  Returns the top-layer output sequences.  save=True keeps network 0's activations for backward().
+        t_eff < T: only the first t_eff steps are computed, the outputs of the rest are zero -- for padded batches whose
+        steps >= t_eff carry no loss (see DeviceLearner.loss)."""
         self._handle(xs[0].device)
         nets = len(xs)
         T, rows, hid = xs[0].shape
+        t_run = T if t_eff is None else max(1, min(int(t_eff), T))
+        self._last_T, self._last_t_run = T, t_run
         assert hid == HID and nets in (1, 2) and len(params) == nets
         xs = [x.contiguous() for x in xs]
         keep = [[p.detach().contiguous() for p in ps] for ps in params]
@@ -79,11 +83,14 @@ class LstmWorkspace:
             assert len(ps) == 8 and all(p.is_cuda and p.dtype == torch.float32 for p in ps)
             assert tuple(ps[0].shape) == (4 * HID, HID) and tuple(ps[2].shape) == (4 * HID,)
         ys = [torch.empty_like(x) for x in xs]
+        if t_run < T:
+            for y in ys:
+                y[t_run:].zero_()
         xp = (ctypes.c_void_p * 2)(*[x.data_ptr() for x in xs])
         yp = (ctypes.c_void_p * 2)(*[y.data_ptr() for y in ys])
         ws = (HbLstmWeights * 2)(*[self._weights(ps) for ps in keep])
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        check(lib().hb_lstm_forward(self._handle(), int(T), int(rows), nets, xp, ws, yp, int(bool(save)), ctypes.c_void_p(stream)))
+        check(lib().hb_lstm_forward(self._handle(), int(t_run), int(rows), nets, xp, ws, yp, int(bool(save)), ctypes.c_void_p(stream)))
         return ys
 
     def backward(self, dy, need_dx=True):
@@ -92,6 +99,8 @@ class LstmWorkspace:
         dy = dy.contiguous()
         assert dy.is_cuda and dy.dtype == torch.float32
         dx = torch.empty_like(dy) if need_dx else None
+        if need_dx and self._last_t_run < self._last_T:   # the saved forward ran a prefix of the steps: no gradient beyond it
+            dx[self._last_t_run:].zero_()
         f32 = dict(dtype=torch.float32, device=dy.device)
         grads = []
         g = HbLstmGrads()
@@ -109,21 +118,21 @@ class _LstmFn(torch.autograd.Function):
     """y = LSTM(x; 8 parameters), optionally with a second, gradient-free network run in the same kernels."""
 
     @staticmethod
-    def forward(ctx, ws, x, x2, params2, *params):
+    def forward(ctx, ws, t_eff, x, x2, params2, *params):
         ctx.ws = ws
         ctx.need_dx = x.requires_grad
         xs, ps = [x.detach()], [list(params)]
         if x2 is not None:
             xs.append(x2.detach())
             ps.append(list(params2))
-        ys = ws.forward(xs, ps, save=True)
+        ys = ws.forward(xs, ps, save=True, t_eff=t_eff)
         ctx.mark_non_differentiable(*ys[1:])
         return tuple(ys) if x2 is not None else ys[0]
 
     @staticmethod
     def backward(ctx, dy, *unused):
         dx, grads = ctx.ws.backward(dy, need_dx=ctx.need_dx)
-        return (None, dx, None, None) + tuple(grads)
+        return (None, None, dx, None, None) + tuple(grads)
 
 
 class DeviceLSTM(nn.Module):
@@ -140,12 +149,12 @@ class DeviceLSTM(nn.Module):
     def _params(self):
         return [getattr(self, n) for n in PARAM_NAMES]
 
-    def forward(self, x):
+    def forward(self, x, t_eff=None):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params())):
-            return _LstmFn.apply(self._ws, x, None, None, *self._params())
-        return self._ws.forward([x], [self._params()], save=False)[0]
+            return _LstmFn.apply(self._ws, t_eff, x, None, None, *self._params())
+        return self._ws.forward([x], [self._params()], save=False, t_eff=t_eff)[0]
 
-    def forward_pair(self, x, other, x_other):
+    def forward_pair(self, x, other, x_other, t_eff=None):
         """This network on `x` (differentiable) and `other` (a second DeviceLSTM, no gradient) on `x_other` in one pass --
         the online / target pair of R2D2Agent.td_error (r2d2.py:398-401)."""
-        return _LstmFn.apply(self._ws, x, x_other, [p.detach() for p in other._params()], *self._params())
+        return _LstmFn.apply(self._ws, t_eff, x, x_other, [p.detach() for p in other._params()], *self._params())

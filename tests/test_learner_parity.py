@@ -52,15 +52,16 @@ def test_device_learner_is_a_drop_in_for_the_reference_agent_object():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("vdn,B,pred_weight", [(False, 128, 0.0), (True, 64, 0.25), (False, 20, 0.25)], ids=["iql_b128", "vdn_b64_aux", "iql_b20_aux_padded_rows"])
-def test_loss_priority_and_gradients_match_the_reference_learner(gpu_or_skip, vdn, B, pred_weight):
+@pytest.mark.parametrize("vdn,B,pred_weight,max_seq", [(False, 128, 0.0, 80), (True, 64, 0.25, 80), (False, 20, 0.25, 80), (True, 64, 0.25, 23), (False, 128, 0.0, 41)],
+                         ids=["iql_b128", "vdn_b64_aux", "iql_b20_aux_padded_rows", "vdn_short_episodes_skip_padding", "iql_short_episodes_skip_padding"])
+def test_loss_priority_and_gradients_match_the_reference_learner(gpu_or_skip, vdn, B, pred_weight, max_seq):
     from hanabi_sad_b200.learner import DeviceLearner
     from hanabi_sad_b200.rela import RNNTransition
     from profile_learner import synthetic_batch
 
     T = 80
     ag = _ref_agent(vdn)
-    obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, B, 2, 838, 21, 5, vdn, "cpu", seed=3)
+    obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, B, 2, 838, 21, 5, vdn, "cpu", seed=3, max_seq=max_seq)
     weight = torch.rand(B) + 0.5
     loss, prio = ag.loss(RNNTransition(obs, action, reward, terminal, bootstrap, seq_len), pred_weight, _Stat())
     (loss * weight).mean().backward()
@@ -73,6 +74,7 @@ def test_loss_priority_and_gradients_match_the_reference_learner(gpu_or_skip, vd
     loss_d, prio_d = lr.loss(RNNTransition(mv(obs), mv(action), reward.to(dev), terminal.to(dev), bootstrap.to(dev), seq_len.to(dev)), pred_weight, _Stat())
     (loss_d * weight.to(dev)).mean().backward()
     assert lr.workspace.launches() > 0   # the device kernels ran (no silent torch path)
+    assert lr.workspace._last_t_run == int(seq_len.max())   # the recurrences stop at the longest episode: the rest is padding
 
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
     assert rel(loss_d.detach().cpu(), loss.detach()) < 2e-4, rel(loss_d.detach().cpu(), loss.detach())

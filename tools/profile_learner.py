@@ -18,10 +18,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref", "pyhanabi"))
 
 
-def synthetic_batch(T, B, P, F, A, H, vdn, dev, seed=0):
+def synthetic_batch(T, B, P, F, A, H, vdn, dev, seed=0, max_seq=None):
+    """A padded replay batch in the reference's layout (RNNTransition::makeBatch, transition.cc:160-202): episodes of random
+    length <= max_seq (default T), everything at and beyond an episode's length is padding (zero obs, terminal, no bootstrap)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     shp = (T, B, P) if vdn else (T, B)
-    seq_len = torch.randint(10, T + 1, (B,), generator=g).float()
+    max_seq = T if max_seq is None else max_seq
+    seq_len = torch.randint(min(10, max_seq), max_seq + 1, (B,), generator=g).float()
     priv_s = (torch.rand(*shp, F, generator=g) < 0.3).float()
     legal = (torch.rand(*shp, A, generator=g) < 0.5).float()
     legal[..., A - 1] = 1.0
@@ -33,6 +36,10 @@ def synthetic_batch(T, B, P, F, A, H, vdn, dev, seed=0):
     obs["temperature"] = torch.zeros(*shp).to(dev)
     action = {"a": a.to(dev), "greedy_a": a.clone().to(dev)}
     t = torch.arange(T).unsqueeze(1)
+    live = (t < seq_len.unsqueeze(0))
+    lv = live.unsqueeze(-1) if vdn else live
+    obs = {k: v * (lv.unsqueeze(-1) if v.dim() > lv.dim() else lv).to(v.dtype).to(dev) for k, v in obs.items()}
+    action = {k: v * lv.to(v.dtype).to(dev) for k, v in action.items()}
     terminal = (t >= seq_len.unsqueeze(0) - 1)
     reward = torch.rand(T, B, generator=g) * (t < seq_len.unsqueeze(0)).float()
     bootstrap = (t + 3 < seq_len.unsqueeze(0)).float()
@@ -45,6 +52,7 @@ def main():
     ap.add_argument("--batchsize", type=int, default=128)
     ap.add_argument("--pred_weight", type=float, default=0.0)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--max_seq", type=int, default=80, help="longest episode in the synthetic batch (trained agents: 60-80; early training: 5-30)")
     ap.add_argument("--impl", default="reference", choices=["reference", "device"],
                     help="reference: r2d2.R2D2Agent as is (cuDNN LSTM); device: hanabi_sad_b200.learner.DeviceLearner (LSTM on csrc/hb_lstm.cu)")
     a = ap.parse_args()
@@ -62,7 +70,7 @@ def main():
 
         agent = DeviceLearner.from_agent(agent, max_T=T, max_rows=a.batchsize * (P if vdn else 1))
     optim = torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
-    obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, a.batchsize, P, F, A, H, vdn, dev)
+    obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, a.batchsize, P, F, A, H, vdn, dev, max_seq=a.max_seq)
     weight = torch.ones(a.batchsize, device=dev)
 
     class Stat(dict):
@@ -109,7 +117,7 @@ def main():
             total += dt / a.iters / 1e3
             launches += ev.count / a.iters
     rows.sort(reverse=True)
-    print(json.dumps({"impl": a.impl, "method": a.method, "batchsize": a.batchsize, "pred_weight": a.pred_weight, "cudnn_allow_tf32": torch.backends.cudnn.allow_tf32,
+    print(json.dumps({"impl": a.impl, "method": a.method, "batchsize": a.batchsize, "pred_weight": a.pred_weight, "max_seq": a.max_seq, "cudnn_allow_tf32": torch.backends.cudnn.allow_tf32,
                       "matmul_allow_tf32": torch.backends.cuda.matmul.allow_tf32, "wall_ms_per_update": wall_ms,
                       "cuda_kernel_ms_per_update": total, "kernel_launches_per_update": launches,
                       "top": [{"ms": round(r[0], 4), "n": r[1], "name": r[2]} for r in rows[:30]]}, indent=1))
