@@ -96,6 +96,7 @@ class DeviceLearner(nn.Module):
         for name in ("flat_4d", "td_error", "aux_task_iql", "aux_task_vdn"):
             setattr(self, name, getattr(ref_agent_cls, name).__get__(self))
         self._ref_loss = getattr(ref_agent_cls, "loss").__get__(self)
+        self._ref_agent = [None]
         self.skip_padding = True
 
     def loss(self, batch, pred_weight, stat):
@@ -118,7 +119,15 @@ class DeviceLearner(nn.Module):
         lr = cls(type(agent), type(n), agent.vdn, agent.multi_step, agent.gamma, agent.eta, dev, n.in_dim, n.hid_dim, n.out_dim, n.num_lstm_layer,
                  n.hand_size, agent.uniform_priority, num_fc_layer=n.num_fc_layer, skip_connect=n.skip_connect, max_T=max_T, max_rows=max_rows)
         lr.load_state_dict(agent.state_dict())
+        lr._ref_agent = [agent]   # in a list: not a sub-module (the state_dict keys stay those of R2D2Agent)
         return lr
+
+    def clone(self, device, overwrite=None):
+        """R2D2Agent.clone (r2d2.py:212-231), as create.ActGroup / selfplay.py use it for the actors' and the evaluation copies:
+        a genuine reference agent (TorchScript) with the learner's current weights."""
+        agent = self._ref_agent[0]
+        agent.load_state_dict(self.state_dict())
+        return agent.clone(device, overwrite)
 
     def sync_target_with_online(self):
         self.target_net.load_state_dict(self.online_net.state_dict())

@@ -20,12 +20,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PYH = os.path.join(ROOT, "oracle", "_ref", "pyhanabi")
 
 
+DEVICE_LEARNER_PATCH = (
+    "    agent = agent.to(args.train_device)\n"
+    "    from hanabi_sad_b200.learner import DeviceLearner  # INTEGRATION.md: the two lines a maintainer adds\n"
+    "    agent = DeviceLearner.from_agent(agent, max_T=args.max_len, max_rows=args.batchsize * (args.num_player if args.method == 'vdn' else 1))\n")
+
+
 def run(arm, a, out_dir):
     env = dict(os.environ)
-    if arm == "b200":
+    device_arm = arm.startswith("b200")
+    if device_arm:
         env["HB_ACTOR_DUTY"] = str(a.actor_duty)
-    env["PYTHONPATH"] = (os.path.join(ROOT, "hanabi_sad_b200", "compat") if arm == "b200" else os.path.join(ROOT, "oracle", "_ref")) + os.pathsep + env.get("PYTHONPATH", "")
-    cmd = [sys.executable, "selfplay.py", "--save_dir", os.path.join(out_dir, arm), "--method", "iql", "--num_thread", str(a.num_thread),
+    env["PYTHONPATH"] = (os.path.join(ROOT, "hanabi_sad_b200", "compat") if device_arm else os.path.join(ROOT, "oracle", "_ref")) + os.pathsep + env.get("PYTHONPATH", "")
+    script = "selfplay.py"
+    if arm == "b200_device_learner":   # the reference's selfplay.py + the two documented lines, generated next to the logs
+        src = open(os.path.join(PYH, "selfplay.py")).read()
+        anchor = "    agent = agent.to(args.train_device)\n"
+        assert src.count(anchor) == 1
+        script = os.path.join(out_dir, "selfplay_device_learner.py")
+        open(script, "w").write(src.replace(anchor, DEVICE_LEARNER_PATCH))
+        env["PYTHONPATH"] = PYH + os.pathsep + ROOT + os.pathsep + env["PYTHONPATH"]
+    cmd = [sys.executable, script, "--save_dir", os.path.join(out_dir, arm), "--method", "iql", "--num_thread", str(a.num_thread),
            "--num_game_per_thread", str(a.num_game_per_thread), "--sad", "1", "--act_base_eps", "0.1", "--act_eps_alpha", "7", "--lr", "6.25e-05",
            "--eps", "1.5e-05", "--grad_clip", "5", "--gamma", "0.999", "--seed", "1", "--batchsize", "128", "--burn_in_frames", str(a.burn_in),
            "--replay_buffer_size", str(a.replay), "--epoch_len", str(a.epoch_len), "--num_epoch", str(a.num_epoch), "--priority_exponent", "0.9",
@@ -58,7 +73,7 @@ def main():
     a = ap.parse_args()
     res = {}
     with tempfile.TemporaryDirectory() as d:
-        for arm in ("reference", "b200"):
+        for arm in ("reference", "b200", "b200_device_learner"):
             res[arm] = run(arm, a, d)
     r, b = res["reference"], res["b200"]
     if r["train_samples_per_s"] and b["train_samples_per_s"]:
@@ -66,7 +81,9 @@ def main():
             "actor_duty_b200": a.actor_duty,
             "flags": "tools/dev.sh (iql, sad 1, shuffle_color 1, %d x %d games, batchsize 128, burn_in %d), epoch_len %d x %d epochs, actors and learner on cuda:0"
                      % (a.num_thread, a.num_game_per_thread, a.burn_in, a.epoch_len, a.num_epoch),
-            "learner_updates_per_s": {"reference": r["train_samples_per_s"][-1] / 128, "b200": b["train_samples_per_s"][-1] / 128},
+            "learner_updates_per_s": {"reference": r["train_samples_per_s"][-1] / 128, "b200": b["train_samples_per_s"][-1] / 128,
+                                      "b200_device_learner": (res["b200_device_learner"]["train_samples_per_s"] or [0])[-1] / 128},
+            "learner_wallclock_speedup_device_learner_last_epoch": (res["b200_device_learner"]["train_samples_per_s"] or [0])[-1] / r["train_samples_per_s"][-1],
             "learner_wallclock_speedup_last_epoch": b["train_samples_per_s"][-1] / r["train_samples_per_s"][-1],
             "actor_rate_ratio_last_epoch": b["act_per_s"][-1] / max(r["act_per_s"][-1], 1e-9),
             "total_wall_speedup": r["wall_s"] / b["wall_s"],
