@@ -297,6 +297,7 @@ class _DeviceGroup:
                     a.runner._attach(self.engine, self.lock, seat if self.eval else None)
         if replay is not None:
             replay._attach(self.engine, self.lock)
+        self.chunk_min = None
         self.paused = threading.Event()
         self.stop = threading.Event()
         self.done = threading.Event()
@@ -320,7 +321,12 @@ class _DeviceGroup:
                     finally:
                         self.lock.driver_release()
                     if _actor_duty < 1.0:
-                        time.sleep((time.perf_counter() - t0) * (1.0 / _actor_duty - 1.0))
+                        # Idle time is derived from the UNCONTENDED duration of a chunk (the shortest seen), not from this chunk's
+                        # wall time: when the learner's kernels hold the GPU a chunk can take 50x longer, and sleeping in
+                        # proportion to that would starve the actors for seconds.
+                        dt = time.perf_counter() - t0
+                        self.chunk_min = dt if self.chunk_min is None else min(self.chunk_min, dt)
+                        time.sleep(min(0.25, self.chunk_min * (1.0 / _actor_duty - 1.0)))
         finally:
             self.done.set()
 

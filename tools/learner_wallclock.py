@@ -55,9 +55,17 @@ def run(arm, a, out_dir):
     speeds = [tuple(float(x) for x in m) for m in re.findall(r"Speed: train: ([0-9.]+), act: ([0-9.]+), buffer_add: ([0-9.]+)", out)]
     scores = [float(x) for x in re.findall(r"eval score: ([0-9.]+)", out)]
     burn = out.count("warming up replay buffer")
+    # the reference's own Stopwatch buckets of the LAST epoch (selfplay.py:216-241): where a loop iteration goes
+    buckets = {}
+    for blk in out.split("@@@Time")[1:]:
+        buckets = {m[0].strip(): int(m[1]) for m in re.findall(r"\t([^:\n]+): (\d+) MS", blk.split("@@@total")[0])}
+        tot = re.search(r"@@@total time per iter: ([0-9.]+) ms", blk)
+        if tot:
+            buckets["total_ms_per_iter"] = float(tot.group(1))
     return {"arm": arm, "returncode": p.returncode, "wall_s": wall, "burn_in_wait_s": burn, "epochs": len(speeds),
             "train_samples_per_s": [s[0] for s in speeds], "act_per_s": [s[1] for s in speeds], "buffer_add_per_s": [s[2] for s in speeds],
-            "eval_scores": scores, "tail": out[-600:] if p.returncode else ""}
+            "eval_scores": scores, "stopwatch_ms_last_epoch": buckets,
+            "problems": [l for l in out.splitlines() if re.search(r"Traceback|Error|error|nan|NaN|Exception", l)][:20], "tail": out[-2500:] if (p.returncode or not speeds or min(s[1] for s in speeds) <= 0) else ""}
 
 
 def main():
@@ -69,14 +77,15 @@ def main():
     ap.add_argument("--burn_in", type=int, default=5000)
     ap.add_argument("--replay", type=int, default=32768)
     ap.add_argument("--timeout", type=int, default=900)
+    ap.add_argument("--arms", default="reference,b200,b200_device_learner")
     ap.add_argument("--actor_duty", type=float, default=1.0, help="share of the time the device actors keep the GPU busy (hanabi_sad_b200.rela.set_actor_duty)")
     a = ap.parse_args()
     res = {}
     with tempfile.TemporaryDirectory() as d:
-        for arm in ("reference", "b200", "b200_device_learner"):
+        for arm in a.arms.split(","):
             res[arm] = run(arm, a, d)
-    r, b = res["reference"], res["b200"]
-    if r["train_samples_per_s"] and b["train_samples_per_s"]:
+    r, b = res.get("reference"), res.get("b200")
+    if r and b and "b200_device_learner" in res and r["train_samples_per_s"] and b["train_samples_per_s"]:
         res["summary"] = {
             "actor_duty_b200": a.actor_duty,
             "flags": "tools/dev.sh (iql, sad 1, shuffle_color 1, %d x %d games, batchsize 128, burn_in %d), epoch_len %d x %d epochs, actors and learner on cuda:0"
