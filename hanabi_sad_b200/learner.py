@@ -86,7 +86,7 @@ class DeviceLearner(nn.Module):
                  uniform_priority, num_fc_layer=1, skip_connect=False, max_T=80, max_rows=256):
         super().__init__()
         self.device = torch.device(device)
-        ws = LstmWorkspace(self.device, max_T, max_rows)
+        ws = LstmWorkspace(self.device, max_T, min(max_rows, DeviceLSTM.ROWS_PER_PASS))   # wider batches run in row passes
         mk = lambda: DeviceR2D2Net(ref_net_cls, self.device, in_dim, hid_dim, out_dim, num_lstm_layer, hand_size, num_fc_layer, skip_connect, ws)
         self.online_net, self.target_net = mk(), mk()
         object.__setattr__(self.online_net, "_partner", self.target_net)   # not a sub-module: keeps the state_dict keys of R2D2Agent

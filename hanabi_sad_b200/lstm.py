@@ -138,23 +138,47 @@ class _LstmFn(torch.autograd.Function):
 class DeviceLSTM(nn.Module):
     """nn.LSTM(512, 512, num_layers=2) replacement for the learner.  forward(x) -> output sequence [T, rows, 512]."""
 
+    ROWS_PER_PASS = 256   # 2 networks x 2 row blocks x 32 CTAs = 128 co-resident CTAs: what one B200 holds
+
     def __init__(self, device, max_T=80, max_rows=256, workspace=None):
         super().__init__()
         k = 1.0 / HID ** 0.5
         for name in PARAM_NAMES:
             shape = (4 * HID, HID) if name.startswith("weight") else (4 * HID,)
             self.register_parameter(name, nn.Parameter(torch.empty(shape, device=device).uniform_(-k, k)))   # nn.LSTM's init
-        self._ws = workspace if workspace is not None else LstmWorkspace(device, max_T, max_rows)
+        self._ws = workspace if workspace is not None else LstmWorkspace(device, max_T, min(max_rows, self.ROWS_PER_PASS))
+        self._more_ws = []   # further workspaces for batches wider than one pass (rows are independent sequences)
 
     def _params(self):
         return [getattr(self, n) for n in PARAM_NAMES]
 
+    def _chunks(self, rows):
+        """[(workspace, row0, row1)]: the batch in passes of at most ROWS_PER_PASS rows, each with its own workspace (a
+        workspace keeps ONE saved forward for backward)."""
+        cap = min(self.ROWS_PER_PASS, self._ws.max_rows)
+        n = (rows + cap - 1) // cap
+        while len(self._more_ws) < n - 1:
+            self._more_ws.append(LstmWorkspace(self._ws.device, self._ws.max_T, cap))
+        return [((self._ws if i == 0 else self._more_ws[i - 1]), i * cap, min(rows, (i + 1) * cap)) for i in range(n)]
+
     def forward(self, x, t_eff=None):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params())):
-            return _LstmFn.apply(self._ws, t_eff, x, None, None, *self._params())
-        return self._ws.forward([x], [self._params()], save=False, t_eff=t_eff)[0]
+        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params()))
+        outs = []
+        for ws, a, b in self._chunks(x.size(1)):
+            xc = x if (a == 0 and b == x.size(1)) else x[:, a:b].contiguous()
+            outs.append(_LstmFn.apply(ws, t_eff, xc, None, None, *self._params()) if grad
+                        else ws.forward([xc], [self._params()], save=False, t_eff=t_eff)[0])
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 1)
 
     def forward_pair(self, x, other, x_other, t_eff=None):
         """This network on `x` (differentiable) and `other` (a second DeviceLSTM, no gradient) on `x_other` in one pass --
         the online / target pair of R2D2Agent.td_error (r2d2.py:398-401)."""
-        return _LstmFn.apply(self._ws, t_eff, x, x_other, [p.detach() for p in other._params()], *self._params())
+        p2 = [p.detach() for p in other._params()]
+        ya, yb = [], []
+        for ws, a, b in self._chunks(x.size(1)):
+            whole = a == 0 and b == x.size(1)
+            o1, o2 = _LstmFn.apply(ws, t_eff, x if whole else x[:, a:b].contiguous(), x_other if whole else x_other[:, a:b].contiguous(), p2,
+                                   *self._params())
+            ya.append(o1)
+            yb.append(o2)
+        return (ya[0], yb[0]) if len(ya) == 1 else (torch.cat(ya, 1), torch.cat(yb, 1))

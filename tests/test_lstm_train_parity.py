@@ -80,6 +80,28 @@ def test_lstm_pair_runs_online_and_target_in_one_pass(hbl):
     ws.close()
 
 
+def test_lstm_wide_batches_run_in_row_passes(hbl):
+    """More rows than one pass holds (VDN with 3+ players: batch * P > 256): independent row chunks, one workspace each;
+    forward and all gradients still match."""
+    T, rows = 7, 600
+    ref, x, gy, y = _reference(T, rows, seed=11)
+    ref_b, xb, _, yb = _reference(T, rows, seed=12, scale=0.5)
+    dev = torch.device("cuda", 0)
+    a, b = hbl.DeviceLSTM(dev, max_T=T, max_rows=rows), hbl.DeviceLSTM(dev, max_T=T, max_rows=rows)
+    a.load_state_dict(ref.state_dict())
+    b.load_state_dict(ref_b.state_dict())
+    xd = x.detach().to(dev).requires_grad_(True)
+    yd, ybd = a.forward_pair(xd, b, xb.detach().to(dev))
+    assert yd.shape == (T, rows, 512) and len(a._more_ws) == 2
+    assert float((yd.detach().cpu() - y.detach()).abs().max()) < 1e-4 and float((ybd.cpu() - yb.detach()).abs().max()) < 1e-4
+    (yd * gy.to(dev)).sum().backward()
+    assert _rel(xd.grad.cpu(), x.grad) < 1e-4
+    for name in hbl.PARAM_NAMES:
+        assert _rel(getattr(a, name).grad.cpu(), getattr(ref, name).grad) < 1e-4, name
+    with torch.no_grad():
+        assert float((a(x.detach().to(dev)).cpu() - y.detach()).abs().max()) < 1e-4
+
+
 def test_lstm_rejects_what_it_cannot_serve(hbl):
     from hanabi_sad_b200._lib import HbError
 
