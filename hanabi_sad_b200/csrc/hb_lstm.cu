@@ -634,6 +634,7 @@ struct hb_lstm {
   int T, rows, R_pad, MB;                   // geometry of the last forward
   int saved;                                // 1: net 0's activations of the last forward are valid for backward
   int use_clusters, last_cluster;           // forward recurrence as 4-CTA multicast clusters when they all fit on the device
+  int zero_rpad, zero_rows_max;             // row geometry for which the h-sequence buffers are known to be clean
   HbLstmNetBuf nb[2];
   // saved for backward (net 0)
   __nv_bfloat16 *xT_hi, *xT_lo;             // [512][ldT]
@@ -820,11 +821,17 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     hbl::lstm_prep_x<<<dim3(hbl::HIDN / 32, R_pad / 32, T), dim3(32, 8), 0, st>>>(x[n], T, rows, R_pad, B.xs_hi, B.xs_lo, sv ? L->xT_hi : nullptr, sv ? L->xT_lo : nullptr, ldT);
     L->launches += 7;
   }
-  for (int n = 0; n < nets; ++n)
-    for (int l = 0; l < 2; ++l) {  // block 0 and the padded rows of a previous, differently shaped call
-      HB_CUDA(cudaMemsetAsync(L->nb[n].hs_hi[l], 0, (size_t)(T + 1) * R_pad * hbl::HIDN * bf, st));
-      HB_CUDA(cudaMemsetAsync(L->nb[n].hs_lo[l], 0, (size_t)(T + 1) * R_pad * hbl::HIDN * bf, st));
-    }
+  // Block 0 of the h sequences (h_{-1} = 0) and the padded rows must read as zero.  The kernels never write either, so the
+  // buffers (zeroed at creation) only need clearing when the row geometry changes or rows were valid in an earlier call.
+  if (R_pad != L->zero_rpad || rows < L->zero_rows_max) {
+    for (int n = 0; n < 2; ++n)
+      for (int l = 0; l < 2; ++l) {
+        HB_CUDA(cudaMemsetAsync(L->nb[n].hs_hi[l], 0, (size_t)(L->max_T + 1) * L->max_rpad * hbl::HIDN * bf, st));
+        HB_CUDA(cudaMemsetAsync(L->nb[n].hs_lo[l], 0, (size_t)(L->max_T + 1) * L->max_rpad * hbl::HIDN * bf, st));
+      }
+    L->zero_rpad = R_pad; L->zero_rows_max = rows;
+  }
+  if (rows > L->zero_rows_max) L->zero_rows_max = rows;
   HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
   std::vector<hbl::FwdParams> fp(2);
   memset(fp.data(), 0, 2 * sizeof(hbl::FwdParams));

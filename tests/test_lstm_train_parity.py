@@ -32,7 +32,8 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
 
 
-@pytest.mark.parametrize("T,rows", [(6, 128), (80, 256), (9, 40), (5, 130), (33, 128)], ids=["T6_r128", "T80_r256", "T9_r40_padded", "T5_r130_two_blocks", "T33_odd"])
+@pytest.mark.parametrize("T,rows", [(6, 128), (80, 256), (9, 40), (5, 130), (33, 128), (1, 1), (2, 3)],
+                         ids=["T6_r128", "T80_r256", "T9_r40_padded", "T5_r130_two_blocks", "T33_odd", "T1_single_row", "T2_r3"])
 def test_lstm_forward_backward_match_torch_cpu(hbl, T, rows):
     ref, x, gy, y = _reference(T, rows, seed=T * 1000 + rows)
     dev = torch.device("cuda", 0)
