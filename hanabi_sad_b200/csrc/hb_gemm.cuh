@@ -189,6 +189,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive TMEM columns of this warp's 32 lanes WITHOUT waiting: lets the next load fly while the previous one is
+// being consumed (tmem_wait_ld waits for everything outstanding).
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor: K-major operand tile of [rows][64] bf16, 128-byte swizzle (what TMA's
 // CU_TENSOR_MAP_SWIZZLE_128B writes): 8-row groups are 1024 bytes apart (SBO), descriptor version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
@@ -214,9 +228,14 @@ __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f
 __device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 __device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi_ptr, __nv_bfloat16* lo_ptr) {
-  __align__(16) __nv_bfloat16 h[16], l[16];
+  // two values per conversion (cvt.rn.bf16x2.f32): same round-to-nearest-even results as split_bf16, 40 % fewer instructions
+  __align__(16) __nv_bfloat162 h[8], l[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) split_bf16(v[i], h[i], l[i]);
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 back = __bfloat1622float2(h[i]);
+    l[i] = __floats2bfloat162_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+  }
   reinterpret_cast<uint4*>(hi_ptr)[0] = reinterpret_cast<const uint4*>(h)[0];
   reinterpret_cast<uint4*>(hi_ptr)[1] = reinterpret_cast<const uint4*>(h)[1];
   reinterpret_cast<uint4*>(lo_ptr)[0] = reinterpret_cast<const uint4*>(l)[0];
@@ -419,14 +438,34 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
             for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
       } else if (EPI == EPI_RELU) {
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-          const int col = n_tile * BN + c0;
+        // The mainloop of this layer is short (K = 896), so the epilogue must not be the longer of the two: the tile's 256
+        // biases are staged in shared memory once (instead of 256 global loads per thread), and the accumulator is read 32
+        // columns at a time with the next tcgen05.ld in flight while the previous 32 values are rectified, split and stored.
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous tile's biases
+        for (int i = threadIdx.x - 64; i < BN; i += 128) head_smem[i] = __ldg(p.bias + n_tile * BN + i);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t buf[2][32];
+        tmem_ld32_nowait(taddr, buf[0]);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + col + i), 0.f);
-          const size_t o = row * p.out_ld + p.out_col0 + col;
-          if (valid) store_split16(v, p.out_hi + o, p.out_lo + o);
+        for (int it = 0; it < BN / 32; ++it) {
+          const int c0 = it * 32;
+          tmem_wait_ld();
+          if (it + 1 < BN / 32) tmem_ld32_nowait(taddr + c0 + 32, buf[(it + 1) & 1]);
+          const uint32_t* cur = buf[it & 1];
+          const size_t o = row * p.out_ld + p.out_col0 + (size_t)n_tile * BN + c0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 b = *reinterpret_cast<const float4*>(head_smem + c0 + 16 * h + 4 * i4);
+              v[4 * i4] = fmaxf(__uint_as_float(cur[16 * h + 4 * i4]) + b.x, 0.f);
+              v[4 * i4 + 1] = fmaxf(__uint_as_float(cur[16 * h + 4 * i4 + 1]) + b.y, 0.f);
+              v[4 * i4 + 2] = fmaxf(__uint_as_float(cur[16 * h + 4 * i4 + 2]) + b.z, 0.f);
+              v[4 * i4 + 3] = fmaxf(__uint_as_float(cur[16 * h + 4 * i4 + 3]) + b.w, 0.f);
+            }
+            if (valid) store_split16(v, p.out_hi + o + 16 * h, p.out_lo + o + 16 * h);
+          }
         }
       } else {
         // tile columns: [gate i | f | g | o][64 hidden units]; hidden unit = n_tile*64 + u
