@@ -160,3 +160,43 @@ def test_aggregate_priority_matches_oracle():
     L = rng.integers(1, 81, size=16).astype(np.float32)
     got = aggregate_priority(torch.from_numpy(p), torch.from_numpy(L), 0.9).numpy()
     assert np.allclose(got, ref(p, L, 0.9), rtol=1e-6)
+
+
+def test_actor_duty_cycle_survives_a_contended_chunk(ref_modules, monkeypatch):
+    """rela.set_actor_duty: the driver idles in proportion to the UNCONTENDED chunk time.  One chunk that takes 100x longer
+    (the learner's kernels holding the GPU) must not put the actors to sleep for 100x longer -- that starved them for whole
+    epochs."""
+    create, ref_eval, r2d2, rela = ref_modules
+    import hanabi_sad_b200.rela as hrela
+
+    slow = {"left": 1}
+    orig = FakeEngine.rollout
+
+    def rollout(self, n):
+        orig(self, n)          # ~1 ms
+        if self.ticks > 40 and slow["left"] > 0:
+            slow["left"] -= 1
+            time.sleep(0.1)    # one contended chunk
+
+    monkeypatch.setattr(FakeEngine, "rollout", rollout)
+    monkeypatch.setattr(hrela, "_actor_duty", 0.1)
+    games = create.create_envs(4, 1, 2, 5, 0, [0.1], 80, True, False, False)
+    agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, "cpu", 838, 512, 21, 2, 5, False)
+    replay = rela.RNNPrioritizedReplay(100, 1, 0.9, 0.6, 3)
+    ag = create.ActGroup("vdn", "cpu", agent, 2, 2, 3, 0.999, 0.9, 80, 2, replay)
+    context, threads = create.create_threads(2, 2, ag.actors, games)
+    ag.start()
+    context.start()
+    eng = FakeEngine.instances[0]
+    t0 = time.time()
+    while slow["left"] > 0:
+        assert time.time() - t0 < 10
+        time.sleep(0.005)
+    time.sleep(0.15)           # the contended chunk is over by now
+    a = eng.ticks
+    time.sleep(0.5)
+    b = eng.ticks
+    context.terminate()
+    # duty 0.1 of ~1 ms chunks = one 8-tick chunk every ~10-12 ms: ~40 chunks in 0.5 s; a sleep proportional to the slow chunk
+    # (0.1 s x 9) would allow none
+    assert b - a >= 8 * 10, (a, b)
