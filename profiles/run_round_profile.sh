@@ -13,6 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 100 --csv --l
     python bench.py --steps 20 --warmup 10 --no_cpu_baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"gemm3_kernel|hb_k_tick|hb_k_head" -s 50 -c 5 -f -o gpurun_out/prof_${TAG} \
     python bench.py --steps 6 --warmup 6 --no_cpu_baseline > /dev/null 2>&1
+if [ -n "$SKIP_LEARNER" ]; then ls -la gpurun_out | tail -12; exit 0; fi
 # learner side: LSTM training kernels vs cuDNN, whole-update profiles, launch list + full captures of the recurrences
 python tools/bench_lstm.py --rows 256 > gpurun_out/lstm_${TAG}_rows256.json 2> gpurun_out/lstm_${TAG}.err; cat gpurun_out/lstm_${TAG}_rows256.json
 python tools/bench_lstm.py --rows 128 > gpurun_out/lstm_${TAG}_rows128.json 2>> gpurun_out/lstm_${TAG}.err
