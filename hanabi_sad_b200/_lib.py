@@ -91,6 +91,7 @@ SIGNATURES = {
     "hb_lstm_forward": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(HbLstmWeights), ctypes.POINTER(c_void_p),
                                 c_int, c_void_p]),
     "hb_lstm_backward": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(HbLstmGrads), c_void_p]),
+    "hb_gemm_nt": (c_int, [c_int, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
     "hb_lstm_sync": (c_int, [c_void_p]),
     "hb_lstm_launches": (c_i64, [c_void_p]),
     "hb_debug_operand": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int)]),

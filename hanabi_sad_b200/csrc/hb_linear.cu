@@ -1,0 +1,153 @@
+// hb_linear.cu -- learner side: the dense layers around the LSTM.  The reference learner runs
+// nn.Linear(838 -> 512) + ReLU over all T*rows steps of a batch (pyhanabi/r2d2.py:42-46, 99) and its weight gradient in
+// fp32 on the CUDA cores (cuBLAS SIMT sgemm, 0.7 + 0.45 ms per update at rows = 256).  hb_gemm_nt is the same contraction
+// at fp32-class accuracy on the tensor cores: C[M,N] = A[M,K] B[N,K]^T (+ bias) with both operands split into bf16
+// hi/lo pairs and multiplied as hi*lo + lo*hi + hi*hi in the tcgen05 GEMM template of hb_gemm.cuh (EPI_F32).  Shapes are
+// padded internally to the template's 128 x 256 x 64 tiles; when a problem has few output tiles and a long K (the weight
+// gradient: [512, T*rows] x [T*rows, 838]) it is split over K into partial problems of ONE launch and summed afterwards,
+// so that all SMs work.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+#include <vector>
+
+#include "hb_engine.h"
+#include "hb_gemm.cuh"
+#include "hb_gemm_host.h"
+
+using hbg::Params;
+
+namespace {
+
+constexpr int MAX_SPLIT = 16;
+
+struct GemmScratch {            // grow-only device scratch per GPU (one learner process per GPU: calls are serialized by the caller)
+  __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  size_t a_cap = 0, b_cap = 0;  // elements
+  float* c_part = nullptr;      // [split][M_pad][N_pad]
+  size_t c_cap = 0;
+  Params* d_params = nullptr;   // [MAX_SPLIT]
+  int* d_error = nullptr;
+  int sm_count = 0;
+  bool attrs = false;
+};
+GemmScratch g_scratch[16];
+
+// fp32 [rows][cols] (row stride ld) -> bf16 hi/lo [rows_pad][cols_pad], zero padded
+__global__ void split_pad(const float* __restrict__ src, long long ld, int rows, int cols, int rows_pad, int cols_pad,
+                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows_pad * cols_pad) return;
+  const int r = (int)(i / cols_pad), c = (int)(i - (long long)r * cols_pad);
+  const float v = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.f;
+  __nv_bfloat16 h, l;
+  hbg::split_bf16(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+// C[r][c] = sum_s part[s][r][c] (+ bias[c]) for r < M, c < N
+__global__ void sum_parts(const float* __restrict__ part, int split, long long part_stride, int n_pad, const float* __restrict__ bias,
+                          float* __restrict__ C, long long ldc, int M, int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int r = (int)(i / N), c = (int)(i - (long long)r * N);
+  float acc = bias ? bias[c] : 0.f;
+  for (int s = 0; s < split; ++s) acc += part[(long long)s * part_stride + (long long)r * n_pad + c];
+  C[(long long)r * ldc + c] = acc;
+}
+
+int grow(void** p, size_t* cap, size_t need, size_t elem) {
+  if (*cap >= need) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  if (cudaMalloc(p, need * elem) != cudaSuccess) { hb_set_error("hb_gemm_nt: out of device memory (%zu bytes)", need * elem); return -2; }
+  *cap = need;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int hb_gemm_nt(int device, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                          int M, int N, int K, void* stream) {
+  if (!A || !B || !C) { hb_set_error("hb_gemm_nt: null argument"); return -1; }
+  if (M < 1 || N < 1 || K < 1 || lda < K || ldb < K || ldc < N) { hb_set_error("hb_gemm_nt: bad shape M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld", M, N, K, (long long)lda, (long long)ldb, (long long)ldc); return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { hb_set_error("hb_gemm_nt: no CUDA device -- libhanabi_b200 has no CPU path"); return -2; }
+  if (device < 0 || device >= ndev || device >= 16) { hb_set_error("hb_gemm_nt: bad device ordinal"); return -1; }
+  HB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmScratch& S = g_scratch[device];
+  if (!S.sm_count) {
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, device));
+    S.sm_count = prop.multiProcessorCount;
+    HB_CUDA(cudaMalloc((void**)&S.d_params, MAX_SPLIT * sizeof(Params)));
+    HB_CUDA(cudaMalloc((void**)&S.d_error, sizeof(int)));
+    HB_CUDA(cudaMemset(S.d_error, 0, sizeof(int)));
+    HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
+    HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
+  }
+  const int Mp = (M + hbg::BM - 1) / hbg::BM * hbg::BM, Np = (N + hbg::BN - 1) / hbg::BN * hbg::BN;
+  const int mt = Mp / hbg::BM, nt = Np / hbg::BN;
+  // split K so that the launch has about one tile per SM (each part at least 8 K-chunks)
+  const int kc_total = (K + hbg::BK - 1) / hbg::BK;
+  int split = 1;
+  while (split < MAX_SPLIT && mt * nt * split * 2 <= S.sm_count && kc_total / (split * 2) >= 8) split *= 2;
+  const int kc_part = (kc_total + split - 1) / split;
+  const int Kp = kc_part * split * hbg::BK;
+  const bool direct = split == 1 && Mp == M && Np == N && ldc == N;   // the template can write the caller's C itself
+  int rc = 0;
+  if (S.a_cap < (size_t)Mp * Kp) {   // hi and lo grow together (cudaFree synchronises the device: nothing queued still reads them)
+    size_t c1 = 0, c2 = 0;
+    if (S.a_hi) cudaFree(S.a_hi);
+    if (S.a_lo) cudaFree(S.a_lo);
+    S.a_hi = S.a_lo = nullptr; S.a_cap = 0;
+    rc |= grow((void**)&S.a_hi, &c1, (size_t)Mp * Kp, sizeof(__nv_bfloat16));
+    rc |= grow((void**)&S.a_lo, &c2, (size_t)Mp * Kp, sizeof(__nv_bfloat16));
+    if (rc) return rc;
+    S.a_cap = (size_t)Mp * Kp;
+  }
+  if (S.b_cap < (size_t)Np * Kp) {
+    size_t c1 = 0, c2 = 0;
+    if (S.b_hi) cudaFree(S.b_hi);
+    if (S.b_lo) cudaFree(S.b_lo);
+    S.b_hi = S.b_lo = nullptr; S.b_cap = 0;
+    rc |= grow((void**)&S.b_hi, &c1, (size_t)Np * Kp, sizeof(__nv_bfloat16));
+    rc |= grow((void**)&S.b_lo, &c2, (size_t)Np * Kp, sizeof(__nv_bfloat16));
+    if (rc) return rc;
+    S.b_cap = (size_t)Np * Kp;
+  }
+  if (!direct) { rc = grow((void**)&S.c_part, &S.c_cap, (size_t)split * Mp * Np, sizeof(float)); if (rc) return rc; }
+  const long long na = (long long)Mp * Kp, nb = (long long)Np * Kp;
+  split_pad<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo);
+  split_pad<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, ldb, N, K, Np, Kp, S.b_hi, S.b_lo);
+  const int cl = (mt % 2 == 0) ? 2 : 1;
+  std::vector<Params> hp(split);
+  for (int s = 0; s < split; ++s) {
+    Params& p = hp[s];
+    memset(&p, 0, sizeof(p));
+    const size_t koff = (size_t)s * kc_part * hbg::BK;
+    rc |= hb_make_tmap(&p.a_hi[0], S.a_hi + koff, Mp, (uint64_t)kc_part * hbg::BK, hbg::BM, Kp);
+    rc |= hb_make_tmap(&p.a_lo[0], S.a_lo + koff, Mp, (uint64_t)kc_part * hbg::BK, hbg::BM, Kp);
+    p.a_hi[1] = p.a_hi[0]; p.a_lo[1] = p.a_lo[0];
+    rc |= hb_make_tmap(&p.b_hi, S.b_hi + koff, Np, (uint64_t)kc_part * hbg::BK, hbg::BN / cl, Kp);
+    rc |= hb_make_tmap(&p.b_lo, S.b_lo + koff, Np, (uint64_t)kc_part * hbg::BK, hbg::BN / cl, Kp);
+    p.k_chunks = kc_part; p.k_chunks_seg0 = kc_part; p.lo_first = 0; p.lo_last = kc_part; p.split = 1;
+    p.bias = direct ? bias : nullptr;
+    p.c_f32 = direct ? C : S.c_part + (size_t)s * Mp * Np;
+    p.ldc = direct ? (int)ldc : Np;
+    p.error_flag = S.d_error; p.row_mul = 1; p.row_add = 0; p.valid_rows = Mp;
+  }
+  if (rc) return -2;
+  HB_CUDA(cudaMemcpyAsync(S.d_params, hp.data(), split * sizeof(Params), cudaMemcpyHostToDevice, st));
+  if (cl == 2) rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_F32, 3>, 2, S.sm_count, st, S.d_params, nt, mt, split);
+  else rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_F32, 1>, 1, S.sm_count, st, S.d_params, nt, mt, split);
+  if (rc) return rc;
+  if (!direct) {
+    const long long n = (long long)M * N;
+    sum_parts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S.c_part, split, (long long)Mp * Np, Np, bias, C, ldc, M, N);
+  }
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}

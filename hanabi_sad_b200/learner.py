@@ -12,7 +12,7 @@ half up.  No fallback: without a CUDA device `loss` raises."""
 import torch
 from torch import nn
 
-from .lstm import DeviceLSTM, LstmWorkspace
+from .lstm import DeviceLSTM, LstmWorkspace, device_linear
 
 
 class DeviceR2D2Net(nn.Module):
@@ -36,6 +36,11 @@ class DeviceR2D2Net(nn.Module):
         self._ref_cross_entropy = ref_net_cls.cross_entropy
         self._partner = None      # the network whose LSTM rides along with this one's forward (target net)
         self._ride = None         # (input tensor, lstm output) left by the partner's forward
+        # fc layers on hb_gemm_nt (bf16x3 on the tensor cores) instead of torch's linear (cuBLAS SIMT sgemm): 0.7 ms faster
+        # per full-length update.  Off by default: its pre-activations differ from fp32 sgemm's by ~3e-6 instead of ~1e-7,
+        # which flips the ReLU gate of the ~1e-5 of them that sit that close to zero -- harmless for training, but the
+        # gradient of net.0 then matches the reference to 5e-4 of its largest entry instead of 1.4e-5.
+        self.device_fc = False
         self._t_eff = None        # longest episode of the batch in flight (set by DeviceLearner.loss): later steps are padding
 
     def cross_entropy(self, net, lstm_o, target_p, hand_slot_mask, seq_len):
@@ -44,16 +49,25 @@ class DeviceR2D2Net(nn.Module):
     def pred_loss_1st(self, lstm_o, target, hand_slot_mask, seq_len):
         return self.cross_entropy(self.pred, lstm_o, target, hand_slot_mask, seq_len)
 
+    def _fc(self, ps):
+        """self.net (Linear + ReLU per fc layer, r2d2.py:42-46) with the contractions on the device GEMM."""
+        if not self.device_fc:
+            return self.net(ps)
+        x = ps
+        for layer in self.net:
+            x = device_linear(x, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(x)
+        return x
+
     def _lstm_out(self, key, ps):
         """LSTM output for the (already truncated) input `ps`; `key` identifies the batch (the caller's full priv_s tensor)."""
         if self._ride is not None and self._ride[0] is key:   # computed during the online network's forward
             o, self._ride = self._ride[1], None
             return o
-        x = self.net(ps)
+        x = self._fc(ps)
         p = self._partner
         if p is not None and torch.is_grad_enabled():
             with torch.no_grad():
-                xp = p.net(ps)
+                xp = p._fc(ps)
             o, op = self.lstm.forward_pair(x, p.lstm, xp)
             p._ride = (key, op)
             return o
@@ -112,13 +126,15 @@ class DeviceLearner(nn.Module):
             self.online_net._t_eff = self.target_net._t_eff = None
 
     @classmethod
-    def from_agent(cls, agent, max_T=80, max_rows=256):
-        """`agent`: a reference r2d2.R2D2Agent; hyper-parameters and weights are taken from it."""
+    def from_agent(cls, agent, max_T=80, max_rows=256, device_fc=False):
+        """`agent`: a reference r2d2.R2D2Agent; hyper-parameters and weights are taken from it.  device_fc: also run the fc
+        layers on the device GEMM (see DeviceR2D2Net.device_fc)."""
         n = agent.online_net
         dev = next(n.parameters()).device
         lr = cls(type(agent), type(n), agent.vdn, agent.multi_step, agent.gamma, agent.eta, dev, n.in_dim, n.hid_dim, n.out_dim, n.num_lstm_layer,
                  n.hand_size, agent.uniform_priority, num_fc_layer=n.num_fc_layer, skip_connect=n.skip_connect, max_T=max_T, max_rows=max_rows)
         lr.load_state_dict(agent.state_dict())
+        lr.online_net.device_fc = lr.target_net.device_fc = bool(device_fc)
         lr._ref_agent = [agent]   # in a list: not a sub-module (the state_dict keys stay those of R2D2Agent)
         return lr
 

@@ -114,6 +114,52 @@ class LstmWorkspace:
         return dx, grads
 
 
+def gemm_nt(a, b, bias=None):
+    """a [M, K] @ b [N, K]^T (+ bias [N]) -> [M, N]: float32 CUDA tensors, fp32-class accuracy on the tensor cores
+    (hb_gemm_nt, csrc/hb_linear.cu).  Rows may be strided (row stride >= K), the inner dimension must be contiguous."""
+    assert a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
+    assert a.size(1) == b.size(1), (tuple(a.shape), tuple(b.shape))
+    if a.stride(1) != 1:
+        a = a.contiguous()
+    if b.stride(1) != 1:
+        b = b.contiguous()
+    M, K = a.shape
+    N = b.size(0)
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if bias is not None:
+        bias = bias.detach().contiguous()
+    stream = torch.cuda.current_stream(a.device).cuda_stream
+    check(lib().hb_gemm_nt(a.device.index or 0, a.data_ptr(), int(a.stride(0)), b.data_ptr(), int(b.stride(0)), bias.data_ptr() if bias is not None else None,
+                           c.data_ptr(), N, int(M), int(N), int(K), ctypes.c_void_p(stream)))
+    return c
+
+
+class _LinearFn(torch.autograd.Function):
+    """torch.nn.functional.linear on hb_gemm_nt: y = x W^T + b; dX = dY W, dW = dY^T X, db = sum(dY)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return gemm_nt(x.detach(), w.detach(), b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = gemm_nt(dy, w.detach().t().contiguous()) if ctx.needs_input_grad[0] else None     # [M, N] x [K, N]^T
+        dw = gemm_nt(dy.t().contiguous(), x.detach().t().contiguous()) if ctx.needs_input_grad[1] else None   # [N, M] x [K, M]^T
+        db = dy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def device_linear(x, weight, bias=None):
+    """F.linear(x, weight, bias) for x [..., K] on the device GEMM (autograd-aware)."""
+    lead = x.shape[:-1]
+    y = _LinearFn.apply(x.reshape(-1, x.size(-1)), weight, bias)
+    return y.view(*lead, weight.size(0))
+
+
 class _LstmFn(torch.autograd.Function):
     """y = LSTM(x; 8 parameters), optionally with a second, gradient-free network run in the same kernels."""
 

@@ -250,6 +250,14 @@ int hb_lstm_forward(hb_lstm* l, int T, int rows, int nets, const float* const* x
  * NULL) and the parameter gradients. */
 int hb_lstm_backward(hb_lstm* l, const float* dy, float* dx, const hb_lstm_grads* g, void* stream);
 
+/* The dense layers around the LSTM (nn.Linear(838, 512) of R2D2Net.net over all T*rows steps, pyhanabi/r2d2.py:42-46, 99,
+ * and its weight gradient): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) on DEVICE fp32 row-major buffers (row strides lda, ldb,
+ * ldc in elements) at fp32-class accuracy on the tensor cores (bf16x3) -- what cuBLAS runs as a SIMT sgemm when TF32 is off
+ * (torch's default for matmul).  Any M, N, K >= 1 (padded internally; long-K problems with few output tiles are split over
+ * K).  Asynchronous on `stream`; scratch is per device and grow-only, so calls on one device must not overlap. */
+int hb_gemm_nt(int device, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+               int M, int N, int K, void* stream);
+
 /* Waits for the last hb_lstm_forward / hb_lstm_backward and reports its device-side status. */
 int hb_lstm_sync(hb_lstm* l);
 

@@ -52,9 +52,12 @@ def test_device_learner_is_a_drop_in_for_the_reference_agent_object():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("vdn,B,pred_weight,max_seq", [(False, 128, 0.0, 80), (True, 64, 0.25, 80), (False, 20, 0.25, 80), (True, 64, 0.25, 23), (False, 128, 0.0, 41)],
-                         ids=["iql_b128", "vdn_b64_aux", "iql_b20_aux_padded_rows", "vdn_short_episodes_skip_padding", "iql_short_episodes_skip_padding"])
-def test_loss_priority_and_gradients_match_the_reference_learner(gpu_or_skip, vdn, B, pred_weight, max_seq):
+@pytest.mark.parametrize("vdn,B,pred_weight,max_seq,device_fc",
+                         [(False, 128, 0.0, 80, False), (True, 64, 0.25, 80, False), (False, 20, 0.25, 80, False), (True, 64, 0.25, 23, False),
+                          (False, 128, 0.0, 41, False), (False, 128, 0.0, 41, True)],
+                         ids=["iql_b128", "vdn_b64_aux", "iql_b20_aux_padded_rows", "vdn_short_episodes_skip_padding", "iql_short_episodes_skip_padding",
+                              "iql_device_fc"])
+def test_loss_priority_and_gradients_match_the_reference_learner(gpu_or_skip, vdn, B, pred_weight, max_seq, device_fc):
     from hanabi_sad_b200.learner import DeviceLearner
     from hanabi_sad_b200.rela import RNNTransition
     from profile_learner import synthetic_batch
@@ -67,7 +70,7 @@ def test_loss_priority_and_gradients_match_the_reference_learner(gpu_or_skip, vd
     (loss * weight).mean().backward()
 
     dev = torch.device("cuda", 0)
-    lr = DeviceLearner.from_agent(ag.to("cpu"), max_T=T, max_rows=B * (2 if vdn else 1)).to(dev)
+    lr = DeviceLearner.from_agent(ag.to("cpu"), max_T=T, max_rows=B * (2 if vdn else 1), device_fc=device_fc).to(dev)
     assert lr.online_net.lstm.weight_hh_l0.is_cuda
     mv = lambda d: {k: v.to(dev) for k, v in d.items()}
     n0 = lr.workspace._h
@@ -86,5 +89,7 @@ def test_loss_priority_and_gradients_match_the_reference_learner(gpu_or_skip, vd
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
             continue
         assert p.grad is not None, name
-        assert rel(p.grad.cpu(), want) < 5e-4, (name, rel(p.grad.cpu(), want))
+        # with the fc layers on the bf16x3 GEMM a few ReLU gates at |pre-activation| < 3e-6 flip (learner.py): net.0 only
+        tol = 2e-3 if (device_fc and name.startswith("net.")) else 2e-4
+        assert rel(p.grad.cpu(), want) < tol, (name, rel(p.grad.cpu(), want))
     assert all(p.grad is None for p in lr.target_net.parameters())

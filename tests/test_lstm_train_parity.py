@@ -116,3 +116,37 @@ def test_lstm_rejects_what_it_cannot_serve(hbl):
     with pytest.raises(RuntimeError, match="no CPU path"):
         hbl.DeviceLSTM("cpu")(torch.zeros(2, 4, 512))
     ws.close()
+
+
+@pytest.mark.parametrize("M,N,K", [(20480, 512, 838), (512, 838, 20480), (300, 21, 512), (1, 1, 1), (130, 512, 70)],
+                         ids=["fc_forward", "fc_weight_grad_splitK", "head_like", "tiny", "ragged"])
+def test_gemm_nt_is_fp32_class(hbl, M, N, K):
+    """hb_gemm_nt (bf16x3 on tcgen05, padded / split over K) against float64 on the CPU: fp32-class, i.e. within 2e-5 of the
+    largest output (a dropped lo*lo term is 2^-16 relative per product; plain bf16 would be ~4e-3)."""
+    torch.manual_seed(M + N + K)
+    a, b, bias = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N)
+    want = (a.double() @ b.double().t() + bias.double())
+    dev = torch.device("cuda", 0)
+    got = hbl.gemm_nt(a.to(dev), b.to(dev), bias.to(dev)).cpu().double()
+    scale = float(want.abs().max())
+    err = float((got - want).abs().max())
+    assert err < 2e-5 * max(scale, 1.0), (err, scale)
+    # strided rows (a view into a wider buffer)
+    wide = torch.randn(M, K + 7, device=dev)
+    got2 = hbl.gemm_nt(wide[:, :K], b.to(dev)).cpu().double()
+    assert float((got2 - wide[:, :K].cpu().double() @ b.double().t()).abs().max()) < 2e-5 * max(scale, 1.0)
+
+
+def test_device_linear_gradients(hbl):
+    torch.manual_seed(3)
+    x, w, b = torch.randn(7, 96, 838), torch.randn(512, 838) / 29.0, torch.randn(512)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    g = torch.randn(7, 96, 512)
+    (torch.nn.functional.linear(xr, wr, br) * g).sum().backward()
+    dev = torch.device("cuda", 0)
+    xd, wd, bd = (t.to(dev).requires_grad_(True) for t in (x, w, b))
+    y = hbl.device_linear(xd, wd, bd)
+    assert y.shape == (7, 96, 512)
+    (y * g.to(dev)).sum().backward()
+    for got, want in ((xd.grad, xr.grad), (wd.grad, wr.grad), (bd.grad, br.grad)):
+        assert _rel(got.cpu(), want) < 1e-5

@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--pred_weight", type=float, default=0.0)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--max_seq", type=int, default=80, help="longest episode in the synthetic batch (trained agents: 60-80; early training: 5-30)")
+    ap.add_argument("--device_fc", type=int, default=0, help="device impl only: fc layers on hb_gemm_nt as well")
     ap.add_argument("--impl", default="reference", choices=["reference", "device"],
                     help="reference: r2d2.R2D2Agent as is (cuDNN LSTM); device: hanabi_sad_b200.learner.DeviceLearner (LSTM on csrc/hb_lstm.cu)")
     a = ap.parse_args()
@@ -68,7 +69,7 @@ def main():
     if a.impl == "device":
         from hanabi_sad_b200.learner import DeviceLearner
 
-        agent = DeviceLearner.from_agent(agent, max_T=T, max_rows=a.batchsize * (P if vdn else 1))
+        agent = DeviceLearner.from_agent(agent, max_T=T, max_rows=a.batchsize * (P if vdn else 1), device_fc=bool(a.device_fc))
     optim = torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
     obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, a.batchsize, P, F, A, H, vdn, dev, max_seq=a.max_seq)
     weight = torch.ones(a.batchsize, device=dev)
