@@ -8,7 +8,7 @@ if _root not in _sys.path:
     _sys.path.insert(0, _root)
 
 from hanabi_sad_b200.rela import *  # noqa: F401,F403,E402
-from hanabi_sad_b200.rela import aggregate_priority, BatchRunner, Context, R2D2Actor, RNNPrioritizedReplay, RNNTransition, ThreadLoop  # noqa: F401,E402
+from hanabi_sad_b200.rela import aggregate_priority, BatchRunner, Context, FFTransition, R2D2Actor, RNNPrioritizedReplay, RNNTransition, ThreadLoop  # noqa: F401,E402
 from hanabi_sad_b200 import build as _build  # noqa: E402
 
 # pyhanabi/create.py:20-21 asserts that the module is a compiled extension; the code behind this module is this library

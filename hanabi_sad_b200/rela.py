@@ -98,6 +98,20 @@ class RNNTransition:
                              self.seq_len.to(device))
 
 
+class FFTransition:
+    """rela.FFTransition (rela/pybind.cc:17-23): obs, action, reward, terminal, bootstrap, next_obs.  Bound by the reference for
+    completeness -- nothing in pyhanabi produces or consumes one (the FF replay binding is commented out, pybind.cc:34-44);
+    the same copy-on-read dict semantics as RNNTransition."""
+
+    def __init__(self, obs=None, action=None, reward=None, terminal=None, bootstrap=None, next_obs=None):
+        self._obs, self._action, self._next_obs = dict(obs or {}), dict(action or {}), dict(next_obs or {})
+        self.reward, self.terminal, self.bootstrap = reward, terminal, bootstrap
+
+    obs = property(lambda self: dict(self._obs), lambda self, v: setattr(self, "_obs", dict(v)))
+    action = property(lambda self: dict(self._action), lambda self, v: setattr(self, "_action", dict(v)))
+    next_obs = property(lambda self: dict(self._next_obs), lambda self, v: setattr(self, "_next_obs", dict(v)))
+
+
 class RNNPrioritizedReplay:
     """rela.RNNPrioritizedReplay(capacity, seed, alpha, beta, prefetch) (rela/prioritized_replay.h:176-265).  The storage is
     the device ring of the engine(s) created by Context.start(); `prefetch` is accepted and ignored (sampling is a

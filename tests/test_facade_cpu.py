@@ -89,6 +89,13 @@ def ref_modules(monkeypatch):
     import rela
 
     assert rela.__file__.endswith(".so") and rela.Context is hrela.Context
+    # every name the reference's rela module exports (rela/pybind.cc:16-93)
+    for name in ("FFTransition", "RNNTransition", "RNNPrioritizedReplay", "ThreadLoop", "Context", "R2D2Actor", "BatchRunner", "aggregate_priority"):
+        assert hasattr(rela, name), name
+    ff = rela.FFTransition({"s": torch.zeros(2)}, {"a": torch.zeros(1)}, torch.zeros(1), torch.zeros(1), torch.ones(1), {"s": torch.ones(2)})
+    d = ff.obs
+    d["s"] = None
+    assert ff.obs["s"] is not None and float(ff.next_obs["s"].sum()) == 2.0
     yield create, ref_eval, r2d2, rela
     for m in ("rela", "hanalearn", "create", "eval", "r2d2", "utils"):
         sys.modules.pop(m, None)
