@@ -116,6 +116,19 @@ class HanabiEnv:
         i = self._info()
         return i.last_score
 
+    def deck_history(self):
+        """HanabiEnv::deckHistory (hanabi_env.h:112-114 -> HanabiDeck::DeckHistory, hanabi_state.h:73-92): the episode's whole
+        deal order as "<rank><colour letter>" strings ("3b" = rank 3 of colour b).  The reference gets it by dealing the rest of
+        the deck (which ends the game's usefulness); here the order exists up front (pre-shuffled deck) and reading it changes
+        nothing."""
+        e = self._eng()
+        if self._lock is not None:
+            with self._lock:
+                deck = e.get_deck(self._slot)
+        else:
+            deck = e.get_deck(self._slot)
+        return ["%d%s" % (int(c) % 5 + 1, "abcde"[int(c) // 5]) for c in deck]
+
     def get_score(self):
         return self._info().score
 

@@ -46,6 +46,9 @@ def _run_known_answer(hb, row, policy, n_ep):
         env.inject(orc.peek_deck(), orc.eps_idx(), orc.perms())
         obs = env.reset()
         feed_obs(h, obs)
+        # HanabiEnv.deck_history (cpp/pybind.cc:32): the episode's deal order as "<rank><colour letter>" strings
+        dh = env.deck_history()
+        assert dh == ["%d%s" % (int(c) % 5 + 1, "abcde"[int(c) // 5]) for c in orc.peek_deck()] and len(dh) == 50
         n = 0
         while True:
             cur = env.get_current_player()
