@@ -37,6 +37,12 @@
 using hbg::Params;
 using namespace hbg;
 
+// 1: the backward recurrence accumulates the split-K partials of dh_{t-1} with vector reductions at L2 instead of
+// exchanging 32 partial tiles per row block (see lstm_bwd_kernel)
+#ifndef HBL_BWD_ATOMIC
+#define HBL_BWD_ATOMIC 1
+#endif
+
 namespace hbl {
 
 constexpr int HIDN = 512;
@@ -381,7 +387,8 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
     const bool valid = row < P.rows;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int unit = slice * UPC;
-    const size_t part_dom = (size_t)P.MB * SLICES;   // partial blocks per buffer
+    const size_t part_dom = (size_t)P.MB * SLICES;   // partial blocks per buffer (exchange variant)
+    (void)part_dom;
     float dc[UPC];
 #pragma unroll
     for (int i = 0; i < UPC; ++i) dc[i] = 0.f;
@@ -412,6 +419,17 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         if (lane == 0) wait_counter(ctr, (unsigned)(SLICES * (T - 1 - t)), ef, dead);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
         if (!dead) {
+#if HBL_BWD_ATOMIC
+          // the 32 CTAs of the row block ADDED their partials into one [rows][512] accumulator (red.global.add.v4.f32 at L2):
+          // one 64-byte read instead of 32, then clear the slice for the step after next (same buffer parity)
+          float4* acc4 = reinterpret_cast<float4*>(P.part + (((size_t)((t + 1) & 1) * P.MB + dom) * BM + r) * HIDN + unit);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = __ldcg(acc4 + i);
+            dh[4 * i] += v.x; dh[4 * i + 1] += v.y; dh[4 * i + 2] += v.z; dh[4 * i + 3] += v.w;
+            __stcg(acc4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+#else
           const float* pb = P.part + ((((size_t)((t + 1) & 1) * part_dom + (size_t)dom * SLICES) * BM + r) * HIDN + unit);
 #pragma unroll
           for (int j0 = 0; j0 < SLICES; j0 += 8) {   // 32 independent 16-byte loads in flight per thread
@@ -427,6 +445,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
 #pragma unroll
               for (int i = 0; i < 4; ++i) { dh[4 * i] += v[j][i].x; dh[4 * i + 1] += v[j][i].y; dh[4 * i + 2] += v[j][i].z; dh[4 * i + 3] += v[j][i].w; }
           }
+#endif
         }
       }
       // pointwise backward of the cell (gate activations saved by the forward kernel)
@@ -468,7 +487,11 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         for (int i = 0; i < NC / 8; ++i) { d0[i] = reinterpret_cast<const uint4*>(ghi)[i]; d1[i] = reinterpret_cast<const uint4*>(glo)[i]; }
       }
       if (t == 0) break;
+#if HBL_BWD_ATOMIC
+      float* dst = P.part + (((size_t)(t & 1) * P.MB + dom) * BM + r) * HIDN;
+#else
       float* dst = P.part + ((((size_t)(t & 1) * part_dom + (size_t)dom * SLICES + slice) * BM + r) * HIDN);
+#endif
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         wait_bar(bar_tfull + 8 * half, (uint32_t)(T - 1 - t) & 1u, ef, dead);
@@ -481,9 +504,16 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
           tmem_ld32_nowait(taddr + c0 + 32, v + 32);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
+          for (int i = 0; i < 16; ++i) {
+#if HBL_BWD_ATOMIC
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * i), "f"(__uint_as_float(v[4 * i])),
+                         "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
+                         : "memory");
+#else
             __stcg(reinterpret_cast<float4*>(dst + c0) + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                                                                          __uint_as_float(v[4 * i + 3])));
+#endif
+          }
         }
       }
       tc_fence_before();
@@ -926,6 +956,9 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
       const size_t bf = sizeof(__nv_bfloat16);
       HB_CUDA(cudaMemsetAsync(L->dg_hi[l], 0, N * hbl::G4 * bf, st)); HB_CUDA(cudaMemsetAsync(L->dg_lo[l], 0, N * hbl::G4 * bf, st));
     }
+#if HBL_BWD_ATOMIC
+    HB_CUDA(cudaMemsetAsync(L->part, 0, (size_t)2 * R_pad * hbl::HIDN * sizeof(float), st));   // the two dh accumulators
+#endif
     HB_CUDA(cudaMemcpyAsync(L->d_bwd + l, &Q, sizeof(Q), cudaMemcpyHostToDevice, st));
     hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, st>>>(L->d_bwd + l);
     hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(N / 64)), 256, 0, st>>>(L->dg_hi[l], L->dg_lo[l], hbl::G4, L->dgT_hi[l], L->dgT_lo[l], (long long)N);
