@@ -12,15 +12,16 @@
 //                      network run in the same launch.
 //   backward           lstm_bwd_kernel, same residency idea with the contraction split over K: a CTA turns dh_t of its 16
 //                      units into its 64 dgate columns, multiplies them (as the A operand, written to swizzled shared
-//                      memory) with its resident 64 x 512 slice of W_hh and writes a [128 x 512] partial of dh_{t-1};
-//                      the partials of the 32 CTAs are summed by their consumers after the step barrier.
+//                      memory) with its resident 64 x 512 slice of W_hh and ADDS its [128 x 512] partial of dh_{t-1} into
+//                      the row block's accumulator with red.global.add.v4.f32 (the 32-way sum happens at L2); after the
+//                      step barrier a consumer reads its 64 bytes and clears them.
 //   dX, dW, db         dX = dG W_ih and the four weight gradients dG^T X / dG^T H_{t-1} as GEMM-template launches (the four
 //                      as problems of ONE launch); the recurrence kernels leave h and dG row-major as bf16 hi/lo, a tiled
 //                      transpose (lstm_transpose_pair) adds the other orientation after each recurrence; db by a reduction.
 //
-// Measured (B200, T = 80, rows = 256): forward recurrence 10 us / step for both networks, backward 24 us /
+// Measured (B200, T = 80, rows = 256): forward recurrence 10 us / step for both networks, backward 19 us /
 // step -- bound by the per-step dependency chain through L2 (publish -> counter -> TMA ring -> MMA -> TMEM), not by the
-// tensor pipe (13-17 % busy); whole LSTM part of an update 7.4 ms vs cuDNN 8.6 ms (TF32) / 18.1 ms (fp32).
+// tensor pipe (13-17 % busy); whole LSTM part of an update 6.3 ms vs cuDNN 8.4 ms (TF32) / 18.1 ms (fp32).
 //
 // Arithmetic: fp32-class everywhere (bf16x3 products accumulated in fp32, pointwise math in fp32); parity target: CPU fp32
 // torch.nn.LSTM forward / autograd within 1e-4 (tests/test_lstm_train_parity.py).
