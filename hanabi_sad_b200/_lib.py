@@ -19,7 +19,7 @@ class HbConfig(ctypes.Structure):
         ("vdn", c_i32), ("multi_step", c_i32), ("gamma", c_float), ("eta", c_float), ("seq_len", c_i32),
         ("replay_capacity", c_i32), ("alpha", c_float), ("beta", c_float), ("hid_dim", c_i32),
         ("num_lstm_layer", c_i32), ("num_fc_layer", c_i32), ("skip_connect", c_i32), ("priority_mode", c_i32),
-        ("eval_seats", c_i32), ("reserved", c_i32 * 6),
+        ("eval_seats", c_i32), ("replay_block", c_i32), ("reserved", c_i32 * 5),
     ]
 
 
@@ -43,6 +43,15 @@ class HbWeights(ctypes.Structure):
 class HbBatch(ctypes.Structure):
     _fields_ = [(k, c_void_p) for k in ("priv_s", "legal_move", "own_hand", "eps", "a", "greedy_a", "reward", "bootstrap", "terminal",
                                         "seq_len", "weight", "ids")]
+
+
+class HbReplayInfo(ctypes.Structure):
+    _fields_ = [(k, c_i64) for k in ("size", "num_add", "num_act", "dropped", "stalled_ticks", "popped", "capacity", "phys_slots", "sampleable")] + [
+        ("weight_sum", ctypes.c_double)]
+
+
+class HbSampleOpts(ctypes.Structure):
+    _fields_ = [("targets", c_void_p), ("total_weight", ctypes.c_double), ("total_size", ctypes.c_double), ("normalize", c_i32)]
 
 
 class HbLstmWeights(ctypes.Structure):
@@ -74,6 +83,7 @@ SIGNATURES = {
     "hb_env_get_deck": (c_int, [c_void_p, c_int, c_void_p]),
     "hb_env_check_invariants": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "hb_env_get_actions": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "hb_env_set_actions": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hb_env_get_result": (c_int, [c_void_p, c_void_p, c_void_p]),
     "hb_env_random_actions": (c_int, [c_void_p, c_u64]),
     "hb_policy_set_weights": (c_int, [c_void_p, c_int, ctypes.POINTER(HbWeights)]),
@@ -82,6 +92,8 @@ SIGNATURES = {
     "hb_rollout": (c_int, [c_void_p, c_int]),
     "hb_counters": (c_int, [c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "hb_replay_sample": (c_int, [c_void_p, c_int, ctypes.POINTER(HbBatch)]),
+    "hb_replay_stats": (c_int, [c_void_p, ctypes.POINTER(HbReplayInfo)]),
+    "hb_replay_sample_ex": (c_int, [c_void_p, c_int, ctypes.POINTER(HbBatch), ctypes.POINTER(HbSampleOpts)]),
     "hb_replay_get": (c_int, [c_void_p, c_i64, ctypes.POINTER(HbBatch)]),
     "hb_replay_update_priority": (c_int, [c_void_p, c_void_p, c_int]),
     "hb_profile": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

@@ -15,6 +15,35 @@ void hb_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int hb_policy_error_ptr(hb_engine* e, int** out);   // hb_policy.cu
+
+int hb_status_post(hb_engine* e) {
+  int* perr = nullptr;
+  hb_policy_error_ptr(e, &perr);
+  if (perr) HB_CUDA(cudaMemcpyAsync(e->h_status, perr, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaMemcpyAsync(e->h_status + 1, e->d_flags + 3, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaEventRecord(e->ev_status, e->stream));
+  e->status_pending = 1;
+  return 0;
+}
+
+int hb_status_poll(hb_engine* e, bool wait) {
+  if (!e->status_pending) return 0;
+  if (wait) HB_CUDA(cudaEventSynchronize(e->ev_status));
+  else if (cudaEventQuery(e->ev_status) != cudaSuccess) { (void)cudaGetLastError(); return 0; }   // still in flight: examined later
+  e->status_pending = 0;
+  const int gemm = e->h_status[0], illegal = e->h_status[1];
+  if (!gemm && !illegal) return 0;
+  e->h_status[0] = e->h_status[1] = 0;
+  int* perr = nullptr;
+  hb_policy_error_ptr(e, &perr);
+  if (perr) cudaMemsetAsync(perr, 0, sizeof(int), e->stream);
+  cudaMemsetAsync(e->d_flags + 3, 0, sizeof(int), e->stream);
+  if (gemm) hb_set_error("policy GEMM: a pipeline barrier timed out (spin guard) during an earlier tick -- the actions since then are not trustworthy");
+  else hb_set_error("hb_rollout: %d illegal action(s) reached the environment (the reference aborts here, hanabi_env.cc:63-80); those episodes were dropped", illegal);
+  return -4;
+}
+
 extern "C" {
 
 const char* hb_last_error(void) { return g_err; }
@@ -77,6 +106,10 @@ int hb_create(const hb_config* cfg, hb_engine** out) {
   HB_CUDA(cudaMalloc(&e->d_greedy_a, G * P * sizeof(int64_t)));
   HB_CUDA(cudaMalloc(&e->d_flags, 4 * sizeof(int)));
   HB_CUDA(cudaMallocHost(&e->h_flags, 4 * sizeof(int)));
+  HB_CUDA(cudaMallocHost(&e->h_status, 2 * sizeof(int)));
+  e->h_status[0] = e->h_status[1] = 0;
+  HB_CUDA(cudaEventCreateWithFlags(&e->ev_status, cudaEventDisableTiming));
+  HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 4 * sizeof(int), e->stream));
   HB_CUDA(cudaMemcpyAsync(e->d_eps_list, cfg->eps_list, cfg->num_eps * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   HB_CUDA(cudaMemsetAsync(e->d_decks, 0, G * HB_DECK_STRIDE, e->stream));
   HB_CUDA(cudaMemsetAsync(e->d_inject, 0, G * sizeof(HbInject), e->stream));
@@ -115,6 +148,8 @@ void hb_destroy(hb_engine* e) {
   cudaFree(e->obs.priv_s); cudaFree(e->obs.legal_move); cudaFree(e->obs.own_hand); cudaFree(e->obs.eps);
   cudaFree(e->d_reward); cudaFree(e->d_terminal); cudaFree(e->d_a); cudaFree(e->d_greedy_a); cudaFree(e->d_flags);
   cudaFreeHost(e->h_flags);
+  if (e->h_status) cudaFreeHost(e->h_status);
+  if (e->ev_status) cudaEventDestroy(e->ev_status);
   for (int k = 0; k < 2 * HB_PROF_N; ++k) if (e->prof_ev[k]) cudaEventDestroy(e->prof_ev[k]);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -128,8 +163,12 @@ int64_t hb_kernel_launches(const hb_engine* e) { return e ? e->launches : -1; }
 
 int hb_sync(hb_engine* e) {
   if (!e) return hb_fail(-1, "hb_sync: null engine");
+  HB_CUDA(cudaSetDevice(e->device));
   HB_CUDA(cudaStreamSynchronize(e->stream));
-  return 0;
+  if (!e->policy) return 0;
+  int rc = hb_status_post(e);
+  if (rc) return rc;
+  return hb_status_poll(e, true);
 }
 
 int hb_env_inject(hb_engine* e, int game, const int8_t* deck50, const int32_t* eps_idx, const int32_t* perms) {
@@ -308,6 +347,17 @@ int hb_env_get_actions(hb_engine* e, int64_t* a, int64_t* greedy_a) {
   if (a) HB_CUDA(cudaMemcpyAsync(a, e->d_a, nb, cudaMemcpyDeviceToHost, e->stream));
   if (greedy_a) HB_CUDA(cudaMemcpyAsync(greedy_a, e->d_greedy_a, nb, cudaMemcpyDeviceToHost, e->stream));
   HB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int hb_env_set_actions(hb_engine* e, const int64_t* a, const int64_t* greedy_a) {
+  if (!e || !a) return hb_fail(-1, "hb_env_set_actions: null argument");
+  HB_CUDA(cudaSetDevice(e->device));
+  const size_t nb = (size_t)e->rows * sizeof(int64_t);
+  HB_CUDA(cudaMemcpyAsync(e->d_a, a, nb, cudaMemcpyHostToDevice, e->stream));
+  HB_CUDA(cudaMemcpyAsync(e->d_greedy_a, greedy_a ? greedy_a : a, nb, cudaMemcpyHostToDevice, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  e->pending_actions = 1;
   return 0;
 }
 

@@ -72,8 +72,13 @@ struct hb_engine {
   uint8_t* d_terminal;   // [G]
   int64_t* d_a;          // [G,P]
   int64_t* d_greedy_a;   // [G,P]
-  int* d_flags;          // [4]: 0 any_terminated, 1 illegal count
+  int* d_flags;          // [4]: 0 any_terminated, 1 illegal count of the last launch, 2 invariant violations, 3 illegal count (sticky)
   int* h_flags;          // pinned mirror
+  // device-side guards (policy GEMM spin guard, illegal action inside hb_rollout): mirrored to pinned memory at the end of
+  // every hb_rollout, examined by the next call / hb_sync / hb_counters
+  int* h_status;         // pinned [2]: 0 policy d_error, 1 sticky illegal count
+  cudaEvent_t ev_status;
+  int status_pending;
 
   // ---- policy / replay (hb_policy.cu, hb_replay.cu) -- opaque here
   struct HbPolicy* policy;
@@ -99,6 +104,10 @@ struct HbProfScope {
     }                                                                                                   \
   } while (0)
 
+// hb_api.cu: queue the mirror copy (hb_status_post), examine it (hb_status_poll: wait = block until the copy has landed;
+// returns -4 with the message set if a guard fired, clearing it)
+int hb_status_post(hb_engine* e);
+int hb_status_poll(hb_engine* e, bool wait);
 HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e);  // hb_policy.cu
 int hb_launch_tick(hb_engine* e, int do_step, int do_reset);  // hb_rollout.cu
 // hb_env_kernels.cu

@@ -480,6 +480,8 @@ int hb_launch_gemm(HbGemmKernel k, int cl, int sm_count, cudaStream_t st, const 
   return 0;
 }
 
+int hb_policy_error_ptr(hb_engine* e, int** out) { *out = e->policy ? e->policy->d_error : nullptr; return 0; }
+
 HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e) {
   HbHidPtrs h = {nullptr, nullptr, nullptr, 0};
   if (e->policy) { HbPolicy* P = e->policy; h.h_hi = P->h_hi[P->parity]; h.h_lo = P->h_lo[P->parity]; h.c = P->c[P->parity]; h.rows_pad = P->rows_pad; }

@@ -12,6 +12,14 @@
 
 #define HB_SCAN_THREADS 1024
 
+// First arrival number still held: replay_block -> what sample() popped so far (ConcurrentQueue::blockPop); free-running
+// ring -> everything but the `cap_slots` most recent commits.
+__device__ __forceinline__ long long hb_ring_oldest(const HbRing& R) {
+  const long long commits = (long long)R.counters[HB_CNT_COMMIT];
+  if (R.block) return (long long)R.counters[HB_CNT_POPPED];
+  return commits > R.cap_slots ? commits - R.cap_slots : 0;
+}
+
 __device__ __forceinline__ float hb_entry_weight(const HbRing& R, int i, long long oldest) {
   const int slot = i / R.NE;
   if (R.state[slot] != HB_SLOT_COMMITTED) return 0.f;
@@ -25,8 +33,7 @@ __global__ void __launch_bounds__(HB_SCAN_THREADS) hb_k_replay_prefix(HbRing R, 
   __shared__ double part[HB_SCAN_THREADS];
   __shared__ int cnt[HB_SCAN_THREADS];
   const int n = R.phys_slots * R.NE, tid = threadIdx.x;
-  const long long commits = (long long)R.counters[HB_CNT_COMMIT];
-  const long long oldest = commits - R.cap_slots;
+  const long long oldest = hb_ring_oldest(R);
   const int chunk = (n + HB_SCAN_THREADS - 1) / HB_SCAN_THREADS;
   const int lo = tid * chunk, hi = min(n, lo + chunk);
   double s = 0;
@@ -46,9 +53,12 @@ __global__ void __launch_bounds__(HB_SCAN_THREADS) hb_k_replay_prefix(HbRing R, 
   if (tid == HB_SCAN_THREADS - 1) { out[0] = part[tid]; out[1] = (double)cnt[tid]; }
 }
 
-// One thread per batch element: stratified draw, binary search, importance weight.
+// One thread per batch element: stratified draw, binary search, importance weight.  `targets` (device, may be null):
+// draw positions inside [0, sum) supplied by the caller (a replay sharded over engines splits ONE global stratified draw);
+// norm_sum / norm_size: the sum_w and N of the importance weight (<= 0: this shard's); normalize: divide by the batch max.
 __global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, const double* __restrict__ tot, int B, float beta, uint64_t seed,
-                                 unsigned long long draw, int* __restrict__ idx_out, long long* __restrict__ seq_out, float* __restrict__ w_out,
+                                 unsigned long long draw, const double* __restrict__ targets, double norm_sum, double norm_size, int normalize,
+                                 int* __restrict__ idx_out, long long* __restrict__ seq_out, float* __restrict__ w_out,
                                  float* __restrict__ is_weight) {
   __shared__ float red[32];
   const int b = threadIdx.x, n = R.phys_slots * R.NE;
@@ -56,9 +66,14 @@ __global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, co
   const float size = (float)tot[1];
   float isw = 0.f;
   if (b < B) {
-    const float segment = sum / (float)B;
-    HbRng rng(seed, (uint32_t)b, (uint32_t)draw, HB_RNG_SAMPLE);
-    float r = rng.uniform() * segment + (float)b * segment;   // dist(rng_) + i * segment (prioritized_replay.h:296)
+    float r;
+    if (targets != nullptr) {
+      r = (float)targets[b];
+    } else {
+      const float segment = sum / (float)B;
+      HbRng rng(seed, (uint32_t)b, (uint32_t)draw, HB_RNG_SAMPLE);
+      r = rng.uniform() * segment + (float)b * segment;       // dist(rng_) + i * segment (prioritized_replay.h:296)
+    }
     r = fminf(sum - 0.1f, r);
     int lo = 0, hi = n - 1;                                   // first i with prefix[i] > 0 and prefix[i] >= r
     while (lo < hi) {
@@ -70,7 +85,8 @@ __global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, co
     idx_out[b] = lo;
     seq_out[b] = R.commit_seq[lo / R.NE];
     w_out[b] = w;
-    isw = powf(size * (w / sum), -beta);                      // prioritized_replay.h:337-338
+    const float ns = norm_sum > 0.0 ? (float)norm_sum : sum, nn = norm_size > 0.0 ? (float)norm_size : size;
+    isw = powf(nn * (w / ns), -beta);                         // prioritized_replay.h:337-338
   }
   float m = isw;
 #pragma unroll
@@ -84,7 +100,11 @@ __global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, co
     if (threadIdx.x == 0) red[0] = m;
   }
   __syncthreads();
-  if (b < B) is_weight[b] = isw / red[0];                     // weights /= weights.max()
+  if (b < B) is_weight[b] = normalize ? isw / red[0] : isw;   // weights /= weights.max()
+  if (b == 0 && R.block) {   // "pop storage if full" (prioritized_replay.h:326-332): evict down to `capacity`, AFTER the draw
+    const long long commits = (long long)R.counters[HB_CNT_COMMIT], popped = (long long)R.counters[HB_CNT_POPPED];
+    if (commits - popped > R.cap_slots) R.counters[HB_CNT_POPPED] = (unsigned long long)(commits - R.cap_slots);
+  }
 }
 
 struct HbBatchPtrs {
@@ -149,8 +169,7 @@ __global__ void hb_k_replay_update(HbRing R, const int* __restrict__ idx, const 
 __global__ void hb_k_replay_find(HbRing R, long long idx, int* __restrict__ entry_out) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= R.phys_slots) return;
-  const long long commits = (long long)R.counters[HB_CNT_COMMIT];
-  const long long oldest = commits > R.cap_slots ? commits - R.cap_slots : 0;
+  const long long oldest = hb_ring_oldest(R);
   if (R.state[slot] == HB_SLOT_COMMITTED && R.commit_seq[slot] == oldest + idx / R.NE) entry_out[0] = slot * R.NE + (int)(idx % R.NE);
 }
 
@@ -182,7 +201,12 @@ int hb_replay_create(hb_engine* e) {
   R.NE = c.vdn ? 1 : e->P;
   Q->capacity = c.replay_capacity;
   R.cap_slots = (c.replay_capacity + R.NE - 1) / R.NE;
-  R.phys_slots = R.cap_slots + 2 * e->G + 64;
+  R.block = c.replay_block ? 1 : 0;
+  R.limit_slots = ((int)(1.25 * c.replay_capacity) + R.NE - 1) / R.NE;   // storage_(int(1.25 * capacity)), prioritized_replay.h:183
+  if (R.limit_slots < R.cap_slots + 1) R.limit_slots = R.cap_slots + 1;
+  // free-running ring: the `cap_slots` newest commits + one episode in flight per game + slack for commit-order skew;
+  // replay_block: up to limit_slots held + one in flight per game (a game claims only after its commit went through)
+  R.phys_slots = R.block ? R.limit_slots + e->G + 64 : R.cap_slots + 2 * e->G + 64;
   R.n_step = c.multi_step; R.gamma = c.gamma; R.eta = c.eta; R.alpha = c.alpha;
   double gn = 1.0;
   for (int i = 0; i < c.multi_step; ++i) gn *= (double)c.gamma;  // python: self.gamma ** self.multi_step
@@ -211,6 +235,7 @@ int hb_replay_create(hb_engine* e) {
   HB_RALLOC(Q->sampled_seq, Q->max_batch * sizeof(long long));
   HB_RALLOC(Q->sampled_w, Q->max_batch * sizeof(float));
   HB_RALLOC(Q->d_prio, Q->max_batch * sizeof(float));
+  HB_RALLOC(Q->d_targets, Q->max_batch * sizeof(double));
   HB_CUDA(cudaMallocHost((void**)&Q->h_counters, (HB_CNT_N + 2) * sizeof(unsigned long long)));
   return 0;
 }
@@ -222,10 +247,23 @@ void hb_replay_destroy(hb_engine* e) {
   cudaFree(R.states); cudaFree(R.a); cudaFree(R.greedy_a); cudaFree(R.reward);
   cudaFree(R.bootstrap); cudaFree(R.seq_len); cudaFree(R.weight); cudaFree(R.commit_seq); cudaFree(R.state); cudaFree(R.game_slot);
   cudaFree(R.sc_reward); cudaFree(R.sc_oq); cudaFree(R.sc_tq); cudaFree(R.counters);
-  cudaFree(Q->prefix); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio);
+  cudaFree(Q->prefix); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio); cudaFree(Q->d_targets);
   cudaFreeHost(Q->h_counters);
   delete Q;
   e->replay = nullptr;
+}
+
+static int hb_read_counters(hb_engine* e) {   // synchronising copy of the ring counters into the pinned mirror
+  HbReplay* Q = e->replay;
+  HB_CUDA(cudaSetDevice(e->device));
+  HB_CUDA(cudaMemcpyAsync(Q->h_counters, Q->ring.counters, HB_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  HB_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+static long long hb_held_slots(const HbReplay* Q) {
+  const long long commits = (long long)Q->h_counters[HB_CNT_COMMIT];
+  if (Q->ring.block) return commits - (long long)Q->h_counters[HB_CNT_POPPED];
+  return commits < Q->ring.cap_slots ? commits : Q->ring.cap_slots;
 }
 
 int hb_counters(hb_engine* e, int64_t* size, int64_t* num_add, int64_t* num_act) {
@@ -235,17 +273,50 @@ int hb_counters(hb_engine* e, int64_t* size, int64_t* num_add, int64_t* num_act)
   if (num_add) *num_add = 0;
   HbReplay* Q = e->replay;
   if (!Q) return 0;
-  HB_CUDA(cudaSetDevice(e->device));
-  HB_CUDA(cudaMemcpyAsync(Q->h_counters, Q->ring.counters, HB_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-  HB_CUDA(cudaStreamSynchronize(e->stream));
-  const long long commits = (long long)Q->h_counters[HB_CNT_COMMIT];
-  const long long held = commits < Q->ring.cap_slots ? commits : Q->ring.cap_slots;
-  if (size) *size = held * Q->ring.NE;
-  if (num_add) *num_add = commits * Q->ring.NE;
+  int rc = hb_read_counters(e);
+  if (rc) return rc;
+  if (size) *size = hb_held_slots(Q) * Q->ring.NE;
+  if (num_add) *num_add = (long long)Q->h_counters[HB_CNT_COMMIT] * Q->ring.NE;
+  // a game waiting in blockAppend does not act (the reference's thread sits in cvSize_.wait): its ticks do not count
+  if (num_act) *num_act = e->num_act - (int64_t)Q->h_counters[HB_CNT_STALLED];
+  if (e->policy) {
+    rc = hb_status_post(e);
+    if (rc) return rc;
+    return hb_status_poll(e, true);
+  }
   return 0;
 }
 
-int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) {
+int hb_replay_stats(hb_engine* e, hb_replay_info* out) {
+  if (!e || !out) { hb_set_error("hb_replay_stats: null argument"); return -1; }
+  memset(out, 0, sizeof(*out));
+  out->num_act = e->num_act;
+  HbReplay* Q = e->replay;
+  if (!Q) return 0;
+  HbRing& R = Q->ring;
+  double* tot = Q->prefix + (size_t)R.phys_slots * R.NE;
+  HB_CUDA(cudaSetDevice(e->device));
+  hb_k_replay_prefix<<<1, HB_SCAN_THREADS, 0, e->stream>>>(R, Q->prefix, tot);
+  HB_CUDA(cudaGetLastError());
+  e->launches += 1;
+  double h_tot[2] = {0, 0};
+  HB_CUDA(cudaMemcpyAsync(h_tot, tot, sizeof(h_tot), cudaMemcpyDeviceToHost, e->stream));
+  int rc = hb_read_counters(e);
+  if (rc) return rc;
+  out->size = hb_held_slots(Q) * R.NE;
+  out->num_add = (long long)Q->h_counters[HB_CNT_COMMIT] * R.NE;
+  out->num_act = e->num_act - (int64_t)Q->h_counters[HB_CNT_STALLED];
+  out->dropped = (int64_t)Q->h_counters[HB_CNT_DROPPED];
+  out->stalled_ticks = (int64_t)Q->h_counters[HB_CNT_STALLED];
+  out->popped = R.block ? (int64_t)Q->h_counters[HB_CNT_POPPED] * R.NE : (out->num_add - out->size);
+  out->capacity = Q->capacity;
+  out->phys_slots = R.phys_slots;
+  out->weight_sum = h_tot[0];
+  out->sampleable = (int64_t)h_tot[1];
+  return 0;
+}
+
+int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts) {
   if (!e || !out) { hb_set_error("hb_replay_sample: null argument"); return -1; }
   HbReplay* Q = e->replay;
   if (!Q) { hb_set_error("hb_replay_sample: this engine has no replay (replay_capacity = 0)"); return -1; }
@@ -254,16 +325,22 @@ int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) {
     hb_set_error("hb_replay_sample: previous samples' priority has not been updated");
     return -3;
   }
-  int64_t size = 0;
-  int rc = hb_counters(e, &size, nullptr, nullptr);
+  int rc = hb_read_counters(e);
   if (rc) return rc;
+  const int64_t size = hb_held_slots(Q) * Q->ring.NE;
   if (size < batchsize) { hb_set_error("hb_replay_sample: replay holds %lld entries, fewer than the batch size %d", (long long)size, batchsize); return -3; }
   HbRing& R = Q->ring;
   double* tot = Q->prefix + (size_t)R.phys_slots * R.NE;
+  const double* d_targets = nullptr;
+  if (opts && opts->targets) {
+    HB_CUDA(cudaMemcpyAsync(Q->d_targets, opts->targets, batchsize * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    d_targets = Q->d_targets;
+  }
   hb_k_replay_prefix<<<1, HB_SCAN_THREADS, 0, e->stream>>>(R, Q->prefix, tot);
   const int threads = (batchsize + 31) / 32 * 32;
-  hb_k_replay_draw<<<1, threads, 0, e->stream>>>(R, Q->prefix, tot, batchsize, Q->beta, Q->seed, Q->sample_count, Q->sampled_idx, Q->sampled_seq,
-                                                 Q->sampled_w, out->weight);
+  hb_k_replay_draw<<<1, threads, 0, e->stream>>>(R, Q->prefix, tot, batchsize, Q->beta, Q->seed, Q->sample_count, d_targets,
+                                                 opts ? opts->total_weight : 0.0, opts ? opts->total_size : 0.0, opts ? opts->normalize : 1,
+                                                 Q->sampled_idx, Q->sampled_seq, Q->sampled_w, out->weight);
   HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
   hb_k_replay_gather<<<dim3(batchsize, R.T), 128, 0, e->stream>>>(R, Q->sampled_idx, batchsize, bp, e->env, e->d_eps_list);
   HB_CUDA(cudaGetLastError());
@@ -274,6 +351,8 @@ int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) {
   Q->n_sampled = batchsize;
   return 0;
 }
+
+int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) { return hb_replay_sample_ex(e, batchsize, out, nullptr); }
 
 int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out) {
   if (!e || !out) { hb_set_error("hb_replay_get: null argument"); return -1; }

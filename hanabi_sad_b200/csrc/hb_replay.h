@@ -12,12 +12,17 @@
 #include "hb_types.h"
 
 enum { HB_SLOT_FREE = 0, HB_SLOT_INFLIGHT = 1, HB_SLOT_COMMITTED = 2 };
-enum { HB_CNT_HEAD = 0, HB_CNT_COMMIT = 1, HB_CNT_DROPPED = 2, HB_CNT_TICK = 3, HB_CNT_N = 8 };
+enum { HB_CNT_HEAD = 0, HB_CNT_COMMIT = 1, HB_CNT_DROPPED = 2, HB_CNT_TICK = 3, HB_CNT_POPPED = 4, HB_CNT_STALLED = 5, HB_CNT_N = 8 };
+// game_slot flag: the game's episode is finished but its commit is waiting for room in the ring (replay_block = 1:
+// ConcurrentQueue::blockAppend, rela/prioritized_replay.h:44-48); the game does not start its next episode meanwhile
+#define HB_SLOT_PENDING 0x40000000
 
 struct HbRing {                 // device pointers + geometry, passed by value to kernels
   int T, P, F, A, OH;           // seq_len, players, feature size, num_action, 3*hand_size
   int NE;                       // replay entries per episode slot: 1 (vdn) or P (iql, one per player)
   int cap_slots, phys_slots;
+  int block;                    // 1: reference back-pressure -- hold up to limit_slots committed episodes, evict only what sample() popped
+  int limit_slots;              // int(1.25 * capacity) / NE (prioritized_replay.h:183)
   int n_step;
   float gamma, gamma_n, eta, alpha;
   int uniform_priority;
@@ -49,6 +54,7 @@ struct HbReplay {
   long long* sampled_seq;       // [max_batch] commit_seq at sampling time (evicted-since check, prioritized_replay.h:106-120)
   float* sampled_w;             // [max_batch]
   float* d_prio;                // [max_batch] staging for update_priority
+  double* d_targets;            // [max_batch] caller-supplied draw positions (hb_replay_sample_ex)
   int n_sampled;
   int max_batch;
   unsigned long long* h_counters;  // pinned mirror

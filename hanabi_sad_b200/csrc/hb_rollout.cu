@@ -41,14 +41,24 @@ struct HbTickArgs {
   HbRing ring;
 };
 
+__device__ __forceinline__ unsigned long long hb_ld_counter(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
+
+// A slot for the episode that starts now: a free one, or a committed one that is no longer sampleable -- free-running ring:
+// not among the `cap_slots` most recent commits (commit order, not ring order: episodes differ in length); replay_block:
+// already popped by sample() (prioritized_replay.h:326-332).  Everything else is skipped; -1 only if the ring has no such
+// slot within reach (counted in HB_CNT_DROPPED by the caller).
 __device__ __forceinline__ int hb_claim_slot(const HbRing& R) {
   for (int tries = 0; tries < 4 * R.phys_slots; ++tries) {
     const unsigned long long id = atomicAdd(&R.counters[HB_CNT_HEAD], 1ULL);
     const int slot = (int)(id % (unsigned long long)R.phys_slots);
     const int old = atomicCAS(&R.state[slot], HB_SLOT_FREE, HB_SLOT_INFLIGHT);
     if (old == HB_SLOT_FREE) return slot;
-    if (old == HB_SLOT_COMMITTED && atomicCAS(&R.state[slot], HB_SLOT_COMMITTED, HB_SLOT_INFLIGHT) == HB_SLOT_COMMITTED) {
-      for (int e = 0; e < R.NE; ++e) R.weight[(size_t)slot * R.NE + e] = 0.f;  // evicted: the oldest episode makes room
+    if (old != HB_SLOT_COMMITTED) continue;
+    const long long limit = R.block ? (long long)hb_ld_counter(&R.counters[HB_CNT_POPPED])
+                                    : (long long)hb_ld_counter(&R.counters[HB_CNT_COMMIT]) - R.cap_slots;
+    if (*(const volatile long long*)&R.commit_seq[slot] >= limit) continue;   // still held by the replay
+    if (atomicCAS(&R.state[slot], HB_SLOT_COMMITTED, HB_SLOT_INFLIGHT) == HB_SLOT_COMMITTED) {
+      for (int e = 0; e < R.NE; ++e) R.weight[(size_t)slot * R.NE + e] = 0.f;
       R.commit_seq[slot] = -1;
       return slot;
     }
@@ -57,8 +67,9 @@ __device__ __forceinline__ int hb_claim_slot(const HbRing& R) {
 }
 
 // Turn the finished episode of game g (length Len, raw data in the sc_* scratch rows) into replay form and commit it.
-// All threads of the CTA; `red` is shared scratch of 2 * (blockDim.x / 32) floats.
-__device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, int slot, int Len, float* red) {
+// All threads of the CTA; `red` is shared scratch of 2 * (blockDim.x / 32) floats.  *committed (shared) = 0 if the ring is
+// full under replay_block: nothing is published, the caller retries next tick (the computation is idempotent).
+__device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, int slot, int Len, float* red, int* committed) {
   const int T = R.T, P = R.P, n = R.n_step;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const float* r = R.sc_reward + (size_t)g * T;
@@ -106,10 +117,26 @@ __device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, 
   }
   if (tid == 0) {
     R.seq_len[slot] = Len;
-    __threadfence();
-    R.commit_seq[slot] = (long long)atomicAdd(&R.counters[HB_CNT_COMMIT], 1ULL);
-    __threadfence();
-    atomicExch(&R.state[slot], HB_SLOT_COMMITTED);
+    bool ok = true;
+    unsigned long long seq;
+    if (R.block) {   // blockAppend: size_ + 1 <= int(1.25 * capacity), else wait (prioritized_replay.h:44-48)
+      seq = hb_ld_counter(&R.counters[HB_CNT_COMMIT]);
+      for (;;) {
+        if ((long long)(seq - hb_ld_counter(&R.counters[HB_CNT_POPPED])) >= (long long)R.limit_slots) { ok = false; break; }
+        const unsigned long long prev = atomicCAS(&R.counters[HB_CNT_COMMIT], seq, seq + 1ULL);
+        if (prev == seq) break;
+        seq = prev;
+      }
+    } else {
+      seq = atomicAdd(&R.counters[HB_CNT_COMMIT], 1ULL);
+    }
+    if (ok) {
+      __threadfence();
+      R.commit_seq[slot] = (long long)seq;
+      __threadfence();
+      atomicExch(&R.state[slot], HB_SLOT_COMMITTED);
+    }
+    *committed = ok ? 1 : 0;
   }
 }
 
@@ -124,7 +151,7 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_co
   __shared__ HbEncTables tab;
   __shared__ HbFastEnc enc;
   __shared__ __align__(16) uint8_t deck[HB_DECK_STRIDE];
-  __shared__ int sh_did_step, sh_t, sh_term, sh_reset, sh_slot, sh_drop;
+  __shared__ int sh_did_step, sh_t, sh_term, sh_reset, sh_slot, sh_drop, sh_retry, sh_committed;
   __shared__ float red[2 * HB_TICK_THREADS / 32];
   const int g = blockIdx.x, tid = threadIdx.x;
   HbEnvCfg cfg = A.cfg;
@@ -136,8 +163,10 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_co
   else if (tid < 20) reinterpret_cast<uint4*>(deck)[tid - 16] = reinterpret_cast<const uint4*>(A.decks + (size_t)g * HB_DECK_STRIDE)[tid - 16];
   __syncthreads();
   if (tid == 0) {
-    sh_did_step = 0; sh_term = 0; sh_reset = 0; sh_drop = 0; sh_t = 0;
-    sh_slot = A.has_replay ? R.game_slot[g] : -1;
+    sh_did_step = 0; sh_term = 0; sh_reset = 0; sh_drop = 0; sh_t = 0; sh_retry = 0; sh_committed = 1;
+    const int raw = A.has_replay ? R.game_slot[g] : -1;
+    sh_slot = raw >= 0 ? (raw & ~HB_SLOT_PENDING) : -1;
+    if (raw >= 0 && (raw & HB_SLOT_PENDING)) sh_retry = 1;   // finished episode still waiting for room in the ring
     if (g == 0 && A.has_replay) atomicAdd(&R.counters[HB_CNT_TICK], 1ULL);
     if (A.do_step && !s.terminated) {
       const int t = s.ep_len;
@@ -147,7 +176,7 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_co
       sh_did_step = 1; sh_t = t; sh_term = term ? 1 : 0;
       A.reward[g] = s.reward;
       A.terminal[g] = term ? 1 : 0;
-      if (s.illegal) { atomicAdd(&A.flags[1], 1); sh_drop = 1; }
+      if (s.illegal) { atomicAdd(&A.flags[1], 1); atomicAdd(&A.flags[3], 1); sh_drop = 1; }   // flags[3]: sticky, reported by hb_sync / hb_rollout
     } else if (A.do_step) {
       A.reward[g] = 0.f;
       A.terminal[g] = 1;
@@ -169,16 +198,28 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_co
     }
     if (sh_term) {
       __syncthreads();  // the scratch rows written above are read by other threads below
-      hb_cta_finalize_episode(R, g, slot, min(t + 1, R.T), red);
+      hb_cta_finalize_episode(R, g, slot, min(t + 1, R.T), red, &sh_committed);
     }
+  } else if (sh_retry && slot >= 0) {
+    hb_cta_finalize_episode(R, g, slot, min((int)s.ep_len, R.T), red, &sh_committed);
   }
   __syncthreads();
   if (tid == 0) {
     if (sh_drop && slot >= 0) { atomicExch(&R.state[slot], HB_SLOT_FREE); atomicAdd(&R.counters[HB_CNT_DROPPED], 1ULL); }
-    if (A.do_reset && s.terminated) {
+    const bool stalled = !sh_committed;
+    if (stalled) {   // the actor waits in blockAppend: no new episode, same slot, try again next tick
+      R.game_slot[g] = slot | HB_SLOT_PENDING;
+      atomicAdd(&R.counters[HB_CNT_STALLED], 1ULL);
+    }
+    if (A.do_reset && s.terminated && !stalled) {
       hb_begin_episode(s, deck, A.inject + g, cfg, A.seed, g);
+      s.illegal = 0;   // an illegal action was counted (flags[3]) and its episode dropped; the seat carries on with a fresh game
       sh_reset = 1;
-      if (A.has_replay) { sh_slot = hb_claim_slot(R); R.game_slot[g] = sh_slot; }
+      if (A.has_replay) {
+        sh_slot = hb_claim_slot(R);
+        R.game_slot[g] = sh_slot;
+        if (sh_slot < 0) atomicAdd(&R.counters[HB_CNT_DROPPED], 1ULL);
+      }
     }
     if (s.terminated) atomicOr(&A.flags[0], 1);
   }
@@ -237,7 +278,13 @@ extern "C" {
 int hb_rollout(hb_engine* e, int n_ticks) {
   if (!e) { hb_set_error("hb_rollout: null engine"); return -1; }
   if (!e->policy || !e->policy->have_weights[0]) { hb_set_error("hb_rollout: no policy weights (hb_policy_set_weights)"); return -1; }
+  if (e->replay && e->cfg.priority_mode != 1 && !e->policy->have_weights[1]) {
+    // compute_priority needs Q_target (r2d2.py:345-348); without it every priority would silently use a zero bootstrap
+    hb_set_error("hb_rollout: the replay computes priorities from the target network (priority_mode %d) but net 1 has no weights", e->cfg.priority_mode);
+    return -1;
+  }
   HB_CUDA(cudaSetDevice(e->device));
+  { const int src = hb_status_poll(e, false); if (src) return src; }   // a guard that fired during an EARLIER call
   for (int i = 0; i < n_ticks; ++i) {
     int rc = hb_launch_tick(e, e->pending_actions, 1);
     if (rc) return rc;
@@ -254,7 +301,7 @@ int hb_rollout(hb_engine* e, int n_ticks) {
       }
     }
   }
-  return 0;
+  return hb_status_post(e);
 }
 
 // Device time per kernel class of the fused tick, measured with CUDA events on the engine stream while `on`:

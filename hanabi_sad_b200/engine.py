@@ -4,7 +4,7 @@ import ctypes
 
 import numpy as np
 
-from ._lib import HbBatch, HbConfig, HbGameInfo, HbWeights, check, lib
+from ._lib import HbBatch, HbConfig, HbGameInfo, HbReplayInfo, HbSampleOpts, HbWeights, check, lib
 
 
 def _ptr(a):
@@ -15,7 +15,7 @@ class Engine:
     def __init__(self, num_games, players=2, hand_size=5, bomb=0, max_len=80, sad=True, shuffle_color=False,
                  eps_list=(0.0,), seed=1, device=0, vdn=True, multi_step=3, gamma=0.999, eta=0.9, seq_len=80,
                  replay_capacity=0, alpha=0.6, beta=0.4, hid_dim=512, num_lstm_layer=2, num_fc_layer=1,
-                 skip_connect=False, priority_mode=0, eval_seats=False):
+                 skip_connect=False, priority_mode=0, eval_seats=False, replay_block=False):
         L = lib()
         self._eps = np.ascontiguousarray(eps_list, dtype=np.float32)
         cfg = HbConfig()
@@ -29,6 +29,7 @@ class Engine:
         cfg.hid_dim, cfg.num_lstm_layer, cfg.num_fc_layer = int(hid_dim), int(num_lstm_layer), int(num_fc_layer)
         cfg.skip_connect, cfg.priority_mode = int(bool(skip_connect)), int(priority_mode)
         cfg.eval_seats = int(bool(eval_seats))
+        cfg.replay_block = int(bool(replay_block))
         self.cfg = cfg
         h = ctypes.c_void_p()
         check(L.hb_create(ctypes.byref(cfg), ctypes.byref(h)))
@@ -123,6 +124,12 @@ class Engine:
         check(lib().hb_env_get_actions(self._h, _ptr(a), _ptr(g)))
         return a, g
 
+    def set_actions(self, a, greedy_a=None):
+        """Overwrite the pending reply (test hook, hb_env_set_actions)."""
+        a = np.ascontiguousarray(a, dtype=np.int64).reshape(self.G, self.P)
+        ga = None if greedy_a is None else np.ascontiguousarray(greedy_a, dtype=np.int64).reshape(self.G, self.P)
+        check(lib().hb_env_set_actions(self._h, _ptr(a), _ptr(ga)))
+
     def result(self):
         r = np.empty((self.G,), np.float32)
         t = np.empty((self.G,), np.uint8)
@@ -137,17 +144,27 @@ class Engine:
     def set_weights(self, net, state_dict, skip_connect=False):
         """`state_dict` = R2D2Net.state_dict() (torch tensors on any device, or numpy arrays); net 0 online, 1 target -- or,
         on an eval_seats engine, the seat index; there a second fc layer (`net.2.*`) and `skip_connect` are honoured."""
-        keep, ptr = [], {}
+        keep, ptr, cuda_devs = [], {}, set()
         keys = self.WEIGHT_KEYS + (("net.2.weight", "net.2.bias") if "net.2.weight" in state_dict else ())
         for k in keys:
             v = state_dict[k]
             if hasattr(v, "data_ptr"):
                 v = v.detach().float().contiguous()
                 ptr[k] = v.data_ptr()
+                if v.is_cuda:
+                    cuda_devs.add(v.device)
             else:
                 v = np.ascontiguousarray(v, dtype=np.float32)
                 ptr[k] = v.ctypes.data
             keep.append(v)
+        if cuda_devs:
+            # hb_policy_set_weights reads the tensors with cudaMemcpyAsync on the ENGINE's stream, which is not ordered against
+            # torch's: a load_state_dict / optimizer step / .float() copy still queued on torch's stream must finish first, or
+            # the actors would get a mix of old and new weights.
+            import torch
+
+            for d in cuda_devs:
+                torch.cuda.current_stream(d).synchronize()
         shapes = {"net.0.weight": (512, self.F), "lstm.weight_ih_l0": (2048, 512), "lstm.weight_hh_l1": (2048, 512), "fc_a.weight": (self.A, 512),
                   "fc_v.weight": (1, 512)}
         for k, shp in shapes.items():
@@ -198,8 +215,16 @@ class Engine:
         check(lib().hb_counters(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return int(a.value), int(b.value), int(c.value)
 
-    def sample(self, batchsize, device=None):
-        """PrioritizedReplay::sample: torch tensors on the engine's GPU in the learner's layout + importance weights."""
+    def replay_stats(self):
+        """hb_replay_stats as a dict (size, num_add, num_act, dropped, stalled_ticks, popped, capacity, phys_slots, sampleable,
+        weight_sum)."""
+        info = HbReplayInfo()
+        check(lib().hb_replay_stats(self._h, ctypes.byref(info)))
+        return {k: getattr(info, k) for k, _ in HbReplayInfo._fields_}
+
+    def sample(self, batchsize, device=None, targets=None, total_weight=0.0, total_size=0.0, normalize=True):
+        """PrioritizedReplay::sample: torch tensors on the engine's GPU in the learner's layout + importance weights.
+        targets / total_weight / total_size / normalize: hb_replay_sample_ex (a replay sharded over engines or ranks)."""
         import torch
 
         dev = torch.device("cuda", self.cfg.device)
@@ -218,7 +243,15 @@ class Engine:
         for k, v in t.items():
             setattr(hb, k, v.data_ptr())
         torch.cuda.current_stream(dev).synchronize()  # the allocator may hand back memory still in use on torch's stream
-        check(lib().hb_replay_sample(self._h, B, ctypes.byref(hb)))
+        if targets is None and total_weight <= 0 and total_size <= 0 and normalize:
+            check(lib().hb_replay_sample(self._h, B, ctypes.byref(hb)))
+        else:
+            opts = HbSampleOpts()
+            tg = None if targets is None else np.ascontiguousarray(targets, dtype=np.float64)
+            assert tg is None or tg.shape == (B,)
+            opts.targets = None if tg is None else tg.ctypes.data
+            opts.total_weight, opts.total_size, opts.normalize = float(total_weight), float(total_size), int(bool(normalize))
+            check(lib().hb_replay_sample_ex(self._h, B, ctypes.byref(hb), ctypes.byref(opts)))
         t["terminal"] = t["terminal"].bool()
         return t
 

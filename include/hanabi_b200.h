@@ -61,7 +61,12 @@ typedef struct hb_config {
   int32_t eval_seats;      /* 1: evaluation engine -- one network PER SEAT (hb_policy_set_weights net = seat index), which may
                             * differ in weights and in architecture variant (num_fc_layer 1|2, skip_connect): tools/eval_model.py
                             * cross-play (utils.load_op_model, utils.py:35-84).  No target network, no replay. */
-  int32_t reserved[6];
+  int32_t replay_block;    /* 0: free-running ring -- once `replay_capacity` episodes are held every new commit evicts the oldest
+                            *    (actors never wait; throughput runs without a learner);
+                            * 1: the reference's back-pressure (ConcurrentQueue::blockAppend, rela/prioritized_replay.h:44-48,183):
+                            *    the ring holds up to int(1.25*capacity) entries, a game whose finished episode finds it full WAITS
+                            *    (does not start its next episode) until hb_replay_sample pops down to `capacity` (:326-332). */
+  int32_t reserved[5];
 } hb_config;
 
 /* Snapshot of one game, for tests / eval (HanabiEnv getters, cpp/pybind.cc:23-38). */
@@ -140,6 +145,9 @@ int hb_env_random_actions(hb_engine* e, uint64_t counter);
 /* Host copies of the engine's device-resident action buffers (the reply of R2D2Actor::act, r2d2_actor.h:78-96:
  * a / greedy_a int64 [G,P]) and of the last step's result (reward float [G], terminal uint8 [G]).  NULL skips. */
 int hb_env_get_actions(hb_engine* e, int64_t* a, int64_t* greedy_a);
+/* The other direction: overwrite the pending reply (host int64 [G,P]; greedy_a NULL = a) that the next hb_env_step_dev(e, NULL,
+ * NULL) / hb_rollout tick applies -- a test hook (e.g. to drive an illegal action into the fused loop). */
+int hb_env_set_actions(hb_engine* e, const int64_t* a, const int64_t* greedy_a);
 int hb_env_get_result(hb_engine* e, float* reward, uint8_t* terminal);
 
 /* ---- policy: the R2D2 act forward (pyhanabi/r2d2.py:65-78, 234-303) ---------------------------------- */
@@ -180,8 +188,20 @@ int hb_policy_get(hb_engine* e, float* adv, float* online_q, float* target_q, fl
 int hb_rollout(hb_engine* e, int n_ticks);
 
 /* RNNPrioritizedReplay::size / numAdd (rela/prioritized_replay.h:259-265) and the sum of R2D2Actor::numAct
- * (rela/r2d2_actor.h:57-59) in env-steps.  NULL skips.  Synchronises with the engine stream. */
+ * (rela/r2d2_actor.h:57-59) in env-steps.  NULL skips.  Synchronises with the engine stream and, like hb_sync, returns -4
+ * if a device-side guard fired since the last report (see hb_sync). */
 int hb_counters(hb_engine* e, int64_t* size, int64_t* num_add, int64_t* num_act);
+
+/* Everything the replay knows about itself (one synchronising read).  `size` .. `num_act` as hb_counters; `dropped` =
+ * episodes that could not be recorded (no free slot: cannot happen with replay_block = 1); `stalled_ticks` = game-ticks spent
+ * waiting for room (replay_block = 1; the reference's actors sit in cvSize_.wait, prioritized_replay.h:48); `popped` = entries
+ * evicted so far (ConcurrentQueue::blockPop); `weight_sum` / `sampleable` = sum of priority^alpha and count over the entries
+ * a sample() issued now would draw from (safeSize(&sum), :278-279). */
+typedef struct hb_replay_info {
+  int64_t size, num_add, num_act, dropped, stalled_ticks, popped, capacity, phys_slots, sampleable;
+  double weight_sum;
+} hb_replay_info;
+int hb_replay_stats(hb_engine* e, hb_replay_info* out);
 
 /* Destination of one sampled batch: DEVICE pointers owned by the caller, in the layouts RNNTransition::makeBatch
  * produces (rela/transition.cc:160-202).  With vdn: priv_s [T,B,P,F], legal_move [T,B,P,A], own_hand [T,B,P,3H],
@@ -197,6 +217,21 @@ typedef struct hb_batch {
 /* PrioritizedReplay::sample (rela/prioritized_replay.h:208-240, 274-345).  Returns -3 if the replay holds fewer than
  * `batchsize` entries or the previous batch's priorities were not written back. */
 int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out);
+
+/* hb_replay_sample with the two hooks a replay SHARDED over several engines / ranks needs to reproduce the reference's
+ * importance weights (N * w_i / sum_w)^-beta / max over the UNION of the shards (prioritized_replay.h:334-339):
+ *   targets      host double [batchsize] or NULL: the stratified draw positions inside this shard's cumulative weight
+ *                [0, weight_sum) chosen by the caller (who splits one global stratified draw, :287-297, over the shards);
+ *                NULL = draw here (Philox);
+ *   total_weight / total_size   sum_w and N the importance weight is computed with; <= 0 = this shard's own;
+ *   normalize    != 0: divide by the batch maximum here (single shard); 0: leave (N*w/sum)^-beta raw -- the caller divides
+ *                by the maximum over all shards / ranks. */
+typedef struct hb_sample_opts {
+  const double* targets;
+  double total_weight, total_size;
+  int32_t normalize;
+} hb_sample_opts;
+int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts);
 
 /* PrioritizedReplay::get (rela/prioritized_replay.h:259-261 -> ConcurrentQueue::get, :125-128; used by
  * pyhanabi/tools/action_matrix.py:90-107): the idx-th OLDEST entry still held (0 <= idx < size), written UNBATCHED into
@@ -267,7 +302,11 @@ int64_t hb_lstm_launches(const hb_lstm* l); /* kernels launched through this han
  * tick's encoder, as bit patterns [G*P][*ks] (host; hi or lo may be NULL; *ks = row length, F rounded up to 64). */
 int hb_debug_operand(hb_engine* e, uint16_t* hi, uint16_t* lo, int* ks);
 
-int hb_sync(hb_engine* e); /* cudaStreamSynchronize on the engine stream */
+/* cudaStreamSynchronize on the engine stream, then the device-side guards: returns -4 (hb_last_error says which) if, since
+ * the last report, a pipeline barrier of the policy GEMMs ran into its spin guard (the actions of that tick are garbage) or
+ * an illegal action reached a game inside hb_rollout (the reference aborts there, hanabi_env.cc:63-80).  hb_rollout itself is
+ * asynchronous: it reports such a failure of an EARLIER call as soon as it has seen it. */
+int hb_sync(hb_engine* e);
 void* hb_stream(hb_engine* e); /* cudaStream_t the engine launches on (for CUDA-event timing) */
 int64_t hb_kernel_launches(const hb_engine* e); /* kernels launched by this engine so far */
 
