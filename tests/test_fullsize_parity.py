@@ -155,6 +155,7 @@ def test_fused_rollout_at_baseline_size(hb, cfg):
         b = {k_: v.cpu().numpy() for k_, v in eng.sample(B).items()}
         hb_ = _row_hash(_obs_rows(b["priv_s"], b["legal_move"], b["own_hand"], b["eps"])).reshape(T, B)
         w_exp = np.zeros(B, np.float64)
+        agg = np.zeros(B, np.float32)
         for j in range(B):
             L = int(b["seq_len"][j])
             key = _episode_key(hb_[:L, j], b["a"][:L, j])
@@ -174,11 +175,12 @@ def test_fused_rollout_at_baseline_size(hb, cfg):
             tn[: max(0, L - n_step)] = t_[n_step:L]
             pad = np.zeros((T, 1), np.float32)
             pad[:L, 0] = ro.step_priority(rew, boot, gamma, n_step, o, tn)
-            w_exp[j] = float(ro.aggregate_priority(pad, np.asarray([L], np.float32), eta)[0]) ** alpha
+            agg[j] = ro.aggregate_priority(pad, np.asarray([L], np.float32), eta)[0]
+            w_exp[j] = float(agg[j]) ** alpha
         want = w_exp ** -beta
         want /= want.max()
         assert np.allclose(b["weight"], want, rtol=5e-4, atol=1e-6), float(np.abs(b["weight"] - want).max())
-        eng.update_priority(np.ones(B, np.float32))
+        eng.update_priority(agg)   # the same priorities back: later batches must see unchanged weights
     assert len(seen) > 4 * B
     eng.sync()   # also reports device-side guards (GEMM spin guard, illegal actions)
     eng.close()
