@@ -54,6 +54,16 @@ class HbSampleOpts(ctypes.Structure):
     _fields_ = [("targets", c_void_p), ("total_weight", ctypes.c_double), ("total_size", ctypes.c_double), ("normalize", c_i32)]
 
 
+class HbTrainerConfig(ctypes.Structure):
+    _fields_ = [("device", c_i32), ("in_dim", c_i32), ("num_action", c_i32), ("hand_size", c_i32), ("num_player", c_i32), ("vdn", c_i32),
+                ("multi_step", c_i32), ("seq_len", c_i32), ("max_batch", c_i32), ("gamma", c_float), ("eta", c_float), ("lr", c_float),
+                ("adam_eps", c_float), ("beta1", c_float), ("beta2", c_float), ("grad_clip", c_float), ("reserved", c_i32 * 8)]
+
+
+class HbTrainStats(ctypes.Structure):
+    _fields_ = [("loss", c_float), ("rl_loss", c_float), ("aux_xent", c_float), ("grad_norm", c_float), ("num_update", c_i64), ("launches", c_i64)]
+
+
 class HbLstmWeights(ctypes.Structure):
     _fields_ = [("w_ih", c_void_p * 2), ("w_hh", c_void_p * 2), ("b_ih", c_void_p * 2), ("b_hh", c_void_p * 2)]
 
@@ -106,6 +116,16 @@ SIGNATURES = {
     "hb_gemm_nt": (c_int, [c_int, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
     "hb_lstm_sync": (c_int, [c_void_p]),
     "hb_lstm_launches": (c_i64, [c_void_p]),
+    "hb_trainer_layout": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_i64)]),
+    "hb_trainer_create": (c_int, [ctypes.POINTER(HbTrainerConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
+    "hb_trainer_destroy": (None, [c_void_p]),
+    "hb_trainer_backward": (c_int, [c_void_p, ctypes.POINTER(HbBatch), c_int, c_int, c_float, c_void_p, c_void_p]),
+    "hb_trainer_optim_step": (c_int, [c_void_p, c_void_p]),
+    "hb_trainer_sync_target": (c_int, [c_void_p, c_void_p]),
+    "hb_trainer_stats": (c_int, [c_void_p, ctypes.POINTER(HbTrainStats)]),
+    "hb_replay_last_max_len": (c_int, [c_void_p]),
+    "hb_stream_wait": (c_int, [c_void_p, c_void_p]),
+    "hb_stream_wait_engine": (c_int, [c_void_p, c_void_p]),
     "hb_debug_operand": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_int)]),
     "hb_sync": (c_int, [c_void_p]),
     "hb_stream": (c_void_p, [c_void_p]),

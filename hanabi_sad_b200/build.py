@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhanabi_b200.so")
-SOURCES = ["hb_api.cu", "hb_env_kernels.cu", "hb_policy.cu", "hb_replay.cu", "hb_rollout.cu", "hb_lstm.cu", "hb_linear.cu"]
+SOURCES = ["hb_api.cu", "hb_env_kernels.cu", "hb_policy.cu", "hb_replay.cu", "hb_rollout.cu", "hb_lstm.cu", "hb_linear.cu", "hb_trainer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--threads", "0",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "-shared",

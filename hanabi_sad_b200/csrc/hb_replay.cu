@@ -59,8 +59,11 @@ __global__ void __launch_bounds__(HB_SCAN_THREADS) hb_k_replay_prefix(HbRing R, 
 __global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, const double* __restrict__ tot, int B, float beta, uint64_t seed,
                                  unsigned long long draw, const double* __restrict__ targets, double norm_sum, double norm_size, int normalize,
                                  int* __restrict__ idx_out, long long* __restrict__ seq_out, float* __restrict__ w_out,
-                                 float* __restrict__ is_weight) {
+                                 float* __restrict__ is_weight, int* __restrict__ max_len_out) {
   __shared__ float red[32];
+  __shared__ int max_len;
+  if (threadIdx.x == 0) max_len = 0;
+  __syncthreads();
   const int b = threadIdx.x, n = R.phys_slots * R.NE;
   const float sum = (float)tot[0];
   const float size = (float)tot[1];
@@ -84,6 +87,7 @@ __global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, co
     const float w = (float)(prefix[lo] - (lo > 0 ? prefix[lo - 1] : 0.0));
     idx_out[b] = lo;
     seq_out[b] = R.commit_seq[lo / R.NE];
+    atomicMax(&max_len, R.seq_len[lo / R.NE]);
     w_out[b] = w;
     const float ns = norm_sum > 0.0 ? (float)norm_sum : sum, nn = norm_size > 0.0 ? (float)norm_size : size;
     isw = powf(nn * (w / ns), -beta);                         // prioritized_replay.h:337-338
@@ -101,6 +105,7 @@ __global__ void hb_k_replay_draw(HbRing R, const double* __restrict__ prefix, co
   }
   __syncthreads();
   if (b < B) is_weight[b] = normalize ? isw / red[0] : isw;   // weights /= weights.max()
+  if (b == 0) *max_len_out = max_len;
   if (b == 0 && R.block) {   // "pop storage if full" (prioritized_replay.h:326-332): evict down to `capacity`, AFTER the draw
     const long long commits = (long long)R.counters[HB_CNT_COMMIT], popped = (long long)R.counters[HB_CNT_POPPED];
     if (commits - popped > R.cap_slots) R.counters[HB_CNT_POPPED] = (unsigned long long)(commits - R.cap_slots);
@@ -236,6 +241,9 @@ int hb_replay_create(hb_engine* e) {
   HB_RALLOC(Q->sampled_w, Q->max_batch * sizeof(float));
   HB_RALLOC(Q->d_prio, Q->max_batch * sizeof(float));
   HB_RALLOC(Q->d_targets, Q->max_batch * sizeof(double));
+  HB_RALLOC(Q->d_max_len, sizeof(int));
+  HB_CUDA(cudaMallocHost((void**)&Q->h_max_len, sizeof(int)));
+  *Q->h_max_len = 0;
   HB_CUDA(cudaMallocHost((void**)&Q->h_counters, (HB_CNT_N + 2) * sizeof(unsigned long long)));
   return 0;
 }
@@ -247,7 +255,7 @@ void hb_replay_destroy(hb_engine* e) {
   cudaFree(R.states); cudaFree(R.a); cudaFree(R.greedy_a); cudaFree(R.reward);
   cudaFree(R.bootstrap); cudaFree(R.seq_len); cudaFree(R.weight); cudaFree(R.commit_seq); cudaFree(R.state); cudaFree(R.game_slot);
   cudaFree(R.sc_reward); cudaFree(R.sc_oq); cudaFree(R.sc_tq); cudaFree(R.counters);
-  cudaFree(Q->prefix); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio); cudaFree(Q->d_targets);
+  cudaFree(Q->prefix); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio); cudaFree(Q->d_targets); cudaFree(Q->d_max_len); cudaFreeHost(Q->h_max_len);
   cudaFreeHost(Q->h_counters);
   delete Q;
   e->replay = nullptr;
@@ -340,7 +348,8 @@ int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const 
   const int threads = (batchsize + 31) / 32 * 32;
   hb_k_replay_draw<<<1, threads, 0, e->stream>>>(R, Q->prefix, tot, batchsize, Q->beta, Q->seed, Q->sample_count, d_targets,
                                                  opts ? opts->total_weight : 0.0, opts ? opts->total_size : 0.0, opts ? opts->normalize : 1,
-                                                 Q->sampled_idx, Q->sampled_seq, Q->sampled_w, out->weight);
+                                                 Q->sampled_idx, Q->sampled_seq, Q->sampled_w, out->weight, Q->d_max_len);
+  HB_CUDA(cudaMemcpyAsync(Q->h_max_len, Q->d_max_len, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
   hb_k_replay_gather<<<dim3(batchsize, R.T), 128, 0, e->stream>>>(R, Q->sampled_idx, batchsize, bp, e->env, e->d_eps_list);
   HB_CUDA(cudaGetLastError());
@@ -353,6 +362,29 @@ int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const 
 }
 
 int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) { return hb_replay_sample_ex(e, batchsize, out, nullptr); }
+
+int hb_replay_last_max_len(hb_engine* e) { return (e && e->replay) ? *e->replay->h_max_len : -1; }
+
+int hb_stream_wait(hb_engine* e, void* stream) {
+  if (!e) { hb_set_error("hb_stream_wait: null engine"); return -1; }
+  HB_CUDA(cudaSetDevice(e->device));
+  cudaEvent_t ev;
+  HB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  HB_CUDA(cudaEventRecord(ev, (cudaStream_t)stream));
+  HB_CUDA(cudaStreamWaitEvent(e->stream, ev, 0));
+  HB_CUDA(cudaEventDestroy(ev));   // released once the wait has been satisfied
+  return 0;
+}
+int hb_stream_wait_engine(hb_engine* e, void* stream) {
+  if (!e) { hb_set_error("hb_stream_wait_engine: null engine"); return -1; }
+  HB_CUDA(cudaSetDevice(e->device));
+  cudaEvent_t ev;
+  HB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  HB_CUDA(cudaEventRecord(ev, e->stream));
+  HB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
+  HB_CUDA(cudaEventDestroy(ev));
+  return 0;
+}
 
 int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out) {
   if (!e || !out) { hb_set_error("hb_replay_get: null argument"); return -1; }
@@ -385,10 +417,15 @@ int hb_replay_update_priority(hb_engine* e, const float* priority, int n) {
   if (n == 0) { Q->n_sampled = 0; return 0; }  // prioritized_replay.h:243-246
   if (!priority || n != Q->n_sampled) { hb_set_error("hb_replay_update_priority: expected %d priorities, got %d", Q->n_sampled, n); return -1; }
   HB_CUDA(cudaSetDevice(e->device));
+  cudaPointerAttributes pa;
+  const bool on_device = cudaPointerGetAttributes(&pa, priority) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+  (void)cudaGetLastError();
   HB_CUDA(cudaMemcpyAsync(Q->d_prio, priority, n * sizeof(float), cudaMemcpyDefault, e->stream));
   hb_k_replay_update<<<(n + 127) / 128, 128, 0, e->stream>>>(Q->ring, Q->sampled_idx, Q->sampled_seq, Q->d_prio, n);
   HB_CUDA(cudaGetLastError());
-  HB_CUDA(cudaStreamSynchronize(e->stream));
+  // host memory may be released by the caller as soon as this returns; device memory is stream-ordered (the caller keeps it
+  // valid until the engine stream has passed this point, see hb_stream_wait), so a learner loop never blocks here
+  if (!on_device) HB_CUDA(cudaStreamSynchronize(e->stream));
   e->launches += 1;
   Q->n_sampled = 0;
   return 0;

@@ -55,6 +55,7 @@ struct HbReplay {
   float* sampled_w;             // [max_batch]
   float* d_prio;                // [max_batch] staging for update_priority
   double* d_targets;            // [max_batch] caller-supplied draw positions (hb_replay_sample_ex)
+  int *d_max_len, *h_max_len;   // longest episode of the last sampled batch (device, pinned mirror)
   int n_sampled;
   int max_batch;
   unsigned long long* h_counters;  // pinned mirror

@@ -287,6 +287,7 @@ class Engine:
                 import torch
 
                 torch.cuda.current_stream(p.device).synchronize()
+                self._keep_prio = p   # read asynchronously on the engine stream: keep it alive until the next call
             check(lib().hb_replay_update_priority(self._h, p.data_ptr(), int(p.numel())))
         else:
             p = np.ascontiguousarray(priority, dtype=np.float32)

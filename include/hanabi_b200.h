@@ -239,7 +239,9 @@ int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const 
  * out->weight is not written; out->ids (or NULL) receives the physical entry index.  Does not touch the sampling state. */
 int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out);
 
-/* PrioritizedReplay::updatePriority (rela/prioritized_replay.h:242-257): `priority` float [n], host or device. */
+/* PrioritizedReplay::updatePriority (rela/prioritized_replay.h:242-257): `priority` float [n], host or device.  Host memory:
+ * synchronous.  Device memory: queued on the engine stream -- the buffer must stay valid (and be complete: hb_stream_wait)
+ * until that stream has consumed it. */
 int hb_replay_update_priority(hb_engine* e, const float* priority, int n);
 
 /* Measurement hook: device time per kernel class of the fused tick (CUDA events on the engine stream).  Returns the
@@ -297,6 +299,49 @@ int hb_gemm_nt(int device, const float* A, int64_t lda, const float* B, int64_t 
 int hb_lstm_sync(hb_lstm* l);
 
 int64_t hb_lstm_launches(const hb_lstm* l); /* kernels launched through this handle so far */
+
+/* ---- learner side: one whole R2D2 update on the device ------------------------------------------------------ */
+
+/* What pyhanabi/selfplay.py:208-244 does per iteration between replay.sample() and replay.update_priority():
+ * R2D2Agent.loss (pyhanabi/r2d2.py:461-499: td_error :383-428, smooth-L1, aux task :430-459), (loss * weight).mean().backward(),
+ * clip_grad_norm_, Adam.step, rela.aggregate_priority -- as kernels on the caller's stream, no host synchronisation.
+ * Parameters / gradients / Adam moments are FLAT fp32 device buffers owned by the caller (hb_trainer_layout: element offsets of
+ * net.0.weight, net.0.bias, lstm.{weight_ih, weight_hh, bias_ih, bias_hh}_l0, .._l1, fc_v.weight, fc_v.bias, fc_a.weight,
+ * fc_a.bias, pred.weight, pred.bias in that order, then the total length; every tensor starts 16-byte aligned). */
+typedef struct hb_trainer hb_trainer;
+typedef struct hb_trainer_config {
+  int32_t device;
+  int32_t in_dim, num_action, hand_size;   /* R2D2Net(in_dim, 512, num_action, 2, hand_size) */
+  int32_t num_player;                       /* player axis of one replay entry: P with vdn, 1 with iql */
+  int32_t vdn, multi_step, seq_len, max_batch;   /* max_batch * num_player <= 256 rows */
+  float gamma, eta;
+  float lr, adam_eps, beta1, beta2;        /* torch.optim.Adam(lr, eps) with its default betas (selfplay.py:141) */
+  float grad_clip;                          /* clip_grad_norm_ max_norm; <= 0: none */
+  int32_t reserved[8];
+} hb_trainer_config;
+typedef struct hb_train_stats {
+  float loss, rl_loss, aux_xent, grad_norm;   /* selfplay.py stat["loss"], ["rl_loss"], ["aux1"], ["grad_norm"] of the last update */
+  int64_t num_update, launches;
+} hb_train_stats;
+
+int hb_trainer_layout(int in_dim, int num_action, int hand_size, int64_t* offsets /* [17] */);
+int hb_trainer_create(const hb_trainer_config* cfg, float* online, float* target, float* grads, float* adam_m, float* adam_v, hb_trainer** out);
+void hb_trainer_destroy(hb_trainer* t);
+/* loss + backward for one sampled batch (DEVICE pointers in the layouts of hb_batch, batch->weight = importance weights);
+ * t_eff = longest episode of the batch (steps beyond it are padding in every row and are skipped; pass seq_len to disable);
+ * gradients -> the flat `grads` buffer (overwritten), aggregated priorities -> priority (device float [batchsize]). */
+int hb_trainer_backward(hb_trainer* t, const hb_batch* batch, int batchsize, int t_eff, float pred_weight, float* priority, void* stream);
+/* clip_grad_norm_ + Adam.step on the online network (a data-parallel learner all-reduces `grads` before this call). */
+int hb_trainer_optim_step(hb_trainer* t, void* stream);
+int hb_trainer_sync_target(hb_trainer* t, void* stream);      /* R2D2Agent.sync_target_with_online (r2d2.py:208-210) */
+int hb_trainer_stats(hb_trainer* t, hb_train_stats* out);     /* waits for the last update */
+
+/* Longest episode (steps) among the entries of the last hb_replay_sample* of this engine: the t_eff of hb_trainer_backward. */
+int hb_replay_last_max_len(hb_engine* e);
+/* Make the engine's stream wait for everything queued so far on `stream` (and the other way round): lets a learner on its own
+ * stream hand priorities to hb_replay_update_priority, or consume a sampled batch, without a host synchronisation. */
+int hb_stream_wait(hb_engine* e, void* stream);
+int hb_stream_wait_engine(hb_engine* e, void* stream);
 
 /* Diagnostic: the observation as the policy consumes it -- the bf16 hi / lo operand of the first GEMM written by the fused
  * tick's encoder, as bit patterns [G*P][*ks] (host; hi or lo may be NULL; *ks = row length, F rounded up to 64). */
