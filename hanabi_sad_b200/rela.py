@@ -32,6 +32,20 @@ def set_actor_duty(duty):
     _actor_duty = float(duty)
 
 
+# The reference ties the actors to the learner through its replay: ConcurrentQueue::blockAppend (rela/prioritized_replay.h:44-48)
+# makes an actor thread wait while the ring holds int(1.25 * capacity) entries, and only sample() pops it back to `capacity`
+# (:326-332).  The device ring implements the same rule (hb_config.replay_block: a game whose finished episode finds the ring
+# full does not start its next episode) and the driver thread stops queuing ticks while the ring is full.  HB_REPLAY_EVICT=1
+# (or set_replay_block(False)) selects the free-running ring instead: the newest `capacity` episodes are kept, the actors
+# never wait -- throughput runs without a learner.
+_replay_block = os.environ.get("HB_REPLAY_EVICT", "0") != "1"
+
+
+def set_replay_block(on):
+    global _replay_block
+    _replay_block = bool(on)
+
+
 class _EngineLock:
     """Mutex around one engine (the C ABI is single-caller) that lets foreground callers -- the learner thread's sample /
     update_priority / update_model / counters -- overtake the rollout driver thread, which would otherwise re-acquire a
@@ -114,13 +128,15 @@ class FFTransition:
 
 class RNNPrioritizedReplay:
     """rela.RNNPrioritizedReplay(capacity, seed, alpha, beta, prefetch) (rela/prioritized_replay.h:176-265).  The storage is
-    the device ring of the engine(s) created by Context.start(); `prefetch` is accepted and ignored (sampling is a
-    device kernel, there is nothing to overlap with host threads)."""
+    the device ring of the engine(s) created by Context.start() -- with several act devices each engine holds a shard of
+    capacity // n_engines entries; `prefetch` is accepted and ignored (sampling is a device kernel, there is nothing to overlap
+    with host threads)."""
 
     def __init__(self, capacity, seed, alpha, beta, prefetch=0):
         self.capacity, self.seed, self.alpha, self.beta, self.prefetch = int(capacity), int(seed), float(alpha), float(beta), int(prefetch)
         self._engines = []       # (engine, lock)
         self._last = []          # engines sampled from (with counts) awaiting update_priority
+        self._rng = np.random.default_rng(self.seed)
 
     def _attach(self, engine, lock):
         self._engines.append((engine, lock))
@@ -139,26 +155,59 @@ class RNNPrioritizedReplay:
                 n += e.counters()[1]
         return n
 
+    def _sample_shards(self, batchsize):
+        """One GLOBAL stratified draw over the union of the shards (prioritized_replay.h:281-297): the cumulative weight of the
+        shards laid end to end, one uniform draw per segment of width sum / batchsize; every shard then resolves the draws that
+        fell into its stretch.  Importance weights use the union's N and sum_w (:334-339) and are normalised by the maximum over
+        the whole batch -- not per shard."""
+        stats = []
+        for e, lk in self._engines:
+            with lk:
+                stats.append(e.replay_stats())
+        sums = np.array([st["weight_sum"] for st in stats], np.float64)
+        total, n_total = float(sums.sum()), float(sum(st["sampleable"] for st in stats))
+        if n_total < batchsize:
+            raise RuntimeError("replay holds %d entries, fewer than the batch size %d" % (n_total, batchsize))
+        seg = total / batchsize
+        r = np.minimum(self._rng.random(batchsize) * seg + np.arange(batchsize) * seg, total - 0.1)
+        edges = np.concatenate([[0.0], np.cumsum(sums)])
+        shard = np.clip(np.searchsorted(edges, r, side="right") - 1, 0, len(stats) - 1)
+        parts = []
+        try:
+            for k, (e, lk) in enumerate(self._engines):
+                mine = r[shard == k] - edges[k]
+                if mine.size == 0:
+                    continue
+                with lk:
+                    t = e.sample(int(mine.size), targets=mine, total_weight=total, total_size=n_total, normalize=False)
+                parts.append(t)
+                self._last.append((e, lk, int(mine.size)))
+        except Exception:
+            for e, lk, _ in self._last:   # leave no shard waiting for priorities that will never come
+                with lk:
+                    e.update_priority(np.zeros((0,), np.float32))
+            self._last = []
+            raise
+        return parts
+
     def sample(self, batchsize, device):
         if self._last:
             raise RuntimeError("Error: previous samples' priority has not been updated.")  # prioritized_replay.h:209-212
         assert self._engines, "the replay is filled by a started rela.Context"
-        n_eng = len(self._engines)
-        parts, shares = [], [batchsize // n_eng + (1 if i < batchsize % n_eng else 0) for i in range(n_eng)]
-        for (e, lk), b in zip(self._engines, shares):
-            if b == 0:
-                continue
+        if len(self._engines) == 1:
+            e, lk = self._engines[0]
             with lk:
-                t = e.sample(b)
-            parts.append(t)
-            self._last.append((e, lk, b))
+                parts = [e.sample(batchsize)]
+            self._last.append((e, lk, batchsize))
+        else:
+            parts = self._sample_shards(batchsize)
         dev = torch.device(device)
         cat = lambda k, dim: torch.cat([p[k].to(dev) for p in parts], dim) if len(parts) > 1 else parts[0][k].to(dev)
         obs = {k: cat(k, 1) for k in ("priv_s", "legal_move", "eps", "own_hand")}
         action = {k: cat(k, 1) for k in ("a", "greedy_a")}
         batch = RNNTransition(obs, action, cat("reward", 1), cat("terminal", 1), cat("bootstrap", 1), cat("seq_len", 0))
         weight = cat("weight", 0)
-        if len(parts) > 1:
+        if len(self._engines) > 1:
             weight = weight / weight.max()
         return batch, weight
 
@@ -267,7 +316,7 @@ class ThreadLoop:
 class _DeviceGroup:
     """All thread loops of one act device = one engine + one host driver thread."""
 
-    def __init__(self, loops):
+    def __init__(self, loops, n_groups=1):
         from .hanalearn import HanabiEnv  # noqa: F401
 
         self.loops = loops
@@ -293,7 +342,8 @@ class _DeviceGroup:
         self.engine = Engine(
             len(self.envs), env0.players, env0.hand_size, env0.bomb, env0.max_len, env0.sad, env0.shuffle_color, env0.eps_list,
             seed=env0.seed, device=runner._device_index(), vdn=not self.iql, multi_step=a0.multi_step, gamma=a0.gamma, eta=a0.eta,
-            seq_len=a0.seq_len, replay_capacity=(replay.capacity if replay is not None else 0),
+            seq_len=a0.seq_len, replay_capacity=(max(1, replay.capacity // n_groups) if replay is not None else 0),
+            replay_block=(replay is not None and _replay_block),
             alpha=(replay.alpha if replay is not None else 0.6), beta=(replay.beta if replay is not None else 0.4), hid_dim=hid,
             num_lstm_layer=runner.agent.online_net.num_lstm_layer,
             num_fc_layer=(1 if self.eval else runner.agent.online_net.num_fc_layer),
@@ -312,6 +362,9 @@ class _DeviceGroup:
         if replay is not None:
             replay._attach(self.engine, self.lock)
         self.chunk_min = None
+        # blockAppend at the host level: entries the shard may hold before its actors wait (prioritized_replay.h:44-48, 183)
+        self.block_limit = int(1.25 * max(1, replay.capacity // n_groups)) if (replay is not None and _replay_block) else None
+        self.stalls = 0
         self.paused = threading.Event()
         self.stop = threading.Event()
         self.done = threading.Event()
@@ -328,12 +381,21 @@ class _DeviceGroup:
                         continue
                     self.lock.driver_acquire()
                     t0 = time.perf_counter()
+                    full = False
                     try:
                         if not self.paused.is_set() and not self.stop.is_set():  # pause() may have won the race for the lock
-                            self.engine.rollout(ROLLOUT_CHUNK)
-                            self.engine.sync()
+                            # every game is waiting in blockAppend: queue nothing (the reference's env threads sleep in
+                            # cvSize_.wait); sample() pops the ring and the next look lets them go on
+                            full = self.block_limit is not None and self.engine.counters()[0] >= self.block_limit
+                            if not full:
+                                self.engine.rollout(ROLLOUT_CHUNK)
+                                self.engine.sync()
                     finally:
                         self.lock.driver_release()
+                    if full:
+                        self.stalls += 1
+                        time.sleep(0.001)
+                        continue
                     if _actor_duty < 1.0:
                         # Idle time is derived from the UNCONTENDED duration of a chunk (the shortest seen), not from this chunk's
                         # wall time: when the learner's kernels hold the GPU a chunk can take 50x longer, and sleeping in
@@ -383,7 +445,7 @@ class Context:
         by_dev = {}
         for lp in self.loops:
             by_dev.setdefault(lp.actors[0].runner.device, []).append(lp)
-        self.groups = [_DeviceGroup(lps) for lps in by_dev.values()]
+        self.groups = [_DeviceGroup(lps, len(by_dev)) for lps in by_dev.values()]
         for g in self.groups:
             g.thread = threading.Thread(target=g.run, daemon=True)
             g.thread.start()

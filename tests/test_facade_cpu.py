@@ -24,6 +24,10 @@ class FakeEngine:
         self.F, self.A = 838 if sad else 783, 21
         self.ticks, self.weights, self.closed, self.sampled, self.updated = 0, [], False, 0, 0
         self.eval_ticks = 0
+        self.popped = 0                       # ConcurrentQueue::blockPop bookkeeping of the fake ring
+        self.entry_w = None                   # per-entry priority^alpha of the fake ring (set by the sharded-sampling test)
+        self.beta = kw.get("beta", 0.4)
+        self.last_idx = None
         FakeEngine.instances.append(self)
 
     def rollout(self, n):
@@ -34,20 +38,39 @@ class FakeEngine:
         pass
 
     def counters(self):
-        return (min(self.ticks // 4, self.kw["replay_capacity"]), self.ticks // 4, self.ticks * self.G)
+        adds, cap = self.ticks // 4, self.kw["replay_capacity"]
+        if self.kw.get("replay_block"):       # reference semantics: holds up to int(1.25 * capacity), only sample() pops
+            return (adds - self.popped, adds, self.ticks * self.G)
+        return (min(adds, cap), adds, self.ticks * self.G)
+
+    def replay_stats(self):
+        w = self.entry_w if self.entry_w is not None else np.ones(self.counters()[0], np.float32)
+        return {"weight_sum": float(np.sum(w, dtype=np.float64)), "sampleable": int(len(w)), "size": int(len(w))}
 
     def set_weights(self, net, sd, skip_connect=False):
         assert "lstm.weight_ih_l0" in sd
         self.weights.append(net)
 
-    def sample(self, b):
+    def sample(self, b, targets=None, total_weight=0.0, total_size=0.0, normalize=True):
         assert self.sampled == self.updated
         self.sampled += 1
         T, pp = self.kw["seq_len"], ((self.P,) if self.kw["vdn"] else ())
+        if self.kw.get("replay_block"):       # "pop storage if full" after the draw (prioritized_replay.h:326-332)
+            size = self.counters()[0]
+            if size > self.kw["replay_capacity"]:
+                self.popped += size - self.kw["replay_capacity"]
+        weight = torch.ones(b)
+        if targets is not None:               # the device draw kernel's contract (hb_replay_sample_ex)
+            w = self.entry_w.astype(np.float32)
+            acc = np.cumsum(w, dtype=np.float64)
+            idx = np.array([int(np.nonzero((acc > 0) & (acc >= np.float32(min(np.float32(acc[-1]) - np.float32(0.1), np.float32(t)))))[0][0]) for t in targets])
+            self.last_idx = idx
+            weight = torch.from_numpy((np.float32(total_size) * (w[idx] / np.float32(total_weight))) ** np.float32(-self.beta))
+            assert not normalize
         return {"priv_s": torch.zeros((T, b) + pp + (self.F,)), "legal_move": torch.ones((T, b) + pp + (self.A,)), "own_hand": torch.zeros((T, b) + pp + (15,)),
                 "eps": torch.zeros((T, b) + pp), "a": torch.zeros((T, b) + pp, dtype=torch.long), "greedy_a": torch.zeros((T, b) + pp, dtype=torch.long),
                 "reward": torch.zeros(T, b), "bootstrap": torch.ones(T, b), "terminal": torch.zeros(T, b, dtype=torch.bool), "seq_len": torch.full((b,), 7.0),
-                "weight": torch.ones(b), "ids": torch.zeros(b, dtype=torch.int32)}
+                "weight": weight, "ids": torch.zeros(b, dtype=torch.int32)}
 
     def update_priority(self, p):
         self.updated += 1
@@ -207,3 +230,86 @@ def test_actor_duty_cycle_survives_a_contended_chunk(ref_modules, monkeypatch):
     # duty 0.1 of ~1 ms chunks = one 8-tick chunk every ~10-12 ms: ~40 chunks in 0.5 s; a sleep proportional to the slow chunk
     # (0.1 s x 9) would allow none
     assert b - a >= 8 * 10, (a, b)
+
+
+def test_block_append_back_pressure(ref_modules):
+    """ConcurrentQueue::blockAppend (rela/prioritized_replay.h:44-48): with nobody sampling, the actors fill the ring to
+    int(1.25 * capacity) and then WAIT -- the driver thread queues no more ticks; sample() pops the ring back to capacity
+    (:326-332) and the actors resume."""
+    create, ref_eval, r2d2, rela = ref_modules
+    games = create.create_envs(4, 1, 2, 5, 0, [0.1], 80, True, False, False)
+    agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, "cpu", 838, 512, 21, 2, 5, False)
+    cap = 40
+    replay = rela.RNNPrioritizedReplay(cap, 1, 0.9, 0.6, 3)
+    ag = create.ActGroup("vdn", "cpu", agent, 2, 2, 3, 0.999, 0.9, 80, 2, replay)
+    context, threads = create.create_threads(2, 2, ag.actors, games)
+    ag.start()
+    context.start()
+    eng, grp = FakeEngine.instances[0], context.groups[0]
+    assert eng.kw["replay_block"] is True and grp.block_limit == 50
+    t0 = time.time()
+    while grp.stalls < 20:
+        assert time.time() - t0 < 20
+        time.sleep(0.005)
+    held, ticks = replay.size(), eng.ticks
+    assert 50 <= held <= 50 + 2          # one 8-tick chunk of the fake adds 2 entries
+    time.sleep(0.1)
+    assert eng.ticks == ticks and replay.size() == held, "the actors must wait while the ring is full"
+    batch, w = replay.sample(8, "cpu")  # pops down to capacity -> room for 0.25 * capacity new episodes
+    replay.update_priority(torch.ones(8))
+    t0 = time.time()
+    while eng.ticks == ticks:
+        assert time.time() - t0 < 5, "sample() must release the actors"
+        time.sleep(0.005)
+    t0 = time.time()
+    while replay.size() < 50:
+        assert time.time() - t0 < 20
+        time.sleep(0.005)
+    assert replay.num_add() >= held + 10
+    context.terminate()
+
+
+def test_sharded_replay_importance_weights_over_the_union(ref_modules, monkeypatch):
+    """Two act devices = two replay shards.  sample() must behave like ONE PrioritizedReplay over their union
+    (prioritized_replay.h:274-345): one stratified draw over the concatenated cumulative weights, importance weights
+    (N * w / sum_w)^-beta with the union's N and sum, normalised by the maximum of the WHOLE batch; each shard holds
+    capacity / 2 entries."""
+    create, ref_eval, r2d2, rela = ref_modules
+    import hanabi_sad_b200.rela as hrela
+
+    monkeypatch.setattr(hrela.BatchRunner, "_device_index", lambda self: int(self.device[-1]) if self.device[-1].isdigit() else 0)
+    games = create.create_envs(8, 1, 2, 5, 0, [0.1], 80, True, False, False)
+    agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, "cpu", 838, 512, 21, 2, 5, False)
+    replay = rela.RNNPrioritizedReplay(1000, 5, 0.9, 0.6, 0)
+    runners = [rela.BatchRunner(agent, d, 100, ["act"]) for d in ("fake:0", "fake:1")]
+    actors = [rela.R2D2Actor(runners[t % 2], 3, 2, 0.999, 0.9, 80, 2, replay) for t in range(4)]
+    context, threads = create.create_threads(4, 2, actors, games)
+    hrela.set_actor_duty(1.0)
+    context.start()
+    context.pause()
+    assert len(FakeEngine.instances) == 2 and all(e.kw["replay_capacity"] == 500 for e in FakeEngine.instances)
+    rng = np.random.default_rng(0)
+    ws = [rng.gamma(2.0, 1.0, 300).astype(np.float32), (5.0 * rng.gamma(2.0, 1.0, 200)).astype(np.float32)]   # very different shard totals
+    for e, w in zip(FakeEngine.instances, ws):
+        e.entry_w, e.beta = w, 0.6
+    B = 64
+    batch, weight = replay.sample(B, "cpu")
+    # the reference's single-replay computation over the union, with the same uniform draws
+    allw = np.concatenate(ws)
+    total, n = float(np.sum(ws[0], dtype=np.float64) + np.sum(ws[1], dtype=np.float64)), len(allw)
+    seg = total / B
+    r = np.minimum(np.random.default_rng(5).random(B) * seg + np.arange(B) * seg, total - 0.1)
+    acc = np.cumsum(allw, dtype=np.float64)
+    want_idx = np.array([int(np.nonzero(acc >= t)[0][0]) for t in r])
+    got_idx = np.concatenate([FakeEngine.instances[0].last_idx, FakeEngine.instances[1].last_idx + 300])
+    # a draw within float32 rounding of a shard / entry boundary may resolve to the neighbour; everything else must agree
+    assert (got_idx == want_idx).mean() > 0.95 and np.abs(got_idx - want_idx).max() <= 1
+    want = (n * allw[got_idx] / total) ** -0.6
+    want /= want.max()
+    assert np.allclose(weight.numpy(), want, rtol=1e-4), np.abs(weight.numpy() - want).max()
+    assert float(weight.max()) == 1.0 and batch.obs["priv_s"].shape[1] == B
+    # per-shard normalisation (the round-1 behaviour) would have put a 1.0 into BOTH shards' parts
+    n0 = len(FakeEngine.instances[0].last_idx)
+    assert min(float(weight[:n0].max()), float(weight[n0:].max())) < 0.9
+    replay.update_priority(torch.ones(B))
+    context.terminate()
