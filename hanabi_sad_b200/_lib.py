@@ -98,6 +98,7 @@ SIGNATURES = {
     "hb_env_random_actions": (c_int, [c_void_p, c_u64]),
     "hb_policy_set_weights": (c_int, [c_void_p, c_int, ctypes.POINTER(HbWeights)]),
     "hb_policy_act": (c_int, [c_void_p, c_int]),
+    "hb_eval_rollout": (c_int, [c_void_p, c_int, c_void_p, ctypes.POINTER(c_int)]),
     "hb_policy_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hb_rollout": (c_int, [c_void_p, c_int]),
     "hb_counters": (c_int, [c_void_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),

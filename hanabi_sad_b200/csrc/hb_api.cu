@@ -5,6 +5,7 @@
 #include <new>
 
 #include "hb_engine.h"
+#include "hb_policy.h"
 
 static thread_local char g_err[512] = "";
 
@@ -104,12 +105,12 @@ int hb_create(const hb_config* cfg, hb_engine** out) {
   HB_CUDA(cudaMalloc(&e->d_terminal, G));
   HB_CUDA(cudaMalloc(&e->d_a, G * P * sizeof(int64_t)));
   HB_CUDA(cudaMalloc(&e->d_greedy_a, G * P * sizeof(int64_t)));
-  HB_CUDA(cudaMalloc(&e->d_flags, 4 * sizeof(int)));
-  HB_CUDA(cudaMallocHost(&e->h_flags, 4 * sizeof(int)));
+  HB_CUDA(cudaMalloc(&e->d_flags, 8 * sizeof(int)));
+  HB_CUDA(cudaMallocHost(&e->h_flags, 8 * sizeof(int)));
   HB_CUDA(cudaMallocHost(&e->h_status, 2 * sizeof(int)));
   e->h_status[0] = e->h_status[1] = 0;
   HB_CUDA(cudaEventCreateWithFlags(&e->ev_status, cudaEventDisableTiming));
-  HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 4 * sizeof(int), e->stream));
+  HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 8 * sizeof(int), e->stream));
   HB_CUDA(cudaMemcpyAsync(e->d_eps_list, cfg->eps_list, cfg->num_eps * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   HB_CUDA(cudaMemsetAsync(e->d_decks, 0, G * HB_DECK_STRIDE, e->stream));
   HB_CUDA(cudaMemsetAsync(e->d_inject, 0, G * sizeof(HbInject), e->stream));
@@ -368,6 +369,50 @@ int hb_env_get_result(hb_engine* e, float* reward, uint8_t* terminal) {
   if (terminal) HB_CUDA(cudaMemcpyAsync(terminal, e->d_terminal, (size_t)e->G, cudaMemcpyDeviceToHost, e->stream));
   HB_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
+}
+
+// The evaluation loop of HanabiThreadLoop(eval = true) (cpp/thread_loop.h:74-86) / pyhanabi/eval.py:19-66 on the device: every
+// game plays ONE episode (act -> step, finished games stay frozen).  Ticks are queued in chunks; after each chunk the number
+// of games still running travels to pinned memory asynchronously and is looked at one chunk LATER, so the stream never drains
+// and the host never waits inside the loop (a finished evaluation costs at most one surplus chunk of no-op ticks).
+int hb_eval_rollout(hb_engine* e, int max_ticks, int32_t* scores, int* ticks_run) {
+  if (!e) return hb_fail(-1, "hb_eval_rollout: null engine");
+  if (!e->policy || !e->policy->have_weights[0]) return hb_fail(-1, "hb_eval_rollout: no policy weights (hb_policy_set_weights)");
+  if (e->replay) return hb_fail(-1, "hb_eval_rollout: evaluation engines have no replay (actors with eval = true never call postAct)");
+  if (max_ticks <= 0) max_ticks = 512;
+  HB_CUDA(cudaSetDevice(e->device));
+  int rc = hb_launch_env(e, 1, 0, nullptr, nullptr);   // VectorEnv::reset: start every game that is not running
+  if (rc) return rc;
+  const int CH = 8;
+  cudaEvent_t ev[2];
+  HB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  HB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  int ticks = 0, chunk = 0;
+  bool done = false;
+  while (!done && ticks < max_ticks) {
+    for (int i = 0; i < CH && ticks < max_ticks; ++i, ++ticks) {
+      rc = hb_policy_forward(e, 0);
+      if (!rc) rc = hb_launch_env(e, 0, 1, e->d_a, e->d_greedy_a);
+      if (rc) { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); return rc; }
+    }
+    cudaMemcpyAsync(e->h_flags + 4 + (chunk & 1), e->d_flags + 4, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    cudaEventRecord(ev[chunk & 1], e->stream);
+    if (chunk > 0) {   // the PREVIOUS chunk's count: by now almost certainly there
+      cudaEventSynchronize(ev[(chunk - 1) & 1]);
+      if (e->h_flags[4 + ((chunk - 1) & 1)] == 0) done = true;
+    }
+    ++chunk;
+  }
+  cudaEventSynchronize(ev[(chunk - 1) & 1]);
+  const int live = e->h_flags[4 + ((chunk - 1) & 1)];
+  cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+  e->pending_actions = 0;
+  if (ticks_run) *ticks_run = ticks;
+  if (live != 0) { hb_set_error("hb_eval_rollout: %d game(s) still running after %d ticks", live, ticks); return -3; }
+  rc = hb_status_post(e);
+  if (!rc) rc = hb_status_poll(e, true);
+  if (rc) return rc;
+  return scores ? hb_env_last_scores(e, scores) : 0;
 }
 
 int hb_env_random_actions(hb_engine* e, uint64_t counter) {

@@ -38,6 +38,7 @@ hb_k_env(HbGame* __restrict__ games, uint8_t* __restrict__ decks, HbInject* __re
     }
     if (do_reset && s.terminated) { hb_begin_episode(s, deck, inject + g, cfg, seed, g); did_reset = 1; }
     if (s.terminated) atomicOr(&flags[0], 1);
+    else atomicAdd(&flags[4], 1);   // games still being played (hb_eval_rollout's stop condition)
   }
   __syncthreads();
   if (did_reset) hb_cta_zero_hidden(hid, g, geo.P);
@@ -144,6 +145,7 @@ int hb_launch_check_invariants(hb_engine* e) {
 
 int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev) {
   HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
+  HB_CUDA(cudaMemsetAsync(e->d_flags + 4, 0, sizeof(int), e->stream));
   hb_k_env<<<e->G, HB_ENV_THREADS, 0, e->stream>>>(e->d_games, e->d_decks, e->d_inject, e->env, e->cfg.seed, do_reset, do_step,
                                                    a_dev, greedy_a_dev, e->obs, e->d_eps_list, e->d_reward, e->d_terminal,
                                                    e->d_flags, hb_policy_hidden_ptrs(e));

@@ -185,6 +185,14 @@ class Engine:
     def policy_act(self, greedy_only=False):
         check(lib().hb_policy_act(self._h, int(bool(greedy_only))))
 
+    def eval_rollout(self, max_ticks=0):
+        """eval.py:19-66 as one call (hb_eval_rollout): every game plays one episode on the device; returns (scores int32 [G],
+        ticks queued)."""
+        scores = np.empty((self.G,), np.int32)
+        n = ctypes.c_int()
+        check(lib().hb_eval_rollout(self._h, int(max_ticks), _ptr(scores), ctypes.byref(n)))
+        return scores, int(n.value)
+
     def policy_get(self, hidden=False):
         out = {"adv": np.empty((self.G, self.P, self.A), np.float32), "online_q": np.empty((self.G, self.P), np.float32),
                "target_q": np.empty((self.G, self.P), np.float32)}

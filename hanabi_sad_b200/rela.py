@@ -407,19 +407,11 @@ class _DeviceGroup:
             self.done.set()
 
     def _run_eval(self):
-        """HanabiThreadLoop(eval=True) (cpp/thread_loop.h:74-86): every game plays ONE episode, no replay, no restart."""
+        """HanabiThreadLoop(eval=True) (cpp/thread_loop.h:74-86): every game plays ONE episode, no replay, no restart -- one
+        device loop (hb_eval_rollout), one read-back of the scores."""
         e = self.engine
         with self.lock:
-            e.reset()
-        while not self.stop.is_set():
-            with self.lock:
-                e.policy_act()
-                e.step_dev()
-                _, term = e.result()
-            if term.all():
-                break
-        with self.lock:
-            scores = e.last_scores()
+            scores, self.eval_ticks = e.eval_rollout()
         for g, s in zip(self.envs, scores):
             g._last_score = int(s)
             g._engine, g._lock = None, None

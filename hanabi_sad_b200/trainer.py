@@ -8,7 +8,9 @@ pyhanabi/selfplay.py:218-241 (agent.loss -> backward -> clip_grad_norm_ -> optim
 Between `backward()` and `optim_step()` a data-parallel learner all-reduces `trainer.grads` (tools/train_multi_gpu.py).
 
 No fallback: without the CUDA library / a GPU every call raises."""
+import ast
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -24,6 +26,26 @@ def param_shapes(in_dim, num_action, hand_size):
     w = (4 * HID, HID)
     return dict(zip(PARAM_NAMES, ((HID, in_dim), (HID,), w, w, (4 * HID,), (4 * HID,), w, w, (4 * HID,), (4 * HID,), (1, HID), (1,),
                                   (num_action, HID), (num_action,), (3 * hand_size, HID), (3 * hand_size,))))
+
+
+def read_train_config(weight_file):
+    """The hyper-parameters a run was started with: selfplay.py:96-101 prints pprint(vars(args)) as the first thing into
+    <save_dir>/train.log, next to the checkpoints (what utils.get_train_config, pyhanabi/utils.py:87-116, parses).  None if the
+    checkpoint has no train.log beside it."""
+    log = os.path.join(os.path.dirname(os.path.abspath(weight_file)), "train.log")
+    if not os.path.exists(log):
+        return None
+    text = open(log).read()
+    start = text.find("{")
+    if start < 0:
+        return None
+    depth = 0
+    for i in range(start, len(text)):
+        depth += text[i] == "{"
+        depth -= text[i] == "}"
+        if depth == 0:
+            return ast.literal_eval(text[start:i + 1])
+    return None
 
 
 class _NetView:
@@ -102,6 +124,25 @@ class DeviceTrainer:
                 grad_clip, uniform_priority=agent.uniform_priority)
         t.load_state_dict(agent.state_dict())
         t._ref_agent = agent
+        return t
+
+    @classmethod
+    def from_checkpoint(cls, weight_file, device=0, **overrides):
+        """A learner from a reference checkpoint: `.pthw` = online_net.state_dict() (common_utils/saver.py:17-44), hyper-parameters
+        from the train.log header beside it (read_train_config); the target network starts as a copy of the online one."""
+        sd = torch.load(weight_file, map_location="cpu")
+        cfg = dict(read_train_config(weight_file) or {})
+        cfg.update(overrides)
+        in_dim, num_action = sd["net.0.weight"].shape[1], sd["fc_a.weight"].shape[0]
+        hand_size = int(cfg.get("hand_size", sd["pred.weight"].shape[0] // 3 if "pred.weight" in sd else 5))
+        t = cls(in_dim, num_action, hand_size, int(cfg.get("num_player", 2)), cfg.get("method", "vdn") == "vdn", int(cfg.get("multi_step", 3)),
+                float(cfg.get("gamma", 0.999)), float(cfg.get("eta", 0.9)), device, int(cfg.get("batchsize", 128)), int(cfg.get("max_len", 80)),
+                float(cfg.get("lr", 6.25e-5)), float(cfg.get("eps", 1.5e-5)), float(cfg.get("grad_clip", 5.0)))
+        full = {k: sd[k] for k in PARAM_NAMES if k in sd}
+        for k, shp in param_shapes(in_dim, num_action, hand_size).items():   # utils.load_weight keeps what the file lacks (:282-285)
+            full.setdefault(k, torch.zeros(shp))
+        t.load_state_dict({p + k: v for p in ("online_net.", "target_net.") for k, v in full.items()})
+        t.train_config = cfg
         return t
 
     def state_dict(self):

@@ -174,6 +174,12 @@ int hb_policy_set_weights(hb_engine* e, int net, const hb_weights* w);
  * advances.  greedy_only != 0 ignores eps (eval actors). */
 int hb_policy_act(hb_engine* e, int greedy_only);
 
+/* pyhanabi/eval.py:19-66 / HanabiThreadLoop(eval = true) (cpp/thread_loop.h:74-86) as ONE call: (re)start every game, then
+ * act -> step on the device until every game has finished its episode (finished games stay frozen; at most max_ticks ticks,
+ * <= 0: 512), without a host round trip per tick; scores: host int32 [G] = HanabiEnv::lastScore of every game (may be NULL),
+ * *ticks_run (may be NULL) = ticks queued.  For engines without a replay (evaluation actors never call postAct). */
+int hb_eval_rollout(hb_engine* e, int max_ticks, int32_t* scores, int* ticks_run);
+
 /* Host copies of the last forward's outputs (NULL skips): adv float [G*P,A] online advantages; online_q / target_q
  * float [G*P] = the dueling Q-values compute_priority uses (r2d2.py:344-348); h, c float [2, G*P, 512] = the
  * CURRENT hidden state (R2D2Actor::hidden_). */

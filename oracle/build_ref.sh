@@ -50,4 +50,6 @@ g++ -shared -o "../hanalearn$EXT" hl_pybind.o hanabi_env.o ../libhanabi.a $LIBS
 cp -r "$REF/pyhanabi/common_utils" "$OUT/pyhanabi/" 2>/dev/null || true
 for f in utils.py create.py eval.py set_path.py selfplay.py; do cp "$REF/pyhanabi/$f" "$OUT/pyhanabi/$f"; done
 sed 's/% s\.dim()/% priv_s.dim()/' "$REF/pyhanabi/r2d2.py" > "$OUT/pyhanabi/r2d2.py"
+mkdir -p "$OUT/pyhanabi/tools"
+for f in eval_model.py convert_model.py obl_model.py action_matrix.py; do cp "$REF/pyhanabi/tools/$f" "$OUT/pyhanabi/tools/$f"; done
 echo "[build_ref] done -> $OUT"

@@ -64,6 +64,31 @@ def test_trainer_layout_and_state_dict_cpu():
             DeviceTrainer(838, 21, 5, device="cpu")
 
 
+@pytest.mark.skipif(not os.path.isdir(REF_PY), reason="oracle/_ref not built")
+def test_train_log_header_is_read_like_the_reference(tmp_path):
+    """utils.get_train_config (pyhanabi/utils.py:87-116) vs hanabi_sad_b200.trainer.read_train_config on a header written the way
+    selfplay.py:96-101 writes it (pprint of vars(args), then the training log)."""
+    import pprint
+
+    from hanabi_sad_b200.trainer import read_train_config
+
+    args = {"method": "iql", "num_player": 2, "hand_size": 5, "sad": 1, "shuffle_color": 1, "lr": 6.25e-05, "eps": 1.5e-05, "grad_clip": 5.0,
+            "gamma": 0.999, "eta": 0.9, "multi_step": 3, "batchsize": 128, "max_len": 80, "save_dir": str(tmp_path), "load_model": "", "pred_weight": 0.25,
+            "act_base_eps": 0.1, "act_eps_alpha": 7.0, "train_device": "cuda:0", "act_device": "cuda:1", "num_thread": 80, "num_game_per_thread": 80}
+    with open(tmp_path / "train.log", "w") as f:
+        f.write(pprint.pformat(args) + "\n")
+        f.write("{'not': 'the config'}\nbeginning of epoch:  0\n")
+    got = read_train_config(str(tmp_path / "model0.pthw"))
+    assert got == args
+    assert read_train_config(str(tmp_path / "elsewhere" / "model0.pthw")) is None
+    src = open(os.path.join(REF_PY, "utils.py")).read()
+    ns = {"os": os, "json": __import__("json")}
+    i, j = src.index("def parse_first_dict"), src.index("def flatten_dict")
+    exec(src[i:j], ns)                       # the reference's two functions, as they are (utils.py imports need the .so modules)
+    want = ns["get_train_config"](str(tmp_path / "model0.pthw"))
+    assert {k: (bool(v) if isinstance(v, bool) else v) for k, v in want.items()} == got
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.isdir(REF_PY), reason="oracle/_ref not built")
 @pytest.mark.parametrize("vdn,B,pred_weight,max_seq", [(False, 128, 0.0, 80), (True, 64, 0.25, 80), (True, 128, 0.0, 37), (False, 20, 0.25, 51)],
@@ -115,7 +140,8 @@ def test_update_matches_the_reference_learner(gpu_or_skip, vdn, B, pred_weight, 
                 assert float(grads[name].abs().max()) == 0.0, name
                 continue
             # fc layers on the bf16x3 GEMM: a few ReLU gates at |pre-activation| < 3e-6 flip against an fp32 sgemm -- net.0 only
-            tol = 2e-3 if name.startswith("net.") else 2e-4
+            # (second iteration: the two learners' weights already differ by their first Adam steps' rounding)
+            tol = (2e-3 if it == 0 else 5e-3) if name.startswith("net.") else 2e-4
             assert rel(grads[name].cpu(), want) < tol, (it, name, rel(grads[name].cpu(), want))
         # parameters after the step: Adam's first steps move every weight by up to ~lr whatever the gradient's size, so compare
         # the UPDATES (new - old) -- direction and size -- rather than the weights themselves
