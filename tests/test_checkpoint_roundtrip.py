@@ -55,9 +55,10 @@ def test_eval_rollout_equals_the_per_tick_path(gpu_or_skip):
     got, queued = b.eval_rollout()
     assert np.array_equal(got, want) and ticks <= queued <= ticks + 16
     assert (got >= 0).all() and got.max() <= 25
-    # a second evaluation on the same engine starts new games (next Philox episode): different deals, still complete
+    deck0 = b.get_deck(0).copy()
+    # a second evaluation on the same engine starts new games (next Philox episode): different deals, complete again
     got2, _ = b.eval_rollout()
-    assert not np.array_equal(got2, got) and (got2 >= 0).all()
+    assert not np.array_equal(b.get_deck(0), deck0) and (got2 >= 0).all() and b.query(0).episode == 2
     b.close()
 
 

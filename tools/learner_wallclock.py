@@ -26,6 +26,36 @@ DEVICE_LEARNER_PATCH = (
     "    agent = DeviceLearner.from_agent(agent, max_T=args.max_len, max_rows=args.batchsize * (args.num_player if args.method == 'vdn' else 1))\n")
 
 
+# The whole update on the device (hanabi_sad_b200.trainer.DeviceTrainer, csrc/hb_trainer.cu): the learner object is replaced
+# after construction and the loop body of selfplay.py:218-241 (loss -> backward -> clip -> Adam -> aggregate_priority) becomes
+# one call.  Everything else -- sampling, priority write-back, weight sync, evaluation, saving, logging -- is the reference's.
+TRAINER_PATCHES = [
+    ("    agent = agent.to(args.train_device)\n",
+     "    agent = agent.to(args.train_device)\n"
+     "    from hanabi_sad_b200.trainer import DeviceTrainer\n"
+     "    agent = DeviceTrainer.from_agent(agent, lr=args.lr, eps=args.eps, grad_clip=args.grad_clip, max_batch=args.batchsize,\n"
+     "                                     seq_len=args.max_len, num_player=args.num_player)\n"),
+    ("            loss, priority = agent.loss(batch, args.pred_weight, stat)\n"
+     "            priority = rela.aggregate_priority(\n"
+     "                priority.cpu(), batch.seq_len.cpu(), args.eta\n"
+     "            )\n"
+     "            loss = (loss * weight).mean()\n"
+     "            loss.backward()\n",
+     "            priority = agent.update(batch, weight, args.pred_weight)\n"),
+    ("            g_norm = torch.nn.utils.clip_grad_norm_(\n"
+     "                agent.online_net.parameters(), args.grad_clip\n"
+     "            )\n"
+     "            optim.step()\n"
+     "            optim.zero_grad()\n", ""),
+    ("            stat[\"loss\"].feed(loss.detach().item())\n"
+     "            stat[\"grad_norm\"].feed(g_norm)\n",
+     "            _st = agent.stats()\n"
+     "            stat[\"loss\"].feed(_st[\"loss\"])\n"
+     "            stat[\"rl_loss\"].feed(_st[\"rl_loss\"])\n"
+     "            stat[\"grad_norm\"].feed(_st[\"grad_norm\"])\n"),
+]
+
+
 def run(arm, a, out_dir):
     env = dict(os.environ)
     device_arm = arm.startswith("b200")
@@ -40,9 +70,17 @@ def run(arm, a, out_dir):
         script = os.path.join(out_dir, "selfplay_device_learner.py")
         open(script, "w").write(src.replace(anchor, DEVICE_LEARNER_PATCH))
         env["PYTHONPATH"] = PYH + os.pathsep + ROOT + os.pathsep + env["PYTHONPATH"]
-    cmd = [sys.executable, script, "--save_dir", os.path.join(out_dir, arm), "--method", "iql", "--num_thread", str(a.num_thread),
+    if arm == "b200_device_trainer":
+        src = open(os.path.join(PYH, "selfplay.py")).read()
+        for old, new in TRAINER_PATCHES:
+            assert src.count(old) == 1, old
+            src = src.replace(old, new)
+        script = os.path.join(out_dir, "selfplay_device_trainer.py")
+        open(script, "w").write(src)
+        env["PYTHONPATH"] = PYH + os.pathsep + ROOT + os.pathsep + env["PYTHONPATH"]
+    cmd = [sys.executable, script, "--save_dir", os.path.join(out_dir, arm), "--method", a.method, "--num_thread", str(a.num_thread),
            "--num_game_per_thread", str(a.num_game_per_thread), "--sad", "1", "--act_base_eps", "0.1", "--act_eps_alpha", "7", "--lr", "6.25e-05",
-           "--eps", "1.5e-05", "--grad_clip", "5", "--gamma", "0.999", "--seed", "1", "--batchsize", "128", "--burn_in_frames", str(a.burn_in),
+           "--eps", "1.5e-05", "--grad_clip", "5", "--gamma", "0.999", "--seed", "1", "--batchsize", str(a.batchsize), "--burn_in_frames", str(a.burn_in),
            "--replay_buffer_size", str(a.replay), "--epoch_len", str(a.epoch_len), "--num_epoch", str(a.num_epoch), "--priority_exponent", "0.9",
            "--priority_weight", "0.6", "--train_bomb", "0", "--eval_bomb", "0", "--num_player", "2", "--rnn_hid_dim", "512", "--act_device", "cuda:0",
            "--shuffle_color", "1"]
@@ -77,7 +115,9 @@ def main():
     ap.add_argument("--burn_in", type=int, default=5000)
     ap.add_argument("--replay", type=int, default=32768)
     ap.add_argument("--timeout", type=int, default=900)
-    ap.add_argument("--arms", default="reference,b200,b200_device_learner")
+    ap.add_argument("--arms", default="reference,b200,b200_device_learner,b200_device_trainer")
+    ap.add_argument("--method", default="iql")
+    ap.add_argument("--batchsize", type=int, default=128)
     ap.add_argument("--actor_duty", type=float, default=1.0, help="share of the time the device actors keep the GPU busy (hanabi_sad_b200.rela.set_actor_duty)")
     a = ap.parse_args()
     res = {}
@@ -90,8 +130,12 @@ def main():
             "actor_duty_b200": a.actor_duty,
             "flags": "tools/dev.sh (iql, sad 1, shuffle_color 1, %d x %d games, batchsize 128, burn_in %d), epoch_len %d x %d epochs, actors and learner on cuda:0"
                      % (a.num_thread, a.num_game_per_thread, a.burn_in, a.epoch_len, a.num_epoch),
-            "learner_updates_per_s": {"reference": r["train_samples_per_s"][-1] / 128, "b200": b["train_samples_per_s"][-1] / 128,
-                                      "b200_device_learner": (res["b200_device_learner"]["train_samples_per_s"] or [0])[-1] / 128},
+            "learner_updates_per_s": {k: (v["train_samples_per_s"] or [0])[-1] / a.batchsize for k, v in res.items() if isinstance(v, dict) and "arm" in v},
+            "learner_wallclock_speedup_last_epoch_by_arm": {k: (v["train_samples_per_s"] or [0])[-1] / r["train_samples_per_s"][-1]
+                                                            for k, v in res.items() if isinstance(v, dict) and "arm" in v},
+            "learner_wallclock_speedup_all_epochs_by_arm": {k: (sum(v["train_samples_per_s"]) / max(1, len(v["train_samples_per_s"]))) /
+                                                            (sum(r["train_samples_per_s"]) / max(1, len(r["train_samples_per_s"])))
+                                                            for k, v in res.items() if isinstance(v, dict) and "arm" in v},
             "learner_wallclock_speedup_device_learner_last_epoch": (res["b200_device_learner"]["train_samples_per_s"] or [0])[-1] / r["train_samples_per_s"][-1],
             "learner_wallclock_speedup_last_epoch": b["train_samples_per_s"][-1] / r["train_samples_per_s"][-1],
             "actor_rate_ratio_last_epoch": b["act_per_s"][-1] / max(r["act_per_s"][-1], 1e-9),

@@ -54,7 +54,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--max_seq", type=int, default=80, help="longest episode in the synthetic batch (trained agents: 60-80; early training: 5-30)")
     ap.add_argument("--device_fc", type=int, default=0, help="device impl only: fc layers on hb_gemm_nt as well")
-    ap.add_argument("--impl", default="reference", choices=["reference", "device"],
+    ap.add_argument("--impl", default="reference", choices=["reference", "device", "trainer"],
                     help="reference: r2d2.R2D2Agent as is (cuDNN LSTM); device: hanabi_sad_b200.learner.DeviceLearner (LSTM on csrc/hb_lstm.cu)")
     a = ap.parse_args()
     import r2d2
@@ -70,7 +70,12 @@ def main():
         from hanabi_sad_b200.learner import DeviceLearner
 
         agent = DeviceLearner.from_agent(agent, max_T=T, max_rows=a.batchsize * (P if vdn else 1), device_fc=bool(a.device_fc))
-    optim = torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
+    trainer = None
+    if a.impl == "trainer":   # the whole update on the device (hanabi_sad_b200.trainer.DeviceTrainer, csrc/hb_trainer.cu)
+        from hanabi_sad_b200.trainer import DeviceTrainer
+
+        trainer = DeviceTrainer.from_agent(agent, max_batch=a.batchsize)
+    optim = None if trainer else torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
     obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, a.batchsize, P, F, A, H, vdn, dev, max_seq=a.max_seq)
     weight = torch.ones(a.batchsize, device=dev)
 
@@ -81,7 +86,12 @@ def main():
 
     stat = Stat()
 
+    tbatch = dict(obs, **action, reward=reward, bootstrap=bootstrap, seq_len=seq_len)
+    t_eff = int(seq_len.max().item())
+
     def update():
+        if trainer is not None:
+            return trainer.update(tbatch, weight, a.pred_weight, t_eff=t_eff)
         batch = RNNTransition(obs, action, reward, terminal, bootstrap, seq_len)
         loss, priority = agent.loss(batch, a.pred_weight, stat)
         loss = (loss * weight).mean()
