@@ -38,12 +38,6 @@
 using hbg::Params;
 using namespace hbg;
 
-// 1: the backward recurrence accumulates the split-K partials of dh_{t-1} with vector reductions at L2 instead of
-// exchanging 32 partial tiles per row block (see lstm_bwd_kernel)
-#ifndef HBL_BWD_ATOMIC
-#define HBL_BWD_ATOMIC 1
-#endif
-
 namespace hbl {
 
 constexpr int HIDN = 512;
@@ -90,6 +84,10 @@ struct __align__(64) BwdParams {
   int T, rows, R_pad, MB;
   unsigned* ctr;
   int* error_flag;
+  // layer wavefront (layer 0 only, null otherwise): dh_ext of steps [T - (c+1)*chunk, T - c*chunk) is complete once
+  // chunk_flags[c] != 0 (set by the host-side pipeline after the dX GEMM of that time chunk of layer 1)
+  const unsigned* chunk_flags;
+  int chunk;
 };
 
 __device__ __forceinline__ constexpr uint32_t idesc_mn(int m, int n) {
@@ -388,14 +386,16 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
     const bool valid = row < P.rows;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int unit = slice * UPC;
-    const size_t part_dom = (size_t)P.MB * SLICES;   // partial blocks per buffer (exchange variant)
-    (void)part_dom;
     float dc[UPC];
 #pragma unroll
     for (int i = 0; i < UPC; ++i) dc[i] = 0.f;
     for (int t = T - 1; t >= 0; --t) {
       const size_t grow = (size_t)t * R_pad + row;
       float dh[UPC], a[NC], ct[UPC], cp[UPC];
+      if (P.chunk_flags != nullptr && (T - 1 - t) % P.chunk == 0) {   // entering a new time chunk of the layer above's gradient
+        if (lane == 0) wait_counter(P.chunk_flags + (T - 1 - t) / P.chunk, 1u, ef, dead);
+        dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
+      }
       {
         const float4* s0 = reinterpret_cast<const float4*>(P.dh_ext + ((size_t)t * P.dh_rows + row) * HIDN + unit);
         const float4* s1 = reinterpret_cast<const float4*>(P.act + grow * G4 + slice * NC);
@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 v0 = valid ? __ldg(s0 + i) : z, v2 = valid ? __ldg(s2 + i) : z, v3 = (valid && t > 0) ? __ldg(s3 + i) : z;
+          // dh_ext may have been written by a kernel running concurrently (layer wavefront): L2, not the non-coherent path
+          const float4 v0 = valid ? __ldcg(s0 + i) : z, v2 = valid ? __ldg(s2 + i) : z, v3 = (valid && t > 0) ? __ldg(s3 + i) : z;
           dh[4 * i] = v0.x; dh[4 * i + 1] = v0.y; dh[4 * i + 2] = v0.z; dh[4 * i + 3] = v0.w;
           ct[4 * i] = v2.x; ct[4 * i + 1] = v2.y; ct[4 * i + 2] = v2.z; ct[4 * i + 3] = v2.w;
           cp[4 * i] = v3.x; cp[4 * i + 1] = v3.y; cp[4 * i + 2] = v3.z; cp[4 * i + 3] = v3.w;
@@ -420,7 +421,6 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         if (lane == 0) wait_counter(ctr, (unsigned)(SLICES * (T - 1 - t)), ef, dead);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
         if (!dead) {
-#if HBL_BWD_ATOMIC
           // the 32 CTAs of the row block ADDED their partials into one [rows][512] accumulator (red.global.add.v4.f32 at L2):
           // one 64-byte read instead of 32, then clear the slice for the step after next (same buffer parity)
           float4* acc4 = reinterpret_cast<float4*>(P.part + (((size_t)((t + 1) & 1) * P.MB + dom) * BM + r) * HIDN + unit);
@@ -430,23 +430,6 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
             dh[4 * i] += v.x; dh[4 * i + 1] += v.y; dh[4 * i + 2] += v.z; dh[4 * i + 3] += v.w;
             __stcg(acc4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
           }
-#else
-          const float* pb = P.part + ((((size_t)((t + 1) & 1) * part_dom + (size_t)dom * SLICES) * BM + r) * HIDN + unit);
-#pragma unroll
-          for (int j0 = 0; j0 < SLICES; j0 += 8) {   // 32 independent 16-byte loads in flight per thread
-            float4 v[8][4];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4* src = reinterpret_cast<const float4*>(pb + (size_t)(j0 + j) * BM * HIDN);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) v[j][i] = __ldcg(src + i);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { dh[4 * i] += v[j][i].x; dh[4 * i + 1] += v[j][i].y; dh[4 * i + 2] += v[j][i].z; dh[4 * i + 3] += v[j][i].w; }
-          }
-#endif
         }
       }
       // pointwise backward of the cell (gate activations saved by the forward kernel)
@@ -488,11 +471,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         for (int i = 0; i < NC / 8; ++i) { d0[i] = reinterpret_cast<const uint4*>(ghi)[i]; d1[i] = reinterpret_cast<const uint4*>(glo)[i]; }
       }
       if (t == 0) break;
-#if HBL_BWD_ATOMIC
       float* dst = P.part + (((size_t)(t & 1) * P.MB + dom) * BM + r) * HIDN;
-#else
-      float* dst = P.part + ((((size_t)(t & 1) * part_dom + (size_t)dom * SLICES + slice) * BM + r) * HIDN);
-#endif
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         wait_bar(bar_tfull + 8 * half, (uint32_t)(T - 1 - t) & 1u, ef, dead);
@@ -506,20 +485,16 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-#if HBL_BWD_ATOMIC
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * i), "f"(__uint_as_float(v[4 * i])),
                          "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
                          : "memory");
-#else
-            __stcg(reinterpret_cast<float4*>(dst + c0) + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                                                         __uint_as_float(v[4 * i + 3])));
-#endif
           }
         }
       }
       tc_fence_before();
+      fence_async_global();   // the dgate rows of this step are read through TMA by the layer wavefront's GEMM while this kernel runs
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) { fence_acq_rel_gpu(); red_release_add(ctr, 1u); }
+      if (threadIdx.x == 64) { fence_acq_rel_gpu(); fence_async_global(); red_release_add(ctr, 1u); }
     }
   }
   tc_fence_before();
@@ -528,6 +503,18 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+// Layer-wavefront plumbing (one thread each): block a stream until every row block of a recurrence kernel that is still
+// RUNNING has completed `target` step publications; raise a flag the other layer's kernel polls.
+__global__ void lstm_wait_steps(const unsigned* __restrict__ ctr, int MB, unsigned target, int* error_flag) {
+  bool dead = false;
+  for (int d = 0; d < MB; ++d) wait_counter(ctr + (size_t)d * CTR_STRIDE, target, error_flag, dead);
+}
+__global__ void lstm_set_flag(unsigned* flag) {
+  __threadfence();
+  fence_async_global();
+  atomicExch(flag, 1u);
 }
 
 // [rows][cols] bf16 pair -> [cols][ld_dst] (column r of the destination = row r of the source); 64 x 64 tiles
@@ -668,9 +655,13 @@ struct hb_lstm {
   __nv_bfloat16 *dg_hi[2], *dg_lo[2], *dgT_hi[2], *dgT_lo[2];
   float* dh0;                               // [N][512] gradient w.r.t. layer 0's output
   float* dx_pad;                            // [N][512]
-  float* part;                              // [2][MB*32][128][512]
+  float* part;                              // [2 layers][2][R_pad][512] dh accumulators of the backward recurrences
   float* dwp;                               // [4][2048][512]
   unsigned* ctr;
+  unsigned* chunk_flags;                    // [64] layer-wavefront progress flags
+  cudaStream_t ws[3];                       // internal streams of the layer wavefront (recurrence above / chunk GEMMs / recurrence below)
+  cudaEvent_t wev[5];
+  int use_wavefront;
   int* d_error;
   int* h_error;                             // pinned mirror of d_error, filled asynchronously at the end of every call
   cudaEvent_t ev_done;
@@ -701,12 +692,13 @@ static void hbl_gemm_problem(Params& p, int& rc, const __nv_bfloat16* a_hi, cons
   p.row_mul = 1; p.row_add = 0; p.valid_rows = (int)m;
 }
 
-static int hbl_run_gemm(hb_lstm* L, cudaStream_t st, const Params* hp, int nprob, int mt, int nt, int slot) {
+static int hbl_run_gemm(hb_lstm* L, cudaStream_t st, const Params* hp, int nprob, int mt, int nt, int slot, int sm_limit = 0) {
   HB_CUDA(cudaMemcpyAsync(L->d_gemm + slot, hp, nprob * sizeof(Params), cudaMemcpyHostToDevice, st));
   const bool pair = (mt % 2) == 0;
+  const int sms = sm_limit > 0 ? sm_limit : L->sm_count;   // a limit keeps the persistent grid off the SMs a co-running recurrence needs
   L->launches += 1;
-  if (pair) return hb_launch_gemm(gemm3_kernel<EPI_F32, 3>, 2, L->sm_count, st, L->d_gemm + slot, nt, mt, nprob);
-  return hb_launch_gemm(gemm3_kernel<EPI_F32, 1>, 1, L->sm_count, st, L->d_gemm + slot, nt, mt, nprob);
+  if (pair) return hb_launch_gemm(gemm3_kernel<EPI_F32, 3>, 2, sms, st, L->d_gemm + slot, nt, mt, nprob);
+  return hb_launch_gemm(gemm3_kernel<EPI_F32, 1>, 1, sms, st, L->d_gemm + slot, nt, mt, nprob);
 }
 
 extern "C" {
@@ -747,7 +739,11 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   }
   HBL_ALLOC(L->dh0, N * hbl::HIDN * sizeof(float));
   HBL_ALLOC(L->dx_pad, N * hbl::HIDN * sizeof(float));
-  HBL_ALLOC(L->part, (size_t)2 * (L->max_rpad / BM) * hbl::SLICES * BM * hbl::HIDN * sizeof(float));
+  HBL_ALLOC(L->part, (size_t)2 * 2 * L->max_rpad * hbl::HIDN * sizeof(float));
+  HBL_ALLOC(L->chunk_flags, 64 * sizeof(unsigned));
+  for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamCreateWithFlags(&L->ws[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 5; ++i) HB_CUDA(cudaEventCreateWithFlags(&L->wev[i], cudaEventDisableTiming));
+  L->use_wavefront = getenv("HB_LSTM_NO_WAVEFRONT") ? 0 : 1;   // diagnostic switch: the two layers' recurrences one after the other
   HBL_ALLOC(L->dwp, 4 * WN * sizeof(float));
   HBL_ALLOC(L->ctr, 16 * hbl::CTR_STRIDE * sizeof(unsigned));
   HBL_ALLOC(L->d_error, sizeof(int));
@@ -756,7 +752,7 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   HB_CUDA(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
   HBL_ALLOC(L->d_fwd, 2 * sizeof(hbl::FwdParams));
   HBL_ALLOC(L->d_bwd, 2 * sizeof(hbl::BwdParams));
-  HBL_ALLOC(L->d_gemm, 16 * sizeof(Params));
+  HBL_ALLOC(L->d_gemm, 48 * sizeof(Params));
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
   L->use_clusters = getenv("HB_LSTM_NO_CLUSTER") ? 0 : 1;   // diagnostic switch: plain (non-multicast) forward recurrence
@@ -785,7 +781,9 @@ void hb_lstm_destroy(hb_lstm* L) {
     cudaFree(L->dg_hi[l]); cudaFree(L->dg_lo[l]); cudaFree(L->dgT_hi[l]); cudaFree(L->dgT_lo[l]);
   }
   cudaFree(L->dh0); cudaFree(L->dx_pad); cudaFree(L->part); cudaFree(L->dwp); cudaFree(L->ctr); cudaFree(L->d_error);
-  cudaFree(L->d_fwd); cudaFree(L->d_bwd); cudaFree(L->d_gemm);
+  cudaFree(L->d_fwd); cudaFree(L->d_bwd); cudaFree(L->d_gemm); cudaFree(L->chunk_flags);
+  for (int i = 0; i < 3; ++i) if (L->ws[i]) cudaStreamDestroy(L->ws[i]);
+  for (int i = 0; i < 5; ++i) if (L->wev[i]) cudaEventDestroy(L->wev[i]);
   cudaFreeHost(L->h_error); cudaEventDestroy(L->ev_done);
   delete L;
 }
@@ -937,12 +935,21 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
   const int T = L->T, rows = L->rows, R_pad = L->R_pad, MB = L->MB;
   const size_t N = (size_t)T * R_pad;
   const long long ldT = (long long)(T + 1) * R_pad;
-  const int mt = (int)(N / BM), cl = (mt % 2 == 0) ? 2 : 1;
   HbLstmNetBuf& B = L->nb[0];
   HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
   int rc = 0;
   std::vector<hbl::BwdParams> bp(2);
   memset(bp.data(), 0, 2 * sizeof(hbl::BwdParams));
+  // Layer wavefront: the recurrence of layer 0 needs dLoss/dh0_t = dG1_t W_ih1, i.e. layer 1's dgates of the SAME step -- so
+  // the two recurrences can run side by side, layer 0 one time chunk behind: layer 1 (stream 0) publishes its step counter,
+  // the dX GEMM of each finished chunk of steps runs on the SMs both recurrences leave free (stream 1) and raises a flag that
+  // layer 0's kernel (stream 2) waits for before it enters that chunk.  2 * 80 dependent steps become 80 + one chunk.
+  const int gemm_sms = (L->sm_count - 2 * MB * hbl::SLICES) & ~1;
+  int chunk = 8;
+  while ((T + chunk - 1) / chunk > 32) chunk *= 2;
+  const int n_chunks = (T + chunk - 1) / chunk;
+  const bool wave = L->use_wavefront && gemm_sms >= 8 && T >= 2 * chunk;
+  const size_t part_layer = (size_t)2 * L->max_rpad * hbl::HIDN;
   for (int l = 1; l >= 0; --l) {
     hbl::BwdParams& Q = bp[l];
     rc |= hb_make_tmap(&Q.wt_hi, B.whhT_hi[l], hbl::HIDN, hbl::G4, 256);
@@ -951,30 +958,67 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     Q.dh_ext = l == 1 ? dy : L->dh0; Q.dh_rows = l == 1 ? rows : R_pad;
     Q.act = L->act[l]; Q.cs = L->cs[l];
     Q.dg_hi = L->dg_hi[l]; Q.dg_lo = L->dg_lo[l];
-    Q.part = L->part; Q.T = T; Q.rows = rows; Q.R_pad = R_pad; Q.MB = MB;
+    Q.part = L->part + (size_t)l * part_layer; Q.T = T; Q.rows = rows; Q.R_pad = R_pad; Q.MB = MB;
     Q.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; Q.error_flag = L->d_error;
+    Q.chunk_flags = (wave && l == 0) ? L->chunk_flags : nullptr; Q.chunk = chunk;
     if (R_pad != rows) {  // padded rows of the dgate operands must read as zero in the GEMMs below
       const size_t bf = sizeof(__nv_bfloat16);
       HB_CUDA(cudaMemsetAsync(L->dg_hi[l], 0, N * hbl::G4 * bf, st)); HB_CUDA(cudaMemsetAsync(L->dg_lo[l], 0, N * hbl::G4 * bf, st));
     }
-#if HBL_BWD_ATOMIC
-    HB_CUDA(cudaMemsetAsync(L->part, 0, (size_t)2 * R_pad * hbl::HIDN * sizeof(float), st));   // the two dh accumulators
-#endif
-    HB_CUDA(cudaMemcpyAsync(L->d_bwd + l, &Q, sizeof(Q), cudaMemcpyHostToDevice, st));
-    hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, st>>>(L->d_bwd + l);
-    hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(N / 64)), 256, 0, st>>>(L->dg_hi[l], L->dg_lo[l], hbl::G4, L->dgT_hi[l], L->dgT_lo[l], (long long)N);
+    HB_CUDA(cudaMemsetAsync(Q.part, 0, (size_t)2 * R_pad * hbl::HIDN * sizeof(float), st));   // the two dh accumulators
+  }
+  HB_CUDA(cudaMemcpyAsync(L->d_bwd, bp.data(), 2 * sizeof(hbl::BwdParams), cudaMemcpyHostToDevice, st));
+  // dX of layer l over the rows of steps [t0, t1): [rows, 2048] x [2048, 512]
+  auto dx_gemm = [&](int l, int t0, int t1, float* dst, cudaStream_t s, int slot, int sm_limit) -> int {
+    Params gp;
+    int r2 = 0;
+    const size_t r0 = (size_t)t0 * R_pad, nr = (size_t)(t1 - t0) * R_pad;
+    hbl_gemm_problem(gp, r2, L->dg_hi[l] + r0 * hbl::G4, L->dg_lo[l] + r0 * hbl::G4, nr, hbl::G4, B.wihT_hi[l], B.wihT_lo[l], hbl::HIDN, hbl::G4, hbl::G4,
+                     ((nr / BM) % 2 == 0) ? 2 : 1, nullptr, dst + r0 * hbl::HIDN, hbl::HIDN, L->d_error);
+    if (r2) return -2;
+    return hbl_run_gemm(L, s, &gp, 1, (int)(nr / BM), hbl::HIDN / BN, slot, sm_limit);
+  };
+  if (wave) {
+    HB_CUDA(cudaMemsetAsync(L->chunk_flags, 0, 64 * sizeof(unsigned), st));
+    HB_CUDA(cudaEventRecord(L->wev[0], st));
+    for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamWaitEvent(L->ws[i], L->wev[0], 0));
+    hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, L->ws[0]>>>(L->d_bwd + 1);
+    HB_CUDA(cudaEventRecord(L->wev[1], L->ws[0]));
+    hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, L->ws[2]>>>(L->d_bwd + 0);
+    HB_CUDA(cudaEventRecord(L->wev[3], L->ws[2]));
+    for (int c = 0; c < n_chunks; ++c) {
+      const int t1 = T - c * chunk, t0 = t1 - chunk > 0 ? t1 - chunk : 0;
+      if (t0 > 0) {   // steps t1-1 .. t0 of layer 1 are published when its counter shows (c+1)*chunk completed steps
+        hbl::lstm_wait_steps<<<1, 1, 0, L->ws[1]>>>(bp[1].ctr, MB, (unsigned)(hbl::SLICES * (c + 1) * chunk), L->d_error);
+        L->launches += 1;
+      } else {        // step 0 does not bump the counter: the last chunk waits for the kernel itself
+        HB_CUDA(cudaStreamWaitEvent(L->ws[1], L->wev[1], 0));
+      }
+      rc = dx_gemm(1, t0, t1, L->dh0, L->ws[1], 16 + c, gemm_sms);
+      if (rc) return rc;
+      hbl::lstm_set_flag<<<1, 1, 0, L->ws[1]>>>(L->chunk_flags + c);
+      L->launches += 1;
+    }
+    HB_CUDA(cudaEventRecord(L->wev[2], L->ws[1]));
+    HB_CUDA(cudaGetLastError());
+    for (int i = 1; i <= 3; ++i) HB_CUDA(cudaStreamWaitEvent(st, L->wev[i], 0));
+    L->launches += 2;
+  } else {
+    hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, st>>>(L->d_bwd + 1);
+    rc = dx_gemm(1, 0, T, L->dh0, st, 5, 0);
+    if (rc) return rc;
+    hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, st>>>(L->d_bwd + 0);
     HB_CUDA(cudaGetLastError());
     L->launches += 2;
-    // gradient w.r.t. this layer's input sequence: dX = dG W_ih  ([N, 2048] x [2048, 512])
-    Params gp;
-    float* dst = l == 1 ? L->dh0 : ((dx && R_pad == rows) ? dx : L->dx_pad);
-    if (l == 1 || dx) {
-      hbl_gemm_problem(gp, rc, L->dg_hi[l], L->dg_lo[l], N, hbl::G4, B.wihT_hi[l], B.wihT_lo[l], hbl::HIDN, hbl::G4, hbl::G4, cl, nullptr, dst, hbl::HIDN, L->d_error);
-      if (rc) return -2;
-      rc = hbl_run_gemm(L, st, &gp, 1, mt, hbl::HIDN / BN, 4 + l);
-      if (rc) return rc;
-      if (l == 0 && dst != dx) { hbl::lstm_unpad<<<dim3(rows, T), 128, 0, st>>>(L->dx_pad, dx, rows, R_pad); L->launches += 1; }
-    }
+  }
+  for (int l = 0; l < 2; ++l)
+    hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(N / 64)), 256, 0, st>>>(L->dg_hi[l], L->dg_lo[l], hbl::G4, L->dgT_hi[l], L->dgT_lo[l], (long long)N);
+  L->launches += 2;
+  if (dx) {   // gradient w.r.t. the input sequence of layer 0
+    float* dst = R_pad == rows ? dx : L->dx_pad;
+    rc = dx_gemm(0, 0, T, dst, st, 4, 0);
+    if (rc) return rc;
+    if (dst != dx) { hbl::lstm_unpad<<<dim3(rows, T), 128, 0, st>>>(L->dx_pad, dx, rows, R_pad); L->launches += 1; }
   }
   // ---- weight gradients: four [2048, 512] = dG^T [2048, N] x (operand^T [512, N])^T problems in one launch
   Params wp[4];
