@@ -53,7 +53,8 @@ constexpr int FWD_STAGE = 2 * A_TILE;       // h hi + lo chunk: 32 KB
 constexpr int FWD_SMEM = W_BYTES + FWD_NST * FWD_STAGE + 1024 + 256;
 constexpr int BWD_WT_HALF = 256 * BK * 2;   // 32 KB: [256 x 64] bf16 tile
 constexpr int BWD_WT_BYTES = 4 * BWD_WT_HALF;  // 128 KB: [512 x 64] hi + lo
-constexpr int BWD_SMEM = BWD_WT_BYTES + 2 * A_TILE + 1024 + 256;
+constexpr int BWD_STAGE = 64 * BM * 4;       // 32 KB: one [64 columns][128 rows] fp32 piece of the dh partial, staged for a bulk reduction
+constexpr int BWD_SMEM = BWD_WT_BYTES + 2 * A_TILE + 2 * BWD_STAGE + 1024 + 256;
 constexpr int CTR_STRIDE = 32;        // unsigned ints between two domains' step counters (128 bytes)
 
 struct FwdNet {
@@ -72,6 +73,9 @@ struct __align__(64) FwdParams {
   long long ldT;
   unsigned* ctr;
   int* error_flag;
+  // layer wavefront (layer 1 only, null otherwise): gx of steps [c*chunk, (c+1)*chunk) is complete once chunk_flags[c] != 0
+  const unsigned* chunk_flags;
+  int chunk;
 };
 struct __align__(64) BwdParams {
   CUtensorMap wt_hi, wt_lo;           // W_hh^T [512][2048 slice-order columns], box 256 x 64
@@ -112,16 +116,16 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
     if ((spin & 1023u) == 1023u) {
       if (*(volatile int*)error_flag != 0) { dead = true; return; }
-      if (spin > (1u << 22)) { atomicExch(error_flag, 1); dead = true; return; }
+      if (spin > (1u << 22)) { atomicCAS(error_flag, 0, 1); dead = true; return; }
     }
   }
 }
-__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, int* error_flag, bool& dead) {
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, int* error_flag, bool& dead, int code = 2) {
   if (dead) return;
   for (uint32_t spin = 0; ld_relaxed(ctr) < target; ++spin) {
     if ((spin & 255u) == 255u) {
       if (*(volatile int*)error_flag != 0) { dead = true; return; }
-      if (spin > (1u << 20)) { atomicExch(error_flag, 2); dead = true; return; }
+      if (spin > (1u << 20)) { atomicCAS(error_flag, 0, code); dead = true; return; }   // the FIRST failure's code is kept
     }
   }
   fence_acq_rel_gpu();
@@ -250,11 +254,16 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
     for (int t = 0; t < T; ++t) {
       const size_t grow = (size_t)t * R_pad + row;
       float g[NC];
+      if (P.chunk_flags != nullptr && t % P.chunk == 0) {   // entering a new time chunk of the layer below's input projection
+        if (lane == 0) wait_counter(P.chunk_flags + t / P.chunk, 1u, ef, dead, 4);
+        dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
+      }
       {
         const float4* src = reinterpret_cast<const float4*>(N.gx + grow * G4 + slice * NC);
 #pragma unroll
         for (int i = 0; i < NC / 4; ++i) {
-          const float4 v = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // gx may have been written by a GEMM running concurrently (layer wavefront): L2, not the non-coherent path
+          const float4 v = valid ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
           g[4 * i] = v.x; g[4 * i + 1] = v.y; g[4 * i + 2] = v.z; g[4 * i + 3] = v.w;
         }
       }
@@ -323,7 +332,8 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
   const BwdParams& P = *pp;
   const int slice = blockIdx.x % SLICES, dom = blockIdx.x / SLICES, mb = dom;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t wt_base = base, a_base = base + BWD_WT_BYTES, bar_base = a_base + 2 * A_TILE;
+  const uint32_t wt_base = base, a_base = base + BWD_WT_BYTES, stage_base = a_base + 2 * A_TILE, bar_base = stage_base + 2 * BWD_STAGE;
+  float* stage_ptr = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw)));
   const uint32_t bar_w = bar_base, bar_a = bar_w + 8, bar_tfull = bar_a + 8, tmem_slot = bar_tfull + 16;   // bar_tfull: one per accumulator half
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* a_ptr = smem_raw + (a_base - smem_u32(smem_raw));
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
       const size_t grow = (size_t)t * R_pad + row;
       float dh[UPC], a[NC], ct[UPC], cp[UPC];
       if (P.chunk_flags != nullptr && (T - 1 - t) % P.chunk == 0) {   // entering a new time chunk of the layer above's gradient
-        if (lane == 0) wait_counter(P.chunk_flags + (T - 1 - t) / P.chunk, 1u, ef, dead);
+        if (lane == 0) wait_counter(P.chunk_flags + (T - 1 - t) / P.chunk, 1u, ef, dead, 4);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
       }
       {
@@ -421,14 +431,13 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         if (lane == 0) wait_counter(ctr, (unsigned)(SLICES * (T - 1 - t)), ef, dead);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
         if (!dead) {
-          // the 32 CTAs of the row block ADDED their partials into one [rows][512] accumulator (red.global.add.v4.f32 at L2):
-          // one 64-byte read instead of 32, then clear the slice for the step after next (same buffer parity)
-          float4* acc4 = reinterpret_cast<float4*>(P.part + (((size_t)((t + 1) & 1) * P.MB + dom) * BM + r) * HIDN + unit);
+          // the 32 CTAs of the row block ADDED their partials into one accumulator (bulk reductions at L2, see the drain below),
+          // laid out [8 pieces][64 columns][128 rows]: 16 coalesced reads, then clear the slice for the step after next
+          float* accp = P.part + ((size_t)((t + 1) & 1) * P.MB + dom) * (size_t)(BM * HIDN) + (size_t)(unit / 64) * (64 * BM) + (size_t)(unit % 64) * BM + r;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 v = __ldcg(acc4 + i);
-            dh[4 * i] += v.x; dh[4 * i + 1] += v.y; dh[4 * i + 2] += v.z; dh[4 * i + 3] += v.w;
-            __stcg(acc4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+          for (int i = 0; i < UPC; ++i) {
+            dh[i] += __ldcg(accp + i * BM);
+            __stcg(accp + i * BM, 0.f);
           }
         }
       }
@@ -471,30 +480,50 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         for (int i = 0; i < NC / 8; ++i) { d0[i] = reinterpret_cast<const uint4*>(ghi)[i]; d1[i] = reinterpret_cast<const uint4*>(glo)[i]; }
       }
       if (t == 0) break;
-      float* dst = P.part + (((size_t)(t & 1) * P.MB + dom) * BM + r) * HIDN;
+      // Drain: the [128 x 512] fp32 partial of dh_{t-1} leaves TMEM in eight [64 columns][128 rows] pieces; each is staged in
+      // shared memory (conflict-free: consecutive threads = consecutive rows) and ADDED into the row block's accumulator by ONE
+      // bulk reduction (cp.reduce.async.bulk .add.f32: the 32-way sum happens at L2, the SM issues 8 instructions per step
+      // instead of 16 384 vector atomics).  Two staging buffers: piece p+2 waits until the reduction of piece p has read its.
+      float* dst = P.part + ((size_t)(t & 1) * P.MB + dom) * (size_t)(BM * HIDN);
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         wait_bar(bar_tfull + 8 * half, (uint32_t)(T - 1 - t) & 1u, ef, dead);
         tc_fence_after();
-        if (dead) continue;
 #pragma unroll 1
-        for (int c0 = half * 256; c0 < half * 256 + 256; c0 += 64) {   // two 32-column TMEM loads in flight, then 16 stores
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int pc = half * 4 + q4, buf = pc & 1;
           uint32_t v[64];
-          tmem_ld32_nowait(taddr + c0, v);
-          tmem_ld32_nowait(taddr + c0 + 32, v + 32);
-          tmem_wait_ld();
+          if (!dead) {
+            tmem_ld32_nowait(taddr + pc * 64, v);
+            tmem_ld32_nowait(taddr + pc * 64 + 32, v + 32);
+            tmem_wait_ld();
+          }
+          if (pc >= 2) {
+            if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+          float* sb = stage_ptr + buf * (BWD_STAGE / 4) + r;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * i), "f"(__uint_as_float(v[4 * i])),
-                         "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
+          for (int i = 0; i < 64; ++i) sb[i * BM] = dead ? 0.f : __uint_as_float(v[i]);
+          fence_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) {
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst + (size_t)pc * (64 * BM)),
+                         "r"(stage_base + (uint32_t)buf * BWD_STAGE), "r"(BWD_STAGE)
                          : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       }
       tc_fence_before();
       fence_async_global();   // the dgate rows of this step are read through TMA by the layer wavefront's GEMM while this kernel runs
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) { fence_acq_rel_gpu(); fence_async_global(); red_release_add(ctr, 1u); }
+      if (threadIdx.x == 64) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all eight reductions have been performed
+        fence_async_global();
+        fence_acq_rel_gpu();
+        red_release_add(ctr, 1u);
+      }
     }
   }
   tc_fence_before();
@@ -509,7 +538,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
 // RUNNING has completed `target` step publications; raise a flag the other layer's kernel polls.
 __global__ void lstm_wait_steps(const unsigned* __restrict__ ctr, int MB, unsigned target, int* error_flag) {
   bool dead = false;
-  for (int d = 0; d < MB; ++d) wait_counter(ctr + (size_t)d * CTR_STRIDE, target, error_flag, dead);
+  for (int d = 0; d < MB; ++d) wait_counter(ctr + (size_t)d * CTR_STRIDE, target, error_flag, dead, 3);
 }
 __global__ void lstm_set_flag(unsigned* flag) {
   __threadfence();
@@ -637,7 +666,8 @@ struct HbLstmNetBuf {                       // per network (0: the one that may 
   float* bias[2];                           // [2048p]
   __nv_bfloat16 *xs_hi, *xs_lo;             // [N][512]
   __nv_bfloat16 *hs_hi[2], *hs_lo[2];       // [(T+1)*R_pad][512] per layer
-  float* gx;                                // [N][2048] (reused by both layers)
+  float* gx;                                // [N][2048] input projection of layer 0 (and of layer 1 without the layer wavefront)
+  float* gx1;                               // [N][2048] input projection of layer 1 (layer wavefront: both are live at once)
 };
 
 struct hb_lstm {
@@ -729,6 +759,7 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
     }
     HBL_ALLOC(B.xs_hi, N * hbl::HIDN * bf); HBL_ALLOC(B.xs_lo, N * hbl::HIDN * bf);
     HBL_ALLOC(B.gx, N * hbl::G4 * sizeof(float));
+    HBL_ALLOC(B.gx1, N * hbl::G4 * sizeof(float));
   }
   HBL_ALLOC(L->xT_hi, N1 * hbl::HIDN * bf); HBL_ALLOC(L->xT_lo, N1 * hbl::HIDN * bf);
   for (int l = 0; l < 2; ++l) {
@@ -744,6 +775,17 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamCreateWithFlags(&L->ws[i], cudaStreamNonBlocking));
   for (int i = 0; i < 5; ++i) HB_CUDA(cudaEventCreateWithFlags(&L->wev[i], cudaEventDisableTiming));
   L->use_wavefront = getenv("HB_LSTM_NO_WAVEFRONT") ? 0 : 1;   // diagnostic switch: the two layers' recurrences one after the other
+  {
+    // CUDA loads kernels lazily, and loading one may wait for the device to go idle.  Inside the layer wavefront a first-time
+    // launch would then wait for a recurrence kernel that is itself waiting for what that launch produces: load everything now.
+    cudaFuncAttributes fa;
+    HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_wait_steps));
+    HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_set_flag));
+    HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_transpose_pair));
+    HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_unpad));
+    HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_bias_grad));
+    HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_unperm_rows));
+  }
   HBL_ALLOC(L->dwp, 4 * WN * sizeof(float));
   HBL_ALLOC(L->ctr, 16 * hbl::CTR_STRIDE * sizeof(unsigned));
   HBL_ALLOC(L->d_error, sizeof(int));
@@ -773,7 +815,7 @@ void hb_lstm_destroy(hb_lstm* L) {
       cudaFree(B.wihT_hi[l]); cudaFree(B.wihT_lo[l]); cudaFree(B.whhT_hi[l]); cudaFree(B.whhT_lo[l]);
       cudaFree(B.bias[l]); cudaFree(B.hs_hi[l]); cudaFree(B.hs_lo[l]);
     }
-    cudaFree(B.xs_hi); cudaFree(B.xs_lo); cudaFree(B.gx);
+    cudaFree(B.xs_hi); cudaFree(B.xs_lo); cudaFree(B.gx); cudaFree(B.gx1);
   }
   cudaFree(L->xT_hi); cudaFree(L->xT_lo);
   for (int l = 0; l < 2; ++l) {
@@ -825,7 +867,6 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
   { const int prc = hbl_check_previous(L, false); if (prc) return prc; }
   cudaStream_t st = (cudaStream_t)stream;
   const int R_pad = (rows + BM - 1) / BM * BM, MB = R_pad / BM;
-  const size_t N = (size_t)T * R_pad;
   const long long ldT = (long long)(T + 1) * R_pad;
   const size_t bf = sizeof(__nv_bfloat16);
   L->T = T; L->rows = rows; L->R_pad = R_pad; L->MB = MB; L->saved = 0;
@@ -858,22 +899,34 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
   std::vector<hbl::FwdParams> fp(2);
   memset(fp.data(), 0, 2 * sizeof(hbl::FwdParams));
   int rc = 0;
-  const int mt = (int)(N / BM), cl = (mt % 2 == 0) ? 2 : 1;
-  for (int l = 0; l < 2; ++l) {
-    // ---- input projection of layer l for all steps (both networks as two problems of one launch)
+  const int n_ctas = nets * MB * hbl::SLICES;
+  // Layer wavefront (see hb_lstm_backward): layer 1's recurrence runs next to layer 0's, one time chunk behind; its input
+  // projection is computed chunk by chunk on the SMs the two recurrences leave free.
+  const int gemm_sms = (L->sm_count - 2 * n_ctas) & ~1;
+  int chunk = 8;
+  while ((T + chunk - 1) / chunk > 32) chunk *= 2;
+  const int n_chunks = (T + chunk - 1) / chunk;
+  const bool wave = L->use_wavefront && gemm_sms >= 8 && T >= 2 * chunk;
+  // input projection of layer l over the steps [t0, t1), both networks as problems of one launch
+  auto gx_gemm = [&](int l, int t0, int t1, cudaStream_t s, int slot, int sm_limit) -> int {
     Params gp[2];
+    int r2 = 0;
+    const size_t r0 = (size_t)t0 * R_pad, nr = (size_t)(t1 - t0) * R_pad;
     for (int n = 0; n < nets; ++n) {
       HbLstmNetBuf& B = L->nb[n];
       const __nv_bfloat16* a_hi = l == 0 ? B.xs_hi : B.hs_hi[0] + (size_t)R_pad * hbl::HIDN;   // layer 1 consumes h^0_t = block t+1
       const __nv_bfloat16* a_lo = l == 0 ? B.xs_lo : B.hs_lo[0] + (size_t)R_pad * hbl::HIDN;
-      hbl_gemm_problem(gp[n], rc, a_hi, a_lo, N, hbl::HIDN, B.wih_hi[l], B.wih_lo[l], hbl::G4, hbl::HIDN, hbl::HIDN, cl, B.bias[l], B.gx, hbl::G4, L->d_error);
+      float* dst = (l == 0 || !wave) ? B.gx : B.gx1;
+      hbl_gemm_problem(gp[n], r2, a_hi + r0 * hbl::HIDN, a_lo + r0 * hbl::HIDN, nr, hbl::HIDN, B.wih_hi[l], B.wih_lo[l], hbl::G4, hbl::HIDN, hbl::HIDN,
+                       ((nr / BM) % 2 == 0) ? 2 : 1, B.bias[l], dst + r0 * hbl::G4, hbl::G4, L->d_error);
     }
-    if (rc) return -2;
-    rc = hbl_run_gemm(L, st, gp, nets, mt, hbl::G4 / BN, l * 2);
-    if (rc) return rc;
-    // ---- recurrence of layer l
+    if (r2) return -2;
+    return hbl_run_gemm(L, s, gp, nets, (int)(nr / BM), hbl::G4 / BN, slot, sm_limit);
+  };
+  for (int l = 0; l < 2; ++l) {
     hbl::FwdParams& F = fp[l];
     F.T = T; F.rows = rows; F.R_pad = R_pad; F.MB = MB; F.ldT = ldT; F.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; F.error_flag = L->d_error;
+    F.chunk_flags = (wave && l == 1) ? L->chunk_flags : nullptr; F.chunk = chunk;
     for (int n = 0; n < nets; ++n) {
       HbLstmNetBuf& B = L->nb[n];
       hbl::FwdNet& Q = F.net[n];
@@ -882,43 +935,77 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
       rc |= hb_make_tmap(&Q.w_lo, B.whh_lo[l], hbl::G4, hbl::HIDN, hbl::NC);
       rc |= hb_make_tmap(&Q.h_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
       rc |= hb_make_tmap(&Q.h_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
-      Q.gx = B.gx; Q.hs_hi = B.hs_hi[l]; Q.hs_lo = B.hs_lo[l];
+      Q.gx = (l == 0 || !wave) ? B.gx : B.gx1; Q.hs_hi = B.hs_hi[l]; Q.hs_lo = B.hs_lo[l];
       rc |= hb_make_tmap(&Q.hq_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / 4);
       rc |= hb_make_tmap(&Q.hq_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / 4);
       Q.y = l == 1 ? y[n] : nullptr;
       Q.act = sv ? L->act[l] : nullptr; Q.cs = sv ? L->cs[l] : nullptr;
     }
-    if (rc) return -2;
-    HB_CUDA(cudaMemcpyAsync(L->d_fwd + l, &F, sizeof(F), cudaMemcpyHostToDevice, st));
-    {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(nets * MB * hbl::SLICES), 1, 1);
-      cfg.blockDim = dim3(192, 1, 1);
-      cfg.dynamicSmemBytes = hbl::FWD_SMEM;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      int max_clusters = 0;   // every CTA must be resident at once (step barrier): use clusters only if they all fit
-      const bool cl4 = L->use_clusters && cudaOccupancyMaxActiveClusters(&max_clusters, hbl::lstm_fwd_kernel<4>, &cfg) == cudaSuccess &&
-                       max_clusters * 4 >= nets * MB * hbl::SLICES;
-      const hbl::FwdParams* dp = L->d_fwd + l;
-      if (cl4) {
-        HB_CUDA(cudaLaunchKernelEx(&cfg, hbl::lstm_fwd_kernel<4>, dp));
-      } else {
-        (void)cudaGetLastError();
-        hbl::lstm_fwd_kernel<1><<<nets * MB * hbl::SLICES, 192, hbl::FWD_SMEM, st>>>(dp);
-      }
-      L->last_cluster = cl4 ? 4 : 1;
+  }
+  if (rc) return -2;
+  HB_CUDA(cudaMemcpyAsync(L->d_fwd, fp.data(), 2 * sizeof(hbl::FwdParams), cudaMemcpyHostToDevice, st));
+  auto launch_rec = [&](int l, cudaStream_t s) -> int {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_ctas, 1, 1);
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = hbl::FWD_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;   // every CTA must be resident at once (step barrier): use clusters only if they all fit
+    const bool cl4 = L->use_clusters && cudaOccupancyMaxActiveClusters(&max_clusters, hbl::lstm_fwd_kernel<4>, &cfg) == cudaSuccess &&
+                     max_clusters * 4 >= (wave ? 2 : 1) * n_ctas;
+    const hbl::FwdParams* dp = L->d_fwd + l;
+    if (cl4) {
+      HB_CUDA(cudaLaunchKernelEx(&cfg, hbl::lstm_fwd_kernel<4>, dp));
+    } else {
+      (void)cudaGetLastError();
+      hbl::lstm_fwd_kernel<1><<<n_ctas, 192, hbl::FWD_SMEM, s>>>(dp);
     }
+    L->last_cluster = cl4 ? 4 : 1;
     HB_CUDA(cudaGetLastError());
     L->launches += 1;
-    if (save) {  // transposed copy of net 0's h sequence (block 0 = zeros included): operand of the weight-gradient GEMMs
+    return 0;
+  };
+  rc = gx_gemm(0, 0, T, st, 0, 0);
+  if (rc) return rc;
+  if (wave) {
+    HB_CUDA(cudaMemsetAsync(L->chunk_flags, 0, 64 * sizeof(unsigned), st));
+    HB_CUDA(cudaEventRecord(L->wev[0], st));
+    for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamWaitEvent(L->ws[i], L->wev[0], 0));
+    rc = launch_rec(0, L->ws[0]);
+    if (rc) return rc;
+    HB_CUDA(cudaEventRecord(L->wev[1], L->ws[0]));
+    rc = launch_rec(1, L->ws[2]);
+    if (rc) return rc;
+    HB_CUDA(cudaEventRecord(L->wev[3], L->ws[2]));
+    for (int c = 0; c < n_chunks; ++c) {
+      const int t0 = c * chunk, t1 = t0 + chunk < T ? t0 + chunk : T;
+      // h^0 of steps < t1 is published once layer 0's step counters show t1 completed steps (32 CTAs per row block)
+      hbl::lstm_wait_steps<<<1, 1, 0, L->ws[1]>>>(fp[0].ctr, nets * MB, (unsigned)(hbl::SLICES * t1), L->d_error);
+      rc = gx_gemm(1, t0, t1, L->ws[1], 16 + 2 * c, gemm_sms);
+      if (rc) return rc;
+      hbl::lstm_set_flag<<<1, 1, 0, L->ws[1]>>>(L->chunk_flags + c);
+      L->launches += 2;
+    }
+    HB_CUDA(cudaEventRecord(L->wev[2], L->ws[1]));
+    HB_CUDA(cudaGetLastError());
+    for (int i = 1; i <= 3; ++i) HB_CUDA(cudaStreamWaitEvent(st, L->wev[i], 0));
+  } else {
+    rc = launch_rec(0, st);
+    if (rc) return rc;
+    rc = gx_gemm(1, 0, T, st, 2, 0);
+    if (rc) return rc;
+    rc = launch_rec(1, st);
+    if (rc) return rc;
+  }
+  if (save) {  // transposed copies of net 0's h sequences (block 0 = zeros included): operands of the weight-gradient GEMMs
+    for (int l = 0; l < 2; ++l)
       hbl::lstm_transpose_pair<<<dim3(hbl::HIDN / 64, (unsigned)((size_t)(T + 1) * R_pad / 64)), 256, 0, st>>>(L->nb[0].hs_hi[l], L->nb[0].hs_lo[l], hbl::HIDN,
                                                                                                           L->hsT_hi[l], L->hsT_lo[l], ldT);
-      L->launches += 1;
-    }
+    L->launches += 2;
   }
   L->saved = save ? 1 : 0;
   return hbl_finish_call(L, st);
