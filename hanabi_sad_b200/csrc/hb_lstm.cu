@@ -76,6 +76,7 @@ struct __align__(64) FwdParams {
   // layer wavefront (layer 1 only, null otherwise): gx of steps [c*chunk, (c+1)*chunk) is complete once chunk_flags[c] != 0
   const unsigned* chunk_flags;
   int chunk;
+  long long* trace;                   // diagnostic (HB_LSTM_TRACE): %globaltimer stamps of CTA 0, [T][16]; null in production
 };
 struct __align__(64) BwdParams {
   CUtensorMap wt_hi, wt_lo;           // W_hh^T [512][2048 slice-order columns], box 256 x 64
@@ -92,7 +93,15 @@ struct __align__(64) BwdParams {
   // chunk_flags[c] != 0 (set by the host-side pipeline after the dX GEMM of that time chunk of layer 1)
   const unsigned* chunk_flags;
   int chunk;
+  long long* trace;                   // diagnostic (HB_LSTM_TRACE): %globaltimer stamps of CTA 0, [T][16]; null in production
 };
+
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define HBL_STAMP(tr, step, k) do { if ((tr) != nullptr) (tr)[(size_t)(step) * 16 + (k)] = gtimer(); } while (0)
 
 __device__ __forceinline__ constexpr uint32_t idesc_mn(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -164,6 +173,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
   unsigned* ctr = P.ctr + (size_t)dom * CTR_STRIDE;
   int* ef = P.error_flag;
   bool dead = false;
+  long long* tr = blockIdx.x == 0 ? P.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&N.w_hi); tma_prefetch_desc(&N.w_lo); tma_prefetch_desc(&N.h_hi); tma_prefetch_desc(&N.h_lo);
@@ -192,6 +202,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
       uint32_t it = 0;
       for (int t = 1; t < T; ++t) {
         wait_counter(ctr, (unsigned)(SLICES * t), ef, dead);   // h_{t-1} of this row block is complete
+        HBL_STAMP(tr, t, 0);
         fence_async_global();
         for (int kc = 0; kc < KCH; ++kc, ++it) {
           const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
@@ -209,6 +220,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
             tma_load_2d_mc(st + A_TILE + q, &N.hq_lo, bar_full + 8 * s, kc * BK, row0 + rank * (BM / CL), CMASK);
           }
         }
+        HBL_STAMP(tr, t, 1);
       }
     }
   } else if (warp == 1) {
@@ -224,6 +236,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
           const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
           wait_bar(bar_full + 8 * s, ph, ef, dead);
           if (dead) break;
+          if (kc == 0) HBL_STAMP(tr, t, 2);
           tc_fence_after();
           const uint32_t st = ring + s * FWD_STAGE;
           const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
@@ -241,6 +254,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
         }
         if (dead) break;
         umma_commit(bar_tfull);
+        HBL_STAMP(tr, t, 3);
       }
     }
   } else {
@@ -269,6 +283,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
       }
       if (t > 0) {
         wait_bar(bar_tfull, (uint32_t)(t - 1) & 1u, ef, dead);
+        if (threadIdx.x == 64) HBL_STAMP(tr, t, 4);
         tc_fence_after();
         if (!dead) {
 #pragma unroll
@@ -296,7 +311,9 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
         const size_t o = ((size_t)(t + 1) * R_pad + row) * HIDN + unit;
         store_split16(h, N.hs_hi + o, N.hs_lo + o);
       }
+      if (threadIdx.x == 64) HBL_STAMP(tr, t, 5);
       publish_step(ctr);
+      if (threadIdx.x == 64) HBL_STAMP(tr, t, 6);
       // everything only later kernels read overlaps with the other CTAs' next step
       if (valid && !dead) {
         if (N.y) {
@@ -342,6 +359,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
   unsigned* ctr = P.ctr + (size_t)dom * CTR_STRIDE;
   int* ef = P.error_flag;
   bool dead = false;
+  long long* tr = (blockIdx.x == 0 && threadIdx.x == 64) ? P.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.wt_hi); tma_prefetch_desc(&P.wt_lo);
@@ -402,6 +420,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
     for (int t = T - 1; t >= 0; --t) {
       const size_t grow = (size_t)t * R_pad + row;
       float dh[UPC], a[NC], ct[UPC], cp[UPC];
+      HBL_STAMP(tr, t, 0);
       if (P.chunk_flags != nullptr && (T - 1 - t) % P.chunk == 0) {   // entering a new time chunk of the layer above's gradient
         if (lane == 0) wait_counter(P.chunk_flags + (T - 1 - t) / P.chunk, 1u, ef, dead, 4);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
@@ -430,6 +449,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         // dh_t += sum over the 32 CTAs' partials written at step t+1 (buffer (t+1)&1)
         if (lane == 0) wait_counter(ctr, (unsigned)(SLICES * (T - 1 - t)), ef, dead);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
+        HBL_STAMP(tr, t, 1);
         if (!dead) {
           // the 32 CTAs of the row block ADDED their partials into one accumulator (bulk reductions at L2, see the drain below),
           // laid out [8 pieces][64 columns][128 rows]: 16 coalesced reads, then clear the slice for the step after next
@@ -471,6 +491,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) mbar_arrive(bar_a);
+        HBL_STAMP(tr, t, 2);
       }
       // while the tensor core works: the row-major dgate copy the dX / dW GEMMs read after this kernel
       if (valid && !dead) {
@@ -488,6 +509,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         wait_bar(bar_tfull + 8 * half, (uint32_t)(T - 1 - t) & 1u, ef, dead);
+        HBL_STAMP(tr, t, 3 + 2 * half);
         tc_fence_after();
 #pragma unroll 1
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -514,15 +536,19 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
+        HBL_STAMP(tr, t, 4 + 2 * half);
       }
       tc_fence_before();
       fence_async_global();   // the dgate rows of this step are read through TMA by the layer wavefront's GEMM while this kernel runs
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      HBL_STAMP(tr, t, 7);
       if (threadIdx.x == 64) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all eight reductions have been performed
+        HBL_STAMP(tr, t, 8);
         fence_async_global();
         fence_acq_rel_gpu();
         red_release_add(ctr, 1u);
+        HBL_STAMP(tr, t, 9);
       }
     }
   }
@@ -689,6 +715,7 @@ struct hb_lstm {
   float* dwp;                               // [4][2048][512]
   unsigned* ctr;
   unsigned* chunk_flags;                    // [64] layer-wavefront progress flags
+  long long* d_trace;                       // diagnostic (HB_LSTM_TRACE=<file>): [4 kernels][max_T][16] time stamps
   cudaStream_t ws[3];                       // internal streams of the layer wavefront (recurrence above / chunk GEMMs / recurrence below)
   cudaEvent_t wev[5];
   int use_wavefront;
@@ -775,6 +802,7 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamCreateWithFlags(&L->ws[i], cudaStreamNonBlocking));
   for (int i = 0; i < 5; ++i) HB_CUDA(cudaEventCreateWithFlags(&L->wev[i], cudaEventDisableTiming));
   L->use_wavefront = getenv("HB_LSTM_NO_WAVEFRONT") ? 0 : 1;   // diagnostic switch: the two layers' recurrences one after the other
+  if (getenv("HB_LSTM_TRACE")) HBL_ALLOC(L->d_trace, (size_t)4 * max_T * 16 * sizeof(long long));
   {
     // CUDA loads kernels lazily, and loading one may wait for the device to go idle.  Inside the layer wavefront a first-time
     // launch would then wait for a recurrence kernel that is itself waiting for what that launch produces: load everything now.
@@ -823,7 +851,7 @@ void hb_lstm_destroy(hb_lstm* L) {
     cudaFree(L->dg_hi[l]); cudaFree(L->dg_lo[l]); cudaFree(L->dgT_hi[l]); cudaFree(L->dgT_lo[l]);
   }
   cudaFree(L->dh0); cudaFree(L->dx_pad); cudaFree(L->part); cudaFree(L->dwp); cudaFree(L->ctr); cudaFree(L->d_error);
-  cudaFree(L->d_fwd); cudaFree(L->d_bwd); cudaFree(L->d_gemm); cudaFree(L->chunk_flags);
+  cudaFree(L->d_fwd); cudaFree(L->d_bwd); cudaFree(L->d_gemm); cudaFree(L->chunk_flags); cudaFree(L->d_trace);
   for (int i = 0; i < 3; ++i) if (L->ws[i]) cudaStreamDestroy(L->ws[i]);
   for (int i = 0; i < 5; ++i) if (L->wev[i]) cudaEventDestroy(L->wev[i]);
   cudaFreeHost(L->h_error); cudaEventDestroy(L->ev_done);
@@ -832,6 +860,24 @@ void hb_lstm_destroy(hb_lstm* L) {
 
 // The calls are asynchronous (work is queued on the caller's stream).  The kernels' spin guards raise d_error; its value
 // travels to a pinned mirror at the end of every call and is examined at the START of the next one (or by hb_lstm_sync).
+// Diagnostic: append the time stamps CTA 0 of each recurrence kernel took (ns, %globaltimer) to the file HB_LSTM_TRACE names.
+static void hbl_dump_trace(hb_lstm* L, cudaStream_t st, int first, int T, const char* tag) {
+  if (!L->d_trace) return;
+  cudaStreamSynchronize(st);
+  std::vector<long long> h((size_t)2 * L->max_T * 16);
+  cudaMemcpy(h.data(), L->d_trace + (size_t)first * L->max_T * 16, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(L->d_trace + (size_t)first * L->max_T * 16, 0, h.size() * sizeof(long long));
+  FILE* f = fopen(getenv("HB_LSTM_TRACE"), "a");
+  if (!f) return;
+  for (int l = 0; l < 2; ++l)
+    for (int t = 0; t < T; ++t) {
+      fprintf(f, "%s layer %d t %d", tag, l, t);
+      for (int k = 0; k < 12; ++k) fprintf(f, " %lld", h[((size_t)l * L->max_T + t) * 16 + k]);
+      fprintf(f, "\n");
+    }
+  fclose(f);
+}
+
 static int hbl_finish_call(hb_lstm* L, cudaStream_t st) {
   HB_CUDA(cudaMemcpyAsync(L->h_error, L->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
   HB_CUDA(cudaEventRecord(L->ev_done, st));
@@ -927,6 +973,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     hbl::FwdParams& F = fp[l];
     F.T = T; F.rows = rows; F.R_pad = R_pad; F.MB = MB; F.ldT = ldT; F.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; F.error_flag = L->d_error;
     F.chunk_flags = (wave && l == 1) ? L->chunk_flags : nullptr; F.chunk = chunk;
+    F.trace = L->d_trace ? L->d_trace + (size_t)l * L->max_T * 16 : nullptr;
     for (int n = 0; n < nets; ++n) {
       HbLstmNetBuf& B = L->nb[n];
       hbl::FwdNet& Q = F.net[n];
@@ -1008,6 +1055,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     L->launches += 2;
   }
   L->saved = save ? 1 : 0;
+  hbl_dump_trace(L, st, 0, T, "fwd");
   return hbl_finish_call(L, st);
 }
 
@@ -1048,6 +1096,7 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     Q.part = L->part + (size_t)l * part_layer; Q.T = T; Q.rows = rows; Q.R_pad = R_pad; Q.MB = MB;
     Q.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; Q.error_flag = L->d_error;
     Q.chunk_flags = (wave && l == 0) ? L->chunk_flags : nullptr; Q.chunk = chunk;
+    Q.trace = L->d_trace ? L->d_trace + (size_t)(2 + l) * L->max_T * 16 : nullptr;
     if (R_pad != rows) {  // padded rows of the dgate operands must read as zero in the GEMMs below
       const size_t bf = sizeof(__nv_bfloat16);
       HB_CUDA(cudaMemsetAsync(L->dg_hi[l], 0, N * hbl::G4 * bf, st)); HB_CUDA(cudaMemsetAsync(L->dg_lo[l], 0, N * hbl::G4 * bf, st));
@@ -1122,6 +1171,7 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
   for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, st>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
   HB_CUDA(cudaGetLastError());
   L->launches += 6;
+  hbl_dump_trace(L, st, 2, T, "bwd");
   return hbl_finish_call(L, st);
 }
 
