@@ -112,6 +112,11 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   return v;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -137,14 +142,16 @@ __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned targe
       if (spin > (1u << 20)) { atomicCAS(error_flag, 0, code); dead = true; return; }   // the FIRST failure's code is kept
     }
   }
-  fence_acq_rel_gpu();
+  // the counter only grows: an acquire load of it now synchronises with every release that contributed to the value seen
+  // (cheaper on the step chain than a full fence, which also waits for this thread's own outstanding loads)
+  (void)ld_acquire(ctr);
 }
 // Step publication (the grid.sync idiom): every thread's stores are ordered before the CTA barrier, ONE thread then
 // fences at GPU scope (cumulative over what the barrier ordered) and bumps the domain's step counter.
 __device__ __forceinline__ void publish_step(unsigned* ctr) {
   fence_async_global();
   asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (threadIdx.x == 64) { fence_acq_rel_gpu(); fence_async_global(); red_release_add(ctr, 1u); }
+  if (threadIdx.x == 64) red_release_add(ctr, 1u);   // release is cumulative over what the barrier ordered before it
 }
 
 // ------------------------------------------------------------------------------------------------ forward recurrence
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t wt_base = base, a_base = base + BWD_WT_BYTES, stage_base = a_base + 2 * A_TILE, bar_base = stage_base + 2 * BWD_STAGE;
   float* stage_ptr = reinterpret_cast<float*>(smem_raw + (stage_base - smem_u32(smem_raw)));
-  const uint32_t bar_w = bar_base, bar_a = bar_w + 8, bar_tfull = bar_a + 8, tmem_slot = bar_tfull + 16;   // bar_tfull: one per accumulator half
+  const uint32_t bar_w = bar_base, bar_a = bar_w + 8, bar_tfull = bar_a + 8, tmem_slot = bar_tfull + 32;   // bar_tfull: one per accumulator quarter
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* a_ptr = smem_raw + (a_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -363,7 +370,8 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.wt_hi); tma_prefetch_desc(&P.wt_lo);
-    mbar_init(bar_w, 1); mbar_init(bar_a, 1); mbar_init(bar_tfull, 1); mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_w, 1); mbar_init(bar_a, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(bar_tfull + 8 * q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_mn(BM, 256);
+      constexpr uint32_t idesc = idesc_mn(BM, 128);
       wait_bar(bar_w, 0, ef, dead);
       for (int t = T - 1; t >= 1; --t) {
         wait_bar(bar_a, (uint32_t)(T - 1 - t) & 1u, ef, dead);   // A tile of step t staged, accumulator of step t+1 drained
@@ -395,9 +403,10 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         tc_fence_after();
         const uint64_t a_hi = make_desc_sw128(a_base), a_lo = make_desc_sw128(a_base + A_TILE);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint64_t b_hi = make_desc_sw128(wt_base + half * BWD_WT_HALF), b_lo = make_desc_sw128(wt_base + (2 + half) * BWD_WT_HALF);
-          const uint32_t d = tmem_base + half * 256;
+        for (int qt = 0; qt < 4; ++qt) {   // four 128-column quarters of dh_{t-1}, committed one by one: the drain starts early
+          const uint32_t boff = (uint32_t)(qt >> 1) * BWD_WT_HALF + (uint32_t)(qt & 1) * (128 * 128);   // 128 weight rows = 16 swizzle groups
+          const uint64_t b_hi = make_desc_sw128(wt_base + boff), b_lo = make_desc_sw128(wt_base + 2 * BWD_WT_HALF + boff);
+          const uint32_t d = tmem_base + qt * 128;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
             umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1);
             umma_bf16(d, a_hi + adv, b_hi + adv, idesc, 1);
           }
-          umma_commit(bar_tfull + 8 * half);   // the drain of this half overlaps the MMAs of the other
+          umma_commit(bar_tfull + 8 * qt);
         }
       }
     }
@@ -507,13 +516,13 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
       // instead of 16 384 vector atomics).  Two staging buffers: piece p+2 waits until the reduction of piece p has read its.
       float* dst = P.part + ((size_t)(t & 1) * P.MB + dom) * (size_t)(BM * HIDN);
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        wait_bar(bar_tfull + 8 * half, (uint32_t)(T - 1 - t) & 1u, ef, dead);
-        HBL_STAMP(tr, t, 3 + 2 * half);
+      for (int qt = 0; qt < 4; ++qt) {
+        wait_bar(bar_tfull + 8 * qt, (uint32_t)(T - 1 - t) & 1u, ef, dead);
+        if ((qt & 1) == 0) HBL_STAMP(tr, t, 3 + qt);
         tc_fence_after();
 #pragma unroll 1
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int pc = half * 4 + q4, buf = pc & 1;
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const int pc = qt * 2 + q4, buf = pc & 1;
           uint32_t v[64];
           if (!dead) {
             tmem_ld32_nowait(taddr + pc * 64, v);
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        HBL_STAMP(tr, t, 4 + 2 * half);
+        if (qt & 1) HBL_STAMP(tr, t, 3 + qt);
       }
       tc_fence_before();
       fence_async_global();   // the dgate rows of this step are read through TMA by the layer wavefront's GEMM while this kernel runs
@@ -546,7 +555,6 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all eight reductions have been performed
         HBL_STAMP(tr, t, 8);
         fence_async_global();
-        fence_acq_rel_gpu();
         red_release_add(ctr, 1u);
         HBL_STAMP(tr, t, 9);
       }
