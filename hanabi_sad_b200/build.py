@@ -28,7 +28,8 @@ def build(force=False, verbose=False):
         if os.path.exists(LIB):
             return LIB
         raise RuntimeError("nvcc not found and libhanabi_b200.so is not built")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("HB_NVCC_DEFS", "").split()   # tuning experiments, e.g. HB_NVCC_DEFS="-DHB_TICK_THREADS=64"
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-lcudart"]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

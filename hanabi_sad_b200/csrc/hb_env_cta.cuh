@@ -40,12 +40,32 @@ struct HbRng {  // sequential 32-bit draws out of one Philox stream
   __device__ float uniform() { return (float)(next() >> 8) * (1.0f / 16777216.0f); }           // [0,1)
 };
 
+// The same stream read from a table filled in parallel (hb_cta_fill_draws): draw k = word k % 4 of Philox block k / 4.
+#define HB_EPISODE_DRAW_BLOCKS 20   // 49 (shuffle) + P (eps) + 1 + 4 (P-1) (colour permutations) <= 71 draws -> 18 blocks
+struct HbRngTable {
+  const uint32_t* v;
+  int i;
+  __device__ HbRngTable(const uint32_t* table) : v(table), i(0) {}
+  __device__ uint32_t next() { return v[i++]; }
+  __device__ uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
+};
+// All threads of the CTA: the first 4 * HB_EPISODE_DRAW_BLOCKS draws of (seed, game, episode, HB_RNG_EPISODE), one Philox block
+// per thread, into shared memory -- the 13+ blocks a reset consumes no longer run back to back in one thread.
+__device__ __forceinline__ void hb_cta_fill_draws(uint32_t* table, uint64_t seed, int game, uint32_t episode) {
+  for (int b = threadIdx.x; b < HB_EPISODE_DRAW_BLOCKS; b += blockDim.x) {
+    const uint32_t stream = (uint32_t)game;
+    const uint2 key = make_uint2((uint32_t)seed ^ (stream * 0x9E3779B1u), (uint32_t)(seed >> 32) + stream);
+    const uint4 r = hb_philox(make_uint4((uint32_t)b, episode, HB_RNG_EPISODE, stream), key);
+    table[4 * b] = r.x; table[4 * b + 1] = r.y; table[4 * b + 2] = r.z; table[4 * b + 3] = r.w;
+  }
+}
+
 // Randomness of a new episode (HanabiEnv::reset, hanabi_env.cc:12-44): deck order, eps index per player,
 // colour permutations.  The reference draws cards one at a time with probability proportional to the
 // remaining counts (hanabi_state.cc:285-289, 316-328), which is a uniformly random order of the 50 cards --
 // a Fisher-Yates shuffle is distribution-identical.  One thread.
-__device__ inline void hb_new_episode_random(HbGame& s, uint8_t* deck, const HbEnvCfg& cfg, uint64_t seed, int game) {
-  HbRng rng(seed, (uint32_t)game, s.episode, HB_RNG_EPISODE);
+template <class RNG>
+__device__ inline void hb_new_episode_draw(HbGame& s, uint8_t* deck, const HbEnvCfg& cfg, RNG& rng) {
   int n = 0;
   for (int c = 0; c < HB_NC; ++c)
     for (int r = 0; r < HB_NR; ++r)
@@ -69,13 +89,22 @@ __device__ inline void hb_new_episode_random(HbGame& s, uint8_t* deck, const HbE
     s.perm[p] = fw; s.inv_perm[p] = inv;
   }
 }
+__device__ inline void hb_new_episode_random(HbGame& s, uint8_t* deck, const HbEnvCfg& cfg, uint64_t seed, int game) {
+  HbRng rng(seed, (uint32_t)game, s.episode, HB_RNG_EPISODE);
+  hb_new_episode_draw(s, deck, cfg, rng);
+}
 
-// Start a new episode on `s` (one thread): injected randomness if the host fixed it, Philox otherwise.
-__device__ inline void hb_begin_episode(HbGame& s, uint8_t* deck, HbInject* inj, const HbEnvCfg& cfg, uint64_t seed, int game) {
+// Start a new episode on `s` (one thread): injected randomness if the host fixed it, Philox otherwise -- drawn here, or read
+// from `draws` (hb_cta_fill_draws for this game's CURRENT s.episode) when the caller prepared them in parallel.
+__device__ inline void hb_begin_episode(HbGame& s, uint8_t* deck, HbInject* inj, const HbEnvCfg& cfg, uint64_t seed, int game,
+                                        const uint32_t* draws = nullptr) {
   if (inj != nullptr && inj->flag) {
     for (int i = 0; i < HB_DECK; ++i) deck[i] = inj->deck[i];
     for (int p = 0; p < HB_MAX_P; ++p) { s.eps_idx[p] = inj->eps_idx[p]; s.perm[p] = inj->perm[p]; s.inv_perm[p] = inj->inv_perm[p]; }
     inj->flag = 0;
+  } else if (draws != nullptr) {
+    HbRngTable rng(draws);
+    hb_new_episode_draw(s, deck, cfg, rng);
   } else {
     hb_new_episode_random(s, deck, cfg, seed, game);
   }

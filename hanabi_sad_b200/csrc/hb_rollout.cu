@@ -19,7 +19,12 @@
 #include "hb_policy.h"
 #include "hb_replay.h"
 
+#ifndef HB_TICK_THREADS
 #define HB_TICK_THREADS 96
+#endif
+#ifndef HB_TICK_MIN_CTAS
+#define HB_TICK_MIN_CTAS (HB_TICK_THREADS >= 96 ? 16 : (HB_TICK_THREADS >= 64 ? 24 : 32))
+#endif
 
 struct HbTickArgs {
   HbGame* games;
@@ -146,13 +151,14 @@ __device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, 
 // thread 0 applies the move / starts an episode -- so what helps is more CTAs in flight per SM, not more threads per CTA
 // (7 CTAs of 128 threads: 82 us per 4096-game tick; 12: 71 us; with the fast encoder 58 us, as 16 x 96 threads 54 us).
 template <int TP, int TH, int TSAD>
-__global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_constant__ HbTickArgs A) {
+__global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(const __grid_constant__ HbTickArgs A) {
   __shared__ HbGame s;
   __shared__ HbEncTables tab;
   __shared__ HbFastEnc enc;
   __shared__ __align__(16) uint8_t deck[HB_DECK_STRIDE];
   __shared__ int sh_did_step, sh_t, sh_term, sh_reset, sh_slot, sh_drop, sh_retry, sh_committed;
-  __shared__ float red[2 * HB_TICK_THREADS / 32];
+  __shared__ float red[2 * ((HB_TICK_THREADS + 31) / 32)];
+  __shared__ uint32_t sh_draws[4 * HB_EPISODE_DRAW_BLOCKS];
   const int g = blockIdx.x, tid = threadIdx.x;
   HbEnvCfg cfg = A.cfg;
   if (TP > 0) cfg.g = hb_make_geom(TP, TH, TSAD);
@@ -204,6 +210,12 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_co
     hb_cta_finalize_episode(R, g, slot, min((int)s.ep_len, R.T), red, &sh_committed);
   }
   __syncthreads();
+  // a game that restarts now needs ~60 Philox draws (deck shuffle, eps, colour permutations): one block per thread instead of
+  // thirteen in a row on thread 0 (every other thread of the CTA would wait at the next barrier meanwhile)
+  if (A.do_reset && s.terminated && sh_committed) {
+    hb_cta_fill_draws(sh_draws, A.seed, g, s.episode);
+    __syncthreads();
+  }
   if (tid == 0) {
     if (sh_drop && slot >= 0) { atomicExch(&R.state[slot], HB_SLOT_FREE); atomicAdd(&R.counters[HB_CNT_DROPPED], 1ULL); }
     const bool stalled = !sh_committed;
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_co
       atomicAdd(&R.counters[HB_CNT_STALLED], 1ULL);
     }
     if (A.do_reset && s.terminated && !stalled) {
-      hb_begin_episode(s, deck, A.inject + g, cfg, A.seed, g);
+      hb_begin_episode(s, deck, A.inject + g, cfg, A.seed, g, sh_draws);
       s.illegal = 0;   // an illegal action was counted (flags[3]) and its episode dropped; the seat carries on with a fresh game
       sh_reset = 1;
       if (A.has_replay) {
@@ -237,8 +249,9 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, 16) hb_k_tick(const __grid_co
   // the board record.  It is materialised on demand by hb_refresh_obs when the host asks for it (hb_env_observe*).
   hb_cta_write_obs(s, tab, cfg, nullptr, O.legal_move + (size_t)g * P * geo.A, nullptr, O.eps + (size_t)g * P, A.eps_list);
   if (O.s_hi != nullptr) hb_cta_write_operand_fast(s, tab, cfg, enc, O.s_hi + (size_t)g * P * O.KS, O.s_lo + (size_t)g * P * O.KS, O.KS);
-  if (tid >= 32 && tid < 48 && to_ring)   // the replay keeps the record, not the observation (re-encoded by hb_k_replay_gather)
-    reinterpret_cast<uint4*>(R.states + (size_t)slot * R.T + t_obs)[tid - 32] = reinterpret_cast<const uint4*>(&s)[tid - 32];
+  constexpr int RT0 = HB_TICK_THREADS >= 64 ? 32 : 0;   // the threads that copy the record into the ring (a warp of its own if there is one)
+  if (tid >= RT0 && tid < RT0 + 16 && to_ring)   // the replay keeps the record, not the observation (re-encoded by hb_k_replay_gather)
+    reinterpret_cast<uint4*>(R.states + (size_t)slot * R.T + t_obs)[tid - RT0] = reinterpret_cast<const uint4*>(&s)[tid - RT0];
   if (tid < 16) reinterpret_cast<uint4*>(A.games + g)[tid] = reinterpret_cast<const uint4*>(&s)[tid];
   else if (tid < 20) reinterpret_cast<uint4*>(A.decks + (size_t)g * HB_DECK_STRIDE)[tid - 16] = reinterpret_cast<const uint4*>(deck)[tid - 16];
 }
