@@ -27,18 +27,39 @@ __device__ __forceinline__ float hb_entry_weight(const HbRing& R, int i, long lo
   return R.weight[i];
 }
 
-// Inclusive prefix sums (double, like the reference's running accSum) of the sampleable weights; out[0] = total,
-// out[1] = number of sampleable entries.
-__global__ void __launch_bounds__(HB_SCAN_THREADS) hb_k_replay_prefix(HbRing R, double* __restrict__ prefix, double* __restrict__ out) {
-  __shared__ double part[HB_SCAN_THREADS];
-  __shared__ int cnt[HB_SCAN_THREADS];
-  const int n = R.phys_slots * R.NE, tid = threadIdx.x;
+// Inclusive prefix sums (double, like the reference's running accSum) of the sampleable weights over ALL ring entries, in
+// three small launches so that the reference's default 131 072-episode buffer (selfplay.py --replay_buffer_size) is scanned by
+// the whole GPU instead of one SM: (1) per-block sums of HB_SCAN_BLOCK entries, (2) scan of the block sums by one CTA (also
+// out[0] = total weight, out[1] = number of sampleable entries), (3) per-block scan with the block's offset.
+#define HB_SCAN_BLOCK 2048   // entries per CTA of passes 1 and 3 (256 threads x 8)
+
+__global__ void __launch_bounds__(256) hb_k_replay_blocksum(HbRing R, double* __restrict__ bsum, int* __restrict__ bcnt) {
+  __shared__ double sw[8];
+  __shared__ int sc[8];
+  const int n = R.phys_slots * R.NE, base = blockIdx.x * HB_SCAN_BLOCK;
   const long long oldest = hb_ring_oldest(R);
-  const int chunk = (n + HB_SCAN_THREADS - 1) / HB_SCAN_THREADS;
-  const int lo = tid * chunk, hi = min(n, lo + chunk);
   double s = 0;
   int c = 0;
-  for (int i = lo; i < hi; ++i) { const float w = hb_entry_weight(R, i, oldest); s += w; c += w > 0.f; }
+  for (int i = base + threadIdx.x; i < min(n, base + HB_SCAN_BLOCK); i += 256) { const float w = hb_entry_weight(R, i, oldest); s += w; c += w > 0.f; }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, k); c += __shfl_xor_sync(0xffffffffu, c, k); }
+  if ((threadIdx.x & 31) == 0) { sw[threadIdx.x >> 5] = s; sc[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0; int tc = 0;
+    for (int w = 0; w < 8; ++w) { t += sw[w]; tc += sc[w]; }
+    bsum[blockIdx.x] = t; bcnt[blockIdx.x] = tc;
+  }
+}
+
+// exclusive scan of the block sums in place (bsum[b] = weight before block b); one CTA, sequential per thread chunk
+__global__ void __launch_bounds__(HB_SCAN_THREADS) hb_k_replay_blockscan(double* __restrict__ bsum, const int* __restrict__ bcnt, int nb, double* __restrict__ out) {
+  __shared__ double part[HB_SCAN_THREADS];
+  __shared__ int cnt[HB_SCAN_THREADS];
+  const int tid = threadIdx.x, chunk = (nb + HB_SCAN_THREADS - 1) / HB_SCAN_THREADS;
+  const int lo = tid * chunk, hi = min(nb, lo + chunk);
+  double s = 0; int c = 0;
+  for (int i = lo; i < hi; ++i) { s += bsum[i]; c += bcnt[i]; }
   part[tid] = s; cnt[tid] = c;
   __syncthreads();
   for (int off = 1; off < HB_SCAN_THREADS; off <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
@@ -49,8 +70,44 @@ __global__ void __launch_bounds__(HB_SCAN_THREADS) hb_k_replay_prefix(HbRing R, 
     __syncthreads();
   }
   double acc = tid > 0 ? part[tid - 1] : 0.0;
-  for (int i = lo; i < hi; ++i) { acc += hb_entry_weight(R, i, oldest); prefix[i] = acc; }
+  for (int i = lo; i < hi; ++i) { const double v = bsum[i]; bsum[i] = acc; acc += v; }
   if (tid == HB_SCAN_THREADS - 1) { out[0] = part[tid]; out[1] = (double)cnt[tid]; }
+}
+
+__global__ void __launch_bounds__(256) hb_k_replay_prefix(HbRing R, const double* __restrict__ bsum, double* __restrict__ prefix) {
+  __shared__ double part[256];
+  const int n = R.phys_slots * R.NE, base = blockIdx.x * HB_SCAN_BLOCK, tid = threadIdx.x;
+  const long long oldest = hb_ring_oldest(R);
+  const int lo = base + tid * (HB_SCAN_BLOCK / 256), hi = min(n, lo + HB_SCAN_BLOCK / 256);
+  float w[HB_SCAN_BLOCK / 256];
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < HB_SCAN_BLOCK / 256; ++j) { w[j] = lo + j < hi ? hb_entry_weight(R, lo + j, oldest) : 0.f; s += w[j]; }
+  part[tid] = s;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    double v = 0;
+    if (tid >= off) v = part[tid - off];
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  double acc = bsum[blockIdx.x] + (tid > 0 ? part[tid - 1] : 0.0);
+#pragma unroll
+  for (int j = 0; j < HB_SCAN_BLOCK / 256; ++j) if (lo + j < hi) { acc += w[j]; prefix[lo + j] = acc; }
+}
+
+// the three passes, queued on the engine stream; `tot` (device double[2]) receives the total weight and the entry count
+static int hb_launch_prefix(hb_engine* e, double* tot) {
+  HbReplay* Q = e->replay;
+  const HbRing& R = Q->ring;
+  const int n = R.phys_slots * R.NE, nb = (n + HB_SCAN_BLOCK - 1) / HB_SCAN_BLOCK;
+  hb_k_replay_blocksum<<<nb, 256, 0, e->stream>>>(R, Q->bsum, Q->bcnt);
+  hb_k_replay_blockscan<<<1, HB_SCAN_THREADS, 0, e->stream>>>(Q->bsum, Q->bcnt, nb, tot);
+  hb_k_replay_prefix<<<nb, 256, 0, e->stream>>>(R, Q->bsum, Q->prefix);
+  HB_CUDA(cudaGetLastError());
+  e->launches += 3;
+  return 0;
 }
 
 // One thread per batch element: stratified draw, binary search, importance weight.  `targets` (device, may be null):
@@ -236,6 +293,8 @@ int hb_replay_create(hb_engine* e) {
   HB_RALLOC(R.counters, HB_CNT_N * sizeof(unsigned long long));
   Q->max_batch = 1024;
   HB_RALLOC(Q->prefix, (S * R.NE + 2) * sizeof(double));
+  HB_RALLOC(Q->bsum, ((S * R.NE + HB_SCAN_BLOCK - 1) / HB_SCAN_BLOCK + 1) * sizeof(double));
+  HB_RALLOC(Q->bcnt, ((S * R.NE + HB_SCAN_BLOCK - 1) / HB_SCAN_BLOCK + 1) * sizeof(int));
   HB_RALLOC(Q->sampled_idx, (Q->max_batch + 1) * sizeof(int));
   HB_RALLOC(Q->sampled_seq, Q->max_batch * sizeof(long long));
   HB_RALLOC(Q->sampled_w, Q->max_batch * sizeof(float));
@@ -255,7 +314,7 @@ void hb_replay_destroy(hb_engine* e) {
   cudaFree(R.states); cudaFree(R.a); cudaFree(R.greedy_a); cudaFree(R.reward);
   cudaFree(R.bootstrap); cudaFree(R.seq_len); cudaFree(R.weight); cudaFree(R.commit_seq); cudaFree(R.state); cudaFree(R.game_slot);
   cudaFree(R.sc_reward); cudaFree(R.sc_oq); cudaFree(R.sc_tq); cudaFree(R.counters);
-  cudaFree(Q->prefix); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio); cudaFree(Q->d_targets); cudaFree(Q->d_max_len); cudaFreeHost(Q->h_max_len);
+  cudaFree(Q->prefix); cudaFree(Q->bsum); cudaFree(Q->bcnt); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio); cudaFree(Q->d_targets); cudaFree(Q->d_max_len); cudaFreeHost(Q->h_max_len);
   cudaFreeHost(Q->h_counters);
   delete Q;
   e->replay = nullptr;
@@ -304,9 +363,7 @@ int hb_replay_stats(hb_engine* e, hb_replay_info* out) {
   HbRing& R = Q->ring;
   double* tot = Q->prefix + (size_t)R.phys_slots * R.NE;
   HB_CUDA(cudaSetDevice(e->device));
-  hb_k_replay_prefix<<<1, HB_SCAN_THREADS, 0, e->stream>>>(R, Q->prefix, tot);
-  HB_CUDA(cudaGetLastError());
-  e->launches += 1;
+  { const int prc = hb_launch_prefix(e, tot); if (prc) return prc; }
   double h_tot[2] = {0, 0};
   HB_CUDA(cudaMemcpyAsync(h_tot, tot, sizeof(h_tot), cudaMemcpyDeviceToHost, e->stream));
   int rc = hb_read_counters(e);
@@ -344,7 +401,8 @@ int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const 
     HB_CUDA(cudaMemcpyAsync(Q->d_targets, opts->targets, batchsize * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     d_targets = Q->d_targets;
   }
-  hb_k_replay_prefix<<<1, HB_SCAN_THREADS, 0, e->stream>>>(R, Q->prefix, tot);
+  rc = hb_launch_prefix(e, tot);
+  if (rc) return rc;
   const int threads = (batchsize + 31) / 32 * 32;
   hb_k_replay_draw<<<1, threads, 0, e->stream>>>(R, Q->prefix, tot, batchsize, Q->beta, Q->seed, Q->sample_count, d_targets,
                                                  opts ? opts->total_weight : 0.0, opts ? opts->total_size : 0.0, opts ? opts->normalize : 1,
@@ -355,7 +413,7 @@ int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const 
   HB_CUDA(cudaGetLastError());
   if (out->ids) HB_CUDA(cudaMemcpyAsync(out->ids, Q->sampled_idx, batchsize * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
   HB_CUDA(cudaStreamSynchronize(e->stream));  // the batch tensors are consumed on the caller's own stream
-  e->launches += 3;
+  e->launches += 2;
   Q->sample_count += 1;
   Q->n_sampled = batchsize;
   return 0;

@@ -50,6 +50,8 @@ struct HbReplay {
   unsigned long long sample_count;
   // sampling scratch
   double* prefix;               // [phys*NE]
+  double* bsum;                 // [blocks] per-block weight sums, then (in place) their exclusive scan
+  int* bcnt;                    // [blocks] per-block sampleable counts
   int* sampled_idx;             // [max_batch] entry index = slot*NE + e
   long long* sampled_seq;       // [max_batch] commit_seq at sampling time (evicted-since check, prioritized_replay.h:106-120)
   float* sampled_w;             // [max_batch]

@@ -20,7 +20,7 @@
 #include "hb_replay.h"
 
 #ifndef HB_TICK_THREADS
-#define HB_TICK_THREADS 96
+#define HB_TICK_THREADS 32   // one warp per game: no cross-warp barrier behind thread 0's serial sections, 32 CTAs / SM = one wave at 4096 games (96 threads: 54 us per tick, 64: 57, 32: 46)
 #endif
 #ifndef HB_TICK_MIN_CTAS
 #define HB_TICK_MIN_CTAS (HB_TICK_THREADS >= 96 ? 16 : (HB_TICK_THREADS >= 64 ? 24 : 32))
