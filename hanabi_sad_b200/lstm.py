@@ -22,6 +22,7 @@ class LstmWorkspace:
         self.device = torch.device(device)
         self.max_T, self.max_rows = int(max_T), int(max_rows)
         self._h = None   # created at first use, so that modules can be built (and state_dicts moved around) on any host
+        self._gen = 0    # generation of the forward whose activations the workspace holds (ONE saved forward at a time)
 
     def _handle(self, device=None):
         if device is not None and self._h is None:
@@ -74,6 +75,7 @@ class LstmWorkspace:
         T, rows, hid = xs[0].shape
         t_run = T if t_eff is None else max(1, min(int(t_eff), T))
         self._last_T, self._last_t_run = T, t_run
+        self._gen += 1   # any forward (saving or not) replaces what the workspace held
         assert hid == HID and nets in (1, 2) and len(params) == nets
         xs = [x.contiguous() for x in xs]
         keep = [[p.detach().contiguous() for p in ps] for ps in params]
@@ -93,9 +95,18 @@ class LstmWorkspace:
         check(lib().hb_lstm_forward(self._handle(), int(t_run), int(rows), nets, xp, ws, yp, int(bool(save)), ctypes.c_void_p(stream)))
         return ys
 
-    def backward(self, dy, need_dx=True):
-        """Gradients of the last saving forward: returns (dx or None, [8 parameter gradients in PARAM_NAMES order])."""
+    def backward(self, dy, need_dx=True, gen=None, t_run=None):
+        """Gradients of the last saving forward: returns (dx or None, [8 parameter gradients in PARAM_NAMES order]).  `gen`: the
+        generation stamp the caller took right after ITS forward -- a later forward on the same workspace (a second loss() before
+        the first backward, gradient accumulation over two batches) has overwritten the activations, and silently wrong
+        gradients are not an option: raise."""
         self._handle(dy.device)
+        if gen is not None and gen != self._gen:
+            raise RuntimeError("LstmWorkspace: the forward this backward belongs to (generation %d) was overwritten by a later forward "
+                               "(generation %d) on the same workspace -- call backward() before the next forward, or give each outstanding "
+                               "graph its own workspace" % (gen, self._gen))
+        if t_run is not None:
+            self._last_t_run = t_run
         dy = dy.contiguous()
         assert dy.is_cuda and dy.dtype == torch.float32
         dx = torch.empty_like(dy) if need_dx else None
@@ -172,12 +183,13 @@ class _LstmFn(torch.autograd.Function):
             xs.append(x2.detach())
             ps.append(list(params2))
         ys = ws.forward(xs, ps, save=True, t_eff=t_eff)
+        ctx.gen, ctx.t_run = ws._gen, ws._last_t_run   # which forward this node's backward needs (checked there)
         ctx.mark_non_differentiable(*ys[1:])
         return tuple(ys) if x2 is not None else ys[0]
 
     @staticmethod
     def backward(ctx, dy, *unused):
-        dx, grads = ctx.ws.backward(dy, need_dx=ctx.need_dx)
+        dx, grads = ctx.ws.backward(dy, need_dx=ctx.need_dx, gen=ctx.gen, t_run=ctx.t_run)
         return (None, None, dx, None, None) + tuple(grads)
 
 

@@ -150,3 +150,17 @@ def test_device_linear_gradients(hbl):
     (y * g.to(dev)).sum().backward()
     for got, want in ((xd.grad, xr.grad), (wd.grad, wr.grad), (bd.grad, br.grad)):
         assert _rel(got.cpu(), want) < 1e-5
+
+
+def test_second_forward_before_backward_is_refused(hbl):
+    """A workspace keeps ONE saved forward.  Two forwards before the first backward used to produce silently wrong gradients
+    for the first graph; now the stale backward raises."""
+    dev = torch.device("cuda", 0)
+    mod = hbl.DeviceLSTM(dev, max_T=8, max_rows=32)
+    x1 = torch.randn(8, 32, 512, device=dev, requires_grad=True)
+    x2 = torch.randn(8, 32, 512, device=dev, requires_grad=True)
+    y1 = mod(x1)
+    y2 = mod(x2)
+    y2.sum().backward()          # the most recent forward: fine
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        y1.sum().backward()
