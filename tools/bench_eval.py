@@ -33,7 +33,27 @@ for arm, path in (("reference", os.path.join(ROOT, "oracle", "_ref")), ("b200", 
     p = subprocess.run([sys.executable, "-c", SCRIPT], cwd=PYH, env=env, capture_output=True, text=True, timeout=900)
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
     res[arm] = json.loads(line[-1][7:]) if line else {"error": (p.stdout + p.stderr)[-1500:]}
-if all("1000" in res[a] for a in res):
+# the device loop alone (hb_eval_rollout through the Engine), without eval.py's thread / polling scaffolding
+RAW = r"""
+import sys, time, json
+sys.path.insert(0, %r)
+import hanabi_sad_b200 as hb
+from bench import random_weights
+out = {}
+for n in (1000, 5000):
+    e = hb.Engine(n, 2, 5, 0, -1, True, False, [0.0], seed=9, eval_seats=True)
+    sd = random_weights(e.F, e.A, e.H, 1)
+    e.set_weights(0, sd); e.set_weights(1, sd)
+    e.eval_rollout()
+    t0 = time.perf_counter(); scores, ticks = e.eval_rollout(); dt = time.perf_counter() - t0
+    out[str(n)] = {"ms": dt * 1e3, "ticks_queued": ticks, "games": int(len(scores))}
+    e.close()
+print("RESULT " + json.dumps(out))
+""" % ROOT
+p = subprocess.run([sys.executable, "-c", RAW], capture_output=True, text=True, timeout=600)
+line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+res["b200_device_loop_only"] = json.loads(line[-1][7:]) if line else {"error": (p.stdout + p.stderr)[-1500:]}
+if all("1000" in res[a] for a in ("reference", "b200")):
     res["speedup"] = {n: res["reference"][n]["seconds"] / res["b200"][n]["seconds"] for n in ("1000", "5000")}
     res["note"] = "eval.evaluate polls context.terminated() every 0.5 s (eval.py:55-58): both arms are quantised to that"
 print(json.dumps(res, indent=1))
