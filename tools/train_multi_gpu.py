@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--ticks_per_update", type=int, default=4)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--device_learner", type=int, default=0, help="1: run the reference loss on hanabi_sad_b200.learner.DeviceLearner (LSTM on csrc/hb_lstm.cu)")
+    ap.add_argument("--device_trainer", type=int, default=0, help="1: the whole update on hanabi_sad_b200.trainer.DeviceTrainer (csrc/hb_trainer.cu); "
+                                                                   "the all-reduce then runs on its flat gradient buffer")
     a = ap.parse_args()
 
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -59,7 +61,12 @@ def main():
         from hanabi_sad_b200.learner import DeviceLearner
 
         agent = DeviceLearner.from_agent(agent, max_T=80, max_rows=max(1, a.batchsize // world) * 2)
-    optim = torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
+    trainer = None
+    if a.device_trainer:
+        from hanabi_sad_b200.trainer import DeviceTrainer
+
+        trainer = agent = DeviceTrainer.from_agent(agent, max_batch=max(1, a.batchsize // world))
+    optim = None if trainer else torch.optim.Adam(agent.online_net.parameters(), lr=6.25e-5, eps=1.5e-5)
 
     def push_weights():
         eng.set_weights(0, agent.online_net.state_dict())   # device pointers: a D2D copy + re-tiling kernels
@@ -84,7 +91,22 @@ def main():
         if it % a.actor_sync_freq == 0:
             push_weights()
         eng.rollout(a.ticks_per_update)                      # actors keep running between updates (queued, asynchronous)
-        t = eng.sample(b_local)
+        # the replay is sharded over the ranks: importance weights over the UNION of the shards (N, the probability this
+        # rank's draw really had), normalised by the maximum over all ranks' sub-batches (prioritized_replay.h:334-339)
+        st = eng.replay_stats()
+        n_union, _ = hd.replay_union(st["sampleable"], st["weight_sum"], device=dev)
+        tw, ts = hd.shard_sampling_totals(st["weight_sum"], n_union, world)
+        t = eng.sample(b_local, total_weight=tw, total_size=ts, normalize=False)
+        t["weight"] = hd.normalize_importance_weights(t["weight"])
+        if trainer is not None:
+            prio = trainer.backward(t, t["weight"], a.pred_weight)
+            if world > 1:
+                dist.all_reduce(trainer.grads)               # the ONE collective: 18.6 MB flat fp32 bucket
+                trainer.grads.mul_(1.0 / world)
+            trainer.optim_step()
+            eng.update_priority(prio)
+            losses.append(trainer.stats()["loss"])
+            continue
         obs = {k: t[k] for k in ("priv_s", "legal_move", "eps", "own_hand")}
         if a.pred_weight > 0:
             obs["temperature"] = torch.zeros_like(t["eps"])  # r2d2.py:486 reads a key the reference replay never fills
@@ -102,7 +124,7 @@ def main():
     torch.cuda.synchronize()
     dt = time.time() - t0
     # replicas must hold identical weights after identical all-reduced steps
-    flat = torch.cat([p.detach().reshape(-1) for p in agent.online_net.parameters()])
+    flat = torch.cat([p.detach().reshape(-1) for p in agent.online_net.parameters()]).clone()
     ref = flat.clone()
     if world > 1:
         dist.broadcast(ref, 0)
