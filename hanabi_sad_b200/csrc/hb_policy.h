@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "hb_types.h"
+#include "hb_head.cuh"
 
 namespace hbg { struct Params; }
 
@@ -39,6 +40,9 @@ struct HbPolicy {
   float *adv, *oq, *tq;                 // [rows][A], [rows], [rows]
   hbg::Params* d_params;                // [2 parity][4 launches: fc, fc2, lstm0, lstm1][HB_MAX_P problems]
   int* d_error;
+  int head_pending;                     // the last forward's head / act step has not run yet (deferred into the next fused tick)
+  HbHeadArgs pending_head;
 };
 
-int hb_policy_forward(struct hb_engine* e, int greedy_only);
+int hb_policy_forward(struct hb_engine* e, int greedy_only, int defer_head = 0);
+int hb_policy_flush_head(struct hb_engine* e);

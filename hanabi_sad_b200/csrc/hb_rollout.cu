@@ -44,6 +44,8 @@ struct HbTickArgs {
   const float* oq;
   const float* tq;
   HbRing ring;
+  int do_head;         // run the head / act step of the previous forward first (its output is the action applied below)
+  HbHeadArgs head;
 };
 
 __device__ __forceinline__ unsigned long long hb_ld_counter(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
@@ -167,6 +169,12 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(c
   const int P = geo.P;
   if (tid < 16) reinterpret_cast<uint4*>(&s)[tid] = reinterpret_cast<const uint4*>(A.games + g)[tid];
   else if (tid < 20) reinterpret_cast<uint4*>(deck)[tid - 16] = reinterpret_cast<const uint4*>(A.decks + (size_t)g * HB_DECK_STRIDE)[tid - 16];
+  if (A.do_head) {
+    // R2D2Agent.act's tail for this game's agents (hb_head.cuh), deferred from the previous tick's forward: one launch and
+    // one round trip of (a, greedy_a, Q) through a separate kernel less per tick.  The values it writes are read below by
+    // other threads of this CTA: L2 loads (__ldcg) after the barrier.
+    for (int p = tid >> 5; p < P; p += (HB_TICK_THREADS + 31) / 32) hb_head_row(A.head, g * P + p, tid & 31);
+  }
   __syncthreads();
   if (tid == 0) {
     sh_did_step = 0; sh_term = 0; sh_reset = 0; sh_drop = 0; sh_t = 0; sh_retry = 0; sh_committed = 1;
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(c
     if (A.do_step && !s.terminated) {
       const int t = s.ep_len;
       const int cur = s.cur_player < P ? s.cur_player : 0;
-      const bool term = hb_step_game(s, cfg, deck, (int)A.a[g * P + cur], (int)A.greedy_a[g * P + cur]);
+      const bool term = hb_step_game(s, cfg, deck, (int)__ldcg(A.a + g * P + cur), (int)__ldcg(A.greedy_a + g * P + cur));
       s.ep_len = (int16_t)(t + 1);
       sh_did_step = 1; sh_t = t; sh_term = term ? 1 : 0;
       A.reward[g] = s.reward;
@@ -195,10 +203,10 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(c
     if (t < R.T) {
       if (tid < P) {
         const size_t o = ((size_t)slot * R.T + t) * P + tid;
-        R.a[o] = A.a[g * P + tid];
-        R.greedy_a[o] = A.greedy_a[g * P + tid];
-        R.sc_oq[((size_t)g * R.T + t) * P + tid] = A.oq[g * P + tid];
-        R.sc_tq[((size_t)g * R.T + t) * P + tid] = A.tq != nullptr ? A.tq[g * P + tid] : 0.f;
+        R.a[o] = __ldcg(A.a + g * P + tid);
+        R.greedy_a[o] = __ldcg(A.greedy_a + g * P + tid);
+        R.sc_oq[((size_t)g * R.T + t) * P + tid] = __ldcg(A.oq + g * P + tid);
+        R.sc_tq[((size_t)g * R.T + t) * P + tid] = A.tq != nullptr ? __ldcg(A.tq + g * P + tid) : 0.f;
       }
       if (tid == 0) R.sc_reward[(size_t)g * R.T + t] = s.reward;
     }
@@ -268,6 +276,11 @@ int hb_launch_tick(hb_engine* e, int do_step, int do_reset) {
   a.oq = e->policy ? e->policy->oq : nullptr;
   a.tq = e->policy && e->policy->have_weights[1] && e->cfg.priority_mode != 1 ? e->policy->tq : nullptr;
   if (e->replay) a.ring = hb_replay_ring(e);
+  if (e->policy && e->policy->head_pending) {   // the previous forward left its head / act step to this launch
+    a.do_head = 1;
+    a.head = e->policy->pending_head;
+    e->policy->head_pending = 0;
+  }
   HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
   {
     HbProfScope ps(e, HB_PROF_TICK);
@@ -301,7 +314,9 @@ int hb_rollout(hb_engine* e, int n_ticks) {
   for (int i = 0; i < n_ticks; ++i) {
     int rc = hb_launch_tick(e, e->pending_actions, 1);
     if (rc) return rc;
-    rc = hb_policy_forward(e, 0);
+    // all but the last forward of this call leave their head / act step to the next tick's prologue; in profiling mode every
+    // kernel class keeps its own launch so that the per-class timings stay comparable
+    rc = hb_policy_forward(e, 0, (i + 1 < n_ticks && !e->prof_on) ? 1 : 0);
     if (rc) return rc;
     e->pending_actions = 1;
     e->obs_stale = 1;

@@ -283,3 +283,49 @@ def test_rollout_env_obs_match_oracle(hb):
                 assert np.array_equal(o[k][g].view(np.uint32), ref[k].view(np.uint32)), (tick, g, k)
         prev = eng.actions()
     eng.close()
+
+
+@pytest.mark.parametrize("cfg", [(2, 5, 1, True), (3, 5, 0, False), (5, 4, 1, True)], ids=["vdn_2p", "iql_3p", "vdn_5p"])
+def test_rollout_n_equals_n_rollouts_of_one(hb, cfg):
+    """hb_rollout(n) defers the head / act step of every forward but the last into the NEXT tick's prologue (one launch less per
+    tick); hb_rollout(1) always runs it as its own kernel.  Both paths must produce the same games, actions, Q-values, hidden
+    state and replay -- bit for bit (same Philox streams, same kernels' arithmetic)."""
+    P, H, sad, vdn = cfg
+    G, n = 48, 57
+    eps = [0.05, 0.4, 1.0]
+
+    def run(chunks):
+        e = hb.Engine(G, P, H, 0, 80, bool(sad), True, eps, seed=321, vdn=vdn, replay_capacity=4096)
+        e.set_weights(0, random_state_dict(e.F, 512, e.A, 71, H))
+        e.set_weights(1, random_state_dict(e.F, 512, e.A, 72, H))
+        for c in chunks:
+            e.rollout(c)
+        e.sync()
+        st = e.replay_stats()
+        games = []
+        for g in range(G):
+            q = e.query(g)
+            games.append((q.cur_player, q.score, q.life, q.info, q.deck_size, q.num_step, q.episode, tuple(q.fireworks), tuple(e.get_deck(g).tolist())))
+        a, ga = e.actions()
+        pol = e.policy_get(hidden=True)
+        obs = e.observe()
+        eps_keys = []
+        for i in range(st["size"]):
+            t = e.get(i)
+            L = int(t["seq_len"])
+            eps_keys.append(hashlib.sha1(t["priv_s"][:L].cpu().numpy().tobytes() + t["a"][:L].cpu().numpy().tobytes() + t["reward"][:L].cpu().numpy().tobytes()).hexdigest())
+        e.close()
+        return games, a, ga, pol, obs, sorted(eps_keys), st
+
+    one = run([1] * n)
+    many = run([n])
+    mixed = run([5, 1, 20, 31])
+    for other in (many, mixed):
+        assert other[0] == one[0]
+        assert np.array_equal(other[1], one[1]) and np.array_equal(other[2], one[2])
+        for k in ("adv", "online_q", "target_q", "h", "c"):
+            assert np.array_equal(other[3][k].view(np.uint32), one[3][k].view(np.uint32)), k
+        for k in ("priv_s", "legal_move", "own_hand", "eps"):
+            assert np.array_equal(other[4][k], one[4][k]), k
+        assert other[5] == one[5] and len(one[5]) > G
+        assert other[6]["num_add"] == one[6]["num_add"] and other[6]["num_act"] == one[6]["num_act"] == G * n
