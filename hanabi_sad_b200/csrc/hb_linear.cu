@@ -46,6 +46,29 @@ __global__ void split_pad(const float* __restrict__ src, long long ld, int rows,
   lo[i] = l;
 }
 
+// The same for an operand given TRANSPOSED: src is [cols][rows] row-major (row stride ld), i.e. element (r, c) of the operand is
+// src[c * ld + r] -- the weight-gradient GEMMs contract over the batch rows, which are the SLOW axis of the caller's tensors.
+// 32 x 32 tiles through shared memory: coalesced reads along r, coalesced writes along c; no fp32 transposed copy in between.
+__global__ void split_pad_t(const float* __restrict__ src, long long ld, int rows, int cols, int rows_pad, int cols_pad,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;   // block (32, 8)
+  for (int j = ty; j < 32; j += 8) {   // tile[j][tx] = operand(r0 + tx, c0 + j) = src[(c0 + j) * ld + r0 + tx]
+    const int r = r0 + tx, c = c0 + j;
+    tile[j][tx] = (r < rows && c < cols) ? src[(long long)c * ld + r] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {   // write operand(r0 + j, c0 + tx)
+    const int r = r0 + j, c = c0 + tx;
+    if (r < rows_pad && c < cols_pad) {
+      __nv_bfloat16 h, l;
+      hbg::split_bf16(tile[tx][j], h, l);
+      hi[(long long)r * cols_pad + c] = h;
+      lo[(long long)r * cols_pad + c] = l;
+    }
+  }
+}
+
 // C[r][c] = sum_s part[s][r][c] (+ bias[c]) for r < M, c < N
 __global__ void sum_parts(const float* __restrict__ part, int split, long long part_stride, int n_pad, const float* __restrict__ bias,
                           float* __restrict__ C, long long ldc, int M, int N) {
@@ -68,10 +91,12 @@ int grow(void** p, size_t* cap, size_t need, size_t elem) {
 
 }  // namespace
 
-extern "C" int hb_gemm_nt(int device, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
-                          int M, int N, int K, void* stream) {
+// C[M,N] = op(A) op(B)^T (+ bias): op(X) = X given [rows][K] (trans = 0, row stride ld >= K) or X given [K][rows] (trans = 1,
+// row stride ld >= rows).  hb_gemm_nt (the public entry point) is the trans = 0 case.
+int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, const float* bias, float* C, int64_t ldc,
+                  int M, int N, int K, void* stream) {
   if (!A || !B || !C) { hb_set_error("hb_gemm_nt: null argument"); return -1; }
-  if (M < 1 || N < 1 || K < 1 || lda < K || ldb < K || ldc < N) { hb_set_error("hb_gemm_nt: bad shape M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld", M, N, K, (long long)lda, (long long)ldb, (long long)ldc); return -1; }
+  if (M < 1 || N < 1 || K < 1 || lda < (transA ? M : K) || ldb < (transB ? N : K) || ldc < N) { hb_set_error("hb_gemm_nt: bad shape M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld", M, N, K, (long long)lda, (long long)ldb, (long long)ldc); return -1; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { hb_set_error("hb_gemm_nt: no CUDA device -- libhanabi_b200 has no CPU path"); return -2; }
   if (device < 0 || device >= ndev || device >= 16) { hb_set_error("hb_gemm_nt: bad device ordinal"); return -1; }
@@ -120,8 +145,10 @@ extern "C" int hb_gemm_nt(int device, const float* A, int64_t lda, const float* 
   }
   if (!direct) { rc = grow((void**)&S.c_part, &S.c_cap, (size_t)split * Mp * Np, sizeof(float)); if (rc) return rc; }
   const long long na = (long long)Mp * Kp, nb = (long long)Np * Kp;
-  split_pad<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo);
-  split_pad<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, ldb, N, K, Np, Kp, S.b_hi, S.b_lo);
+  if (transA) split_pad_t<<<dim3((unsigned)((Kp + 31) / 32), (unsigned)((Mp + 31) / 32)), dim3(32, 8), 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo);
+  else split_pad<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo);
+  if (transB) split_pad_t<<<dim3((unsigned)((Kp + 31) / 32), (unsigned)((Np + 31) / 32)), dim3(32, 8), 0, st>>>(B, ldb, N, K, Np, Kp, S.b_hi, S.b_lo);
+  else split_pad<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, ldb, N, K, Np, Kp, S.b_hi, S.b_lo);
   const int cl = (mt % 2 == 0) ? 2 : 1;
   std::vector<Params> hp(split);
   for (int s = 0; s < split; ++s) {
@@ -150,4 +177,9 @@ extern "C" int hb_gemm_nt(int device, const float* A, int64_t lda, const float* 
   }
   HB_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int hb_gemm_nt(int device, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                          int M, int N, int K, void* stream) {
+  return hb_gemm_nt_ex(device, A, lda, 0, B, ldb, 0, bias, C, ldc, M, N, K, stream);
 }

@@ -19,6 +19,9 @@
 
 #include "hb_engine.h"
 
+int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, const float* bias, float* C, int64_t ldc,
+                  int M, int N, int K, void* stream);   // hb_linear.cu
+
 namespace {
 
 constexpr int HID = 512;
@@ -212,17 +215,6 @@ __global__ void ht_colsum(const float* __restrict__ m, long long rows, int cols,
   }
 }
 
-// [rows][cols] -> [cols][ld_out] (32 x 32 tiles, block (32, 8))
-__global__ void ht_transpose(const float* __restrict__ src, long long rows, int cols, float* __restrict__ dst, long long ld_out) {
-  __shared__ float tile[32][33];
-  const long long r0 = (long long)blockIdx.y * 32;
-  const int c0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;
-  for (int j = ty; j < 32; j += 8) tile[j][tx] = (r0 + j < rows && c0 + tx < cols) ? src[(r0 + j) * cols + c0 + tx] : 0.f;
-  __syncthreads();
-  for (int j = ty; j < 32; j += 8)
-    if (c0 + j < cols && r0 + tx < rows) dst[(long long)(c0 + j) * ld_out + r0 + tx] = tile[tx][j];
-}
-
 __global__ void ht_unpack_head_grads(const float* __restrict__ dWh, const float* __restrict__ dbh, int A, int HO, int use_pred, float* __restrict__ g_wa,
                                      float* __restrict__ g_ba, float* __restrict__ g_wv, float* __restrict__ g_bv, float* __restrict__ g_wp, float* __restrict__ g_bp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,7 +284,7 @@ struct hb_trainer {
   hb_lstm* lstm;
   float *x[2], *o[2], *y[2];          // fc output, lstm output, head output of (online, target)
   float *qa[2];                       // [T*rows]
-  float *dy, *dyT, *oT, *dO, *dX, *dXT, *sT;
+  float *dy, *dO, *dX;
   float *Wh[2], *WhT, *bh[2], *dWh, *dbh;
   float* stats;                       // device [8]
   float* h_stats;                     // pinned [8]
@@ -345,8 +337,7 @@ int hb_trainer_create(const hb_trainer_config* cfg, float* online, float* target
     HT_ALLOC(tr->x[n], N * HID); HT_ALLOC(tr->o[n], N * HID); HT_ALLOC(tr->y[n], N * HO); HT_ALLOC(tr->qa[n], N);
     HT_ALLOC(tr->Wh[n], HO * HID); HT_ALLOC(tr->bh[n], HO);
   }
-  HT_ALLOC(tr->dy, N * HO); HT_ALLOC(tr->dyT, HO * N); HT_ALLOC(tr->oT, (size_t)HID * N); HT_ALLOC(tr->dO, N * HID); HT_ALLOC(tr->dX, N * HID);
-  HT_ALLOC(tr->dXT, (size_t)HID * N); HT_ALLOC(tr->sT, (size_t)cfg->in_dim * N);
+  HT_ALLOC(tr->dy, N * HO); HT_ALLOC(tr->dO, N * HID); HT_ALLOC(tr->dX, N * HID);
   HT_ALLOC(tr->WhT, HO * HID); HT_ALLOC(tr->dWh, HO * HID); HT_ALLOC(tr->dbh, HO);
   HT_ALLOC(tr->stats, 8);
   HB_CUDA(cudaMallocHost((void**)&tr->h_stats, 8 * sizeof(float)));
@@ -362,7 +353,7 @@ void hb_trainer_destroy(hb_trainer* tr) {
   cudaDeviceSynchronize();
   hb_lstm_destroy(tr->lstm);
   for (int n = 0; n < 2; ++n) { cudaFree(tr->x[n]); cudaFree(tr->o[n]); cudaFree(tr->y[n]); cudaFree(tr->qa[n]); cudaFree(tr->Wh[n]); cudaFree(tr->bh[n]); }
-  cudaFree(tr->dy); cudaFree(tr->dyT); cudaFree(tr->oT); cudaFree(tr->dO); cudaFree(tr->dX); cudaFree(tr->dXT); cudaFree(tr->sT);
+  cudaFree(tr->dy); cudaFree(tr->dO); cudaFree(tr->dX);
   cudaFree(tr->WhT); cudaFree(tr->dWh); cudaFree(tr->dbh); cudaFree(tr->stats);
   cudaFreeHost(tr->h_stats); cudaEventDestroy(tr->ev_stats);
   delete tr;
@@ -424,9 +415,8 @@ int hb_trainer_backward(hb_trainer* tr, const hb_batch* b, int batchsize, int t_
   // ---- backward: heads
   rc = hb_gemm_nt(tr->device, tr->dy, HO, tr->WhT, HO, nullptr, tr->dO, HID, (int)N, HID, HO, st);                  // dO = dY Wh
   if (rc) return rc;
-  ht_transpose<<<dim3((HO + 31) / 32, blocks(N, 32)), dim3(32, 8), 0, st>>>(tr->dy, N, HO, tr->dyT, N);
-  ht_transpose<<<dim3(HID / 32, blocks(N, 32)), dim3(32, 8), 0, st>>>(tr->o[0], N, HID, tr->oT, N);
-  rc = hb_gemm_nt(tr->device, tr->dyT, N, tr->oT, N, nullptr, tr->dWh, HID, HO, HID, (int)N, st);                    // dWh = dY^T O
+  // dWh = dY^T O: both operands are given with the contraction axis (batch rows) as their SLOW axis -> transposing splits
+  rc = hb_gemm_nt_ex(tr->device, tr->dy, HO, 1, tr->o[0], HID, 1, nullptr, tr->dWh, HID, HO, HID, (int)N, st);
   if (rc) return rc;
   ht_colsum<<<HO, 256, 0, st>>>(tr->dy, N, HO, tr->dbh);
   float* g = tr->grads;
@@ -441,13 +431,11 @@ int hb_trainer_backward(hb_trainer* tr, const hb_batch* b, int batchsize, int t_
   if (rc) return rc;
   ht_relu_bwd<<<blocks(N * HID / 4, 256), 256, 0, st>>>(tr->x[0], tr->dX, N * HID / 4);
   ht_colsum<<<HID, 256, 0, st>>>(tr->dX, N, HID, g + off[P_FC_B]);
-  ht_transpose<<<dim3(HID / 32, blocks(N, 32)), dim3(32, 8), 0, st>>>(tr->dX, N, HID, tr->dXT, N);
-  ht_transpose<<<dim3((F + 31) / 32, blocks(N, 32)), dim3(32, 8), 0, st>>>(b->priv_s, N, F, tr->sT, N);
-  rc = hb_gemm_nt(tr->device, tr->dXT, N, tr->sT, N, nullptr, g + off[P_FC_W], F, HID, F, (int)N, st);              // dW0 = dXpre^T S
+  rc = hb_gemm_nt_ex(tr->device, tr->dX, HID, 1, b->priv_s, F, 1, nullptr, g + off[P_FC_W], F, HID, F, (int)N, st);   // dW0 = dXpre^T S
   if (rc) return rc;
   HB_CUDA(cudaGetLastError());
   tr->last_use_pred = use_pred;
-  tr->launches += 22;
+  tr->launches += 18;
   return 0;
 }
 
