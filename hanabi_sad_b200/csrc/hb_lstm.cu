@@ -177,7 +177,11 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
   const int T = P.T, R_pad = P.R_pad;
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
-  unsigned* ctr = P.ctr + (size_t)dom * CTR_STRIDE;
+  // Step counters per K-CHUNK of the row block: chunk kc (hidden units 64 kc .. 64 kc + 63) is produced by the four CTAs
+  // slice / 4 == kc (one multicast cluster), so a consumer can fetch a chunk as soon as THOSE four have published instead of
+  // waiting for all 32; every CTA walks the chunks starting with its own cluster's (rot), which is the first to be ready.
+  unsigned* ctr = P.ctr + ((size_t)dom * KCH + (size_t)(slice / 4)) * CTR_STRIDE;   // the counter this CTA publishes to
+  const int rot = slice / 4;
   int* ef = P.error_flag;
   bool dead = false;
   long long* tr = blockIdx.x == 0 ? P.trace : nullptr;
@@ -206,28 +210,32 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
         tma_load_2d(w_base + kc * 2 * W_HALF, &N.w_hi, bar_w, kc * BK, slice * NC);
         tma_load_2d(w_base + kc * 2 * W_HALF + W_HALF, &N.w_lo, bar_w, kc * BK, slice * NC);
       }
-      uint32_t it = 0;
+    }
+    if (lane < KCH) {
+      // one lane per chunk position: its counter wait, ring-slot wait and TMA issue overlap with the other lanes' (eight L2
+      // round trips in parallel instead of one counter wait followed by eight dependent slot waits)
+      const int j = lane, kcp = (j + rot) & (KCH - 1);
+      const unsigned* cc = P.ctr + ((size_t)dom * KCH + (size_t)kcp) * CTR_STRIDE;
       for (int t = 1; t < T; ++t) {
-        wait_counter(ctr, (unsigned)(SLICES * t), ef, dead);   // h_{t-1} of this row block is complete
-        HBL_STAMP(tr, t, 0);
+        wait_counter(cc, (unsigned)(4 * t), ef, dead);         // the 64 units of h_{t-1} in this chunk are complete
+        if (j == 0) HBL_STAMP(tr, t, 0);
         fence_async_global();
-        for (int kc = 0; kc < KCH; ++kc, ++it) {
-          const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
-          wait_bar(bar_empty + 8 * s, ph ^ 1u, ef, dead);
-          if (dead) break;
-          const uint32_t st = ring + s * FWD_STAGE;
-          mbar_expect_tx(bar_full + 8 * s, FWD_STAGE);
-          const int row0 = t * R_pad + mb * BM;                // block t of the h sequence = h_{t-1}
-          if (CL == 1) {
-            tma_load_2d(st, &N.h_hi, bar_full + 8 * s, kc * BK, row0);
-            tma_load_2d(st + A_TILE, &N.h_lo, bar_full + 8 * s, kc * BK, row0);
-          } else {                                             // this CTA's quarter of the rows, delivered to all four CTAs
-            const uint32_t q = (uint32_t)rank * (A_TILE / CL);
-            tma_load_2d_mc(st + q, &N.hq_hi, bar_full + 8 * s, kc * BK, row0 + rank * (BM / CL), CMASK);
-            tma_load_2d_mc(st + A_TILE + q, &N.hq_lo, bar_full + 8 * s, kc * BK, row0 + rank * (BM / CL), CMASK);
-          }
+        const uint32_t it = (uint32_t)(t - 1) * KCH + (uint32_t)j;
+        const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
+        wait_bar(bar_empty + 8 * s, ph ^ 1u, ef, dead);
+        if (dead) break;
+        const uint32_t st = ring + s * FWD_STAGE;
+        mbar_expect_tx(bar_full + 8 * s, FWD_STAGE);
+        const int row0 = t * R_pad + mb * BM;                  // block t of the h sequence = h_{t-1}
+        if (CL == 1) {
+          tma_load_2d(st, &N.h_hi, bar_full + 8 * s, kcp * BK, row0);
+          tma_load_2d(st + A_TILE, &N.h_lo, bar_full + 8 * s, kcp * BK, row0);
+        } else {                                               // this CTA's quarter of the rows, delivered to all four CTAs
+          const uint32_t q = (uint32_t)rank * (A_TILE / CL);
+          tma_load_2d_mc(st + q, &N.hq_hi, bar_full + 8 * s, kcp * BK, row0 + rank * (BM / CL), CMASK);
+          tma_load_2d_mc(st + A_TILE + q, &N.hq_lo, bar_full + 8 * s, kcp * BK, row0 + rank * (BM / CL), CMASK);
         }
-        HBL_STAMP(tr, t, 1);
+        if (j == KCH - 1) HBL_STAMP(tr, t, 1);
       }
     }
   } else if (warp == 1) {
@@ -247,7 +255,8 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
           tc_fence_after();
           const uint32_t st = ring + s * FWD_STAGE;
           const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
-          const uint64_t b_hi = make_desc_sw128(w_base + kc * 2 * W_HALF), b_lo = make_desc_sw128(w_base + kc * 2 * W_HALF + W_HALF);
+          const int kcp = (kc + rot) & (KCH - 1);   // the K-chunk the producer put into this slot
+          const uint64_t b_hi = make_desc_sw128(w_base + kcp * 2 * W_HALF), b_lo = make_desc_sw128(w_base + kcp * 2 * W_HALF + W_HALF);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -570,9 +579,9 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
 
 // Layer-wavefront plumbing (one thread each): block a stream until every row block of a recurrence kernel that is still
 // RUNNING has completed `target` step publications; raise a flag the other layer's kernel polls.
-__global__ void lstm_wait_steps(const unsigned* __restrict__ ctr, int MB, unsigned target, int* error_flag) {
+__global__ void lstm_wait_steps(const unsigned* __restrict__ ctr, int n_counters, unsigned target, int* error_flag) {
   bool dead = false;
-  for (int d = 0; d < MB; ++d) wait_counter(ctr + (size_t)d * CTR_STRIDE, target, error_flag, dead, 3);
+  for (int d = 0; d < n_counters; ++d) wait_counter(ctr + (size_t)d * CTR_STRIDE, target, error_flag, dead, 3);
 }
 __global__ void lstm_set_flag(unsigned* flag) {
   __threadfence();
@@ -580,20 +589,31 @@ __global__ void lstm_set_flag(unsigned* flag) {
   atomicExch(flag, 1u);
 }
 
-// [rows][cols] bf16 pair -> [cols][ld_dst] (column r of the destination = row r of the source); 64 x 64 tiles
+// [rows][cols] bf16 pair -> [cols][ld_dst] (column r of the destination = row r of the source); 64 x 64 tiles, 8-byte global
+// accesses on both sides (four bf16 per thread and access: the 2-byte version moved 2.2 TB/s, latency bound)
 __global__ void __launch_bounds__(256) lstm_transpose_pair(const __nv_bfloat16* __restrict__ s_hi, const __nv_bfloat16* __restrict__ s_lo, int cols,
                                                            __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, long long ld_dst) {
-  __shared__ __nv_bfloat16 th[64][66], tl[64][66];
+  __shared__ __align__(8) unsigned short th[64][66], tl[64][66];
   const size_t r0 = (size_t)blockIdx.y * 64;
-  const int c0 = blockIdx.x * 64, tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  for (int j = ty; j < 64; j += 4) {
-    th[j][tx] = s_hi[(r0 + j) * cols + c0 + tx];
-    tl[j][tx] = s_lo[(r0 + j) * cols + c0 + tx];
+  const int c0 = blockIdx.x * 64, q = threadIdx.x & 15, jb = threadIdx.x >> 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = jb + 16 * k;
+    const uint2 a = *reinterpret_cast<const uint2*>(s_hi + (r0 + j) * cols + c0 + 4 * q);
+    const uint2 b = *reinterpret_cast<const uint2*>(s_lo + (r0 + j) * cols + c0 + 4 * q);
+    uint32_t* ph = reinterpret_cast<uint32_t*>(&th[j][4 * q]);
+    uint32_t* pl = reinterpret_cast<uint32_t*>(&tl[j][4 * q]);
+    ph[0] = a.x; ph[1] = a.y; pl[0] = b.x; pl[1] = b.y;
   }
   __syncthreads();
-  for (int j = ty; j < 64; j += 4) {
-    d_hi[(size_t)(c0 + j) * ld_dst + r0 + tx] = th[tx][j];
-    d_lo[(size_t)(c0 + j) * ld_dst + r0 + tx] = tl[tx][j];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = jb + 16 * k;   // destination row = source column
+    uint2 a, b;
+    a.x = (uint32_t)th[4 * q][c] | ((uint32_t)th[4 * q + 1][c] << 16); a.y = (uint32_t)th[4 * q + 2][c] | ((uint32_t)th[4 * q + 3][c] << 16);
+    b.x = (uint32_t)tl[4 * q][c] | ((uint32_t)tl[4 * q + 1][c] << 16); b.y = (uint32_t)tl[4 * q + 2][c] | ((uint32_t)tl[4 * q + 3][c] << 16);
+    *reinterpret_cast<uint2*>(d_hi + (size_t)(c0 + c) * ld_dst + r0 + 4 * q) = a;
+    *reinterpret_cast<uint2*>(d_lo + (size_t)(c0 + c) * ld_dst + r0 + 4 * q) = b;
   }
 }
 
@@ -737,6 +757,10 @@ struct hb_lstm {
   int64_t launches;
 };
 
+// step counters: per layer 64 lines of CTR_STRIDE words (forward: up to 4 row-block domains x 8 K-chunks; backward: one per domain)
+#define HBL_CTR_LAYER (64 * hbl::CTR_STRIDE)
+#define HBL_CTR_WORDS (2 * HBL_CTR_LAYER)
+
 #define HBL_ALLOC(ptr, bytes)                                             \
   do {                                                                    \
     HB_CUDA(cudaMalloc((void**)&(ptr), (bytes)));                         \
@@ -823,7 +847,7 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
     HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_unperm_rows));
   }
   HBL_ALLOC(L->dwp, 4 * WN * sizeof(float));
-  HBL_ALLOC(L->ctr, 16 * hbl::CTR_STRIDE * sizeof(unsigned));
+  HBL_ALLOC(L->ctr, HBL_CTR_WORDS * sizeof(unsigned));
   HBL_ALLOC(L->d_error, sizeof(int));
   HB_CUDA(cudaMallocHost((void**)&L->h_error, sizeof(int)));
   *L->h_error = 0;
@@ -949,7 +973,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     L->zero_rpad = R_pad; L->zero_rows_max = rows;
   }
   if (rows > L->zero_rows_max) L->zero_rows_max = rows;
-  HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
+  HB_CUDA(cudaMemsetAsync(L->ctr, 0, HBL_CTR_WORDS * sizeof(unsigned), st));
   std::vector<hbl::FwdParams> fp(2);
   memset(fp.data(), 0, 2 * sizeof(hbl::FwdParams));
   int rc = 0;
@@ -979,7 +1003,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
   };
   for (int l = 0; l < 2; ++l) {
     hbl::FwdParams& F = fp[l];
-    F.T = T; F.rows = rows; F.R_pad = R_pad; F.MB = MB; F.ldT = ldT; F.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; F.error_flag = L->d_error;
+    F.T = T; F.rows = rows; F.R_pad = R_pad; F.MB = MB; F.ldT = ldT; F.ctr = L->ctr + (size_t)l * HBL_CTR_LAYER; F.error_flag = L->d_error;
     F.chunk_flags = (wave && l == 1) ? L->chunk_flags : nullptr; F.chunk = chunk;
     F.trace = L->d_trace ? L->d_trace + (size_t)l * L->max_T * 16 : nullptr;
     for (int n = 0; n < nets; ++n) {
@@ -1038,8 +1062,8 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     HB_CUDA(cudaEventRecord(L->wev[3], L->ws[2]));
     for (int c = 0; c < n_chunks; ++c) {
       const int t0 = c * chunk, t1 = t0 + chunk < T ? t0 + chunk : T;
-      // h^0 of steps < t1 is published once layer 0's step counters show t1 completed steps (32 CTAs per row block)
-      hbl::lstm_wait_steps<<<1, 1, 0, L->ws[1]>>>(fp[0].ctr, nets * MB, (unsigned)(hbl::SLICES * t1), L->d_error);
+      // h^0 of steps < t1 is published once every chunk counter of layer 0 shows t1 completed steps (4 CTAs per K-chunk)
+      hbl::lstm_wait_steps<<<1, 1, 0, L->ws[1]>>>(fp[0].ctr, nets * MB * hbl::KCH, (unsigned)(4 * t1), L->d_error);
       rc = gx_gemm(1, t0, t1, L->ws[1], 16 + 2 * c, gemm_sms);
       if (rc) return rc;
       hbl::lstm_set_flag<<<1, 1, 0, L->ws[1]>>>(L->chunk_flags + c);
@@ -1079,7 +1103,7 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
   const size_t N = (size_t)T * R_pad;
   const long long ldT = (long long)(T + 1) * R_pad;
   HbLstmNetBuf& B = L->nb[0];
-  HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
+  HB_CUDA(cudaMemsetAsync(L->ctr, 0, HBL_CTR_WORDS * sizeof(unsigned), st));
   int rc = 0;
   std::vector<hbl::BwdParams> bp(2);
   memset(bp.data(), 0, 2 * sizeof(hbl::BwdParams));
@@ -1102,7 +1126,7 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     Q.act = L->act[l]; Q.cs = L->cs[l];
     Q.dg_hi = L->dg_hi[l]; Q.dg_lo = L->dg_lo[l];
     Q.part = L->part + (size_t)l * part_layer; Q.T = T; Q.rows = rows; Q.R_pad = R_pad; Q.MB = MB;
-    Q.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; Q.error_flag = L->d_error;
+    Q.ctr = L->ctr + (size_t)l * HBL_CTR_LAYER; Q.error_flag = L->d_error;
     Q.chunk_flags = (wave && l == 0) ? L->chunk_flags : nullptr; Q.chunk = chunk;
     Q.trace = L->d_trace ? L->d_trace + (size_t)(2 + l) * L->max_T * 16 : nullptr;
     if (R_pad != rows) {  // padded rows of the dgate operands must read as zero in the GEMMs below
