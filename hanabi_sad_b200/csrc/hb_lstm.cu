@@ -211,17 +211,17 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
         tma_load_2d(w_base + kc * 2 * W_HALF + W_HALF, &N.w_lo, bar_w, kc * BK, slice * NC);
       }
     }
-    if (lane < KCH) {
-      // one lane per chunk position: its counter wait, ring-slot wait and TMA issue overlap with the other lanes' (eight L2
-      // round trips in parallel instead of one counter wait followed by eight dependent slot waits)
-      const int j = lane, kcp = (j + rot) & (KCH - 1);
-      const unsigned* cc = P.ctr + ((size_t)dom * KCH + (size_t)kcp) * CTR_STRIDE;
-      for (int t = 1; t < T; ++t) {
-        wait_counter(cc, (unsigned)(4 * t), ef, dead);         // the 64 units of h_{t-1} in this chunk are complete
+    if (lane < FWD_NST) {
+      // one lane per RING SLOT: lane s fills slot s with the chunks it = s, s + NST, s + 2 NST, ... (in order, so the parity
+      // waits of one slot never alias); the three lanes' counter waits, slot waits and TMA issues overlap with each other
+      // instead of one counter wait followed by eight dependent slot waits
+      const uint32_t s = (uint32_t)lane, total = (uint32_t)(T - 1) * KCH;
+      for (uint32_t it = s; it < total; it += FWD_NST) {
+        const int t = (int)(it / KCH) + 1, j = (int)(it % KCH), kcp = (j + rot) & (KCH - 1);
+        wait_counter(P.ctr + ((size_t)dom * KCH + (size_t)kcp) * CTR_STRIDE, (unsigned)(4 * t), ef, dead);   // this chunk of h_{t-1} is complete
         if (j == 0) HBL_STAMP(tr, t, 0);
         fence_async_global();
-        const uint32_t it = (uint32_t)(t - 1) * KCH + (uint32_t)j;
-        const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
+        const uint32_t ph = (it / FWD_NST) & 1u;
         wait_bar(bar_empty + 8 * s, ph ^ 1u, ef, dead);
         if (dead) break;
         const uint32_t st = ring + s * FWD_STAGE;
