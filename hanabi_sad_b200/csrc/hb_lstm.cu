@@ -177,11 +177,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
   const int T = P.T, R_pad = P.R_pad;
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
-  // Step counters per K-CHUNK of the row block: chunk kc (hidden units 64 kc .. 64 kc + 63) is produced by the four CTAs
-  // slice / 4 == kc (one multicast cluster), so a consumer can fetch a chunk as soon as THOSE four have published instead of
-  // waiting for all 32; every CTA walks the chunks starting with its own cluster's (rot), which is the first to be ready.
-  unsigned* ctr = P.ctr + ((size_t)dom * KCH + (size_t)(slice / 4)) * CTR_STRIDE;   // the counter this CTA publishes to
-  const int rot = slice / 4;
+  unsigned* ctr = P.ctr + (size_t)dom * CTR_STRIDE;
   int* ef = P.error_flag;
   bool dead = false;
   long long* tr = blockIdx.x == 0 ? P.trace : nullptr;
@@ -210,32 +206,28 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
         tma_load_2d(w_base + kc * 2 * W_HALF, &N.w_hi, bar_w, kc * BK, slice * NC);
         tma_load_2d(w_base + kc * 2 * W_HALF + W_HALF, &N.w_lo, bar_w, kc * BK, slice * NC);
       }
-    }
-    if (lane < FWD_NST) {
-      // one lane per RING SLOT: lane s fills slot s with the chunks it = s, s + NST, s + 2 NST, ... (in order, so the parity
-      // waits of one slot never alias); the three lanes' counter waits, slot waits and TMA issues overlap with each other
-      // instead of one counter wait followed by eight dependent slot waits
-      const uint32_t s = (uint32_t)lane, total = (uint32_t)(T - 1) * KCH;
-      for (uint32_t it = s; it < total; it += FWD_NST) {
-        const int t = (int)(it / KCH) + 1, j = (int)(it % KCH), kcp = (j + rot) & (KCH - 1);
-        wait_counter(P.ctr + ((size_t)dom * KCH + (size_t)kcp) * CTR_STRIDE, (unsigned)(4 * t), ef, dead);   // this chunk of h_{t-1} is complete
-        if (j == 0) HBL_STAMP(tr, t, 0);
+      uint32_t it = 0;
+      for (int t = 1; t < T; ++t) {
+        wait_counter(ctr, (unsigned)(SLICES * t), ef, dead);   // h_{t-1} of this row block is complete
+        HBL_STAMP(tr, t, 0);
         fence_async_global();
-        const uint32_t ph = (it / FWD_NST) & 1u;
-        wait_bar(bar_empty + 8 * s, ph ^ 1u, ef, dead);
-        if (dead) break;
-        const uint32_t st = ring + s * FWD_STAGE;
-        mbar_expect_tx(bar_full + 8 * s, FWD_STAGE);
-        const int row0 = t * R_pad + mb * BM;                  // block t of the h sequence = h_{t-1}
-        if (CL == 1) {
-          tma_load_2d(st, &N.h_hi, bar_full + 8 * s, kcp * BK, row0);
-          tma_load_2d(st + A_TILE, &N.h_lo, bar_full + 8 * s, kcp * BK, row0);
-        } else {                                               // this CTA's quarter of the rows, delivered to all four CTAs
-          const uint32_t q = (uint32_t)rank * (A_TILE / CL);
-          tma_load_2d_mc(st + q, &N.hq_hi, bar_full + 8 * s, kcp * BK, row0 + rank * (BM / CL), CMASK);
-          tma_load_2d_mc(st + A_TILE + q, &N.hq_lo, bar_full + 8 * s, kcp * BK, row0 + rank * (BM / CL), CMASK);
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % FWD_NST, ph = (it / FWD_NST) & 1u;
+          wait_bar(bar_empty + 8 * s, ph ^ 1u, ef, dead);
+          if (dead) break;
+          const uint32_t st = ring + s * FWD_STAGE;
+          mbar_expect_tx(bar_full + 8 * s, FWD_STAGE);
+          const int row0 = t * R_pad + mb * BM;                // block t of the h sequence = h_{t-1}
+          if (CL == 1) {
+            tma_load_2d(st, &N.h_hi, bar_full + 8 * s, kc * BK, row0);
+            tma_load_2d(st + A_TILE, &N.h_lo, bar_full + 8 * s, kc * BK, row0);
+          } else {                                             // this CTA's quarter of the rows, delivered to all four CTAs
+            const uint32_t q = (uint32_t)rank * (A_TILE / CL);
+            tma_load_2d_mc(st + q, &N.hq_hi, bar_full + 8 * s, kc * BK, row0 + rank * (BM / CL), CMASK);
+            tma_load_2d_mc(st + A_TILE + q, &N.hq_lo, bar_full + 8 * s, kc * BK, row0 + rank * (BM / CL), CMASK);
+          }
         }
-        if (j == KCH - 1) HBL_STAMP(tr, t, 1);
+        HBL_STAMP(tr, t, 1);
       }
     }
   } else if (warp == 1) {
@@ -255,8 +247,7 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
           tc_fence_after();
           const uint32_t st = ring + s * FWD_STAGE;
           const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + A_TILE);
-          const int kcp = (kc + rot) & (KCH - 1);   // the K-chunk the producer put into this slot
-          const uint64_t b_hi = make_desc_sw128(w_base + kcp * 2 * W_HALF), b_lo = make_desc_sw128(w_base + kcp * 2 * W_HALF + W_HALF);
+          const uint64_t b_hi = make_desc_sw128(w_base + kc * 2 * W_HALF), b_lo = make_desc_sw128(w_base + kc * 2 * W_HALF + W_HALF);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -579,9 +570,9 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
 
 // Layer-wavefront plumbing (one thread each): block a stream until every row block of a recurrence kernel that is still
 // RUNNING has completed `target` step publications; raise a flag the other layer's kernel polls.
-__global__ void lstm_wait_steps(const unsigned* __restrict__ ctr, int n_counters, unsigned target, int* error_flag) {
+__global__ void lstm_wait_steps(const unsigned* __restrict__ ctr, int MB, unsigned target, int* error_flag) {
   bool dead = false;
-  for (int d = 0; d < n_counters; ++d) wait_counter(ctr + (size_t)d * CTR_STRIDE, target, error_flag, dead, 3);
+  for (int d = 0; d < MB; ++d) wait_counter(ctr + (size_t)d * CTR_STRIDE, target, error_flag, dead, 3);
 }
 __global__ void lstm_set_flag(unsigned* flag) {
   __threadfence();
@@ -757,10 +748,6 @@ struct hb_lstm {
   int64_t launches;
 };
 
-// step counters: per layer 64 lines of CTR_STRIDE words (forward: up to 4 row-block domains x 8 K-chunks; backward: one per domain)
-#define HBL_CTR_LAYER (64 * hbl::CTR_STRIDE)
-#define HBL_CTR_WORDS (2 * HBL_CTR_LAYER)
-
 #define HBL_ALLOC(ptr, bytes)                                             \
   do {                                                                    \
     HB_CUDA(cudaMalloc((void**)&(ptr), (bytes)));                         \
@@ -847,7 +834,7 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
     HB_CUDA(cudaFuncGetAttributes(&fa, hbl::lstm_unperm_rows));
   }
   HBL_ALLOC(L->dwp, 4 * WN * sizeof(float));
-  HBL_ALLOC(L->ctr, HBL_CTR_WORDS * sizeof(unsigned));
+  HBL_ALLOC(L->ctr, 16 * hbl::CTR_STRIDE * sizeof(unsigned));
   HBL_ALLOC(L->d_error, sizeof(int));
   HB_CUDA(cudaMallocHost((void**)&L->h_error, sizeof(int)));
   *L->h_error = 0;
@@ -973,7 +960,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     L->zero_rpad = R_pad; L->zero_rows_max = rows;
   }
   if (rows > L->zero_rows_max) L->zero_rows_max = rows;
-  HB_CUDA(cudaMemsetAsync(L->ctr, 0, HBL_CTR_WORDS * sizeof(unsigned), st));
+  HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
   std::vector<hbl::FwdParams> fp(2);
   memset(fp.data(), 0, 2 * sizeof(hbl::FwdParams));
   int rc = 0;
@@ -1003,7 +990,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
   };
   for (int l = 0; l < 2; ++l) {
     hbl::FwdParams& F = fp[l];
-    F.T = T; F.rows = rows; F.R_pad = R_pad; F.MB = MB; F.ldT = ldT; F.ctr = L->ctr + (size_t)l * HBL_CTR_LAYER; F.error_flag = L->d_error;
+    F.T = T; F.rows = rows; F.R_pad = R_pad; F.MB = MB; F.ldT = ldT; F.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; F.error_flag = L->d_error;
     F.chunk_flags = (wave && l == 1) ? L->chunk_flags : nullptr; F.chunk = chunk;
     F.trace = L->d_trace ? L->d_trace + (size_t)l * L->max_T * 16 : nullptr;
     for (int n = 0; n < nets; ++n) {
@@ -1062,8 +1049,8 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     HB_CUDA(cudaEventRecord(L->wev[3], L->ws[2]));
     for (int c = 0; c < n_chunks; ++c) {
       const int t0 = c * chunk, t1 = t0 + chunk < T ? t0 + chunk : T;
-      // h^0 of steps < t1 is published once every chunk counter of layer 0 shows t1 completed steps (4 CTAs per K-chunk)
-      hbl::lstm_wait_steps<<<1, 1, 0, L->ws[1]>>>(fp[0].ctr, nets * MB * hbl::KCH, (unsigned)(4 * t1), L->d_error);
+      // h^0 of steps < t1 is published once layer 0's step counters show t1 completed steps (32 CTAs per row block)
+      hbl::lstm_wait_steps<<<1, 1, 0, L->ws[1]>>>(fp[0].ctr, nets * MB, (unsigned)(hbl::SLICES * t1), L->d_error);
       rc = gx_gemm(1, t0, t1, L->ws[1], 16 + 2 * c, gemm_sms);
       if (rc) return rc;
       hbl::lstm_set_flag<<<1, 1, 0, L->ws[1]>>>(L->chunk_flags + c);
@@ -1103,7 +1090,7 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
   const size_t N = (size_t)T * R_pad;
   const long long ldT = (long long)(T + 1) * R_pad;
   HbLstmNetBuf& B = L->nb[0];
-  HB_CUDA(cudaMemsetAsync(L->ctr, 0, HBL_CTR_WORDS * sizeof(unsigned), st));
+  HB_CUDA(cudaMemsetAsync(L->ctr, 0, 16 * hbl::CTR_STRIDE * sizeof(unsigned), st));
   int rc = 0;
   std::vector<hbl::BwdParams> bp(2);
   memset(bp.data(), 0, 2 * sizeof(hbl::BwdParams));
@@ -1126,7 +1113,7 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     Q.act = L->act[l]; Q.cs = L->cs[l];
     Q.dg_hi = L->dg_hi[l]; Q.dg_lo = L->dg_lo[l];
     Q.part = L->part + (size_t)l * part_layer; Q.T = T; Q.rows = rows; Q.R_pad = R_pad; Q.MB = MB;
-    Q.ctr = L->ctr + (size_t)l * HBL_CTR_LAYER; Q.error_flag = L->d_error;
+    Q.ctr = L->ctr + (size_t)l * 8 * hbl::CTR_STRIDE; Q.error_flag = L->d_error;
     Q.chunk_flags = (wave && l == 0) ? L->chunk_flags : nullptr; Q.chunk = chunk;
     Q.trace = L->d_trace ? L->d_trace + (size_t)(2 + l) * L->max_T * 16 : nullptr;
     if (R_pad != rows) {  // padded rows of the dgate operands must read as zero in the GEMMs below
