@@ -20,6 +20,28 @@ def _deps():
     return out
 
 
+def build_compat(force=False):
+    """compat/{rela,hanalearn}<EXT_SUFFIX>: the two tiny pybind11 extension modules with the reference's module names (g++ and
+    the pybind11 headers torch bundles).  Returns their paths."""
+    import sysconfig
+
+    import torch
+
+    src = os.path.join(HERE, "compat", "src", "stub.cpp")
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    inc = [os.path.join(os.path.dirname(torch.__file__), "include"), sysconfig.get_paths()["include"]]
+    out = []
+    for name in ("rela", "hanalearn"):
+        dst = os.path.join(HERE, "compat", name + ext)
+        out.append(dst)
+        if not force and os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
+            continue
+        gxx = os.environ.get("CXX", "g++")
+        cmd = [gxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DHB_STUB_" + name.upper(), "-o", dst, src] + ["-I" + i for i in inc]
+        subprocess.check_call(cmd)
+    return out
+
+
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in _deps()):
@@ -37,3 +59,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_compat(force="--force" in sys.argv))

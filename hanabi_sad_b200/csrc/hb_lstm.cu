@@ -136,15 +136,21 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity, int* err
 }
 __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, int* error_flag, bool& dead, int code = 2) {
   if (dead) return;
+#ifdef HBL_POLL_ACQUIRE
+  for (uint32_t spin = 0; ld_acquire(ctr) < target; ++spin) {   // every poll is an acquire: no extra round trip once the value is seen
+#else
   for (uint32_t spin = 0; ld_relaxed(ctr) < target; ++spin) {
+#endif
     if ((spin & 255u) == 255u) {
       if (*(volatile int*)error_flag != 0) { dead = true; return; }
       if (spin > (1u << 20)) { atomicCAS(error_flag, 0, code); dead = true; return; }   // the FIRST failure's code is kept
     }
   }
+#ifndef HBL_POLL_ACQUIRE
   // the counter only grows: an acquire load of it now synchronises with every release that contributed to the value seen
   // (cheaper on the step chain than a full fence, which also waits for this thread's own outstanding loads)
   (void)ld_acquire(ctr);
+#endif
 }
 // Step publication (the grid.sync idiom): every thread's stores are ordered before the CTA barrier, ONE thread then
 // fences at GPU scope (cumulative over what the barrier ordered) and bumps the domain's step counter.
@@ -844,7 +850,8 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   HBL_ALLOC(L->d_gemm, 48 * sizeof(Params));
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
-  L->use_clusters = getenv("HB_LSTM_NO_CLUSTER") ? 0 : 1;   // diagnostic switch: plain (non-multicast) forward recurrence
+  HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
+  L->use_clusters = getenv("HB_LSTM_NO_CLUSTER") ? 0 : (getenv("HB_LSTM_CL") ? atoi(getenv("HB_LSTM_CL")) : 4);   // diagnostic: multicast cluster size of the forward recurrence (0 / 1: none)
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::BWD_SMEM)));
   HB_CUDA((cudaFuncSetAttribute(gemm3_kernel<EPI_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
   HB_CUDA((cudaFuncSetAttribute(gemm3_kernel<EPI_F32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
@@ -1002,8 +1009,9 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
       rc |= hb_make_tmap(&Q.h_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
       rc |= hb_make_tmap(&Q.h_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM);
       Q.gx = (l == 0 || !wave) ? B.gx : B.gx1; Q.hs_hi = B.hs_hi[l]; Q.hs_lo = B.hs_lo[l];
-      rc |= hb_make_tmap(&Q.hq_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / 4);
-      rc |= hb_make_tmap(&Q.hq_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / 4);
+      const int clq = L->use_clusters == 2 ? 2 : 4;
+      rc |= hb_make_tmap(&Q.hq_hi, B.hs_hi[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / clq);
+      rc |= hb_make_tmap(&Q.hq_lo, B.hs_lo[l], (uint64_t)(T + 1) * R_pad, hbl::HIDN, BM / clq);
       Q.y = l == 1 ? y[n] : nullptr;
       Q.act = sv ? L->act[l] : nullptr; Q.cs = sv ? L->cs[l] : nullptr;
     }
@@ -1018,19 +1026,22 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    const int clw = L->use_clusters == 2 ? 2 : 4;
+    attr[0].val.clusterDim.x = (unsigned)clw; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int max_clusters = 0;   // every CTA must be resident at once (step barrier): use clusters only if they all fit
-    const bool cl4 = L->use_clusters && cudaOccupancyMaxActiveClusters(&max_clusters, hbl::lstm_fwd_kernel<4>, &cfg) == cudaSuccess &&
-                     max_clusters * 4 >= (wave ? 2 : 1) * n_ctas;
+    const bool cl4 = L->use_clusters > 1 &&
+                     cudaOccupancyMaxActiveClusters(&max_clusters, clw == 2 ? hbl::lstm_fwd_kernel<2> : hbl::lstm_fwd_kernel<4>, &cfg) == cudaSuccess &&
+                     max_clusters * clw >= (wave ? 2 : 1) * n_ctas;
     const hbl::FwdParams* dp = L->d_fwd + l;
     if (cl4) {
-      HB_CUDA(cudaLaunchKernelEx(&cfg, hbl::lstm_fwd_kernel<4>, dp));
+      if (clw == 2) HB_CUDA(cudaLaunchKernelEx(&cfg, hbl::lstm_fwd_kernel<2>, dp));
+      else HB_CUDA(cudaLaunchKernelEx(&cfg, hbl::lstm_fwd_kernel<4>, dp));
     } else {
       (void)cudaGetLastError();
       hbl::lstm_fwd_kernel<1><<<n_ctas, 192, hbl::FWD_SMEM, s>>>(dp);
     }
-    L->last_cluster = cl4 ? 4 : 1;
+    L->last_cluster = cl4 ? clw : 1;
     HB_CUDA(cudaGetLastError());
     L->launches += 1;
     return 0;

@@ -101,6 +101,9 @@ class FakeEngine:
 
 @pytest.fixture()
 def ref_modules(monkeypatch):
+    from hanabi_sad_b200 import build as hb_build
+
+    hb_build.build_compat()   # the pybind11 stub modules named `rela` / `hanalearn` (no-op when they are up to date)
     monkeypatch.syspath_prepend(PYH)
     monkeypatch.syspath_prepend(os.path.join(ROOT, "hanabi_sad_b200", "compat"))
     for m in ("rela", "hanalearn", "create", "eval", "r2d2", "utils"):
