@@ -208,6 +208,11 @@ def import_ref():
         spec = importlib.util.spec_from_file_location(name, path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        if os.path.abspath(getattr(mod, "__file__", "")) != os.path.abspath(path):
+            # CPython hands back an already initialised extension module of the same name: this process imported another
+            # `rela` / `hanalearn` .so before (e.g. the stub modules of hanabi_sad_b200/compat)
+            raise ImportError("oracle.import_ref: an extension module named %r from %s is already loaded in this interpreter; the reference's "
+                              "%s cannot be loaded next to it" % (name, getattr(mod, "__file__", "?"), path))
         sys.modules[key] = mod
         mods[name] = mod
     return mods["rela"], mods["hanalearn"]

@@ -101,14 +101,24 @@ class FakeEngine:
 
 @pytest.fixture()
 def ref_modules(monkeypatch):
+    # In THIS process the names `rela` / `hanalearn` are served by module objects that re-export the facades, exactly what the
+    # stub extension modules of hanabi_sad_b200/compat do.  The real stubs are exercised in a subprocess
+    # (test_compat_stub_modules_in_a_fresh_interpreter): two extension modules with the same name cannot live in one
+    # interpreter, and other tests of this session load the REFERENCE's `rela` / `hanalearn` (.so) for the oracle pins.
+    import types
+
+    import hanabi_sad_b200.hanalearn as hhl
+    import hanabi_sad_b200.rela as hrela
     from hanabi_sad_b200 import build as hb_build
 
-    hb_build.build_compat()   # the pybind11 stub modules named `rela` / `hanalearn` (no-op when they are up to date)
     monkeypatch.syspath_prepend(PYH)
-    monkeypatch.syspath_prepend(os.path.join(ROOT, "hanabi_sad_b200", "compat"))
     for m in ("rela", "hanalearn", "create", "eval", "r2d2", "utils"):
         sys.modules.pop(m, None)
-    import hanabi_sad_b200.rela as hrela
+    for name, impl in (("rela", hrela), ("hanalearn", hhl)):
+        mod = types.ModuleType(name)
+        mod.__dict__.update({k: v for k, v in vars(impl).items() if not k.startswith("__")})
+        mod.__file__ = hb_build.LIB      # create.py:20-21 asserts a compiled module; the stubs' __file__ is their own .so
+        monkeypatch.setitem(sys.modules, name, mod)
 
     monkeypatch.setattr(hrela, "Engine", FakeEngine)
     monkeypatch.setattr(hrela.BatchRunner, "_device_index", lambda self: 0)  # no CUDA here: the act device is "cpu" in this test
@@ -320,3 +330,31 @@ def test_sharded_replay_importance_weights_over_the_union(ref_modules, monkeypat
     assert min(float(weight[:n0].max()), float(weight[n0:].max())) < 0.9
     replay.update_priority(torch.ones(B))
     context.terminate()
+
+
+def test_compat_stub_modules_in_a_fresh_interpreter():
+    """hanabi_sad_b200/compat/{rela,hanalearn}<EXT_SUFFIX> are REAL extension modules (pybind11 stubs, compat/src/stub.cpp): the
+    reference's create.py:17-21 import + `__file__.endswith(".so")` check passes without spoofing, and every name the reference's
+    pybind modules export (rela/pybind.cc:16-93, cpp/pybind.cc:14-56) is the facade's object."""
+    import subprocess
+
+    from hanabi_sad_b200 import build as hb_build
+
+    hb_build.build_compat()
+    code = r"""
+import sys
+sys.path.insert(0, sys.argv[1])
+import rela, hanalearn
+import hanabi_sad_b200.rela as hrela, hanabi_sad_b200.hanalearn as hhl
+assert rela.__file__.endswith(".so") and hanalearn.__file__.endswith(".so") and "compat" in rela.__file__, (rela.__file__, hanalearn.__file__)
+for n in ("FFTransition", "RNNTransition", "RNNPrioritizedReplay", "ThreadLoop", "Context", "R2D2Actor", "BatchRunner", "aggregate_priority"):
+    assert getattr(rela, n) is getattr(hrela, n), n
+for n in ("HanabiEnv", "HanabiVecEnv", "HanabiThreadLoop"):
+    assert getattr(hanalearn, n) is getattr(hhl, n), n
+env = hanalearn.HanabiEnv({"players": "2", "seed": "1"}, [0.0], 80, True, False, False, False)
+assert env.feature_size() == 838 and env.num_action() == 21
+print("STUBS OK")
+"""
+    p = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "hanabi_sad_b200", "compat")], capture_output=True, text=True, timeout=300,
+                       cwd=os.path.join(ROOT, "tests"))
+    assert p.returncode == 0 and "STUBS OK" in p.stdout, (p.stdout + p.stderr)[-2000:]
