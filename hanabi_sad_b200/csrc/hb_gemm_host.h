@@ -15,3 +15,20 @@ int hb_make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 // clusters of `cl` CTAs; nt / mt = number of 256-column / 128-row tiles, nprob problems (ps[0..nprob)).
 typedef void (*HbGemmKernel)(const hbg::Params*, int, int, int);
 int hb_launch_gemm(HbGemmKernel k, int cl, int sm_count, cudaStream_t st, const hbg::Params* ps, int nt, int mt, int nprob);
+
+// Asynchronous upload of small launch-parameter records (GEMM Params with their tensor maps, recurrence parameters): a
+// cudaMemcpyAsync from PAGEABLE memory makes the host wait until the stream has drained ("a stream sync is performed before the
+// copy is initiated"), i.e. the host would run in lock-step with the device at every such launch and the GPU would idle while
+// the host prepares the next one.  The source is therefore first copied into a slot of a pinned ring; a slot is reused only
+// after the copy that read it has executed (one event per slot, normally long complete).
+struct HbUploadRing {
+  static constexpr int SLOTS = 64;
+  static constexpr size_t SLOT_BYTES = 24 * 1024;
+  unsigned char* base;      // zero-initialised by the owner (a global, or a memset struct): null = not set up
+  cudaEvent_t ev[SLOTS];
+  bool used[SLOTS];
+  int next;
+};
+int hb_upload_init(HbUploadRing* r);
+void hb_upload_destroy(HbUploadRing* r);
+int hb_upload(HbUploadRing* r, void* dst_device, const void* src_host, size_t bytes, cudaStream_t st);

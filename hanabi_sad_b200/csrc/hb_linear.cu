@@ -17,6 +17,35 @@
 
 using hbg::Params;
 
+int hb_upload_init(HbUploadRing* r) {
+  if (r->base) return 0;
+  HB_CUDA(cudaMallocHost((void**)&r->base, HbUploadRing::SLOTS * HbUploadRing::SLOT_BYTES));
+  for (int i = 0; i < HbUploadRing::SLOTS; ++i) { HB_CUDA(cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming)); r->used[i] = false; }
+  r->next = 0;
+  return 0;
+}
+void hb_upload_destroy(HbUploadRing* r) {
+  if (!r->base) return;
+  for (int i = 0; i < HbUploadRing::SLOTS; ++i) cudaEventDestroy(r->ev[i]);
+  cudaFreeHost(r->base);
+  r->base = nullptr;
+}
+int hb_upload(HbUploadRing* r, void* dst_device, const void* src_host, size_t bytes, cudaStream_t st) {
+  if (bytes > HbUploadRing::SLOT_BYTES || !r->base) {   // oversized (or no ring): the synchronous path is still correct
+    HB_CUDA(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  const int slot = r->next;
+  r->next = (r->next + 1) % HbUploadRing::SLOTS;
+  if (r->used[slot]) HB_CUDA(cudaEventSynchronize(r->ev[slot]));   // the copy that last read this slot has executed
+  unsigned char* p = r->base + (size_t)slot * HbUploadRing::SLOT_BYTES;
+  memcpy(p, src_host, bytes);
+  HB_CUDA(cudaMemcpyAsync(dst_device, p, bytes, cudaMemcpyHostToDevice, st));
+  HB_CUDA(cudaEventRecord(r->ev[slot], st));
+  r->used[slot] = true;
+  return 0;
+}
+
 namespace {
 
 constexpr int MAX_SPLIT = 16;
@@ -30,6 +59,7 @@ struct GemmScratch {            // grow-only device scratch per GPU (one learner
   int* d_error = nullptr;
   int sm_count = 0;
   bool attrs = false;
+  HbUploadRing ring;
 };
 GemmScratch g_scratch[16];
 
@@ -110,6 +140,7 @@ int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const flo
     HB_CUDA(cudaMalloc((void**)&S.d_params, MAX_SPLIT * sizeof(Params)));
     HB_CUDA(cudaMalloc((void**)&S.d_error, sizeof(int)));
     HB_CUDA(cudaMemset(S.d_error, 0, sizeof(int)));
+    { const int urc = hb_upload_init(&S.ring); if (urc) return urc; }
     HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
     HB_CUDA((cudaFuncSetAttribute(hbg::gemm3_kernel<hbg::EPI_F32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbg::SMEM_BYTES)));
   }
@@ -167,7 +198,8 @@ int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const flo
     p.error_flag = S.d_error; p.row_mul = 1; p.row_add = 0; p.valid_rows = Mp;
   }
   if (rc) return -2;
-  HB_CUDA(cudaMemcpyAsync(S.d_params, hp.data(), split * sizeof(Params), cudaMemcpyHostToDevice, st));
+  rc = hb_upload(&S.ring, S.d_params, hp.data(), split * sizeof(Params), st);
+  if (rc) return rc;
   if (cl == 2) rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_F32, 3>, 2, S.sm_count, st, S.d_params, nt, mt, split);
   else rc = hb_launch_gemm(hbg::gemm3_kernel<hbg::EPI_F32, 1>, 1, S.sm_count, st, S.d_params, nt, mt, split);
   if (rc) return rc;

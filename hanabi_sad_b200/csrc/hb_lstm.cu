@@ -741,6 +741,7 @@ struct hb_lstm {
   unsigned* ctr;
   unsigned* chunk_flags;                    // [64] layer-wavefront progress flags
   long long* d_trace;                       // diagnostic (HB_LSTM_TRACE=<file>): [4 kernels][max_T][16] time stamps
+  HbUploadRing upload;                      // pinned staging of launch-parameter records (hb_gemm_host.h)
   cudaStream_t ws[3];                       // internal streams of the layer wavefront (recurrence above / chunk GEMMs / recurrence below)
   cudaEvent_t wev[5];
   int use_wavefront;
@@ -775,7 +776,7 @@ static void hbl_gemm_problem(Params& p, int& rc, const __nv_bfloat16* a_hi, cons
 }
 
 static int hbl_run_gemm(hb_lstm* L, cudaStream_t st, const Params* hp, int nprob, int mt, int nt, int slot, int sm_limit = 0) {
-  HB_CUDA(cudaMemcpyAsync(L->d_gemm + slot, hp, nprob * sizeof(Params), cudaMemcpyHostToDevice, st));
+  { const int urc = hb_upload(&L->upload, L->d_gemm + slot, hp, nprob * sizeof(Params), st); if (urc) return urc; }
   const bool pair = (mt % 2) == 0;
   const int sms = sm_limit > 0 ? sm_limit : L->sm_count;   // a limit keeps the persistent grid off the SMs a co-running recurrence needs
   L->launches += 1;
@@ -848,6 +849,7 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   HBL_ALLOC(L->d_fwd, 2 * sizeof(hbl::FwdParams));
   HBL_ALLOC(L->d_bwd, 2 * sizeof(hbl::BwdParams));
   HBL_ALLOC(L->d_gemm, 48 * sizeof(Params));
+  { const int urc = hb_upload_init(&L->upload); if (urc) return urc; }
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
@@ -881,6 +883,7 @@ void hb_lstm_destroy(hb_lstm* L) {
   for (int i = 0; i < 3; ++i) if (L->ws[i]) cudaStreamDestroy(L->ws[i]);
   for (int i = 0; i < 5; ++i) if (L->wev[i]) cudaEventDestroy(L->wev[i]);
   cudaFreeHost(L->h_error); cudaEventDestroy(L->ev_done);
+  hb_upload_destroy(&L->upload);
   delete L;
 }
 
@@ -1017,7 +1020,8 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
     }
   }
   if (rc) return -2;
-  HB_CUDA(cudaMemcpyAsync(L->d_fwd, fp.data(), 2 * sizeof(hbl::FwdParams), cudaMemcpyHostToDevice, st));
+  rc = hb_upload(&L->upload, L->d_fwd, fp.data(), 2 * sizeof(hbl::FwdParams), st);
+  if (rc) return rc;
   auto launch_rec = [&](int l, cudaStream_t s) -> int {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_ctas, 1, 1);
@@ -1133,7 +1137,8 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     }
     HB_CUDA(cudaMemsetAsync(Q.part, 0, (size_t)2 * R_pad * hbl::HIDN * sizeof(float), st));   // the two dh accumulators
   }
-  HB_CUDA(cudaMemcpyAsync(L->d_bwd, bp.data(), 2 * sizeof(hbl::BwdParams), cudaMemcpyHostToDevice, st));
+  rc = hb_upload(&L->upload, L->d_bwd, bp.data(), 2 * sizeof(hbl::BwdParams), st);
+  if (rc) return rc;
   // dX of layer l over the rows of steps [t0, t1): [rows, 2048] x [2048, 512]
   auto dx_gemm = [&](int l, int t0, int t1, float* dst, cudaStream_t s, int slot, int sm_limit) -> int {
     Params gp;
