@@ -121,6 +121,7 @@ SIGNATURES = {
     "hb_trainer_create": (c_int, [ctypes.POINTER(HbTrainerConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
     "hb_trainer_destroy": (None, [c_void_p]),
     "hb_trainer_backward": (c_int, [c_void_p, ctypes.POINTER(HbBatch), c_int, c_int, c_float, c_void_p, c_void_p]),
+    "hb_trainer_backward_ex": (c_int, [c_void_p, ctypes.POINTER(HbBatch), c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p]),
     "hb_trainer_optim_step": (c_int, [c_void_p, c_void_p]),
     "hb_trainer_sync_target": (c_int, [c_void_p, c_void_p]),
     "hb_trainer_stats": (c_int, [c_void_p, ctypes.POINTER(HbTrainStats)]),

@@ -109,7 +109,7 @@ struct HbProfScope {
 int hb_status_post(hb_engine* e);
 int hb_status_poll(hb_engine* e, bool wait);
 HbHidPtrs hb_policy_hidden_ptrs(hb_engine* e);  // hb_policy.cu
-int hb_launch_tick(hb_engine* e, int do_step, int do_reset);  // hb_rollout.cu
+int hb_launch_tick(hb_engine* e, int do_step, int do_reset, int clear_flags);  // hb_rollout.cu
 // hb_env_kernels.cu
 int hb_launch_env(hb_engine* e, int do_reset, int do_step, const int64_t* a_dev, const int64_t* greedy_a_dev);
 int hb_launch_random_actions(hb_engine* e, uint64_t counter);

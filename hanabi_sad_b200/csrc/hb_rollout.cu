@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(c
 
 HbRing hb_replay_ring(hb_engine* e);  // hb_replay.cu
 
-int hb_launch_tick(hb_engine* e, int do_step, int do_reset) {
+int hb_launch_tick(hb_engine* e, int do_step, int do_reset, int clear_flags) {
   HbTickArgs a;
   memset(&a, 0, sizeof(a));
   a.games = e->d_games; a.decks = e->d_decks; a.inject = e->d_inject; a.cfg = e->env; a.seed = e->cfg.seed;
@@ -281,7 +281,9 @@ int hb_launch_tick(hb_engine* e, int do_step, int do_reset) {
     a.head = e->policy->pending_head;
     e->policy->head_pending = 0;
   }
-  HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
+  // flags[0..1] describe the LAST tick of a call (hb_env_any_terminated, the per-launch illegal count): cleared before the first
+  // and before the last tick only, not by a memset between every two launches of the loop
+  if (clear_flags) HB_CUDA(cudaMemsetAsync(e->d_flags, 0, 2 * sizeof(int), e->stream));
   {
     HbProfScope ps(e, HB_PROF_TICK);
     const int key = e->P * 100 + e->H * 10 + (e->env.g.sad ? 1 : 0);
@@ -312,7 +314,7 @@ int hb_rollout(hb_engine* e, int n_ticks) {
   HB_CUDA(cudaSetDevice(e->device));
   { const int src = hb_status_poll(e, false); if (src) return src; }   // a guard that fired during an EARLIER call
   for (int i = 0; i < n_ticks; ++i) {
-    int rc = hb_launch_tick(e, e->pending_actions, 1);
+    int rc = hb_launch_tick(e, e->pending_actions, 1, (i == 0 || i + 1 == n_ticks) ? 1 : 0);
     if (rc) return rc;
     // all but the last forward of this call leave their head / act step to the next tick's prologue; in profiling mode every
     // kernel class keeps its own launch so that the per-class timings stay comparable

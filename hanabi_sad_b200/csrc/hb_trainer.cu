@@ -108,6 +108,7 @@ __global__ void ht_q_rows(const float* __restrict__ y_on, const float* __restric
 struct LossArgs {
   int T, B, P, A, H, HO, n_step;   // T = steps computed (t_eff)
   float gamma_n, eta, pred_weight;
+  float Bnorm;                     // entries of the WHOLE batch the mean runs over (>= B when this pass is one micro-batch of it)
   const float *qa_on, *qa_tg;      // [T][B][P]
   const float *y_on;               // [T*B*P][HO]
   const float *legal;              // [T][B][P][A]
@@ -142,8 +143,8 @@ __global__ void ht_loss(LossArgs L) {
     const float ae = fabsf(err);
     loss_t = ae < 1.f ? 0.5f * err * err : ae - 0.5f;
     prio = ae;
-    // d loss / d qa_sum = smooth_l1'(err) * d err / d qa = clamp(err, -1, 1) * (-mask), scaled by weight_b / B
-    const float g = -fminf(fmaxf(err, -1.f), 1.f) * mask * wb / (float)B;
+    // d loss / d qa_sum = smooth_l1'(err) * d err / d qa = clamp(err, -1, 1) * (-mask), scaled by weight_b / (batch entries)
+    const float g = -fminf(fmaxf(err, -1.f), 1.f) * mask * wb / L.Bnorm;
     for (int p = 0; p < P; ++p) {
       const size_t r = tb * P + p;
       float* dy = L.dy + r * HO;
@@ -158,7 +159,7 @@ __global__ void ht_loss(LossArgs L) {
         float msum = 0.f;
         for (int s = 0; s < L.H; ++s) msum += oh[3 * s] + oh[3 * s + 1] + oh[3 * s + 2];
         const float M = fmaxf(msum, 1e-6f);
-        const float coef = L.pred_weight * wb / ((float)B * (float)P);
+        const float coef = L.pred_weight * wb / (L.Bnorm * (float)P);
         for (int s = 0; s < L.H; ++s) {
           const float z0 = y[3 * s], z1 = y[3 * s + 1], z2 = y[3 * s + 2];
           const float mx = fmaxf(z0, fmaxf(z1, z2));
@@ -192,9 +193,9 @@ __global__ void ht_loss(LossArgs L) {
     for (int w = 0; w < nw; ++w) { rl += red[0][w]; ps += red[1][w]; xe += red[2][w]; pm = fmaxf(pm, redm[w]); }
     L.priority[b] = L.eta * pm + (1.f - L.eta) * ps / len;     // aggregate_priority (r2d2_actor.h:10-21)
     const float total = rl + L.pred_weight * xe;
-    atomicAdd(&L.stats[0], total * wb / (float)B);
-    atomicAdd(&L.stats[1], rl / len / (float)B);
-    atomicAdd(&L.stats[2], xe / len / (float)B);
+    atomicAdd(&L.stats[0], total * wb / L.Bnorm);
+    atomicAdd(&L.stats[1], rl / len / L.Bnorm);
+    atomicAdd(&L.stats[2], xe / len / L.Bnorm);
   }
 }
 
@@ -274,6 +275,16 @@ __global__ void ht_adam(float* __restrict__ p, const float* __restrict__ g, floa
   reinterpret_cast<float4*>(p)[i] = P4; reinterpret_cast<float4*>(m)[i] = M4; reinterpret_cast<float4*>(v)[i] = V4;
 }
 
+// g += acc (gradient accumulation over the micro-batches of one update)
+__global__ void ht_add(float* __restrict__ g, const float* __restrict__ acc, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(g)[i];
+  const float4 b = reinterpret_cast<const float4*>(acc)[i];
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  reinterpret_cast<float4*>(g)[i] = a;
+}
+
 }  // namespace
 
 struct hb_trainer {
@@ -286,6 +297,7 @@ struct hb_trainer {
   float *qa[2];                       // [T*rows]
   float *dy, *dO, *dX;
   float *Wh[2], *WhT, *bh[2], *dWh, *dbh;
+  float* acc;                         // gradients of the earlier micro-batches of this update (allocated on first use)
   float* stats;                       // device [8]
   float* h_stats;                     // pinned [8]
   cudaEvent_t ev_stats;
@@ -320,7 +332,11 @@ int hb_trainer_create(const hb_trainer_config* cfg, float* online, float* target
     hb_set_error("hb_trainer_create: need 2 <= num_action <= 63, 1 <= num_player <= 5, seq_len, max_batch, multi_step >= 1");
     return -1;
   }
-  if (rows > 256) { hb_set_error("hb_trainer_create: max_batch * num_player = %d rows; one pass of the LSTM kernels holds 256", rows); return -1; }
+  if (rows > 256) {
+    hb_set_error("hb_trainer_create: max_batch * num_player = %d rows; one pass of the LSTM kernels holds 256 -- split the batch into micro-batches of <= %d "
+                 "entries and accumulate (hb_trainer_backward_ex)", rows, 256 / P);
+    return -1;
+  }
   if (cfg->max_batch > 1024 || cfg->seq_len > 1024) { hb_set_error("hb_trainer_create: max_batch and seq_len must be <= 1024"); return -1; }
   HB_CUDA(cudaSetDevice(cfg->device));
   hb_trainer* tr = new hb_trainer();
@@ -354,17 +370,22 @@ void hb_trainer_destroy(hb_trainer* tr) {
   hb_lstm_destroy(tr->lstm);
   for (int n = 0; n < 2; ++n) { cudaFree(tr->x[n]); cudaFree(tr->o[n]); cudaFree(tr->y[n]); cudaFree(tr->qa[n]); cudaFree(tr->Wh[n]); cudaFree(tr->bh[n]); }
   cudaFree(tr->dy); cudaFree(tr->dO); cudaFree(tr->dX);
-  cudaFree(tr->WhT); cudaFree(tr->dWh); cudaFree(tr->dbh); cudaFree(tr->stats);
+  cudaFree(tr->WhT); cudaFree(tr->dWh); cudaFree(tr->dbh); cudaFree(tr->stats); cudaFree(tr->acc);
   cudaFreeHost(tr->h_stats); cudaEventDestroy(tr->ev_stats);
   delete tr;
 }
 
 // Forward of both networks, loss, priorities and the full backward of the online network: gradients land in the flat
-// `grads` buffer (overwritten), aggregated priorities in `priority` (device float [batchsize]).
-int hb_trainer_backward(hb_trainer* tr, const hb_batch* b, int batchsize, int t_eff, float pred_weight, float* priority, void* stream) {
+// `grads` buffer, aggregated priorities in `priority` (device float [batchsize]).  `total_batch` = entries of the whole batch
+// the loss mean runs over; `accumulate` != 0 adds this pass's gradients and loss statistics to those already there: a batch
+// with more than 256 LSTM rows (3-5 player VDN at the reference's batch sizes) is fed as micro-batches of <= 256 / num_player
+// entries, the first with accumulate = 0.  The rows of a batch are independent up to the mean, so this is exact.
+int hb_trainer_backward_ex(hb_trainer* tr, const hb_batch* b, int batchsize, int t_eff, float pred_weight, float* priority, int total_batch, int accumulate,
+                           void* stream) {
   if (!tr || !b || !priority) { hb_set_error("hb_trainer_backward: null argument"); return -1; }
   const hb_trainer_config& c = tr->cfg;
   if (batchsize < 1 || batchsize > c.max_batch) { hb_set_error("hb_trainer_backward: batchsize must be 1..%d", c.max_batch); return -1; }
+  if (total_batch < batchsize) { hb_set_error("hb_trainer_backward: total_batch %d < batchsize %d", total_batch, batchsize); return -1; }
   if (!b->priv_s || !b->legal_move || !b->a || !b->reward || !b->bootstrap || !b->seq_len || !b->weight || (pred_weight > 0.f && !b->own_hand)) {
     hb_set_error("hb_trainer_backward: the batch lacks a tensor the loss needs");
     return -1;
@@ -377,7 +398,13 @@ int hb_trainer_backward(hb_trainer* tr, const hb_batch* b, int batchsize, int t_
   const int64_t* off = tr->off;
   auto blocks = [](long long n, int t) { return (unsigned)((n + t - 1) / t); };
   int rc;
-  HB_CUDA(cudaMemsetAsync(tr->stats, 0, 8 * sizeof(float), st));
+  const size_t grad_bytes = (size_t)off[P_N] * sizeof(float);
+  if (accumulate) {
+    if (!tr->acc) HB_CUDA(cudaMalloc((void**)&tr->acc, grad_bytes));
+    HB_CUDA(cudaMemcpyAsync(tr->acc, tr->grads, grad_bytes, cudaMemcpyDeviceToDevice, st));
+  } else {
+    HB_CUDA(cudaMemsetAsync(tr->stats, 0, 8 * sizeof(float), st));
+  }
   // ---- forward: fc + ReLU, LSTM (both networks in one pass), heads
   for (int n = 0; n < 2; ++n) {
     const float* p = tr->params[n];
@@ -407,7 +434,7 @@ int hb_trainer_backward(hb_trainer* tr, const hb_batch* b, int batchsize, int t_
   L.T = T; L.B = B; L.P = P; L.A = A; L.H = c.hand_size; L.HO = HO; L.n_step = c.multi_step;
   double gn = 1.0;
   for (int i = 0; i < c.multi_step; ++i) gn *= (double)c.gamma;
-  L.gamma_n = (float)gn; L.eta = c.eta; L.pred_weight = pred_weight;
+  L.gamma_n = (float)gn; L.eta = c.eta; L.pred_weight = pred_weight; L.Bnorm = (float)total_batch;
   L.qa_on = tr->qa[0]; L.qa_tg = tr->qa[1]; L.y_on = tr->y[0]; L.legal = b->legal_move; L.act = b->a; L.own_hand = b->own_hand;
   L.reward = b->reward; L.bootstrap = b->bootstrap; L.seq_len = b->seq_len; L.weight = b->weight;
   L.dy = tr->dy; L.priority = priority; L.stats = tr->stats;
@@ -433,10 +460,15 @@ int hb_trainer_backward(hb_trainer* tr, const hb_batch* b, int batchsize, int t_
   ht_colsum<<<HID, 256, 0, st>>>(tr->dX, N, HID, g + off[P_FC_B]);
   rc = hb_gemm_nt_ex(tr->device, tr->dX, HID, 1, b->priv_s, F, 1, nullptr, g + off[P_FC_W], F, HID, F, (int)N, st);   // dW0 = dXpre^T S
   if (rc) return rc;
+  if (accumulate) ht_add<<<blocks(off[P_N] / 4, 256), 256, 0, st>>>(g, tr->acc, off[P_N] / 4);
   HB_CUDA(cudaGetLastError());
   tr->last_use_pred = use_pred;
-  tr->launches += 18;
+  tr->launches += 18 + (accumulate ? 1 : 0);
   return 0;
+}
+
+int hb_trainer_backward(hb_trainer* tr, const hb_batch* b, int batchsize, int t_eff, float pred_weight, float* priority, void* stream) {
+  return hb_trainer_backward_ex(tr, b, batchsize, t_eff, pred_weight, priority, batchsize, 0, stream);
 }
 
 int hb_trainer_optim_step(hb_trainer* tr, void* stream) {

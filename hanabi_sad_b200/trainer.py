@@ -80,6 +80,9 @@ class DeviceTrainer:
         self.vdn, self.multi_step, self.gamma, self.eta, self.uniform_priority = bool(vdn), int(multi_step), float(gamma), float(eta), bool(uniform_priority)
         self.num_player = int(num_player) if vdn else 1
         self.seq_len, self.max_batch = int(seq_len), int(max_batch)
+        # one pass of the LSTM kernels holds 256 rows: larger batches (3-5 player VDN, IQL beyond 256) are fed as micro-batches
+        # whose gradients accumulate (hb_trainer_backward_ex); exact, batch rows interact only through the loss mean
+        self.micro_batch = min(self.max_batch, max(1, 256 // self.num_player))
         off = (ctypes.c_int64 * 17)()
         check(lib().hb_trainer_layout(self.in_dim, self.num_action, self.hand_size, off))
         self.offsets, self.total = list(off)[:16], int(off[16])
@@ -91,7 +94,7 @@ class DeviceTrainer:
             self._views.append({k: buf[o:o + int(np.prod(shapes[k]))].view(shapes[k]) for k, o in zip(PARAM_NAMES, self.offsets)})
         cfg = HbTrainerConfig()
         cfg.device, cfg.in_dim, cfg.num_action, cfg.hand_size = self.device.index, self.in_dim, self.num_action, self.hand_size
-        cfg.num_player, cfg.vdn, cfg.multi_step, cfg.seq_len, cfg.max_batch = self.num_player, int(self.vdn), self.multi_step, self.seq_len, self.max_batch
+        cfg.num_player, cfg.vdn, cfg.multi_step, cfg.seq_len, cfg.max_batch = self.num_player, int(self.vdn), self.multi_step, self.seq_len, self.micro_batch
         cfg.gamma, cfg.eta, cfg.lr, cfg.adam_eps, cfg.beta1, cfg.beta2, cfg.grad_clip = gamma, eta, lr, eps, betas[0], betas[1], grad_clip
         h = ctypes.c_void_p()
         check(lib().hb_trainer_create(ctypes.byref(cfg), self.online.data_ptr(), self.target.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
@@ -173,9 +176,11 @@ class DeviceTrainer:
         return self
 
     # ---- the update ---------------------------------------------------------------------------------------------
+    _BATCH_KEYS = ("priv_s", "legal_move", "own_hand", "eps", "a", "greedy_a", "reward", "bootstrap", "seq_len")
+
     def _hb_batch(self, t, weight):
         hb = HbBatch()
-        for k in ("priv_s", "legal_move", "own_hand", "eps", "a", "greedy_a", "reward", "bootstrap", "seq_len"):
+        for k in self._BATCH_KEYS:
             v = t.get(k)
             if v is not None:
                 assert v.is_cuda and v.is_contiguous(), k
@@ -202,10 +207,23 @@ class DeviceTrainer:
         weight = weight.detach().to(self.device, torch.float32).contiguous()
         if t_eff is None:
             t_eff = int(t["seq_len"].max().item()) if self.skip_padding else self.seq_len
-        hb = self._hb_batch(t, weight)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(lib().hb_trainer_backward(self._h, ctypes.byref(hb), B, int(t_eff), float(pred_weight), self._prio.data_ptr(), stream))
-        self._keep = (t, weight)                # the kernels are asynchronous: keep the tensors alive until the next call
+        if B <= self.micro_batch:
+            hb = self._hb_batch(t, weight)
+            check(lib().hb_trainer_backward(self._h, ctypes.byref(hb), B, int(t_eff), float(pred_weight), self._prio.data_ptr(), stream))
+            self._keep = (t, weight)            # the kernels are asynchronous: keep the tensors alive until the next call
+        else:
+            keep = []
+            for lo in range(0, B, self.micro_batch):
+                hi = min(B, lo + self.micro_batch)
+                # [T, B, ...] tensors: a slice of the batch axis is strided -> one contiguous copy per micro-batch
+                sub = {k: (t[k][lo:hi] if k == "seq_len" else t[k][:, lo:hi]).contiguous() for k in self._BATCH_KEYS if t.get(k) is not None}
+                w = weight[lo:hi].contiguous()
+                hb = self._hb_batch(sub, w)
+                check(lib().hb_trainer_backward_ex(self._h, ctypes.byref(hb), hi - lo, int(t_eff), float(pred_weight),
+                                                   self._prio.data_ptr() + 4 * lo, B, 1 if lo else 0, stream))
+                keep.append((sub, w))
+            self._keep = keep
         return self._prio[:B]
 
     def optim_step(self):

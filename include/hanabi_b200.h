@@ -337,6 +337,12 @@ void hb_trainer_destroy(hb_trainer* t);
  * t_eff = longest episode of the batch (steps beyond it are padding in every row and are skipped; pass seq_len to disable);
  * gradients -> the flat `grads` buffer (overwritten), aggregated priorities -> priority (device float [batchsize]). */
 int hb_trainer_backward(hb_trainer* t, const hb_batch* batch, int batchsize, int t_eff, float pred_weight, float* priority, void* stream);
+/* The same for ONE MICRO-BATCH of a larger batch (one pass of the LSTM kernels holds 256 rows = 256 / num_player entries; the
+ * reference's learner has no such limit, e.g. 5-player VDN at batchsize 128 = 640 rows): `batch` holds `batchsize` contiguous
+ * entries, the loss mean runs over `total_batch` entries, accumulate != 0 ADDS this pass's gradients and loss statistics to
+ * those of the previous passes (first micro-batch: 0).  Exact: batch rows interact only through the mean. */
+int hb_trainer_backward_ex(hb_trainer* t, const hb_batch* batch, int batchsize, int t_eff, float pred_weight, float* priority, int total_batch,
+                           int accumulate, void* stream);
 /* clip_grad_norm_ + Adam.step on the online network (a data-parallel learner all-reduces `grads` before this call). */
 int hb_trainer_optim_step(hb_trainer* t, void* stream);
 int hb_trainer_sync_target(hb_trainer* t, void* stream);      /* R2D2Agent.sync_target_with_online (r2d2.py:208-210) */

@@ -158,3 +158,32 @@ def test_eval_seats_one_network_per_seat(hb, cfg):
     assert worst < TOL, worst
     assert not alive.all()  # some games finished (no auto-restart in eval: they stay frozen)
     eng.close()
+
+
+def test_set_weights_waits_for_copies_queued_on_torchs_stream(hb):
+    """Engine.set_weights reads CUDA tensors on the engine's own stream: a load_state_dict-style copy still QUEUED on torch's
+    stream (behind a long kernel) must be complete before the engine reads, or the actors get a mix of old and new weights
+    (BatchRunner::updateModel semantics, rela/batch_runner.h:74-77: the model the actors see is the one handed over)."""
+    G, P = 64, 2
+    outs = []
+    new = random_state_dict(838, 512, 21, 31, 5)
+    old = random_state_dict(838, 512, 21, 32, 5)
+    for racy in (False, True):
+        eng = hb.Engine(G, P, 5, 0, 80, True, False, [0.0], seed=12)
+        if not racy:
+            eng.set_weights(0, new)
+        else:
+            dev = torch.device("cuda", 0)
+            gpu_sd = {k: torch.as_tensor(v).to(dev) for k, v in old.items()}
+            pinned = {k: torch.as_tensor(v).pin_memory() for k, v in new.items()}
+            torch.cuda.synchronize()
+            torch.cuda._sleep(400_000_000)                       # ~0.2 s of device time ahead of the copies
+            for k in gpu_sd:
+                gpu_sd[k].copy_(pinned[k], non_blocking=True)    # queued, not executed, when set_weights is called
+            eng.set_weights(0, gpu_sd)
+        eng.set_weights(1, new)
+        eng.reset()
+        eng.policy_act(greedy_only=True)
+        outs.append(eng.policy_get()["adv"].copy())
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])

@@ -91,20 +91,24 @@ def test_train_log_header_is_read_like_the_reference(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.isdir(REF_PY), reason="oracle/_ref not built")
-@pytest.mark.parametrize("vdn,B,pred_weight,max_seq", [(False, 128, 0.0, 80), (True, 64, 0.25, 80), (True, 128, 0.0, 37), (False, 20, 0.25, 51)],
-                         ids=["iql_b128", "vdn_b64_aux", "vdn_b128_short_episodes", "iql_b20_aux"])
-def test_update_matches_the_reference_learner(gpu_or_skip, vdn, B, pred_weight, max_seq):
+@pytest.mark.parametrize("vdn,B,pred_weight,max_seq,P",
+                         [(False, 128, 0.0, 80, 2), (True, 64, 0.25, 80, 2), (True, 128, 0.0, 37, 2), (False, 20, 0.25, 51, 2),
+                          # more than 256 LSTM rows: micro-batches with gradient accumulation (128 + 32 entries; 3 players: 85 + 15)
+                          (True, 160, 0.25, 60, 2), (True, 100, 0.0, 45, 3)],
+                         ids=["iql_b128", "vdn_b64_aux", "vdn_b128_short_episodes", "iql_b20_aux", "vdn_b160_micro_batches", "vdn_3p_b100_micro_batches"])
+def test_update_matches_the_reference_learner(gpu_or_skip, vdn, B, pred_weight, max_seq, P):
     from hanabi_sad_b200.rela import RNNTransition, aggregate_priority
     from hanabi_sad_b200.trainer import PARAM_NAMES, DeviceTrainer
     from profile_learner import synthetic_batch
 
     T, lr, eps, clip = 80, 6.25e-5, 1.5e-5, 5.0
     ag = _ref_agent(vdn)
-    obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, B, 2, 838, 21, 5, vdn, "cpu", seed=3, max_seq=max_seq)
+    obs, action, reward, terminal, bootstrap, seq_len = synthetic_batch(T, B, P, 838, 21, 5, vdn, "cpu", seed=3, max_seq=max_seq)
     weight = torch.rand(B) + 0.5
     dev = torch.device("cuda", 0)
     # the trainer lives on the GPU; the reference agent stays on the CPU
-    tr = DeviceTrainer(838, 21, 5, 2, vdn, 3, 0.999, 0.9, dev, B, T, lr, eps, clip)
+    tr = DeviceTrainer(838, 21, 5, P, vdn, 3, 0.999, 0.9, dev, B, T, lr, eps, clip)
+    assert (tr.micro_batch < B) == (B * (P if vdn else 1) > 256)
     tr.load_state_dict(ag.state_dict())
     mv = lambda d: {k: v.to(dev).contiguous() for k, v in d.items()}
     batch_d = RNNTransition(mv(obs), mv(action), reward.to(dev), terminal.to(dev), bootstrap.to(dev), seq_len.to(dev))
