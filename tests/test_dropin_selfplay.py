@@ -84,3 +84,50 @@ def test_data_parallel_learner_script_single_rank(gpu_or_skip):
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
     d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
     assert d["finite"] and d["replica_weight_drift"] == 0.0 and d["env_steps_total"] > 0
+
+
+ACTION_MATRIX = r"""
+import sys, types
+# the tool imports matplotlib at module level only to draw the figure; the dataset / analysis functions do not use it
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+mpl = _Stub("matplotlib"); plt = _Stub("matplotlib.pyplot")
+mpl.pyplot = plt; sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+sys.path.insert(0, "tools")
+import torch, numpy as np
+import r2d2
+import action_matrix as am
+
+torch.manual_seed(3)
+agent = r2d2.R2D2Agent(False, 3, 0.999, 0.9, "cuda:0", 838, 512, 21, 2, 5, False).to("cuda:0")
+replay, agent2, context = am.create_dataset(agent, True, "cuda:0")
+n = replay.size()
+assert n >= 1000, n
+normed, counts = am.analyze(replay)
+pairs = 0
+for i in range(n):
+    e = replay.get(i)
+    L = int(e.seq_len.item())
+    assert e.action["a"].shape == (80, 2) and 1 <= L <= 80
+    pairs += L - 1
+assert counts.shape == (20, 20) and int(counts.sum()) == pairs, (counts.sum(), pairs)
+rows = counts.sum(1) > 0
+assert np.allclose(normed[rows].sum(1), 1.0)
+print("ACTION_MATRIX episodes %d pairs %d" % (n, pairs))
+context.terminate() if hasattr(context, "terminate") else None
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(PYH, "tools", "action_matrix.py")), reason="oracle/_ref/pyhanabi/tools not generated (oracle/build_ref.sh)")
+def test_reference_action_matrix_tool_runs_on_the_device_replay(gpu_or_skip):
+    """tools/action_matrix.py:31-107: create_dataset -- 100 R2D2Actors in VDN mode filling an RNNPrioritizedReplay,
+    two sample / update_priority rounds -- and analyze(), which walks the replay with `dataset.get(i)`; the reference's own code
+    on this package's `rela` / `hanalearn` modules."""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(ROOT, "hanabi_sad_b200", "compat") + os.pathsep + env.get("PYTHONPATH", "")
+    p = subprocess.run([sys.executable, "-c", ACTION_MATRIX], cwd=PYH, env=env, capture_output=True, text=True, timeout=420)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0, out[-3000:]
+    m = re.search(r"ACTION_MATRIX episodes (\d+) pairs (\d+)", out)
+    assert m and int(m.group(1)) >= 1000 and int(m.group(2)) > 0, out[-2000:]
