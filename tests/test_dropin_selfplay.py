@@ -91,6 +91,8 @@ import sys, types
 # the tool imports matplotlib at module level only to draw the figure; the dataset / analysis functions do not use it
 class _Stub(types.ModuleType):
     def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
         return lambda *a, **k: None
 mpl = _Stub("matplotlib"); plt = _Stub("matplotlib.pyplot")
 mpl.pyplot = plt; sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
