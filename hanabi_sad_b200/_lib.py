@@ -105,6 +105,8 @@ SIGNATURES = {
     "hb_replay_sample": (c_int, [c_void_p, c_int, ctypes.POINTER(HbBatch)]),
     "hb_replay_stats": (c_int, [c_void_p, ctypes.POINTER(HbReplayInfo)]),
     "hb_replay_sample_ex": (c_int, [c_void_p, c_int, ctypes.POINTER(HbBatch), ctypes.POINTER(HbSampleOpts)]),
+    "hb_replay_prefetch": (c_int, [c_void_p, c_int, ctypes.POINTER(HbBatch), ctypes.POINTER(HbSampleOpts)]),
+    "hb_replay_take": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "hb_replay_get": (c_int, [c_void_p, c_i64, ctypes.POINTER(HbBatch)]),
     "hb_replay_update_priority": (c_int, [c_void_p, c_void_p, c_int]),
     "hb_profile": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
@@ -125,6 +127,7 @@ SIGNATURES = {
     "hb_trainer_optim_step": (c_int, [c_void_p, c_void_p]),
     "hb_trainer_sync_target": (c_int, [c_void_p, c_void_p]),
     "hb_trainer_stats": (c_int, [c_void_p, ctypes.POINTER(HbTrainStats)]),
+    "hb_trainer_stats_nowait": (c_int, [c_void_p, ctypes.POINTER(HbTrainStats)]),
     "hb_replay_last_max_len": (c_int, [c_void_p]),
     "hb_stream_wait": (c_int, [c_void_p, c_void_p]),
     "hb_stream_wait_engine": (c_int, [c_void_p, c_void_p]),

@@ -295,14 +295,18 @@ int hb_replay_create(hb_engine* e) {
   HB_RALLOC(Q->prefix, (S * R.NE + 2) * sizeof(double));
   HB_RALLOC(Q->bsum, ((S * R.NE + HB_SCAN_BLOCK - 1) / HB_SCAN_BLOCK + 1) * sizeof(double));
   HB_RALLOC(Q->bcnt, ((S * R.NE + HB_SCAN_BLOCK - 1) / HB_SCAN_BLOCK + 1) * sizeof(int));
-  HB_RALLOC(Q->sampled_idx, (Q->max_batch + 1) * sizeof(int));
-  HB_RALLOC(Q->sampled_seq, Q->max_batch * sizeof(long long));
-  HB_RALLOC(Q->sampled_w, Q->max_batch * sizeof(float));
+  HB_RALLOC(Q->sampled_idx, HB_SAMPLE_SETS * Q->max_batch * sizeof(int));
+  HB_RALLOC(Q->sampled_seq, HB_SAMPLE_SETS * Q->max_batch * sizeof(long long));
+  HB_RALLOC(Q->sampled_w, HB_SAMPLE_SETS * Q->max_batch * sizeof(float));
+  HB_RALLOC(Q->d_entry, sizeof(int));
   HB_RALLOC(Q->d_prio, Q->max_batch * sizeof(float));
   HB_RALLOC(Q->d_targets, Q->max_batch * sizeof(double));
-  HB_RALLOC(Q->d_max_len, sizeof(int));
-  HB_CUDA(cudaMallocHost((void**)&Q->h_max_len, sizeof(int)));
-  *Q->h_max_len = 0;
+  HB_RALLOC(Q->d_max_len, HB_SAMPLE_SETS * sizeof(int));
+  HB_CUDA(cudaMallocHost((void**)&Q->h_max_len, HB_SAMPLE_SETS * sizeof(int)));
+  for (int i = 0; i < HB_SAMPLE_SETS; ++i) {
+    Q->h_max_len[i] = 0;
+    HB_CUDA(cudaEventCreateWithFlags(&Q->set_ev[i], cudaEventDisableTiming));
+  }
   HB_CUDA(cudaMallocHost((void**)&Q->h_counters, (HB_CNT_N + 2) * sizeof(unsigned long long)));
   return 0;
 }
@@ -314,7 +318,8 @@ void hb_replay_destroy(hb_engine* e) {
   cudaFree(R.states); cudaFree(R.a); cudaFree(R.greedy_a); cudaFree(R.reward);
   cudaFree(R.bootstrap); cudaFree(R.seq_len); cudaFree(R.weight); cudaFree(R.commit_seq); cudaFree(R.state); cudaFree(R.game_slot);
   cudaFree(R.sc_reward); cudaFree(R.sc_oq); cudaFree(R.sc_tq); cudaFree(R.counters);
-  cudaFree(Q->prefix); cudaFree(Q->bsum); cudaFree(Q->bcnt); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio); cudaFree(Q->d_targets); cudaFree(Q->d_max_len); cudaFreeHost(Q->h_max_len);
+  cudaFree(Q->prefix); cudaFree(Q->bsum); cudaFree(Q->bcnt); cudaFree(Q->sampled_idx); cudaFree(Q->sampled_seq); cudaFree(Q->sampled_w); cudaFree(Q->d_prio); cudaFree(Q->d_targets); cudaFree(Q->d_max_len); cudaFreeHost(Q->h_max_len); cudaFree(Q->d_entry);
+  for (int i = 0; i < HB_SAMPLE_SETS; ++i) if (Q->set_ev[i]) cudaEventDestroy(Q->set_ev[i]);
   cudaFreeHost(Q->h_counters);
   delete Q;
   e->replay = nullptr;
@@ -381,20 +386,22 @@ int hb_replay_stats(hb_engine* e, hb_replay_info* out) {
   return 0;
 }
 
-int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts) {
-  if (!e || !out) { hb_set_error("hb_replay_sample: null argument"); return -1; }
+// Queue the draw + gather of one batch into the next free id set (no host wait).
+// `fresh_counters` = 0: judge the replay's size by the mirror of the last counter read (it only grows, or stays at capacity)
+// and read it synchronously only if that says "too small" -- a prefetch must not make the host wait for the engine stream.
+static int replay_enqueue(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts, const char* who, bool fresh_counters) {
   HbReplay* Q = e->replay;
-  if (!Q) { hb_set_error("hb_replay_sample: this engine has no replay (replay_capacity = 0)"); return -1; }
-  if (batchsize < 1 || batchsize > Q->max_batch) { hb_set_error("hb_replay_sample: batchsize must be 1..%d", Q->max_batch); return -1; }
-  if (Q->n_sampled != 0) {  // prioritized_replay.h:209-212
-    hb_set_error("hb_replay_sample: previous samples' priority has not been updated");
-    return -3;
-  }
-  int rc = hb_read_counters(e);
+  if (batchsize < 1 || batchsize > Q->max_batch) { hb_set_error("%s: batchsize must be 1..%d", who, Q->max_batch); return -1; }
+  int rc = 0;
+  if (fresh_counters || hb_held_slots(Q) * Q->ring.NE < batchsize) rc = hb_read_counters(e);
   if (rc) return rc;
   const int64_t size = hb_held_slots(Q) * Q->ring.NE;
-  if (size < batchsize) { hb_set_error("hb_replay_sample: replay holds %lld entries, fewer than the batch size %d", (long long)size, batchsize); return -3; }
+  if (size < batchsize) { hb_set_error("%s: replay holds %lld entries, fewer than the batch size %d", who, (long long)size, batchsize); return -3; }
   HbRing& R = Q->ring;
+  const int set = (Q->set_head + Q->set_count) % HB_SAMPLE_SETS;
+  int* s_idx = Q->sampled_idx + (size_t)set * Q->max_batch;
+  long long* s_seq = Q->sampled_seq + (size_t)set * Q->max_batch;
+  float* s_w = Q->sampled_w + (size_t)set * Q->max_batch;
   double* tot = Q->prefix + (size_t)R.phys_slots * R.NE;
   const double* d_targets = nullptr;
   if (opts && opts->targets) {
@@ -406,22 +413,64 @@ int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const 
   const int threads = (batchsize + 31) / 32 * 32;
   hb_k_replay_draw<<<1, threads, 0, e->stream>>>(R, Q->prefix, tot, batchsize, Q->beta, Q->seed, Q->sample_count, d_targets,
                                                  opts ? opts->total_weight : 0.0, opts ? opts->total_size : 0.0, opts ? opts->normalize : 1,
-                                                 Q->sampled_idx, Q->sampled_seq, Q->sampled_w, out->weight, Q->d_max_len);
-  HB_CUDA(cudaMemcpyAsync(Q->h_max_len, Q->d_max_len, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+                                                 s_idx, s_seq, s_w, out->weight, Q->d_max_len + set);
+  HB_CUDA(cudaMemcpyAsync(Q->h_max_len + set, Q->d_max_len + set, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
-  hb_k_replay_gather<<<dim3(batchsize, R.T), 128, 0, e->stream>>>(R, Q->sampled_idx, batchsize, bp, e->env, e->d_eps_list);
+  hb_k_replay_gather<<<dim3(batchsize, R.T), 128, 0, e->stream>>>(R, s_idx, batchsize, bp, e->env, e->d_eps_list);
   HB_CUDA(cudaGetLastError());
-  if (out->ids) HB_CUDA(cudaMemcpyAsync(out->ids, Q->sampled_idx, batchsize * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
-  HB_CUDA(cudaStreamSynchronize(e->stream));  // the batch tensors are consumed on the caller's own stream
+  if (out->ids) HB_CUDA(cudaMemcpyAsync(out->ids, s_idx, batchsize * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+  HB_CUDA(cudaEventRecord(Q->set_ev[set], e->stream));
   e->launches += 2;
   Q->sample_count += 1;
-  Q->n_sampled = batchsize;
+  Q->set_n[set] = batchsize;
+  Q->set_waited[set] = 0;
+  Q->set_count += 1;
   return 0;
+}
+
+int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts) {
+  if (!e || !out) { hb_set_error("hb_replay_sample: null argument"); return -1; }
+  HbReplay* Q = e->replay;
+  if (!Q) { hb_set_error("hb_replay_sample: this engine has no replay (replay_capacity = 0)"); return -1; }
+  if (Q->set_count != 0) {  // prioritized_replay.h:209-212
+    hb_set_error("hb_replay_sample: previous samples' priority has not been updated");
+    return -3;
+  }
+  HB_CUDA(cudaSetDevice(e->device));
+  int rc = replay_enqueue(e, batchsize, out, opts, "hb_replay_sample", true);
+  if (rc) return rc;
+  return hb_replay_take(e, nullptr);   // the batch tensors are consumed on the caller's own stream
 }
 
 int hb_replay_sample(hb_engine* e, int batchsize, const hb_batch* out) { return hb_replay_sample_ex(e, batchsize, out, nullptr); }
 
-int hb_replay_last_max_len(hb_engine* e) { return (e && e->replay) ? *e->replay->h_max_len : -1; }
+int hb_replay_prefetch(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts) {
+  if (!e || !out) { hb_set_error("hb_replay_prefetch: null argument"); return -1; }
+  HbReplay* Q = e->replay;
+  if (!Q) { hb_set_error("hb_replay_prefetch: this engine has no replay (replay_capacity = 0)"); return -1; }
+  if (Q->set_count >= HB_SAMPLE_SETS) { hb_set_error("hb_replay_prefetch: %d batches are outstanding already (update their priorities first)", Q->set_count); return -3; }
+  HB_CUDA(cudaSetDevice(e->device));
+  return replay_enqueue(e, batchsize, out, opts, "hb_replay_prefetch", false);
+}
+
+int hb_replay_take(hb_engine* e, int* batchsize) {
+  if (!e || !e->replay) { hb_set_error("hb_replay_take: no replay"); return -1; }
+  HbReplay* Q = e->replay;
+  if (Q->set_count == 0) { hb_set_error("hb_replay_take: no batch is outstanding (hb_replay_prefetch)"); return -3; }
+  HB_CUDA(cudaSetDevice(e->device));
+  const int set = Q->set_head;
+  if (!Q->set_waited[set]) { HB_CUDA(cudaEventSynchronize(Q->set_ev[set])); Q->set_waited[set] = 1; }
+  if (batchsize) *batchsize = Q->set_n[set];
+  return 0;
+}
+
+int hb_replay_last_max_len(hb_engine* e) {
+  if (!e || !e->replay) return -1;
+  HbReplay* Q = e->replay;
+  // the oldest outstanding batch = the one being trained on; none outstanding: the last one taken
+  const int set = Q->set_count ? Q->set_head : (Q->set_head + HB_SAMPLE_SETS - 1) % HB_SAMPLE_SETS;
+  return Q->h_max_len[set];
+}
 
 int hb_stream_wait(hb_engine* e, void* stream) {
   if (!e) { hb_set_error("hb_stream_wait: null engine"); return -1; }
@@ -453,7 +502,7 @@ int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out) {
   if (rc) return rc;
   if (idx < 0 || idx >= size) { hb_set_error("hb_replay_get: index %lld out of range, the replay holds %lld entries", (long long)idx, (long long)size); return -3; }
   HbRing& R = Q->ring;
-  int* d_entry = Q->sampled_idx + Q->max_batch;  // one spare element behind the sampling scratch
+  int* d_entry = Q->d_entry;
   HB_CUDA(cudaMemsetAsync(d_entry, 0xFF, sizeof(int), e->stream));
   hb_k_replay_find<<<(R.phys_slots + 255) / 256, 256, 0, e->stream>>>(R, (long long)idx, d_entry);
   HbBatchPtrs bp = {out->priv_s, out->legal_move, out->own_hand, out->eps, out->a, out->greedy_a, out->reward, out->bootstrap, out->terminal, out->seq_len};
@@ -472,20 +521,24 @@ int hb_replay_update_priority(hb_engine* e, const float* priority, int n) {
   if (!e) { hb_set_error("hb_replay_update_priority: null engine"); return -1; }
   HbReplay* Q = e->replay;
   if (!Q) { hb_set_error("hb_replay_update_priority: this engine has no replay"); return -1; }
-  if (n == 0) { Q->n_sampled = 0; return 0; }  // prioritized_replay.h:243-246
-  if (!priority || n != Q->n_sampled) { hb_set_error("hb_replay_update_priority: expected %d priorities, got %d", Q->n_sampled, n); return -1; }
+  const int set = Q->set_head;
+  auto pop = [&]() { Q->set_head = (Q->set_head + 1) % HB_SAMPLE_SETS; Q->set_count -= 1; };
+  if (n == 0) { if (Q->set_count) pop(); return 0; }  // prioritized_replay.h:243-246: forget the (oldest) outstanding sample
+  const int want = Q->set_count ? Q->set_n[set] : 0;
+  if (!priority || n != want) { hb_set_error("hb_replay_update_priority: expected %d priorities, got %d", want, n); return -1; }
   HB_CUDA(cudaSetDevice(e->device));
   cudaPointerAttributes pa;
   const bool on_device = cudaPointerGetAttributes(&pa, priority) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
   (void)cudaGetLastError();
   HB_CUDA(cudaMemcpyAsync(Q->d_prio, priority, n * sizeof(float), cudaMemcpyDefault, e->stream));
-  hb_k_replay_update<<<(n + 127) / 128, 128, 0, e->stream>>>(Q->ring, Q->sampled_idx, Q->sampled_seq, Q->d_prio, n);
+  hb_k_replay_update<<<(n + 127) / 128, 128, 0, e->stream>>>(Q->ring, Q->sampled_idx + (size_t)set * Q->max_batch, Q->sampled_seq + (size_t)set * Q->max_batch,
+                                                           Q->d_prio, n);
   HB_CUDA(cudaGetLastError());
   // host memory may be released by the caller as soon as this returns; device memory is stream-ordered (the caller keeps it
   // valid until the engine stream has passed this point, see hb_stream_wait), so a learner loop never blocks here
   if (!on_device) HB_CUDA(cudaStreamSynchronize(e->stream));
   e->launches += 1;
-  Q->n_sampled = 0;
+  pop();
   return 0;
 }
 

@@ -42,6 +42,8 @@ struct HbRing {                 // device pointers + geometry, passed by value t
   unsigned long long* counters; // [HB_CNT_N]
 };
 
+#define HB_SAMPLE_SETS 4   // the reference's default prefetch (3) + the batch being trained on
+
 struct HbReplay {
   HbRing ring;
   int capacity;                 // entries
@@ -52,13 +54,20 @@ struct HbReplay {
   double* prefix;               // [phys*NE]
   double* bsum;                 // [blocks] per-block weight sums, then (in place) their exclusive scan
   int* bcnt;                    // [blocks] per-block sampleable counts
-  int* sampled_idx;             // [max_batch] entry index = slot*NE + e
-  long long* sampled_seq;       // [max_batch] commit_seq at sampling time (evicted-since check, prioritized_replay.h:106-120)
-  float* sampled_w;             // [max_batch]
+  // Outstanding samples, oldest first (a FIFO of HB_SAMPLE_SETS id sets): one for hb_replay_sample, several when batches are
+  // drawn ahead of their use (hb_replay_prefetch = the reference's `prefetch` futures, prioritized_replay.h:219-240).
+  // hb_replay_update_priority always applies to the oldest.
+  int* sampled_idx;             // [SETS][max_batch] entry index = slot*NE + e
+  long long* sampled_seq;       // [SETS][max_batch] commit_seq at sampling time (evicted-since check, prioritized_replay.h:106-120)
+  float* sampled_w;             // [SETS][max_batch]
+  int* d_entry;                 // scratch of hb_replay_get
   float* d_prio;                // [max_batch] staging for update_priority
   double* d_targets;            // [max_batch] caller-supplied draw positions (hb_replay_sample_ex)
-  int *d_max_len, *h_max_len;   // longest episode of the last sampled batch (device, pinned mirror)
-  int n_sampled;
+  int *d_max_len, *h_max_len;   // [SETS] longest episode of each outstanding batch (device, pinned mirror)
+  cudaEvent_t set_ev[HB_SAMPLE_SETS];   // recorded behind the set's gather kernel
+  int set_n[HB_SAMPLE_SETS];    // batch size of the set
+  int set_waited[HB_SAMPLE_SETS];
+  int set_head, set_count;
   int max_batch;
   unsigned long long* h_counters;  // pinned mirror
 };

@@ -302,6 +302,7 @@ struct hb_trainer {
   float* h_stats;                     // pinned [8]
   cudaEvent_t ev_stats;
   int stats_pending;
+  hb_train_stats last;                // statistics of the most recent update known to be complete (hb_trainer_stats_nowait)
   int64_t step;                       // Adam step count
   int last_use_pred;
   int64_t launches;
@@ -501,7 +502,28 @@ int hb_trainer_stats(hb_trainer* tr, hb_train_stats* out) {
   if (tr->stats_pending) { HB_CUDA(cudaEventSynchronize(tr->ev_stats)); tr->stats_pending = 0; }
   out->loss = tr->h_stats[0]; out->rl_loss = tr->h_stats[1]; out->aux_xent = tr->h_stats[2]; out->grad_norm = sqrtf(tr->h_stats[3]);
   out->num_update = tr->step; out->launches = tr->launches + hb_lstm_launches(tr->lstm);
+  tr->last = *out;
   return hb_lstm_sync(tr->lstm);   // also reports a spin-guard failure of the recurrence kernels
+}
+
+// The same without waiting: statistics of the most recent update that HAS completed (out->num_update says which; 0 = none
+// yet).  A training loop that logs every iteration stays asynchronous with this (the values lag by an update or two).
+int hb_trainer_stats_nowait(hb_trainer* tr, hb_train_stats* out) {
+  if (!tr || !out) { hb_set_error("hb_trainer_stats_nowait: null argument"); return -1; }
+  HB_CUDA(cudaSetDevice(tr->device));
+  if (tr->stats_pending) {
+    const cudaError_t q = cudaEventQuery(tr->ev_stats);
+    if (q == cudaSuccess) {
+      tr->stats_pending = 0;
+      tr->last.loss = tr->h_stats[0]; tr->last.rl_loss = tr->h_stats[1]; tr->last.aux_xent = tr->h_stats[2]; tr->last.grad_norm = sqrtf(tr->h_stats[3]);
+      tr->last.num_update = tr->step;
+    } else if (q != cudaErrorNotReady) {
+      HB_CUDA(q);
+    }
+  }
+  *out = tr->last;
+  out->launches = tr->launches + hb_lstm_launches(tr->lstm);
+  return 0;
 }
 
 // R2D2Agent.sync_target_with_online (r2d2.py:208-210)

@@ -230,9 +230,7 @@ class Engine:
         check(lib().hb_replay_stats(self._h, ctypes.byref(info)))
         return {k: getattr(info, k) for k, _ in HbReplayInfo._fields_}
 
-    def sample(self, batchsize, device=None, targets=None, total_weight=0.0, total_size=0.0, normalize=True):
-        """PrioritizedReplay::sample: torch tensors on the engine's GPU in the learner's layout + importance weights.
-        targets / total_weight / total_size / normalize: hb_replay_sample_ex (a replay sharded over engines or ranks)."""
+    def _alloc_batch(self, batchsize):
         import torch
 
         dev = torch.device("cuda", self.cfg.device)
@@ -250,16 +248,76 @@ class Engine:
         hb = HbBatch()
         for k, v in t.items():
             setattr(hb, k, v.data_ptr())
-        torch.cuda.current_stream(dev).synchronize()  # the allocator may hand back memory still in use on torch's stream
+        return dev, t, hb
+
+    @staticmethod
+    def _sample_opts(B, targets, total_weight, total_size, normalize):
         if targets is None and total_weight <= 0 and total_size <= 0 and normalize:
+            return None, None
+        opts = HbSampleOpts()
+        tg = None if targets is None else np.ascontiguousarray(targets, dtype=np.float64)
+        assert tg is None or tg.shape == (B,)
+        opts.targets = None if tg is None else tg.ctypes.data
+        opts.total_weight, opts.total_size, opts.normalize = float(total_weight), float(total_size), int(bool(normalize))
+        return opts, tg
+
+    def sample(self, batchsize, device=None, targets=None, total_weight=0.0, total_size=0.0, normalize=True):
+        """PrioritizedReplay::sample: torch tensors on the engine's GPU in the learner's layout + importance weights.
+        targets / total_weight / total_size / normalize: hb_replay_sample_ex (a replay sharded over engines or ranks)."""
+        import torch
+
+        B = int(batchsize)
+        dev, t, hb = self._alloc_batch(B)
+        torch.cuda.current_stream(dev).synchronize()  # the allocator may hand back memory still in use on torch's stream
+        opts, _tg = self._sample_opts(B, targets, total_weight, total_size, normalize)
+        if opts is None:
             check(lib().hb_replay_sample(self._h, B, ctypes.byref(hb)))
         else:
-            opts = HbSampleOpts()
-            tg = None if targets is None else np.ascontiguousarray(targets, dtype=np.float64)
-            assert tg is None or tg.shape == (B,)
-            opts.targets = None if tg is None else tg.ctypes.data
-            opts.total_weight, opts.total_size, opts.normalize = float(total_weight), float(total_size), int(bool(normalize))
             check(lib().hb_replay_sample_ex(self._h, B, ctypes.byref(hb), ctypes.byref(opts)))
+        t["terminal"] = t["terminal"].bool()
+        return t
+
+    def prefetch(self, batchsize, targets=None, total_weight=0.0, total_size=0.0, normalize=True):
+        """Queue the draw of one more batch on the engine stream and return at once (hb_replay_prefetch: the reference's
+        prefetch futures, prioritized_replay.h:219-240).  `take()` hands the batches out oldest first."""
+        import torch
+
+        B = int(batchsize)
+        # The batch is written on the ENGINE's stream.  Its tensors come from the allocator pool of a side stream on which no
+        # kernel ever runs: a block of that pool was last written by an earlier gather (complete: its batch was taken) and read
+        # on the learner's stream, which take() registers with record_stream -- so the allocator hands it out again only after
+        # those reads, and the engine stream need not wait for the learner's queued work (nor the host, unlike sample()).
+        dev = torch.device("cuda", self.cfg.device)
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._side_stream):
+            dev, t, hb = self._alloc_batch(B)
+        opts, _tg = self._sample_opts(B, targets, total_weight, total_size, normalize)
+        check(lib().hb_replay_prefetch(self._h, B, ctypes.byref(hb), None if opts is None else ctypes.byref(opts)))
+        if not hasattr(self, "_prefetched"):
+            self._prefetched = []
+        self._prefetched.append((t, _tg))
+
+    def n_prefetched(self):
+        return len(getattr(self, "_prefetched", ()))
+
+    def drop_prefetched(self):
+        """Forget every batch drawn ahead and not handed out yet (their priorities are left as they are)."""
+        while self.n_prefetched():
+            self.take()
+            self.update_priority(np.zeros((0,), np.float32))
+
+    def take(self):
+        """The oldest prefetched batch, complete (waits for its gather if it is still running).  Its priorities are the next
+        ones update_priority expects."""
+        assert self.n_prefetched() > 0, "take() without a prefetch()"
+        import torch
+
+        check(lib().hb_replay_take(self._h, None))
+        t, _ = self._prefetched.pop(0)
+        cur = torch.cuda.current_stream(torch.device("cuda", self.cfg.device))
+        for v in t.values():
+            v.record_stream(cur)
         t["terminal"] = t["terminal"].bool()
         return t
 

@@ -129,8 +129,10 @@ class FFTransition:
 class RNNPrioritizedReplay:
     """rela.RNNPrioritizedReplay(capacity, seed, alpha, beta, prefetch) (rela/prioritized_replay.h:176-265).  The storage is
     the device ring of the engine(s) created by Context.start() -- with several act devices each engine holds a shard of
-    capacity // n_engines entries; `prefetch` is accepted and ignored (sampling is a device kernel, there is nothing to overlap
-    with host threads)."""
+    capacity // n_engines entries.  `prefetch` > 0 (selfplay.py --prefetch, default 3) works like the reference's futures
+    (prioritized_replay.h:219-240): sample() hands out a batch that was DRAWN EARLIER and queues the draws of the next ones on
+    the engine's stream, where they run while the learner trains -- the learner never waits for the sampler (single act
+    device; a sharded replay draws synchronously)."""
 
     def __init__(self, capacity, seed, alpha, beta, prefetch=0):
         self.capacity, self.seed, self.alpha, self.beta, self.prefetch = int(capacity), int(seed), float(alpha), float(beta), int(prefetch)
@@ -197,7 +199,15 @@ class RNNPrioritizedReplay:
         if len(self._engines) == 1:
             e, lk = self._engines[0]
             with lk:
-                parts = [e.sample(batchsize)]
+                if self.prefetch > 0 and hasattr(e, "prefetch"):
+                    if e.n_prefetched() == 0:
+                        e.prefetch(batchsize)
+                    parts = [e.take()]
+                    batchsize = int(parts[0]["seq_len"].numel())   # a batch drawn before a change of batchsize keeps its size
+                    while e.n_prefetched() < min(self.prefetch, 3):
+                        e.prefetch(batchsize)
+                else:
+                    parts = [e.sample(batchsize)]
             self._last.append((e, lk, batchsize))
         else:
             parts = self._sample_shards(batchsize)

@@ -234,9 +234,11 @@ class DeviceTrainer:
         self.optim_step()
         return prio
 
-    def stats(self):
+    def stats(self, wait=True):
+        """Statistics of the last update (waits for it); wait=False: of the most recent update that has completed, without
+        stalling the host (`num_update` tells which) -- what a loop that logs every iteration should use."""
         s = HbTrainStats()
-        check(lib().hb_trainer_stats(self._h, ctypes.byref(s)))
+        check((lib().hb_trainer_stats if wait else lib().hb_trainer_stats_nowait)(self._h, ctypes.byref(s)))
         return {"loss": s.loss, "rl_loss": s.rl_loss, "aux1": s.aux_xent, "grad_norm": s.grad_norm, "num_update": s.num_update, "launches": s.launches}
 
     # ---- engine plumbing ---------------------------------------------------------------------------------------
@@ -246,10 +248,18 @@ class DeviceTrainer:
         engine.set_weights(0, self._views[0])
         engine.set_weights(1, self._views[1])
 
-    def train_step(self, engine, batchsize, pred_weight=0.0, full_length=False):
+    def train_step(self, engine, batchsize, pred_weight=0.0, full_length=False, prefetch=False):
         """selfplay.py:218-241 against one device engine: sample -> update -> update_priority.  The only host wait is the one
-        inside the sampler (the batch is produced on the engine's stream)."""
-        b = engine.sample(batchsize)
+        inside the sampler (the batch is produced on the engine's stream); with `prefetch` the batch was drawn during the
+        PREVIOUS step (the reference's --prefetch, prioritized_replay.h:219-240: its draw does not see the priorities of the
+        batch before it) and the draw of the next one is queued before this update, so that wait is normally over already."""
+        if prefetch:
+            if engine.n_prefetched() == 0:
+                engine.prefetch(batchsize)
+            b = engine.take()
+            engine.prefetch(batchsize)
+        else:
+            b = engine.sample(batchsize)
         t_eff = self.seq_len if full_length else lib().hb_replay_last_max_len(engine.handle)
         prio = self.update(b, b["weight"], pred_weight, t_eff=t_eff)
         check(lib().hb_stream_wait(engine.handle, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
@@ -278,7 +288,8 @@ def bench_update(device=0, world=1, dist=None, seconds=3.0, batchsize=128, games
     tr.push_weights(eng)
     eng.rollout(fill_ticks)
     eng.sync()
-    out = {"method": "vdn", "batchsize": batchsize, "lstm_rows": batchsize * 2, "seq_len": 80, "replay_entries": eng.counters()[0]}
+    out = {"method": "vdn", "batchsize": batchsize, "lstm_rows": batchsize * 2, "seq_len": 80, "replay_entries": eng.counters()[0],
+           "sampler": "prefetch: batch k + 1 is drawn on the engine stream while update k runs (selfplay.py --prefetch)"}
     n_par = tr.total
     for tag, full in (("t80", True), ("skip_padding", False)):
         for _ in range(3):
@@ -292,7 +303,10 @@ def bench_update(device=0, world=1, dist=None, seconds=3.0, batchsize=128, games
         t_start = time.perf_counter()
         e0.record()
         while time.perf_counter() - t_start < seconds / 2:
-            b = eng.sample(batchsize)
+            if eng.n_prefetched() == 0:       # the reference's --prefetch: the batch was drawn while the previous update ran
+                eng.prefetch(batchsize)
+            b = eng.take()
+            eng.prefetch(batchsize)
             te = 80 if full else lib().hb_replay_last_max_len(eng.handle)
             prio = tr.backward(b, b["weight"], 0.0, t_eff=te)
             if dist is not None:
@@ -311,6 +325,7 @@ def bench_update(device=0, world=1, dist=None, seconds=3.0, batchsize=128, games
             teff += te
         e1.record()
         torch.cuda.synchronize()
+        eng.drop_prefetched()
         ms = e0.elapsed_time(e1) / n
         out[tag] = {"ms_per_update": ms, "updates_per_s": 1e3 / ms, "mean_t_eff": teff / n, "updates_timed": n,
                     "launches_per_update": (tr.stats()["launches"] - l0) / n + 3}

@@ -239,6 +239,15 @@ typedef struct hb_sample_opts {
 } hb_sample_opts;
 int hb_replay_sample_ex(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts);
 
+/* The reference's `prefetch` (PrioritizedReplay::sample with futures_, rela/prioritized_replay.h:219-240): draw batches AHEAD of
+ * their use.  hb_replay_prefetch queues draw + gather of one more batch on the engine stream and returns at once (up to 4
+ * batches outstanding, the reference's default prefetch 3 + the one being trained on; -3 beyond); the outstanding batches form a
+ * FIFO.  hb_replay_take waits until the OLDEST outstanding batch is complete in `out` of its prefetch call (*batchsize, may be
+ * NULL, receives its size); hb_replay_update_priority and hb_replay_last_max_len refer to that oldest batch, and
+ * update_priority removes it from the FIFO.  hb_replay_sample(_ex) = prefetch + take with nothing else outstanding. */
+int hb_replay_prefetch(hb_engine* e, int batchsize, const hb_batch* out, const hb_sample_opts* opts /* may be NULL */);
+int hb_replay_take(hb_engine* e, int* batchsize);
+
 /* PrioritizedReplay::get (rela/prioritized_replay.h:259-261 -> ConcurrentQueue::get, :125-128; used by
  * pyhanabi/tools/action_matrix.py:90-107): the idx-th OLDEST entry still held (0 <= idx < size), written UNBATCHED into
  * `out` (device pointers; layouts of hb_batch with B = 1, i.e. priv_s [T,(P,)F], ..., reward [T], seq_len [1]).
@@ -247,7 +256,7 @@ int hb_replay_get(hb_engine* e, int64_t idx, const hb_batch* out);
 
 /* PrioritizedReplay::updatePriority (rela/prioritized_replay.h:242-257): `priority` float [n], host or device.  Host memory:
  * synchronous.  Device memory: queued on the engine stream -- the buffer must stay valid (and be complete: hb_stream_wait)
- * until that stream has consumed it. */
+ * until that stream has consumed it.  Applies to the OLDEST outstanding batch; n = 0 forgets it (:243-246). */
 int hb_replay_update_priority(hb_engine* e, const float* priority, int n);
 
 /* Measurement hook: device time per kernel class of the fused tick (CUDA events on the engine stream).  Returns the
@@ -347,8 +356,11 @@ int hb_trainer_backward_ex(hb_trainer* t, const hb_batch* batch, int batchsize, 
 int hb_trainer_optim_step(hb_trainer* t, void* stream);
 int hb_trainer_sync_target(hb_trainer* t, void* stream);      /* R2D2Agent.sync_target_with_online (r2d2.py:208-210) */
 int hb_trainer_stats(hb_trainer* t, hb_train_stats* out);     /* waits for the last update */
+/* Without waiting: statistics of the most recent update that has COMPLETED (out->num_update tells which, 0 = none yet). */
+int hb_trainer_stats_nowait(hb_trainer* t, hb_train_stats* out);
 
-/* Longest episode (steps) among the entries of the last hb_replay_sample* of this engine: the t_eff of hb_trainer_backward. */
+/* Longest episode (steps) among the entries of the oldest outstanding batch of this engine (hb_replay_sample*: the last one;
+ * complete after hb_replay_take): the t_eff of hb_trainer_backward. */
 int hb_replay_last_max_len(hb_engine* e);
 /* Make the engine's stream wait for everything queued so far on `stream` (and the other way round): lets a learner on its own
  * stream hand priorities to hb_replay_update_priority, or consume a sampled batch, without a host synchronisation. */

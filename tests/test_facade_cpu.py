@@ -28,6 +28,7 @@ class FakeEngine:
         self.entry_w = None                   # per-entry priority^alpha of the fake ring (set by the sharded-sampling test)
         self.beta = kw.get("beta", 0.4)
         self.last_idx = None
+        self.fifo, self.fifo_taken, self.take_log, self.updated_serials, self.drawn = [], [], [], [], 0
         FakeEngine.instances.append(self)
 
     def rollout(self, n):
@@ -54,6 +55,9 @@ class FakeEngine:
     def sample(self, b, targets=None, total_weight=0.0, total_size=0.0, normalize=True):
         assert self.sampled == self.updated
         self.sampled += 1
+        return self._draw(b, targets, total_weight, total_size, normalize)
+
+    def _draw(self, b, targets=None, total_weight=0.0, total_size=0.0, normalize=True):
         T, pp = self.kw["seq_len"], ((self.P,) if self.kw["vdn"] else ())
         if self.kw.get("replay_block"):       # "pop storage if full" after the draw (prioritized_replay.h:326-332)
             size = self.counters()[0]
@@ -74,6 +78,26 @@ class FakeEngine:
 
     def update_priority(self, p):
         self.updated += 1
+        if self.fifo_taken:                   # hb_replay_update_priority applies to the OLDEST outstanding batch
+            self.updated_serials.append(self.fifo_taken.pop(0))
+
+    # the prefetch FIFO of the device replay (hb_replay_prefetch / hb_replay_take): every batch carries a serial number in
+    # seq_len so that the test can tell WHEN it was drawn
+    def prefetch(self, b, **kw):
+        assert len(self.fifo) + len(self.fifo_taken) < 4, "the device replay holds four outstanding batches"
+        t = self._draw(b, **kw)
+        self.drawn += 1
+        t["seq_len"] = torch.full((b,), float(self.drawn))
+        self.fifo.append((t, self.ticks))
+
+    def n_prefetched(self):
+        return len(self.fifo)
+
+    def take(self):
+        t, drawn_at_tick = self.fifo.pop(0)
+        self.fifo_taken.append(int(t["seq_len"][0]))
+        self.take_log.append((int(t["seq_len"][0]), drawn_at_tick, self.ticks))
+        return t
 
     # eval primitives
     def reset(self):
@@ -284,6 +308,47 @@ def test_block_append_back_pressure(ref_modules):
         time.sleep(0.005)
     assert replay.num_add() >= held + 10
     context.terminate()
+
+
+def test_prefetch_hands_out_batches_drawn_earlier(ref_modules):
+    """RNNPrioritizedReplay(..., prefetch = 3) (prioritized_replay.h:219-240): the first sample() draws synchronously and queues
+    three more draws; every later sample() returns the OLDEST queued batch -- drawn during an earlier call -- and tops the queue
+    up again; update_priority goes to the batch that was handed out, in order; without its update the next sample() is refused
+    (:209-212).  prefetch = 0 draws at call time."""
+    create, ref_eval, r2d2, rela = ref_modules
+    for prefetch in (3, 0):
+        FakeEngine.instances.clear()
+        games = create.create_envs(4, 1, 2, 5, 0, [0.1], 80, True, False, False)
+        agent = r2d2.R2D2Agent(True, 3, 0.999, 0.9, "cpu", 838, 512, 21, 2, 5, False)
+        replay = rela.RNNPrioritizedReplay(64, 1, 0.9, 0.6, prefetch)
+        ag = create.ActGroup("vdn", "cpu", agent, 2, 2, 3, 0.999, 0.9, 80, 2, replay)
+        context, threads = create.create_threads(2, 2, ag.actors, games)
+        ag.start()
+        context.start()
+        eng = FakeEngine.instances[0]
+        t0 = time.time()
+        while replay.size() < 16:
+            assert time.time() - t0 < 20
+            time.sleep(0.005)
+        serials = []
+        for it in range(6):
+            batch, w = replay.sample(8, "cpu")
+            assert batch.seq_len.shape == (8,) and w.shape == (8,)
+            if prefetch:
+                serials.append(int(batch.seq_len[0]))
+                assert eng.n_prefetched() == 3
+            with pytest.raises(RuntimeError, match="priority has not been updated"):
+                replay.sample(8, "cpu")
+            replay.update_priority(torch.ones(8))
+            time.sleep(0.02)
+        if prefetch:
+            assert serials == [1, 2, 3, 4, 5, 6] and eng.updated_serials == serials
+            # batch k (k >= 2) was drawn while the learner still held an earlier batch: its draw precedes its hand-out
+            assert all(drawn < taken for serial, drawn, taken in eng.take_log[1:]), eng.take_log
+            assert eng.drawn == 6 + 3
+        else:
+            assert eng.drawn == 0 and eng.sampled == 6 == eng.updated
+        context.terminate()
 
 
 def test_sharded_replay_importance_weights_over_the_union(ref_modules, monkeypatch):

@@ -164,6 +164,60 @@ def test_priority_update_changes_the_sampling_distribution(hb):
     eng.close()
 
 
+def test_prefetched_batches_form_a_fifo(hb):
+    """hb_replay_prefetch / hb_replay_take (the reference's prefetch futures, prioritized_replay.h:219-240): up to four batches
+    outstanding, handed out oldest first; hb_replay_update_priority and hb_replay_last_max_len refer to the oldest, and each
+    update lands on ITS batch's entries."""
+    from hanabi_sad_b200._lib import lib
+
+    G = 32
+    eng = hb.Engine(G, 2, 5, 0, 80, True, False, [0.5], seed=5, replay_capacity=512, alpha=1.0, beta=0.5, priority_mode=1)
+    eng.set_weights(0, random_state_dict(eng.F, 512, eng.A, 1))
+    eng.set_weights(1, random_state_dict(eng.F, 512, eng.A, 2))
+    eng.rollout(160)
+    assert eng.counters()[0] >= 128
+    with pytest.raises(AssertionError):
+        eng.take()
+    for b in (16, 24, 32, 8):
+        eng.prefetch(b)
+    with pytest.raises(RuntimeError, match="outstanding"):
+        eng.prefetch(8)                                   # four outstanding: the fifth is refused
+    with pytest.raises(RuntimeError, match="has not been updated"):
+        eng.sample(8)                                     # prioritized_replay.h:209-212
+    first = eng.take()
+    assert first["seq_len"].numel() == 16 and lib().hb_replay_last_max_len(eng.handle) == int(first["seq_len"].max())
+    with pytest.raises(RuntimeError, match="expected 16"):
+        eng.update_priority(np.ones(24, np.float32))      # the oldest batch has 16 entries
+    eng.update_priority(np.full(16, 1e5, np.float32))     # batch 1: very heavy
+    second = eng.take()
+    assert second["seq_len"].numel() == 24 and lib().hb_replay_last_max_len(eng.handle) == int(second["seq_len"].max())
+    eng.update_priority(np.full(24, 1e-5, np.float32))    # batch 2: (almost) never again
+    third = eng.take()
+    assert third["seq_len"].numel() == 32
+    eng.update_priority(np.zeros(0, np.float32))          # forget batch 3 (:243-246)
+    fourth = eng.take()
+    assert fourth["seq_len"].numel() == 8
+    # every batch is internally consistent: legal moves one-hot-ish and the padding rule, like any sampled batch
+    for t in (first, second, third, fourth):
+        L = t["seq_len"].cpu().numpy().astype(int)
+        term = t["terminal"].cpu().numpy()
+        for j, l in enumerate(L):
+            assert term[l - 1:, j].all() and not term[:l - 1, j].any()
+    ids1, ids2 = set(first["ids"].cpu().numpy().tolist()), set(second["ids"].cpu().numpy().tolist())
+    eng.update_priority(np.ones(8, np.float32))
+    heavy, light = ids1 - ids2, ids2 - ids1
+    hits = n = 0
+    for _ in range(6):
+        b = eng.sample(32)
+        ids = b["ids"].cpu().numpy()
+        hits += int(np.isin(ids, list(heavy)).sum())
+        n += len(ids)
+        assert not np.isin(ids, list(light)).any()
+        eng.update_priority(np.where(np.isin(ids, list(heavy)), 1e5, 1.0).astype(np.float32))
+    assert hits / n > 0.9
+    eng.close()
+
+
 def test_ring_evicts_oldest_and_respects_capacity(hb):
     G = 64
     eng = hb.Engine(G, 2, 5, 0, 80, True, False, [1.0], seed=5, replay_capacity=100, priority_mode=1)  # eps=1: random play, short games

@@ -193,6 +193,21 @@ def test_train_step_against_a_device_replay(gpu_or_skip):
         losses.append(tr.stats()["rl_loss"])
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5]), losses
     assert eng.replay_stats()["weight_sum"] != w0
+    # the same loop with batches drawn one step ahead (selfplay.py --prefetch) and statistics read without waiting
+    seen = []
+    for it in range(20):
+        t_eff = tr.train_step(eng, B, prefetch=True)
+        assert 1 <= t_eff <= 80
+        st = tr.stats(wait=False)
+        assert st["num_update"] <= 30 + it + 1
+        seen.append(st["num_update"])
+    assert eng.n_prefetched() == 1
+    assert tr.stats()["num_update"] == 50 and tr.stats(wait=False)["num_update"] == 50 and seen == sorted(seen)
+    assert np.isfinite(tr.stats()["rl_loss"]) and tr.stats()["rl_loss"] < np.mean(losses[:5])
+    eng.drop_prefetched()
+    assert eng.n_prefetched() == 0
+    eng.sample(B)                                         # nothing is outstanding any more
+    eng.update_priority(np.ones(B, np.float32))
     before = eng.policy_get()["adv"].copy()
     tr.push_weights(eng)
     eng.rollout(1)
