@@ -144,7 +144,8 @@ def lib():
     """Load (building first if the sources are newer) libhanabi_b200.so; raises if that is impossible."""
     global _lib
     if _lib is None:
-        path = _build.build()
+        # HB_LIB: measure another build of the SAME ABI side by side (A/B runs on one GPU box); never a fallback
+        path = os.environ.get("HB_LIB") or _build.build()
         L = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)

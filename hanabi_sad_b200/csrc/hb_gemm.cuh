@@ -29,7 +29,7 @@ constexpr int A_TILE = BM * BK * 2;                  // 16 KB
 constexpr int B_TILE = BN * BK * 2;                  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE; // hi+lo of both operands: 96 KB
 constexpr int HEAD_MAX_OUT = 56;                     // advantage head rows + the value head, padded to a multiple of 8
-constexpr int HEAD_SMEM = HEAD_MAX_OUT * 64 * 4;     // one n-tile's slice of the head weights: [out][64 units] fp32
+constexpr int HEAD_SMEM = HEAD_MAX_OUT * 64 * 4;     // one n-tile's slice of the head weights: [64 units][out padded to 8] fp32
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + HEAD_SMEM;
 constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TMEM_COLS = 256;
@@ -59,8 +59,9 @@ struct __align__(64) Params {
   float* c_out;
   float* h_f32;
   // EPI_LSTM, top layer only (null otherwise): the dueling head fused into the epilogue.  head_w = fc_a / fc_v weights
-  // re-tiled as [n_tile][head_out][64 units] fp32 (head_out = A + 1, last row = fc_v); every epilogue thread multiplies
-  // its row's 64 fresh h' values with the tile's slice and writes head_part[n_tile][row][head_out] -- the act kernel
+  // re-tiled as [n_tile][64 units][hop] fp32 (head_out = A + 1, last = fc_v; hop = head_out rounded up to 8, zero padded);
+  // every epilogue thread multiplies
+  // its row's 64 fresh h' values with the tile's slice and writes head_part[n_tile][row][hop] -- the act kernel
   // adds the 8 partial sums.  Keeps h' out of HBM and removes a 512-deep reduction kernel.
   const float* head_w;
   float* head_part;
@@ -224,8 +225,41 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+// LSTM activations on the two MUFU approximations (ex2, rcp; both within 2 ulp).  Written with the bare instructions:
+// __expf / __fdividef wrap them in range extensions for denormal results and for |divisor| > 2^126 (a compare and two
+// predicated multiplies each, 8.4 instructions per activation against 4-5 here), neither of which can matter -- 1 + e^x
+// is never below 1, and a flushed e^x below 2^-126 changes nothing next to that 1.  In the normal range the values are
+// bit-identical to the intrinsics' (same ex2 argument rounding: 2x is exact; 1 - 2r rounds once either way).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_f(float x) { return fmaf(-2.f, rcp_ftz(1.f + ex2_ftz(2.8853900817779268f * x)), 1.f); }
+
+// acc[j] += h[u] * w[u][j] for 2 * NP outputs j, u = 0..63: the fused dueling head of the top LSTM layer's epilogue.
+// w: shared memory, [64][ld] floats (16-byte aligned rows); out: this row's slice of head_part, 16-byte aligned (rows of
+// head_part are padded to `hop` floats, so a thread writes whole 32-byte sectors with 16-byte stores -- with the unpadded
+// [A + 1] rows every scalar store of a warp touched 32 different sectors, which cost 18 us per launch at 5 players).
+template <int NP>
+__device__ __forceinline__ void head_dot(const float* h, const float* w, int ld, float* out, bool valid) {
+  unsigned long long acc[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) acc[j] = 0ull;
+#pragma unroll
+  for (int u = 0; u < 64; ++u) {   // fully unrolled: h[] must stay in registers
+    unsigned long long hh;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(h[u]));
+    const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(w + u * ld);
+#pragma unroll
+    for (int j = 0; j < NP / 2; ++j) {
+      const ulonglong2 ww = wr[j];
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[2 * j]) : "l"(hh), "l"(ww.x));
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[2 * j + 1]) : "l"(hh), "l"(ww.y));
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < NP / 2; ++j) reinterpret_cast<ulonglong2*>(out)[j] = make_ulonglong2(acc[2 * j], acc[2 * j + 1]);
+}
 
 __device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi_ptr, __nv_bfloat16* lo_ptr) {
   // two values per conversion (cvt.rn.bf16x2.f32): same round-to-nearest-even results as split_bf16, 40 % fewer instructions
@@ -415,6 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
     uint32_t lt = 0;
+    int staged_head = -1;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++lt) {
       const int z = tile / tiles_per_problem, r = tile - z * tiles_per_problem;
       const int m_tile = (r / n_tiles_n) * CW + rank, n_tile = r % n_tiles_n;
@@ -423,6 +458,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
       const bool valid = row_local < p.valid_rows;
       const size_t row = (size_t)row_local * p.row_mul + p.row_add;
       const uint32_t acc_stage = lt % ACC_STAGES, aph = (lt / ACC_STAGES) & 1u;
+      if (EPI == EPI_LSTM && p.head_w != nullptr && staged_head != z * 64 + n_tile) {
+        // stage this (network, n-tile)'s slice of the head weights (the 4 epilogue warps only: named barrier 1) BEFORE waiting
+        // for the accumulator, so that the copy runs under the tile's MMAs
+        const int hop_s = (p.head_out + 7) & ~7;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's slice
+        const float4* src = reinterpret_cast<const float4*>(p.head_w + (size_t)n_tile * hop_s * 64);
+        float4* dst = reinterpret_cast<float4*>(head_smem);
+        const int et = threadIdx.x - 64;
+        for (int i = et; i < hop_s * 16; i += 128) dst[i] = __ldg(src + i);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        staged_head = z * 64 + n_tile;
+      }
       mbar_wait(bar_tfull + 8 * acc_stage, aph, p.error_flag, dead);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * TMEM_COLS;
@@ -470,16 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
       } else {
         // tile columns: [gate i | f | g | o][64 hidden units]; hidden unit = n_tile*64 + u
         const bool do_head = p.head_w != nullptr;
-        const int head_out = p.head_out;
-        if (do_head) {
-          // stage this n-tile's slice of the head weights (the 4 epilogue warps only: named barrier 1)
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous tile's slice
-          const float4* src = reinterpret_cast<const float4*>(p.head_w + (size_t)n_tile * head_out * 64);
-          float4* dst = reinterpret_cast<float4*>(head_smem);
-          const int et = threadIdx.x - 64;
-          for (int i = et; i < head_out * 16; i += 128) dst[i] = __ldg(src + i);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
+        const int hop = (p.head_out + 7) & ~7;
         float h_all[64];
 #pragma unroll
         for (int u0 = 0; u0 < 64; u0 += 16) {
@@ -538,23 +576,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
               for (int i = 0; i < 8; ++i) h_all[u + i] += __bfloat162float(ah[i]) + __bfloat162float(bl[i]);
             }
           }
-          float* part = p.head_part + ((size_t)n_tile * p.head_rows + row) * head_out;
-          for (int o0 = 0; o0 < head_out; o0 += 8) {   // 8 outputs at a time: 8 accumulators, weights broadcast from smem
-            float acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-            for (int u = 0; u < 64; u += 4) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 w = *reinterpret_cast<const float4*>(head_smem + (o0 + j) * 64 + u);  // rows past head_out: stale but unused
-                acc[j] = fmaf(h_all[u], w.x, acc[j]); acc[j] = fmaf(h_all[u + 1], w.y, acc[j]);
-                acc[j] = fmaf(h_all[u + 2], w.z, acc[j]); acc[j] = fmaf(h_all[u + 3], w.w, acc[j]);
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (o0 + j < head_out && valid) part[o0 + j] = acc[j];
-          }
+          // 16 (then 8) outputs at a time on packed fp32 FMAs (FFMA2: two accumulators per instruction, each one the same
+          // rn FMA chain over u = 0..63 as a scalar loop would run); the weights of one unit are contiguous in shared
+          // memory, so one broadcast LDS.128 feeds two FFMA2
+          float* part = p.head_part + ((size_t)n_tile * p.head_rows + row) * hop;
+          int o0 = 0;
+          for (; o0 + 16 <= hop; o0 += 16) head_dot<8>(h_all, head_smem + o0, hop, part + o0, valid);
+          if (o0 < hop) head_dot<4>(h_all, head_smem + o0, hop, part + o0, valid);
           continue;  // the accumulator was already released above
         }
       }

@@ -8,7 +8,7 @@
 struct HbHeadArgs {
   int rows, rows_pad, A, have_target;
   int seat_mode, P;           // seat mode: the network of row r is net r % P (no target network)
-  const float* part[2];       // [8][rows_pad][A+1] partial head sums of the online / target network (LSTM-1 epilogue)
+  const float* part[2];       // [8][rows_pad][hop] partial head sums of the online / target network (LSTM-1 epilogue); hop = A + 1 padded to 8
   const float* ba[HB_MAX_P];  // fc_a bias [A] per network (training: 0 online, 1 target)
   const float* bv[HB_MAX_P];  // fc_v bias [1]
   const float* legal;         // [rows][A]
@@ -27,7 +27,7 @@ struct HbHeadArgs {
 
 // Lane l owns outputs l and l+32.  All 32 lanes of the calling warp must be active.
 __device__ __forceinline__ void hb_head_row(const HbHeadArgs& p, int row, int lane) {
-  const int A = p.A, HO = A + 1;
+  const int A = p.A, HO = (A + 1 + 7) & ~7;   // row stride of the partials
   const unsigned FULL = 0xffffffffu;
   const int nets = p.have_target ? 2 : 1;
   float out[2][2], vv[2];

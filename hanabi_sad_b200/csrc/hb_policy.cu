@@ -83,14 +83,15 @@ __global__ void hb_k_prep_lstm_bias(const float* __restrict__ b_ih, const float*
   out[(unit / 64) * 256 + gate * 64 + (unit % 64)] = b_ih[r] + b_hh[r];
 }
 
-// fc_a [A][512] and fc_v [512] -> [8][A+1][64]: the slice of the head every LSTM output tile needs (hb_gemm.cuh).
+// fc_a [A][512] and fc_v [512] -> [8 n-tiles][64 units][hop]: the slice of the head every LSTM output tile needs, outputs of
+// one hidden unit contiguous (hb_gemm.cuh head_dot); hop = A + 1 rounded up to 8, the padding stays zero (cleared at creation).
 __global__ void hb_k_prep_head(const float* __restrict__ wa, const float* __restrict__ wv, int A, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = (A + 1) * HB_HID;
+  const int n = (A + 1) * HB_HID, hop = (A + 1 + 7) & ~7;
   if (idx >= n) return;
   const int o = idx / HB_HID, k = idx % HB_HID;
   const float v = o < A ? wa[(size_t)o * HB_HID + k] : wv[k];
-  out[((size_t)(k / 64) * (A + 1) + o) * 64 + (k % 64)] = v;
+  out[((size_t)(k / 64) * 64 + (k % 64)) * hop + o] = v;
 }
 
 // ---------------------------------------------------------------------------------------- head + action selection
@@ -229,7 +230,10 @@ int hb_policy_create(hb_engine* e) {
     return -1;
   }
   if (c.eval_seats && c.replay_capacity > 0) { hb_set_error("hb_create: an eval_seats engine has no replay"); return -1; }
-  if (e->A > 63) { hb_set_error("hb_create: num_action > 63 is not supported by the head kernel"); return -1; }
+  if (e->A > 63 || ((e->A + 1 + 7) & ~7) > hbg::HEAD_MAX_OUT) {   // 5-player Hanabi has 49 moves incl. the no-op: 50 outputs, padded to 56
+    hb_set_error("hb_create: num_action = %d; the fused head holds %d outputs (advantages + value, padded to 8)", e->A, hbg::HEAD_MAX_OUT);
+    return -1;
+  }
   HbPolicy* P = new HbPolicy();
   memset(P, 0, sizeof(*P));
   e->policy = P;
@@ -245,7 +249,7 @@ int hb_policy_create(hb_engine* e) {
   for (int n = 0; n < 2; ++n) {
     HB_ALLOC(P->x_hi[n], rp * HB_HID * bf);
     HB_ALLOC(P->x_lo[n], rp * HB_HID * bf);
-    HB_ALLOC(P->head_part[n], (size_t)8 * rp * (e->A + 1) * sizeof(float));
+    HB_ALLOC(P->head_part[n], (size_t)8 * rp * ((e->A + 1 + 7) & ~7) * sizeof(float));
     HB_ALLOC(P->h_hi[n], HB_LAYERS * rp * HB_HID * bf);
     HB_ALLOC(P->h_lo[n], HB_LAYERS * rp * HB_HID * bf);
     HB_ALLOC(P->c[n], HB_LAYERS * rp * HB_HID * sizeof(float));
@@ -263,7 +267,7 @@ int hb_policy_create(hb_engine* e) {
     HB_ALLOC(W.wa, (size_t)e->A * HB_HID * sizeof(float));
     HB_ALLOC(W.ba, e->A * sizeof(float));
     HB_ALLOC(W.wv, HB_HID * sizeof(float));
-    HB_ALLOC(W.head_tiles, (size_t)8 * (e->A + 1) * 64 * sizeof(float));
+    HB_ALLOC(W.head_tiles, (size_t)8 * ((e->A + 1 + 7) & ~7) * 64 * sizeof(float));   // zero-filled: the padding columns are never written
     HB_ALLOC(W.bv, sizeof(float));
     size_t raw = (size_t)HB_HID * e->F;
     if (raw < (size_t)4 * HB_HID * HB_HID) raw = (size_t)4 * HB_HID * HB_HID;

@@ -15,7 +15,7 @@ struct HbNetWeights {                   // one network (online or target) in GEM
   __nv_bfloat16 *wl_hi[HB_LAYERS], *wl_lo[HB_LAYERS];  // [2048][1024] = [W_ih | W_hh], rows in gate-interleaved tile order
   float* bl[HB_LAYERS];                 // [2048]           b_ih + b_hh in the same row order
   float *wa, *ba, *wv, *bv;             // fc_a [A][512], [A]; fc_v [512], [1]  (fp32 upload copies; biases are read by the act kernel)
-  float* head_tiles;                    // [8 n-tiles][A+1][64] fp32: fc_a rows then fc_v, sliced per LSTM output tile (hb_gemm.cuh)
+  float* head_tiles;                    // [8 n-tiles][64][hop] fp32: fc_a rows then fc_v (padded to 8), sliced per LSTM output tile (hb_gemm.cuh)
   __nv_bfloat16 *w1_hi, *w1_lo;         // [512][512]       net.2.weight (second fc layer; eval_seats engines only)
   float* b1;                            // [512]
   int has_fc2, skip;                    // architecture variant of this network
@@ -36,7 +36,7 @@ struct HbPolicy {
   __nv_bfloat16 *h_hi[2], *h_lo[2];     // ping-pong halves: [L][rows_pad][512]
   float* c[2];                          // ping-pong halves: [L][rows_pad][512]
   __nv_bfloat16 *th_hi, *th_lo;         // target network layer-0 output
-  float* head_part[2];                  // [8 n-tiles][rows_pad][A+1] per network: partial head sums written by the LSTM-1 epilogue
+  float* head_part[2];                  // [8 n-tiles][rows_pad][hop] per network (hop = A + 1 padded to 8): partial head sums written by the LSTM-1 epilogue
   float *adv, *oq, *tq;                 // [rows][A], [rows], [rows]
   hbg::Params* d_params;                // [2 parity][4 launches: fc, fc2, lstm0, lstm1][HB_MAX_P problems]
   int* d_error;
