@@ -261,19 +261,37 @@ __device__ __forceinline__ void head_dot(const float* h, const float* w, int ld,
   for (int j = 0; j < NP / 2; ++j) reinterpret_cast<ulonglong2*>(out)[j] = make_ulonglong2(acc[2 * j], acc[2 * j + 1]);
 }
 
+// 256-bit global accesses (sm_100: LDG / STG.E.ENL2.256).  In the epilogues a lane owns a ROW: its 16-byte accesses land in
+// 32 different sectors per warp request, half a sector each, and the other half comes with the next request -- 32-byte
+// accesses move whole sectors and halve the LSU's sector transactions (the epilogue's real cost, see head_dot).
+// p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+// 16 values -> bf16 hi / lo halves, 32 bytes each (both pointers 32-byte aligned)
 __device__ __forceinline__ void store_split16(const float* v, __nv_bfloat16* hi_ptr, __nv_bfloat16* lo_ptr) {
   // two values per conversion (cvt.rn.bf16x2.f32): same round-to-nearest-even results as split_bf16, 40 % fewer instructions
-  __align__(16) __nv_bfloat162 h[8], l[8];
+  uint32_t h[8], l[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 back = __bfloat1622float2(h[i]);
-    l[i] = __floats2bfloat162_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 back = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
-  reinterpret_cast<uint4*>(hi_ptr)[0] = reinterpret_cast<const uint4*>(h)[0];
-  reinterpret_cast<uint4*>(hi_ptr)[1] = reinterpret_cast<const uint4*>(h)[1];
-  reinterpret_cast<uint4*>(lo_ptr)[0] = reinterpret_cast<const uint4*>(l)[0];
-  reinterpret_cast<uint4*>(lo_ptr)[1] = reinterpret_cast<const uint4*>(l)[1];
+  stg256(hi_ptr, h);
+  stg256(lo_ptr, l);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -529,11 +547,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           tmem_ld16(taddr + 3 * 64 + u0, go);
           const int unit = n_tile * 64 + u0;
           const float* bias = p.bias + n_tile * BN + u0;
-          const float4* cin = reinterpret_cast<const float4*>(p.c_in + row * HID + unit);
+          if (valid) { ldg256(p.c_in + row * HID + unit, c); ldg256(p.c_in + row * HID + unit + 8, c + 8); }
+          else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t = valid ? cin[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w;
+            for (int i = 0; i < 16; ++i) c[i] = 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -544,11 +561,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
             c[i] = fg * c[i] + ig * g_;
             h[i] = og * tanh_f(c[i]);
           }
-          if (p.c_out && valid) {
-            float4* cout = reinterpret_cast<float4*>(p.c_out + row * HID + unit);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cout[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
-          }
+          if (p.c_out && valid) { stg256(p.c_out + row * HID + unit, c); stg256(p.c_out + row * HID + unit + 8, c + 8); }
           if (p.h_f32 && valid) {
             float4* ho = reinterpret_cast<float4*>(p.h_f32 + row * HID + unit);
 #pragma unroll
