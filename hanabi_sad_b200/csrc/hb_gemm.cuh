@@ -30,7 +30,8 @@ constexpr int B_TILE = BN * BK * 2;                  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE; // hi+lo of both operands: 96 KB
 constexpr int HEAD_MAX_OUT = 56;                     // advantage head rows + the value head, padded to a multiple of 8
 constexpr int HEAD_SMEM = HEAD_MAX_OUT * 64 * 4;     // one n-tile's slice of the head weights: [64 units][out padded to 8] fp32
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + HEAD_SMEM;
+constexpr int BIAS_SMEM = 4 * BN * 4;                // EPI_LSTM: the tile's 256 gate biases, one private copy per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/ + HEAD_SMEM + BIAS_SMEM;
 constexpr int THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TMEM_COLS = 256;
 constexpr int HID = 512;
@@ -340,7 +341,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
   const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * NST, bar_tfull = bar_empty + 8 * NST;
   const uint32_t bar_tempty = bar_tfull + 8 * ACC_STAGES, tmem_slot = bar_tempty + 8 * ACC_STAGES;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* head_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 128 - smem_u32(smem_raw)));  // [head_out][64]
+  float* head_smem = reinterpret_cast<float*>(smem_raw + (bar_base + 128 - smem_u32(smem_raw)));  // [64][hop] (EPI_RELU: the tile's biases)
+  float* bias_smem = head_smem + HEAD_SMEM / 4;   // [4 epilogue warps][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bool dead = false;
@@ -488,6 +490,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
         asm volatile("bar.sync 1, 128;" ::: "memory");
         staged_head = z * 64 + n_tile;
       }
+      if (EPI == EPI_LSTM) {
+        // the tile's 256 gate biases into this warp's private shared-memory copy (two coalesced 16-byte loads per lane
+        // instead of 256 uniform global loads per lane and tile), also ahead of the accumulator wait
+        float* bw = bias_smem + q * BN;
+        __syncwarp();
+        const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n_tile * BN);
+        reinterpret_cast<float4*>(bw)[lane] = __ldg(bsrc + lane);
+        reinterpret_cast<float4*>(bw)[lane + 32] = __ldg(bsrc + lane + 32);
+        __syncwarp();
+      }
       mbar_wait(bar_tfull + 8 * acc_stage, aph, p.error_flag, dead);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * TMEM_COLS;
@@ -546,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           tmem_ld16(taddr + 2 * 64 + u0, gg);
           tmem_ld16(taddr + 3 * 64 + u0, go);
           const int unit = n_tile * 64 + u0;
-          const float* bias = p.bias + n_tile * BN + u0;
+          const float* bias = bias_smem + q * BN + u0;
           if (valid) { ldg256(p.c_in + row * HID + unit, c); ldg256(p.c_in + row * HID + unit + 8, c + 8); }
           else {
 #pragma unroll
@@ -554,10 +566,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float ig = sigmoid_f(gi[i] + __ldg(bias + i));
-            const float fg = sigmoid_f(gf[i] + __ldg(bias + 64 + i));
-            const float g_ = tanh_f(gg[i] + __ldg(bias + 128 + i));
-            const float og = sigmoid_f(go[i] + __ldg(bias + 192 + i));
+            const float ig = sigmoid_f(gi[i] + bias[i]);
+            const float fg = sigmoid_f(gf[i] + bias[64 + i]);
+            const float g_ = tanh_f(gg[i] + bias[128 + i]);
+            const float og = sigmoid_f(go[i] + bias[192 + i]);
             c[i] = fg * c[i] + ig * g_;
             h[i] = og * tanh_f(c[i]);
           }
