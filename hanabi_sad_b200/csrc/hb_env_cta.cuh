@@ -297,16 +297,19 @@ __device__ __forceinline__ void hb_cta_write_operand_fast(const HbGame& s, const
   for (int i = tid; i < P * words; i += nt) {
     const int o = i / words, w = i - o * words;
     const uint32_t m = w < HB_MASK_WORDS ? E.mask[o][w] : 0u;
-    uint4* dst = reinterpret_cast<uint4*>(s_hi + (size_t)o * KS + w * 32);
+    // two 32-byte stores (st.global.v8.b32, sm_100): each lane writes whole sectors -- with 16-byte stores at this 64-byte
+    // lane stride every request touched 32 half sectors and the kernel moved twice the sectors it needed
+    __nv_bfloat16* dst = s_hi + (size_t)o * KS + w * 32;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t b8 = (m >> (8 * q)) & 0xFFu;
-      uint4 v;
-      v.x = ((b8 & 1u) ? 0x3F80u : 0u) | ((b8 & 2u) ? 0x3F800000u : 0u);
-      v.y = ((b8 & 4u) ? 0x3F80u : 0u) | ((b8 & 8u) ? 0x3F800000u : 0u);
-      v.z = ((b8 & 16u) ? 0x3F80u : 0u) | ((b8 & 32u) ? 0x3F800000u : 0u);
-      v.w = ((b8 & 64u) ? 0x3F80u : 0u) | ((b8 & 128u) ? 0x3F800000u : 0u);
-      dst[q] = v;
+    for (int q2 = 0; q2 < 2; ++q2) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t b2 = (m >> (16 * q2 + 2 * j)) & 3u;
+        v[j] = ((b2 & 1u) ? 0x3F80u : 0u) | ((b2 & 2u) ? 0x3F800000u : 0u);
+      }
+      asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                   :: "l"(dst + 16 * q2), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
     }
   }
   __syncthreads();

@@ -39,10 +39,10 @@ __device__ __forceinline__ void hb_head_row(const HbHeadArgs& p, int row, int la
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const float* pr = p.part[net] + ((size_t)t * p.rows_pad + row) * HO;
-      if (lane < A) s0 += pr[lane];
-      if (lane + 32 < A) s1 += pr[lane + 32];
-      sv += pr[A];  // same address for the whole warp: one broadcast load
+      if (lane <= A) s0 += pr[lane];          // lane A (or A - 32 below) carries the value head's partial sums
+      if (lane + 32 <= A) s1 += pr[lane + 32];
     }
+    sv = A < 32 ? __shfl_sync(FULL, s0, A) : __shfl_sync(FULL, s1, A - 32);   // same sum, same order, no extra loads
     const int wn = p.seat_mode ? row % p.P : net;  // whose biases
     out[net][0] = lane < A ? s0 + __ldg(p.ba[wn] + lane) : 0.f;
     out[net][1] = lane + 32 < A ? s1 + __ldg(p.ba[wn] + lane + 32) : 0.f;
