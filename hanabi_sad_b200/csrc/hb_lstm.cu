@@ -285,14 +285,15 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
         if (lane == 0) wait_counter(P.chunk_flags + t / P.chunk, 1u, ef, dead, 4);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
       }
-      {
-        const float4* src = reinterpret_cast<const float4*>(N.gx + grow * G4 + slice * NC);
+      if (valid) {
+        // gx may have been written by a GEMM running concurrently (layer wavefront): L2, not the non-coherent path.  32-byte
+        // accesses: a lane owns a row, so narrower ones would move half sectors (hb_gemm.cuh ldg256)
+        const float* src = N.gx + grow * G4 + slice * NC;
 #pragma unroll
-        for (int i = 0; i < NC / 4; ++i) {
-          // gx may have been written by a GEMM running concurrently (layer wavefront): L2, not the non-coherent path
-          const float4 v = valid ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          g[4 * i] = v.x; g[4 * i + 1] = v.y; g[4 * i + 2] = v.z; g[4 * i + 3] = v.w;
-        }
+        for (int i = 0; i < NC / 8; ++i) ldg256_cg(src + 8 * i, g + 8 * i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) g[i] = 0.f;
       }
       if (t > 0) {
         wait_bar(bar_tfull, (uint32_t)(t - 1) & 1u, ef, dead);
@@ -330,17 +331,15 @@ __global__ void __launch_bounds__(192, 1) lstm_fwd_kernel(const FwdParams* __res
       // everything only later kernels read overlaps with the other CTAs' next step
       if (valid && !dead) {
         if (N.y) {
-          float4* dst = reinterpret_cast<float4*>(N.y + ((size_t)t * P.rows + row) * HIDN + unit);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+          float* dst = N.y + ((size_t)t * P.rows + row) * HIDN + unit;
+          stg256(dst, h); stg256(dst + 8, h + 8);
         }
         if (N.act) {
-          float4* dst = reinterpret_cast<float4*>(N.act + grow * G4 + slice * NC);
+          float* dst = N.act + grow * G4 + slice * NC;
 #pragma unroll
-          for (int i = 0; i < NC / 4; ++i) dst[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
-          float4* dc = reinterpret_cast<float4*>(N.cs + grow * HIDN + unit);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dc[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+          for (int i = 0; i < NC / 8; ++i) stg256(dst + 8 * i, g + 8 * i);
+          float* dc = N.cs + grow * HIDN + unit;
+          stg256(dc, c); stg256(dc + 8, c + 8);
         }
       }
     }
@@ -440,25 +439,26 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         if (lane == 0) wait_counter(P.chunk_flags + (T - 1 - t) / P.chunk, 1u, ef, dead, 4);
         dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
       }
-      {
-        const float4* s0 = reinterpret_cast<const float4*>(P.dh_ext + ((size_t)t * P.dh_rows + row) * HIDN + unit);
-        const float4* s1 = reinterpret_cast<const float4*>(P.act + grow * G4 + slice * NC);
-        const float4* s2 = reinterpret_cast<const float4*>(P.cs + grow * HIDN + unit);
-        const float4* s3 = reinterpret_cast<const float4*>(P.cs + (grow - (size_t)R_pad) * HIDN + unit);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        // 32-byte loads (a lane owns a row).  dh_ext may have been written by a kernel running concurrently (layer wavefront):
+        // L2, not the non-coherent path
+        const float* s0 = P.dh_ext + ((size_t)t * P.dh_rows + row) * HIDN + unit;
+        const float* s1 = P.act + grow * G4 + slice * NC;
+        const float* s2 = P.cs + grow * HIDN + unit;
+        ldg256_cg(s0, dh); ldg256_cg(s0 + 8, dh + 8);
+        ldg256_nc(s2, ct); ldg256_nc(s2 + 8, ct + 8);
+        if (t > 0) { ldg256_nc(s2 - (size_t)R_pad * HIDN, cp); ldg256_nc(s2 - (size_t)R_pad * HIDN + 8, cp + 8); }
+        else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          // dh_ext may have been written by a kernel running concurrently (layer wavefront): L2, not the non-coherent path
-          const float4 v0 = valid ? __ldcg(s0 + i) : z, v2 = valid ? __ldg(s2 + i) : z, v3 = (valid && t > 0) ? __ldg(s3 + i) : z;
-          dh[4 * i] = v0.x; dh[4 * i + 1] = v0.y; dh[4 * i + 2] = v0.z; dh[4 * i + 3] = v0.w;
-          ct[4 * i] = v2.x; ct[4 * i + 1] = v2.y; ct[4 * i + 2] = v2.z; ct[4 * i + 3] = v2.w;
-          cp[4 * i] = v3.x; cp[4 * i + 1] = v3.y; cp[4 * i + 2] = v3.z; cp[4 * i + 3] = v3.w;
+          for (int i = 0; i < UPC; ++i) cp[i] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < NC / 4; ++i) {
-          const float4 v = valid ? __ldg(s1 + i) : z;
-          a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
-        }
+        for (int i = 0; i < NC / 8; ++i) ldg256_nc(s1 + 8 * i, a + 8 * i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < UPC; ++i) { dh[i] = 0.f; ct[i] = 0.f; cp[i] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) a[i] = 0.f;
       }
       if (t < T - 1) {
         // dh_t += sum over the 32 CTAs' partials written at step t+1 (buffer (t+1)&1)
@@ -510,10 +510,13 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
       }
       // while the tensor core works: the row-major dgate copy the dX / dW GEMMs read after this kernel
       if (valid && !dead) {
-        uint4* d0 = reinterpret_cast<uint4*>(P.dg_hi + grow * G4 + slice * NC);
-        uint4* d1 = reinterpret_cast<uint4*>(P.dg_lo + grow * G4 + slice * NC);
+        __nv_bfloat16* d0 = P.dg_hi + grow * G4 + slice * NC;
+        __nv_bfloat16* d1 = P.dg_lo + grow * G4 + slice * NC;
 #pragma unroll
-        for (int i = 0; i < NC / 8; ++i) { d0[i] = reinterpret_cast<const uint4*>(ghi)[i]; d1[i] = reinterpret_cast<const uint4*>(glo)[i]; }
+        for (int i = 0; i < NC / 16; ++i) {
+          stg256(d0 + 16 * i, reinterpret_cast<const uint32_t*>(ghi) + 8 * i);
+          stg256(d1 + 16 * i, reinterpret_cast<const uint32_t*>(glo) + 8 * i);
+        }
       }
       if (t == 0) break;
       // Drain: the [128 x 512] fp32 partial of dh_{t-1} leaves TMEM in eight [64 columns][128 rows] pieces; each is staged in
