@@ -498,8 +498,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
         asm volatile("bar.sync 1, 128;" ::: "memory");
         staged_head = z * 64 + n_tile;
       }
-      if (EPI == EPI_LSTM) {
-        // the tile's 256 gate biases into this warp's private shared-memory copy (two coalesced 16-byte loads per lane
+      if (EPI == EPI_LSTM || (EPI == EPI_F32 && p.bias != nullptr)) {
+        // the tile's 256 (gate) biases into this warp's private shared-memory copy (two coalesced 16-byte loads per lane
         // instead of 256 uniform global loads per lane and tile), also ahead of the accumulator wait
         float* bw = bias_smem + q * BN;
         __syncwarp();
@@ -512,15 +512,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * TMEM_COLS;
       if (EPI == EPI_F32) {
+        // a lane owns a row of C: 32-byte stores (whole sectors) whenever the rows are 32-byte aligned
+        const bool wide = ((reinterpret_cast<uintptr_t>(p.c_f32) | ((uintptr_t)p.ldc * 4u)) & 31u) == 0;
+        const float* bw = bias_smem + q * BN;
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + c0, v);
           float* dst = p.c_f32 + row * p.ldc + (size_t)n_tile * BN + c0;
+          if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += p.bias ? __ldg(p.bias + n_tile * BN + c0 + i) : 0.f;
-          if (valid)
+            for (int i = 0; i < 16; ++i) v[i] += bw[c0 + i];
+          }
+          if (valid) {
+            if (wide) { stg256(dst, v); stg256(dst + 8, v + 8); }
+            else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          }
         }
       } else if (EPI == EPI_RELU) {
         // The mainloop of this layer is short (K = 896), so the epilogue must not be the longer of the two: the tile's 256
