@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
         asm volatile("bar.sync 1, 128;" ::: "memory");
         staged_head = z * 64 + n_tile;
       }
-      if (EPI == EPI_LSTM || (EPI == EPI_F32 && p.bias != nullptr)) {
+      if (EPI == EPI_LSTM || EPI == EPI_RELU || (EPI == EPI_F32 && p.bias != nullptr)) {
         // the tile's 256 (gate) biases into this warp's private shared-memory copy (two coalesced 16-byte loads per lane
         // instead of 256 uniform global loads per lane and tile), also ahead of the accumulator wait
         float* bw = bias_smem + q * BN;
@@ -533,11 +533,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
         }
       } else if (EPI == EPI_RELU) {
         // The mainloop of this layer is short (K = 896), so the epilogue must not be the longer of the two: the tile's 256
-        // biases are staged in shared memory once (instead of 256 global loads per thread), and the accumulator is read 32
+        // biases come from shared memory (instead of 256 global loads per thread), and the accumulator is read 32
         // columns at a time with the next tcgen05.ld in flight while the previous 32 values are rectified, split and stored.
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous tile's biases
-        for (int i = threadIdx.x - 64; i < BN; i += 128) head_smem[i] = __ldg(p.bias + n_tile * BN + i);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* bw = bias_smem + q * BN;   // staged per warp ahead of the accumulator wait (above)
         uint32_t buf[2][32];
         tmem_ld32_nowait(taddr, buf[0]);
 #pragma unroll
@@ -552,7 +550,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
             float v[16];
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 b = *reinterpret_cast<const float4*>(head_smem + c0 + 16 * h + 4 * i4);
+              const float4 b = *reinterpret_cast<const float4*>(bw + c0 + 16 * h + 4 * i4);
               v[4 * i4] = fmaxf(__uint_as_float(cur[16 * h + 4 * i4]) + b.x, 0.f);
               v[4 * i4 + 1] = fmaxf(__uint_as_float(cur[16 * h + 4 * i4 + 1]) + b.y, 0.f);
               v[4 * i4 + 2] = fmaxf(__uint_as_float(cur[16 * h + 4 * i4 + 2]) + b.z, 0.f);

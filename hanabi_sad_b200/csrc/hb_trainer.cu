@@ -199,21 +199,31 @@ __global__ void ht_loss(LossArgs L) {
   }
 }
 
-// out[c] = sum_r m[r][c]; grid = cols, any block size
-__global__ void ht_colsum(const float* __restrict__ m, long long rows, int cols, float* __restrict__ out) {
-  __shared__ float red[32];
-  const int c = blockIdx.x;
+// out[c] = sum_r m[r][c] in two deterministic passes.  Pass 1: grid (ceil(cols / 32), HT_COLSUM_SLICES), 256 threads: a lane
+// owns a COLUMN, a warp reads 128 contiguous bytes of a row (one thread per column walking down the rows would touch a
+// different sector with every lane), the CTA's 8 warps take every 8th row of the slice; part[slice][c].  Pass 2 adds the slices.
+#define HT_COLSUM_SLICES 64
+__global__ void ht_colsum_part(const float* __restrict__ m, long long rows, int cols, float* __restrict__ part) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (long long r = threadIdx.x; r < rows; r += blockDim.x) s += m[r * cols + c];
-#pragma unroll
-  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  if (c < cols)
+    for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) s += m[r * cols + c];
+  red[warp][lane] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0 && c < cols) {
     float t = 0.f;
-    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) t += red[i];
-    out[c] = t;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    part[(size_t)blockIdx.y * cols + c] = t;
   }
+}
+__global__ void ht_colsum_final(const float* __restrict__ part, int slices, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int s = 0; s < slices; ++s) t += part[(size_t)s * cols + c];
+  out[c] = t;
 }
 
 __global__ void ht_unpack_head_grads(const float* __restrict__ dWh, const float* __restrict__ dbh, int A, int HO, int use_pred, float* __restrict__ g_wa,
@@ -297,6 +307,7 @@ struct hb_trainer {
   float *qa[2];                       // [T*rows]
   float *dy, *dO, *dX;
   float *Wh[2], *WhT, *bh[2], *dWh, *dbh;
+  float* colsum_part;                 // [HT_COLSUM_SLICES][512] partial column sums
   float* acc;                         // gradients of the earlier micro-batches of this update (allocated on first use)
   float* stats;                       // device [8]
   float* h_stats;                     // pinned [8]
@@ -356,6 +367,7 @@ int hb_trainer_create(const hb_trainer_config* cfg, float* online, float* target
   }
   HT_ALLOC(tr->dy, N * HO); HT_ALLOC(tr->dO, N * HID); HT_ALLOC(tr->dX, N * HID);
   HT_ALLOC(tr->WhT, HO * HID); HT_ALLOC(tr->dWh, HO * HID); HT_ALLOC(tr->dbh, HO);
+  HT_ALLOC(tr->colsum_part, (size_t)HT_COLSUM_SLICES * HID);
   HT_ALLOC(tr->stats, 8);
   HB_CUDA(cudaMallocHost((void**)&tr->h_stats, 8 * sizeof(float)));
   memset(tr->h_stats, 0, 8 * sizeof(float));
@@ -371,7 +383,7 @@ void hb_trainer_destroy(hb_trainer* tr) {
   hb_lstm_destroy(tr->lstm);
   for (int n = 0; n < 2; ++n) { cudaFree(tr->x[n]); cudaFree(tr->o[n]); cudaFree(tr->y[n]); cudaFree(tr->qa[n]); cudaFree(tr->Wh[n]); cudaFree(tr->bh[n]); }
   cudaFree(tr->dy); cudaFree(tr->dO); cudaFree(tr->dX);
-  cudaFree(tr->WhT); cudaFree(tr->dWh); cudaFree(tr->dbh); cudaFree(tr->stats); cudaFree(tr->acc);
+  cudaFree(tr->WhT); cudaFree(tr->dWh); cudaFree(tr->dbh); cudaFree(tr->stats); cudaFree(tr->acc); cudaFree(tr->colsum_part);
   cudaFreeHost(tr->h_stats); cudaEventDestroy(tr->ev_stats);
   delete tr;
 }
@@ -446,7 +458,8 @@ int hb_trainer_backward_ex(hb_trainer* tr, const hb_batch* b, int batchsize, int
   // dWh = dY^T O: both operands are given with the contraction axis (batch rows) as their SLOW axis -> transposing splits
   rc = hb_gemm_nt_ex(tr->device, tr->dy, HO, 1, tr->o[0], HID, 1, nullptr, tr->dWh, HID, HO, HID, (int)N, st);
   if (rc) return rc;
-  ht_colsum<<<HO, 256, 0, st>>>(tr->dy, N, HO, tr->dbh);
+  ht_colsum_part<<<dim3((HO + 31) / 32, HT_COLSUM_SLICES), 256, 0, st>>>(tr->dy, N, HO, tr->colsum_part);
+  ht_colsum_final<<<(HO + 127) / 128, 128, 0, st>>>(tr->colsum_part, HT_COLSUM_SLICES, HO, tr->dbh);
   float* g = tr->grads;
   const int use_pred = pred_weight > 0.f ? 1 : 0;
   ht_unpack_head_grads<<<blocks((long long)HO * HID, 256), 256, 0, st>>>(tr->dWh, tr->dbh, A, HO, use_pred, g + off[P_FCA_W], g + off[P_FCA_B], g + off[P_FCV_W],
@@ -458,13 +471,14 @@ int hb_trainer_backward_ex(hb_trainer* tr, const hb_batch* b, int batchsize, int
   rc = hb_lstm_backward(tr->lstm, tr->dO, tr->dX, &lg, st);
   if (rc) return rc;
   ht_relu_bwd<<<blocks(N * HID / 4, 256), 256, 0, st>>>(tr->x[0], tr->dX, N * HID / 4);
-  ht_colsum<<<HID, 256, 0, st>>>(tr->dX, N, HID, g + off[P_FC_B]);
+  ht_colsum_part<<<dim3(HID / 32, HT_COLSUM_SLICES), 256, 0, st>>>(tr->dX, N, HID, tr->colsum_part);
+  ht_colsum_final<<<(HID + 127) / 128, 128, 0, st>>>(tr->colsum_part, HT_COLSUM_SLICES, HID, g + off[P_FC_B]);
   rc = hb_gemm_nt_ex(tr->device, tr->dX, HID, 1, b->priv_s, F, 1, nullptr, g + off[P_FC_W], F, HID, F, (int)N, st);   // dW0 = dXpre^T S
   if (rc) return rc;
   if (accumulate) ht_add<<<blocks(off[P_N] / 4, 256), 256, 0, st>>>(g, tr->acc, off[P_N] / 4);
   HB_CUDA(cudaGetLastError());
   tr->last_use_pred = use_pred;
-  tr->launches += 18 + (accumulate ? 1 : 0);
+  tr->launches += 20 + (accumulate ? 1 : 0);
   return 0;
 }
 
