@@ -60,20 +60,40 @@ struct GemmScratch {            // grow-only device scratch per GPU (one learner
   int sm_count = 0;
   bool attrs = false;
   HbUploadRing ring;
+  // the A operand the split buffers hold (hb_gemm_nt_same_a: the two networks' fc layers read the same observations)
+  const float* last_a = nullptr; long long last_lda = 0; int last_m = 0, last_k = 0, last_kp = 0, last_ta = 0;
 };
 GemmScratch g_scratch[16];
 
-// fp32 [rows][cols] (row stride ld) -> bf16 hi/lo [rows_pad][cols_pad], zero padded
+// fp32 [rows][cols] (row stride ld) -> bf16 hi/lo [rows_pad][cols_pad], zero padded.  A thread converts FOUR consecutive
+// columns: one 16-byte (or two 8-byte, rows only 8-byte aligned: ld even) load, two 8-byte stores -- a third of the memory
+// instructions of the one-element-per-thread form, which ran at 40 % of the copy bandwidth (cols_pad is a multiple of 64).
 __global__ void split_pad(const float* __restrict__ src, long long ld, int rows, int cols, int rows_pad, int cols_pad,
-                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)rows_pad * cols_pad) return;
-  const int r = (int)(i / cols_pad), c = (int)(i - (long long)r * cols_pad);
-  const float v = (r < rows && c < cols) ? src[(long long)r * ld + c] : 0.f;
-  __nv_bfloat16 h, l;
-  hbg::split_bf16(v, h, l);
-  hi[i] = h;
-  lo[i] = l;
+                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int align) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q_per_row = cols_pad >> 2;
+  if (i4 >= (long long)rows_pad * q_per_row) return;
+  const int r = (int)(i4 / q_per_row), c = (int)(i4 - (long long)r * q_per_row) << 2;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (r < rows) {
+    const float* p = src + (long long)r * ld + c;
+    if (c + 3 < cols && align == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if (c + 3 < cols && align == 2) {
+      const float2 t0 = *reinterpret_cast<const float2*>(p), t1 = *reinterpret_cast<const float2*>(p + 2);
+      v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (c + j < cols) v[j] = p[j];
+    }
+  }
+  __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) hbg::split_bf16(v[j], h[j], l[j]);
+  const long long o = (long long)r * cols_pad + c;
+  *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
 }
 
 // The same for an operand given TRANSPOSED: src is [cols][rows] row-major (row stride ld), i.e. element (r, c) of the operand is
@@ -110,6 +130,14 @@ __global__ void sum_parts(const float* __restrict__ part, int split, long long p
   C[(long long)r * ldc + c] = acc;
 }
 
+// widest vector load every row of `src` allows: 4 floats (16-byte aligned rows), 2, or 1
+int split_align(const float* src, long long ld) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+  if ((a & 15) == 0 && (ld & 3) == 0) return 4;
+  if ((a & 7) == 0 && (ld & 1) == 0) return 2;
+  return 1;
+}
+
 int grow(void** p, size_t* cap, size_t need, size_t elem) {
   if (*cap >= need) return 0;
   if (*p) cudaFree(*p);
@@ -123,8 +151,8 @@ int grow(void** p, size_t* cap, size_t need, size_t elem) {
 
 // C[M,N] = op(A) op(B)^T (+ bias): op(X) = X given [rows][K] (trans = 0, row stride ld >= K) or X given [K][rows] (trans = 1,
 // row stride ld >= rows).  hb_gemm_nt (the public entry point) is the trans = 0 case.
-int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, const float* bias, float* C, int64_t ldc,
-                  int M, int N, int K, void* stream) {
+static int gemm_nt_impl(int device, const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, const float* bias, float* C, int64_t ldc,
+                        int M, int N, int K, void* stream, bool same_a) {
   if (!A || !B || !C) { hb_set_error("hb_gemm_nt: null argument"); return -1; }
   if (M < 1 || N < 1 || K < 1 || lda < (transA ? M : K) || ldb < (transB ? N : K) || ldc < N) { hb_set_error("hb_gemm_nt: bad shape M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld", M, N, K, (long long)lda, (long long)ldb, (long long)ldc); return -1; }
   int ndev = 0;
@@ -176,10 +204,16 @@ int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const flo
   }
   if (!direct) { rc = grow((void**)&S.c_part, &S.c_cap, (size_t)split * Mp * Np, sizeof(float)); if (rc) return rc; }
   const long long na = (long long)Mp * Kp, nb = (long long)Np * Kp;
-  if (transA) split_pad_t<<<dim3((unsigned)((Kp + 31) / 32), (unsigned)((Mp + 31) / 32)), dim3(32, 8), 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo);
-  else split_pad<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo);
+  if (same_a) {   // the split buffers still hold exactly this operand (no other call of this GPU's GEMM in between)
+    if (S.last_a != A || S.last_lda != lda || S.last_m != M || S.last_k != K || S.last_kp != Kp || S.last_ta != transA) {
+      hb_set_error("hb_gemm_nt_same_a: the previous call used a different A operand");
+      return -1;
+    }
+  } else if (transA) split_pad_t<<<dim3((unsigned)((Kp + 31) / 32), (unsigned)((Mp + 31) / 32)), dim3(32, 8), 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo);
+  else split_pad<<<(unsigned)((na / 4 + 255) / 256), 256, 0, st>>>(A, lda, M, K, Mp, Kp, S.a_hi, S.a_lo, split_align(A, lda));
+  S.last_a = A; S.last_lda = lda; S.last_m = M; S.last_k = K; S.last_kp = Kp; S.last_ta = transA;
   if (transB) split_pad_t<<<dim3((unsigned)((Kp + 31) / 32), (unsigned)((Np + 31) / 32)), dim3(32, 8), 0, st>>>(B, ldb, N, K, Np, Kp, S.b_hi, S.b_lo);
-  else split_pad<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, ldb, N, K, Np, Kp, S.b_hi, S.b_lo);
+  else split_pad<<<(unsigned)((nb / 4 + 255) / 256), 256, 0, st>>>(B, ldb, N, K, Np, Kp, S.b_hi, S.b_lo, split_align(B, ldb));
   const int cl = (mt % 2 == 0) ? 2 : 1;
   std::vector<Params> hp(split);
   for (int s = 0; s < split; ++s) {
@@ -209,6 +243,18 @@ int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const flo
   }
   HB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, const float* bias, float* C, int64_t ldc,
+                  int M, int N, int K, void* stream) {
+  return gemm_nt_impl(device, A, lda, transA, B, ldb, transB, bias, C, ldc, M, N, K, stream, false);
+}
+
+// hb_gemm_nt for a call whose A operand (pointer, shape AND contents) is the one of the immediately preceding GEMM call on this
+// GPU: its bf16 hi / lo split is reused instead of recomputed (the online and the target network read the same observations).
+int hb_gemm_nt_same_a(int device, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc, int M, int N, int K,
+                      void* stream) {
+  return gemm_nt_impl(device, A, lda, 0, B, ldb, 0, bias, C, ldc, M, N, K, stream, true);
 }
 
 extern "C" int hb_gemm_nt(int device, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,

@@ -683,7 +683,17 @@ __global__ void lstm_bias_grad(const __nv_bfloat16* __restrict__ t_hi, const __n
   const int p = blockIdx.x;
   const __nv_bfloat16 *a = t_hi + (size_t)p * n, *b = t_lo + (size_t)p * n;
   float s = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += __bfloat162float(a[i]) + __bfloat162float(b[i]);
+  // n = T * R_pad is a multiple of 128: 16-byte loads (eight bf16 per thread and step)
+  for (long long i = (long long)threadIdx.x * 8; i < n; i += (long long)blockDim.x * 8) {
+    const uint4 va = *reinterpret_cast<const uint4*>(a + i), vb = *reinterpret_cast<const uint4*>(b + i);
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&va);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __bfloat1622float2(pa[j]), fb = __bfloat1622float2(pb[j]);
+      s += (fa.x + fb.x) + (fa.y + fb.y);
+    }
+  }
 #pragma unroll
   for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;

@@ -20,7 +20,9 @@
 #include "hb_engine.h"
 
 int hb_gemm_nt_ex(int device, const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, const float* bias, float* C, int64_t ldc,
-                  int M, int N, int K, void* stream);   // hb_linear.cu
+                  int M, int N, int K, void* stream);
+int hb_gemm_nt_same_a(int device, const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc, int M, int N, int K,
+                      void* stream);   // hb_linear.cu
 
 namespace {
 
@@ -421,7 +423,9 @@ int hb_trainer_backward_ex(hb_trainer* tr, const hb_batch* b, int batchsize, int
   // ---- forward: fc + ReLU, LSTM (both networks in one pass), heads
   for (int n = 0; n < 2; ++n) {
     const float* p = tr->params[n];
-    rc = hb_gemm_nt(tr->device, b->priv_s, F, p + off[P_FC_W], F, p + off[P_FC_B], tr->x[n], HID, (int)N, HID, F, st);
+    // the target network's fc layer reads the same observations: their bf16 split is made once
+    rc = n == 0 ? hb_gemm_nt(tr->device, b->priv_s, F, p + off[P_FC_W], F, p + off[P_FC_B], tr->x[n], HID, (int)N, HID, F, st)
+                : hb_gemm_nt_same_a(tr->device, b->priv_s, F, p + off[P_FC_W], F, p + off[P_FC_B], tr->x[n], HID, (int)N, HID, F, st);
     if (rc) return rc;
     ht_relu<<<blocks(N * HID / 4, 256), 256, 0, st>>>(tr->x[n], N * HID / 4);
     ht_pack_heads<<<blocks((long long)HO * HID, 256), 256, 0, st>>>(p + off[P_FCA_W], p + off[P_FCA_B], p + off[P_FCV_W], p + off[P_FCV_B], p + off[P_PRED_W],
