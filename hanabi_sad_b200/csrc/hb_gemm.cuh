@@ -49,6 +49,7 @@ struct __align__(64) Params {
   // EPI_F32: plain fp32 result (diagnostics / self-test)
   float* c_f32;
   int ldc;
+  int accumulate;                // EPI_F32: C += result (weight gradients summed over time chunks, hb_lstm_backward)
   // EPI_RELU / EPI_LSTM: result written as a bf16 hi/lo pair, [rows][out_ld], starting at column out_col0
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
@@ -522,6 +523,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3_kernel(const Params* __restr
           if (p.bias) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += bw[c0 + i];
+          }
+          if (valid && p.accumulate) {
+            float old[16];
+            if (wide) { ldg256(dst, old); ldg256(dst + 8, old + 8); }
+            else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) old[i] = dst[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += old[i];
           }
           if (valid) {
             if (wide) { stg256(dst, v); stg256(dst + 8, v + 8); }

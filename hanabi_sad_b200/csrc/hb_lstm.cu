@@ -755,8 +755,8 @@ struct hb_lstm {
   unsigned* chunk_flags;                    // [64] layer-wavefront progress flags
   long long* d_trace;                       // diagnostic (HB_LSTM_TRACE=<file>): [4 kernels][max_T][16] time stamps
   HbUploadRing upload;                      // pinned staging of launch-parameter records (hb_gemm_host.h)
-  cudaStream_t ws[3];                       // internal streams of the layer wavefront (recurrence above / chunk GEMMs / recurrence below)
-  cudaEvent_t wev[5];
+  cudaStream_t ws[4];                       // internal streams of the layer wavefront (recurrence above / chunk GEMMs / recurrence below / dW chunks)
+  cudaEvent_t wev[6];
   int use_wavefront;
   int* d_error;
   int* h_error;                             // pinned mirror of d_error, filled asynchronously at the end of every call
@@ -838,8 +838,8 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   HBL_ALLOC(L->dx_pad, N * hbl::HIDN * sizeof(float));
   HBL_ALLOC(L->part, (size_t)2 * 2 * L->max_rpad * hbl::HIDN * sizeof(float));
   HBL_ALLOC(L->chunk_flags, 64 * sizeof(unsigned));
-  for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamCreateWithFlags(&L->ws[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 5; ++i) HB_CUDA(cudaEventCreateWithFlags(&L->wev[i], cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) HB_CUDA(cudaStreamCreateWithFlags(&L->ws[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 6; ++i) HB_CUDA(cudaEventCreateWithFlags(&L->wev[i], cudaEventDisableTiming));
   L->use_wavefront = getenv("HB_LSTM_NO_WAVEFRONT") ? 0 : 1;   // diagnostic switch: the two layers' recurrences one after the other
   if (getenv("HB_LSTM_TRACE")) HBL_ALLOC(L->d_trace, (size_t)4 * max_T * 16 * sizeof(long long));
   {
@@ -861,7 +861,7 @@ int hb_lstm_create(int device, int max_T, int max_rows, hb_lstm** out) {
   HB_CUDA(cudaEventCreateWithFlags(&L->ev_done, cudaEventDisableTiming));
   HBL_ALLOC(L->d_fwd, 2 * sizeof(hbl::FwdParams));
   HBL_ALLOC(L->d_bwd, 2 * sizeof(hbl::BwdParams));
-  HBL_ALLOC(L->d_gemm, 48 * sizeof(Params));
+  HBL_ALLOC(L->d_gemm, 64 * sizeof(Params));
   { const int urc = hb_upload_init(&L->upload); if (urc) return urc; }
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
   HB_CUDA((cudaFuncSetAttribute(hbl::lstm_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, hbl::FWD_SMEM)));
@@ -893,8 +893,8 @@ void hb_lstm_destroy(hb_lstm* L) {
   }
   cudaFree(L->dh0); cudaFree(L->dx_pad); cudaFree(L->part); cudaFree(L->dwp); cudaFree(L->ctr); cudaFree(L->d_error);
   cudaFree(L->d_fwd); cudaFree(L->d_bwd); cudaFree(L->d_gemm); cudaFree(L->chunk_flags); cudaFree(L->d_trace);
-  for (int i = 0; i < 3; ++i) if (L->ws[i]) cudaStreamDestroy(L->ws[i]);
-  for (int i = 0; i < 5; ++i) if (L->wev[i]) cudaEventDestroy(L->wev[i]);
+  for (int i = 0; i < 4; ++i) if (L->ws[i]) cudaStreamDestroy(L->ws[i]);
+  for (int i = 0; i < 6; ++i) if (L->wev[i]) cudaEventDestroy(L->wev[i]);
   cudaFreeHost(L->h_error); cudaEventDestroy(L->ev_done);
   hb_upload_destroy(&L->upload);
   delete L;
@@ -1162,10 +1162,34 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     if (r2) return -2;
     return hbl_run_gemm(L, s, &gp, 1, (int)(nr / BM), hbl::HIDN / BN, slot, sm_limit);
   };
+  // Weight gradients inside the wavefront: with one row block (rows <= 128, the IQL learner) the two recurrences leave more than
+  // half of the SMs idle for a millisecond.  A fourth stream follows both step counters one time chunk behind: transpose the
+  // chunk's dgate rows, then ADD its contribution dG_chunk^T x (x | h)_chunk to the four weight gradients (K = chunk * R_pad per
+  // launch, `accumulate` epilogue; fixed chunk order, so the sums are deterministic).  After the recurrences only the bias sums
+  // and the row permutation are left.  At 256 rows the 20 free SMs could not keep up, so the GEMMs stay behind the wavefront.
+  const size_t WN = (size_t)hbl::G4 * hbl::HIDN;
+  const int dw_sms = (gemm_sms - 16) & ~1;
+  const bool dw_wave = wave && dw_sms >= 48 && getenv("HB_LSTM_NO_DW_WAVE") == nullptr;
+  auto dw_chunk = [&](int l, int t0, int t1, bool first, int slot) -> int {
+    const size_t r0 = (size_t)t0 * R_pad, nr = (size_t)(t1 - t0) * R_pad;
+    hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(nr / 64)), 256, 0, L->ws[3]>>>(L->dg_hi[l] + r0 * hbl::G4, L->dg_lo[l] + r0 * hbl::G4, hbl::G4,
+                                                                                         L->dgT_hi[l] + r0, L->dgT_lo[l] + r0, (long long)N);
+    Params wq[2];
+    int r2 = 0;
+    // layer 0: inputs x_t and h0_{t-1}; layer 1: inputs h0_t (= block t+1 of the h0 sequence) and h1_{t-1}
+    const __nv_bfloat16 *in_hi = l == 0 ? L->xT_hi + r0 : L->hsT_hi[0] + R_pad + r0, *in_lo = l == 0 ? L->xT_lo + r0 : L->hsT_lo[0] + R_pad + r0;
+    hbl_gemm_problem(wq[0], r2, L->dgT_hi[l] + r0, L->dgT_lo[l] + r0, hbl::G4, N, in_hi, in_lo, hbl::HIDN, ldT, nr, 2, nullptr, L->dwp + (2 * l) * WN, hbl::HIDN, L->d_error);
+    hbl_gemm_problem(wq[1], r2, L->dgT_hi[l] + r0, L->dgT_lo[l] + r0, hbl::G4, N, L->hsT_hi[l] + r0, L->hsT_lo[l] + r0, hbl::HIDN, ldT, nr, 2, nullptr,
+                     L->dwp + (2 * l + 1) * WN, hbl::HIDN, L->d_error);
+    if (r2) return -2;
+    wq[0].accumulate = wq[1].accumulate = first ? 0 : 1;
+    L->launches += 1;
+    return hbl_run_gemm(L, L->ws[3], wq, 2, hbl::G4 / BM, hbl::HIDN / BN, slot, dw_sms);
+  };
   if (wave) {
     HB_CUDA(cudaMemsetAsync(L->chunk_flags, 0, 64 * sizeof(unsigned), st));
     HB_CUDA(cudaEventRecord(L->wev[0], st));
-    for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamWaitEvent(L->ws[i], L->wev[0], 0));
+    for (int i = 0; i < 4; ++i) HB_CUDA(cudaStreamWaitEvent(L->ws[i], L->wev[0], 0));
     hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, L->ws[0]>>>(L->d_bwd + 1);
     HB_CUDA(cudaEventRecord(L->wev[1], L->ws[0]));
     hbl::lstm_bwd_kernel<<<MB * hbl::SLICES, 192, hbl::BWD_SMEM, L->ws[2]>>>(L->d_bwd + 0);
@@ -1184,6 +1208,27 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
       L->launches += 1;
     }
     HB_CUDA(cudaEventRecord(L->wev[2], L->ws[1]));
+    if (dw_wave) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int t1 = T - c * chunk, t0 = t1 - chunk > 0 ? t1 - chunk : 0;
+        for (int l = 1; l >= 0; --l) {   // layer 0 runs one chunk behind layer 1: the stream simply waits for it
+          if (t0 > 0) {
+            hbl::lstm_wait_steps<<<1, 1, 0, L->ws[3]>>>(bp[l].ctr, MB, (unsigned)(hbl::SLICES * (c + 1) * chunk), L->d_error);
+            L->launches += 1;
+          } else {
+            HB_CUDA(cudaStreamWaitEvent(L->ws[3], L->wev[l == 1 ? 1 : 3], 0));
+          }
+          rc = dw_chunk(l, t0, t1, c == 0, 48 + 2 * ((2 * c + l) % 8));
+          if (rc) return rc;
+        }
+      }
+      // the row permutation and the bias sums stay on that stream too: they run under the dX GEMM below; joined at the end
+      float* dsts[4] = {g->dw_ih[0], g->dw_hh[0], g->dw_ih[1], g->dw_hh[1]};
+      for (int i = 0; i < 4; ++i) hbl::lstm_unperm_rows<<<hbl::G4, 128, 0, L->ws[3]>>>(L->dwp + i * WN, dsts[i]);
+      for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, L->ws[3]>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
+      L->launches += 6;
+      HB_CUDA(cudaEventRecord(L->wev[4], L->ws[3]));
+    }
     HB_CUDA(cudaGetLastError());
     for (int i = 1; i <= 3; ++i) HB_CUDA(cudaStreamWaitEvent(st, L->wev[i], 0));
     L->launches += 2;
@@ -1195,30 +1240,36 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     HB_CUDA(cudaGetLastError());
     L->launches += 2;
   }
-  for (int l = 0; l < 2; ++l)
-    hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(N / 64)), 256, 0, st>>>(L->dg_hi[l], L->dg_lo[l], hbl::G4, L->dgT_hi[l], L->dgT_lo[l], (long long)N);
-  L->launches += 2;
+  if (!dw_wave) {
+    for (int l = 0; l < 2; ++l)
+      hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(N / 64)), 256, 0, st>>>(L->dg_hi[l], L->dg_lo[l], hbl::G4, L->dgT_hi[l], L->dgT_lo[l], (long long)N);
+    L->launches += 2;
+  }
   if (dx) {   // gradient w.r.t. the input sequence of layer 0
     float* dst = R_pad == rows ? dx : L->dx_pad;
+    // (not chunked into the wavefront: 16 tiles of K = 2048 per chunk on 16 SMs take as long as the chunk itself)
     rc = dx_gemm(0, 0, T, dst, st, 4, 0);
     if (rc) return rc;
     if (dst != dx) { hbl::lstm_unpad<<<dim3(rows, T), 128, 0, st>>>(L->dx_pad, dx, rows, R_pad); L->launches += 1; }
   }
   // ---- weight gradients: four [2048, 512] = dG^T [2048, N] x (operand^T [512, N])^T problems in one launch
   Params wp[4];
-  const size_t WN = (size_t)hbl::G4 * hbl::HIDN;
   hbl_gemm_problem(wp[0], rc, L->dgT_hi[0], L->dgT_lo[0], hbl::G4, N, L->xT_hi, L->xT_lo, hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 0 * WN, hbl::HIDN, L->d_error);
   hbl_gemm_problem(wp[1], rc, L->dgT_hi[0], L->dgT_lo[0], hbl::G4, N, L->hsT_hi[0], L->hsT_lo[0], hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 1 * WN, hbl::HIDN, L->d_error);
   hbl_gemm_problem(wp[2], rc, L->dgT_hi[1], L->dgT_lo[1], hbl::G4, N, L->hsT_hi[0] + R_pad, L->hsT_lo[0] + R_pad, hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 2 * WN, hbl::HIDN, L->d_error);
   hbl_gemm_problem(wp[3], rc, L->dgT_hi[1], L->dgT_lo[1], hbl::G4, N, L->hsT_hi[1], L->hsT_lo[1], hbl::HIDN, ldT, N, 2, nullptr, L->dwp + 3 * WN, hbl::HIDN, L->d_error);
   if (rc) return -2;
-  rc = hbl_run_gemm(L, st, wp, 4, hbl::G4 / BM, hbl::HIDN / BN, 8);
-  if (rc) return rc;
-  float* dsts[4] = {g->dw_ih[0], g->dw_hh[0], g->dw_ih[1], g->dw_hh[1]};
-  for (int i = 0; i < 4; ++i) hbl::lstm_unperm_rows<<<hbl::G4, 128, 0, st>>>(L->dwp + i * WN, dsts[i]);
-  for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, st>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
+  if (!dw_wave) {
+    rc = hbl_run_gemm(L, st, wp, 4, hbl::G4 / BM, hbl::HIDN / BN, 8);
+    if (rc) return rc;
+    float* dsts[4] = {g->dw_ih[0], g->dw_hh[0], g->dw_ih[1], g->dw_hh[1]};
+    for (int i = 0; i < 4; ++i) hbl::lstm_unperm_rows<<<hbl::G4, 128, 0, st>>>(L->dwp + i * WN, dsts[i]);
+    for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, st>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
+    L->launches += 6;
+  } else {
+    HB_CUDA(cudaStreamWaitEvent(st, L->wev[4], 0));   // the weight gradients of the wavefront's fourth stream
+  }
   HB_CUDA(cudaGetLastError());
-  L->launches += 6;
   hbl_dump_trace(L, st, 2, T, "bwd");
   return hbl_finish_call(L, st);
 }

@@ -77,7 +77,7 @@ def test_lstm_pair_runs_online_and_target_in_one_pass(hbl):
     assert _rel(xad.grad.cpu(), xa.grad) < 1e-4
     assert _rel(a.weight_hh_l0.grad.cpu(), ref_a.weight_hh_l0.grad) < 1e-4
     assert all(p.grad is None for p in b.parameters())
-    assert ws.launches() - n0 < 60   # whole sequences per launch, not one launch per step
+    assert ws.launches() - n0 < 90   # whole sequences per launch (plus a handful per 8-step chunk of the layer wavefront), not one per step
     ws.close()
 
 
