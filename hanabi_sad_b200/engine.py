@@ -301,6 +301,10 @@ class Engine:
     def n_prefetched(self):
         return len(getattr(self, "_prefetched", ()))
 
+    def last_max_len(self):
+        """Longest episode (steps) of the batch handed out last (sample / take) and not yet updated: hb_replay_last_max_len."""
+        return int(lib().hb_replay_last_max_len(self._h))
+
     def drop_prefetched(self):
         """Forget every batch drawn ahead and not handed out yet (their priorities are left as they are)."""
         while self.n_prefetched():

@@ -134,11 +134,39 @@ class RNNPrioritizedReplay:
     the engine's stream, where they run while the learner trains -- the learner never waits for the sampler (single act
     device; a sharded replay draws synchronously)."""
 
+    _live = None                 # weak set of the replays of this process (top_up_all)
+
     def __init__(self, capacity, seed, alpha, beta, prefetch=0):
         self.capacity, self.seed, self.alpha, self.beta, self.prefetch = int(capacity), int(seed), float(alpha), float(beta), int(prefetch)
         self._engines = []       # (engine, lock)
         self._last = []          # engines sampled from (with counts) awaiting update_priority
         self._rng = np.random.default_rng(self.seed)
+        self._prefetch_b = 0     # batch size of the draws queued ahead
+        if RNNPrioritizedReplay._live is None:
+            import weakref
+
+            RNNPrioritizedReplay._live = weakref.WeakSet()
+        RNNPrioritizedReplay._live.add(self)
+
+    def _top_up(self):
+        """Queue draws until `prefetch` batches are outstanding (single engine).  Called from sample() and -- so that the
+        enqueue costs no GPU idle time -- by the device trainer right after it has queued an update (top_up_all)."""
+        if self.prefetch <= 0 or self._prefetch_b <= 0 or len(self._engines) != 1:
+            return
+        e, lk = self._engines[0]
+        if not hasattr(e, "prefetch"):
+            return
+        with lk:
+            while e.n_prefetched() < min(self.prefetch, 3):
+                e.prefetch(self._prefetch_b)
+
+    @classmethod
+    def top_up_all(cls):
+        for r in list(cls._live or ()):
+            try:
+                r._top_up()
+            except Exception:      # a replay that cannot be topped up now (too few entries yet) is simply drawn from later
+                pass
 
     def _attach(self, engine, lock):
         self._engines.append((engine, lock))
@@ -196,6 +224,7 @@ class RNNPrioritizedReplay:
         if self._last:
             raise RuntimeError("Error: previous samples' priority has not been updated.")  # prioritized_replay.h:209-212
         assert self._engines, "the replay is filled by a started rela.Context"
+        max_len = None
         if len(self._engines) == 1:
             e, lk = self._engines[0]
             with lk:
@@ -203,12 +232,14 @@ class RNNPrioritizedReplay:
                     if e.n_prefetched() == 0:
                         e.prefetch(batchsize)
                     parts = [e.take()]
+                    self._prefetch_b = int(batchsize)
                     batchsize = int(parts[0]["seq_len"].numel())   # a batch drawn before a change of batchsize keeps its size
-                    while e.n_prefetched() < min(self.prefetch, 3):
-                        e.prefetch(batchsize)
+                    max_len = e.last_max_len() if hasattr(e, "last_max_len") else None
                 else:
                     parts = [e.sample(batchsize)]
+                    max_len = e.last_max_len() if hasattr(e, "last_max_len") else None
             self._last.append((e, lk, batchsize))
+            self._top_up()
         else:
             parts = self._sample_shards(batchsize)
         dev = torch.device(device)
@@ -216,6 +247,7 @@ class RNNPrioritizedReplay:
         obs = {k: cat(k, 1) for k in ("priv_s", "legal_move", "eps", "own_hand")}
         action = {k: cat(k, 1) for k in ("a", "greedy_a")}
         batch = RNNTransition(obs, action, cat("reward", 1), cat("terminal", 1), cat("bootstrap", 1), cat("seq_len", 0))
+        batch.max_seq_len = max_len   # longest episode of the batch, known to the sampler: saves the learner a .max().item() round trip
         weight = cat("weight", 0)
         if len(self._engines) > 1:
             weight = weight / weight.max()

@@ -206,7 +206,8 @@ class DeviceTrainer:
         assert t["priv_s"].numel() == self.seq_len * B * self.num_player * self.in_dim, "batch layout does not match (vdn / num_player)"
         weight = weight.detach().to(self.device, torch.float32).contiguous()
         if t_eff is None:
-            t_eff = int(t["seq_len"].max().item()) if self.skip_padding else self.seq_len
+            known = getattr(batch, "max_seq_len", None)     # the device replay's sampler knows it (rela facade)
+            t_eff = self.seq_len if not self.skip_padding else (int(known) if known else int(t["seq_len"].max().item()))
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         if B <= self.micro_batch:
             hb = self._hb_batch(t, weight)
@@ -232,6 +233,10 @@ class DeviceTrainer:
     def update(self, batch, weight, pred_weight=0.0, t_eff=None):
         prio = self.backward(batch, weight, pred_weight, t_eff)
         self.optim_step()
+        # the update is queued, the GPU busy for milliseconds: the moment to queue the sampler's next draws (selfplay.py --prefetch)
+        from .rela import RNNPrioritizedReplay
+
+        RNNPrioritizedReplay.top_up_all()
         return prio
 
     def stats(self, wait=True):
