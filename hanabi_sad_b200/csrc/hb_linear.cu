@@ -182,27 +182,33 @@ static int gemm_nt_impl(int device, const float* A, int64_t lda, int transA, con
   const int Kp = kc_part * split * hbg::BK;
   const bool direct = split == 1 && Mp == M && Np == N && ldc == N;   // the template can write the caller's C itself
   int rc = 0;
+  // Grow-only scratch, grown GEOMETRICALLY: a learner's batches get longer as its agent learns to survive (t_eff 10 -> 80 steps),
+  // and every regrowth is a cudaFree + cudaMalloc, i.e. a device-wide synchronisation in the middle of an update.
+  auto roomy = [](size_t need, size_t cap) { return need > cap + cap / 2 ? need : cap + cap / 2; };
   if (S.a_cap < (size_t)Mp * Kp) {   // hi and lo grow together (cudaFree synchronises the device: nothing queued still reads them)
     size_t c1 = 0, c2 = 0;
+    const size_t want = roomy((size_t)Mp * Kp, S.a_cap);
     if (S.a_hi) cudaFree(S.a_hi);
     if (S.a_lo) cudaFree(S.a_lo);
     S.a_hi = S.a_lo = nullptr; S.a_cap = 0;
-    rc |= grow((void**)&S.a_hi, &c1, (size_t)Mp * Kp, sizeof(__nv_bfloat16));
-    rc |= grow((void**)&S.a_lo, &c2, (size_t)Mp * Kp, sizeof(__nv_bfloat16));
+    rc |= grow((void**)&S.a_hi, &c1, want, sizeof(__nv_bfloat16));
+    rc |= grow((void**)&S.a_lo, &c2, want, sizeof(__nv_bfloat16));
     if (rc) return rc;
-    S.a_cap = (size_t)Mp * Kp;
+    S.a_cap = want;
+    S.last_a = nullptr;
   }
   if (S.b_cap < (size_t)Np * Kp) {
     size_t c1 = 0, c2 = 0;
+    const size_t want = roomy((size_t)Np * Kp, S.b_cap);
     if (S.b_hi) cudaFree(S.b_hi);
     if (S.b_lo) cudaFree(S.b_lo);
     S.b_hi = S.b_lo = nullptr; S.b_cap = 0;
-    rc |= grow((void**)&S.b_hi, &c1, (size_t)Np * Kp, sizeof(__nv_bfloat16));
-    rc |= grow((void**)&S.b_lo, &c2, (size_t)Np * Kp, sizeof(__nv_bfloat16));
+    rc |= grow((void**)&S.b_hi, &c1, want, sizeof(__nv_bfloat16));
+    rc |= grow((void**)&S.b_lo, &c2, want, sizeof(__nv_bfloat16));
     if (rc) return rc;
-    S.b_cap = (size_t)Np * Kp;
+    S.b_cap = want;
   }
-  if (!direct) { rc = grow((void**)&S.c_part, &S.c_cap, (size_t)split * Mp * Np, sizeof(float)); if (rc) return rc; }
+  if (!direct && S.c_cap < (size_t)split * Mp * Np) { rc = grow((void**)&S.c_part, &S.c_cap, roomy((size_t)split * Mp * Np, S.c_cap), sizeof(float)); if (rc) return rc; }
   const long long na = (long long)Mp * Kp, nb = (long long)Np * Kp;
   if (same_a) {   // the split buffers still hold exactly this operand (no other call of this GPU's GEMM in between)
     if (S.last_a != A || S.last_lda != lda || S.last_m != M || S.last_k != K || S.last_kp != Kp || S.last_ta != transA) {

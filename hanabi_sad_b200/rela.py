@@ -239,7 +239,10 @@ class RNNPrioritizedReplay:
                     parts = [e.sample(batchsize)]
                     max_len = e.last_max_len() if hasattr(e, "last_max_len") else None
             self._last.append((e, lk, batchsize))
-            self._top_up()
+            # queue further draws here only when none is left: with the device trainer the queue is refilled right after the
+            # update's kernels are queued (top_up_all), when the GPU is busy -- here it would idle meanwhile
+            if self.prefetch > 0 and hasattr(e, "n_prefetched") and e.n_prefetched() == 0:
+                self._top_up()
         else:
             parts = self._sample_shards(batchsize)
         dev = torch.device(device)

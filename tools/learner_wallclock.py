@@ -96,10 +96,13 @@ def run(arm, a, out_dir):
     # the reference's own Stopwatch buckets of the LAST epoch (selfplay.py:216-241): where a loop iteration goes
     buckets = {}
     for blk in out.split("@@@Time")[1:]:
-        buckets = {m[0].strip(): int(m[1]) for m in re.findall(r"\t([^:\n]+): (\d+) MS", blk.split("@@@total")[0])}
+        found = re.findall(r"\t([^:\n]+): (\d+) MS, ([0-9.]+)%", blk.split("@@@total")[0])
+        buckets = {m[0].strip(): int(m[1]) for m in found}
         tot = re.search(r"@@@total time per iter: ([0-9.]+) ms", blk)
         if tot:
             buckets["total_ms_per_iter"] = float(tot.group(1))
+            # the Stopwatch prints whole milliseconds but exact percentages: the buckets to 0.01 ms
+            buckets["ms_by_share"] = {m[0].strip(): round(float(m[2]) / 100.0 * float(tot.group(1)), 3) for m in found}
     return {"arm": arm, "returncode": p.returncode, "wall_s": wall, "burn_in_wait_s": burn, "epochs": len(speeds),
             "train_samples_per_s": [s[0] for s in speeds], "act_per_s": [s[1] for s in speeds], "buffer_add_per_s": [s[2] for s in speeds],
             "eval_scores": scores, "stopwatch_ms_last_epoch": buckets,
