@@ -948,6 +948,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
   if (nets < 1 || nets > 2) { hb_set_error("hb_lstm_forward: nets must be 1 or 2"); return -1; }
   for (int n = 0; n < nets; ++n) {
     if (!x[n] || !y[n]) { hb_set_error("hb_lstm_forward: null sequence pointer"); return -1; }
+    if (reinterpret_cast<uintptr_t>(y[n]) & 31) { hb_set_error("hb_lstm_forward: y[%d] must be 32-byte aligned (the kernels write rows with 32-byte stores)", n); return -1; }
     for (int l = 0; l < 2; ++l)
       if (!w[n].w_ih[l] || !w[n].w_hh[l] || !w[n].b_ih[l] || !w[n].b_hh[l]) { hb_set_error("hb_lstm_forward: null weight pointer"); return -1; }
   }
@@ -1109,6 +1110,7 @@ int hb_lstm_forward(hb_lstm* L, int T, int rows, int nets, const float* const* x
 int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads* g, void* stream) {
   if (!L || !dy || !g) { hb_set_error("hb_lstm_backward: null argument"); return -1; }
   if (!L->saved) { hb_set_error("hb_lstm_backward: no saved forward (call hb_lstm_forward with save != 0 first)"); return -1; }
+  if (reinterpret_cast<uintptr_t>(dy) & 31) { hb_set_error("hb_lstm_backward: dy must be 32-byte aligned (the kernels read rows with 32-byte loads)"); return -1; }
   for (int l = 0; l < 2; ++l)
     if (!g->dw_ih[l] || !g->dw_hh[l] || !g->db_ih[l] || !g->db_hh[l]) { hb_set_error("hb_lstm_backward: null gradient pointer"); return -1; }
   HB_CUDA(cudaSetDevice(L->device));

@@ -291,7 +291,8 @@ void hb_lstm_destroy(hb_lstm* l);
 
 /* nn.LSTM.forward for `nets` (1 or 2) independent networks in one pass -- the reference calls online_net and target_net
  * on the same batch back to back (r2d2.py:398-401).  x[n], y[n]: device float [T, rows, 512] (input / top-layer output
- * sequence of network n), w[n] its parameters.  save != 0 keeps network 0's activations for hb_lstm_backward.
+ * sequence of network n), w[n] its parameters; y[n] (and dy of hb_lstm_backward) 32-byte aligned, as any cudaMalloc / torch
+ * allocation is.  save != 0 keeps network 0's activations for hb_lstm_backward.
  * `stream`: cudaStream_t the work is queued on (e.g. torch's current stream).  Asynchronous: returns once everything is
  * queued; buffers must stay valid until the stream reaches that point (stream-ordered allocators do that by themselves).
  * A device-side failure (a spin guard of the persistent kernels) is reported by the NEXT hb_lstm_* call or hb_lstm_sync. */
