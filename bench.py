@@ -472,7 +472,10 @@ def learner_extra(torch, dist, args, world, rank, local):
     learner, fed by a device replay the actors filled; at N >= 2 each update all-reduces the flat gradient bucket."""
     from hanabi_sad_b200 import trainer
 
-    return trainer.bench_update(device=local, world=world, dist=dist if world > 1 else None, seconds=3.0)
+    out = trainer.bench_update(device=local, world=world, dist=dist if world > 1 else None, seconds=3.0)
+    # tools/dev.sh's learner (IQL, 128 LSTM rows): the configuration of north_star's wall-clock target
+    out["iql_b128"] = trainer.bench_update(device=local, world=world, dist=dist if world > 1 else None, seconds=2.0, vdn=False)
+    return out
 
 
 def random_weights(F, A, H, seed):

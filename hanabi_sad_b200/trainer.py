@@ -272,17 +272,17 @@ class DeviceTrainer:
         return t_eff
 
 
-def bench_update(device=0, world=1, dist=None, seconds=3.0, batchsize=128, games=1024, fill_ticks=400):
-    """Measurement helper of bench.py's `extra.learner`: VDN B = 128 (the C2 / sad.sh learner shape: 256 LSTM rows, T = 80)
-    fed from a device replay that random-init actors filled.  Times whole updates (sample + loss + backward + clip + Adam +
+def bench_update(device=0, world=1, dist=None, seconds=3.0, batchsize=128, games=1024, fill_ticks=400, vdn=True):
+    """Measurement helper of bench.py's `extra.learner` / `extra.learner_iql`: VDN B = 128 (the C2 / sad.sh learner shape: 256
+    LSTM rows, T = 80) or IQL B = 128 (tools/dev.sh, the wall-clock configuration: 128 rows) fed from a device replay that random-init actors filled.  Times whole updates (sample + loss + backward + clip + Adam +
     priority write-back) with CUDA events on torch's stream: once with all 80 steps computed (what the reference's learner
     does on every batch) and once with the padding beyond the longest episode skipped.  With `dist` the flat gradient bucket
     is all-reduced (sum, then 1/world) between backward and the optimiser step, as tools/train_multi_gpu.py does."""
     from .engine import Engine
 
     eps = [0.1 ** (1 + i / 79.0 * 7) for i in range(80)]
-    eng = Engine(games, 2, 5, 0, 80, True, False, eps, seed=7 + device, device=device, replay_capacity=8192)
-    tr = DeviceTrainer(eng.F, eng.A, eng.H, 2, True, device=device, max_batch=batchsize)
+    eng = Engine(games, 2, 5, 0, 80, True, False, eps, seed=7 + device, device=device, replay_capacity=8192, vdn=vdn)
+    tr = DeviceTrainer(eng.F, eng.A, eng.H, 2, vdn, device=device, max_batch=batchsize)
     g = torch.Generator(device="cpu").manual_seed(1)
     shapes = param_shapes(eng.F, eng.A, eng.H)
     sd = {}
@@ -293,7 +293,7 @@ def bench_update(device=0, world=1, dist=None, seconds=3.0, batchsize=128, games
     tr.push_weights(eng)
     eng.rollout(fill_ticks)
     eng.sync()
-    out = {"method": "vdn", "batchsize": batchsize, "lstm_rows": batchsize * 2, "seq_len": 80, "replay_entries": eng.counters()[0],
+    out = {"method": "vdn" if vdn else "iql", "batchsize": batchsize, "lstm_rows": batchsize * (2 if vdn else 1), "seq_len": 80, "replay_entries": eng.counters()[0],
            "sampler": "prefetch: batch k + 1 is drawn on the engine stream while update k runs (selfplay.py --prefetch)"}
     n_par = tr.total
     for tag, full in (("t80", True), ("skip_padding", False)):
