@@ -19,12 +19,16 @@
 #include "hb_policy.h"
 #include "hb_replay.h"
 
-#ifndef HB_TICK_THREADS
-#define HB_TICK_THREADS 32   // one warp per game: no cross-warp barrier behind thread 0's serial sections, 32 CTAs / SM = one wave at 4096 games (96 threads: 54 us per tick, 64: 57, 32: 46)
+// Threads per game (= per CTA).  2-3 players: ONE WARP -- no cross-warp barrier behind thread 0's serial sections, 32 CTAs / SM =
+// one wave at 4096 games (2 players, 4096 games: 96 threads 54 us per tick, 64: 57, 32: 46).  4-5 players have 4-5 observers' rows
+// and 4-6x the belief entries per game and far fewer games per GPU (1024 at BASELINE's C4): three warps (5 players, 1024 games:
+// 32 threads 47 us, 64: 38, 96: 37, 128: 35; 4 players 43 -> 36 us; 3 players gain nothing).  HB_TICK_THREADS overrides both.
+#ifdef HB_TICK_THREADS
+#define HB_TICK_NT(P_) HB_TICK_THREADS
+#else
+#define HB_TICK_NT(P_) ((P_) >= 4 ? 96 : 32)
 #endif
-#ifndef HB_TICK_MIN_CTAS
-#define HB_TICK_MIN_CTAS (HB_TICK_THREADS >= 96 ? 16 : (HB_TICK_THREADS >= 64 ? 24 : 32))
-#endif
+#define HB_TICK_MIN_CTAS(NT_) ((NT_) >= 96 ? 16 : ((NT_) >= 64 ? 24 : 32))
 
 struct HbTickArgs {
   HbGame* games;
@@ -152,14 +156,14 @@ __device__ __forceinline__ void hb_cta_finalize_episode(const HbRing& R, int g, 
 // 96 threads, 16 resident CTAs / SM (40 registers): the kernel is latency bound -- all threads wait at barriers while
 // thread 0 applies the move / starts an episode -- so what helps is more CTAs in flight per SM, not more threads per CTA
 // (7 CTAs of 128 threads: 82 us per 4096-game tick; 12: 71 us; with the fast encoder 58 us, as 16 x 96 threads 54 us).
-template <int TP, int TH, int TSAD>
-__global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(const __grid_constant__ HbTickArgs A) {
+template <int TP, int TH, int TSAD, int NT>
+__global__ void __launch_bounds__(NT, HB_TICK_MIN_CTAS(NT)) hb_k_tick(const __grid_constant__ HbTickArgs A) {
   __shared__ HbGame s;
   __shared__ HbEncTables tab;
   __shared__ HbFastEnc enc;
   __shared__ __align__(16) uint8_t deck[HB_DECK_STRIDE];
   __shared__ int sh_did_step, sh_t, sh_term, sh_reset, sh_slot, sh_drop, sh_retry, sh_committed;
-  __shared__ float red[2 * ((HB_TICK_THREADS + 31) / 32)];
+  __shared__ float red[2 * ((NT + 31) / 32)];
   __shared__ uint32_t sh_draws[4 * HB_EPISODE_DRAW_BLOCKS];
   const int g = blockIdx.x, tid = threadIdx.x;
   HbEnvCfg cfg = A.cfg;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(c
     // R2D2Agent.act's tail for this game's agents (hb_head.cuh), deferred from the previous tick's forward: one launch and
     // one round trip of (a, greedy_a, Q) through a separate kernel less per tick.  The values it writes are read below by
     // other threads of this CTA: L2 loads (__ldcg) after the barrier.
-    for (int p = tid >> 5; p < P; p += (HB_TICK_THREADS + 31) / 32) hb_head_row(A.head, g * P + p, tid & 31);
+    for (int p = tid >> 5; p < P; p += (NT + 31) / 32) hb_head_row(A.head, g * P + p, tid & 31);
   }
   __syncthreads();
   if (tid == 0) {
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(HB_TICK_THREADS, HB_TICK_MIN_CTAS) hb_k_tick(c
   // the board record.  It is materialised on demand by hb_refresh_obs when the host asks for it (hb_env_observe*).
   hb_cta_write_obs(s, tab, cfg, nullptr, O.legal_move + (size_t)g * P * geo.A, nullptr, O.eps + (size_t)g * P, A.eps_list);
   if (O.s_hi != nullptr) hb_cta_write_operand_fast(s, tab, cfg, enc, O.s_hi + (size_t)g * P * O.KS, O.s_lo + (size_t)g * P * O.KS, O.KS);
-  constexpr int RT0 = HB_TICK_THREADS >= 64 ? 32 : 0;   // the threads that copy the record into the ring (a warp of its own if there is one)
+  constexpr int RT0 = NT >= 64 ? 32 : 0;   // the threads that copy the record into the ring (a warp of its own if there is one)
   if (tid >= RT0 && tid < RT0 + 16 && to_ring)   // the replay keeps the record, not the observation (re-encoded by hb_k_replay_gather)
     reinterpret_cast<uint4*>(R.states + (size_t)slot * R.T + t_obs)[tid - RT0] = reinterpret_cast<const uint4*>(&s)[tid - RT0];
   if (tid < 16) reinterpret_cast<uint4*>(A.games + g)[tid] = reinterpret_cast<const uint4*>(&s)[tid];
@@ -287,11 +291,11 @@ int hb_launch_tick(hb_engine* e, int do_step, int do_reset, int clear_flags) {
   {
     HbProfScope ps(e, HB_PROF_TICK);
     const int key = e->P * 100 + e->H * 10 + (e->env.g.sad ? 1 : 0);
-#define HB_TICK_CASE(P_, H_, S_) case P_ * 100 + H_ * 10 + S_: hb_k_tick<P_, H_, S_><<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a); break
+#define HB_TICK_CASE(P_, H_, S_) case P_ * 100 + H_ * 10 + S_: hb_k_tick<P_, H_, S_, HB_TICK_NT(P_)><<<e->G, HB_TICK_NT(P_), 0, e->stream>>>(a); break
     switch (key) {
       HB_TICK_CASE(2, 5, 1); HB_TICK_CASE(2, 5, 0); HB_TICK_CASE(3, 5, 1); HB_TICK_CASE(3, 5, 0);
       HB_TICK_CASE(4, 4, 1); HB_TICK_CASE(4, 4, 0); HB_TICK_CASE(5, 4, 1); HB_TICK_CASE(5, 4, 0);
-      default: hb_k_tick<0, 0, 0><<<e->G, HB_TICK_THREADS, 0, e->stream>>>(a); break;
+      default: hb_k_tick<0, 0, 0, HB_TICK_NT(2)><<<e->G, HB_TICK_NT(2), 0, e->stream>>>(a); break;
     }
 #undef HB_TICK_CASE
   }
