@@ -76,6 +76,9 @@ class FakeEngine:
                 "reward": torch.zeros(T, b), "bootstrap": torch.ones(T, b), "terminal": torch.zeros(T, b, dtype=torch.bool), "seq_len": torch.full((b,), 7.0),
                 "weight": weight, "ids": torch.zeros(b, dtype=torch.int32)}
 
+    def last_max_len(self):
+        return 7                              # hb_replay_last_max_len: every fake episode is 7 steps long
+
     def update_priority(self, p):
         self.updated += 1
         if self.fifo_taken:                   # hb_replay_update_priority applies to the OLDEST outstanding batch
@@ -187,6 +190,7 @@ def test_selfplay_call_sequence(ref_modules, method):
         assert time.time() - t0 < 20, "foreground calls are starved by the rollout driver"
         time.sleep(0.01)
     batch, weight = replay.sample(8, "cpu")
+    assert batch.max_seq_len == 7        # the sampler hands the longest episode's length to the learner (padding skip without a sync)
     assert batch.obs["priv_s"].shape == ((80, 8, 2, 838) if method == "vdn" else (80, 8, 838)) and batch.h0 == {} and weight.shape == (8,)
     o1 = batch.obs
     o1["priv_s"] = None  # pybind semantics: every read of .obs is a fresh dict (r2d2.py flat_4d mutates its copy)
