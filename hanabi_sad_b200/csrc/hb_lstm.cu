@@ -1249,7 +1249,13 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
   if (!dw_wave) {
     for (int l = 0; l < 2; ++l)
       hbl::lstm_transpose_pair<<<dim3(hbl::G4 / 64, (unsigned)(N / 64)), 256, 0, st>>>(L->dg_hi[l], L->dg_lo[l], hbl::G4, L->dgT_hi[l], L->dgT_lo[l], (long long)N);
-    L->launches += 2;
+    // the bias sums need nothing but the transposed dgates: on the side stream, under the two GEMMs below (they stream 2 x 84 MB
+    // at 256 rows while the GEMMs keep the tensor cores busy); joined at the end
+    HB_CUDA(cudaEventRecord(L->wev[5], st));
+    HB_CUDA(cudaStreamWaitEvent(L->ws[3], L->wev[5], 0));
+    for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, L->ws[3]>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
+    HB_CUDA(cudaEventRecord(L->wev[4], L->ws[3]));
+    L->launches += 4;
   }
   if (dx) {   // gradient w.r.t. the input sequence of layer 0
     float* dst = R_pad == rows ? dx : L->dx_pad;
@@ -1270,11 +1276,9 @@ int hb_lstm_backward(hb_lstm* L, const float* dy, float* dx, const hb_lstm_grads
     if (rc) return rc;
     float* dsts[4] = {g->dw_ih[0], g->dw_hh[0], g->dw_ih[1], g->dw_hh[1]};
     for (int i = 0; i < 4; ++i) hbl::lstm_unperm_rows<<<hbl::G4, 128, 0, st>>>(L->dwp + i * WN, dsts[i]);
-    for (int l = 0; l < 2; ++l) hbl::lstm_bias_grad<<<hbl::G4, 256, 0, st>>>(L->dgT_hi[l], L->dgT_lo[l], (long long)N, g->db_ih[l], g->db_hh[l]);
-    L->launches += 6;
-  } else {
-    HB_CUDA(cudaStreamWaitEvent(st, L->wev[4], 0));   // the weight gradients of the wavefront's fourth stream
+    L->launches += 4;
   }
+  HB_CUDA(cudaStreamWaitEvent(st, L->wev[4], 0));   // the side stream: bias sums (and, in the wavefront, the weight gradients)
   HB_CUDA(cudaGetLastError());
   hbl_dump_trace(L, st, 2, T, "bwd");
   return hbl_finish_call(L, st);
