@@ -471,12 +471,13 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         HBL_STAMP(tr, t, 1);
         if (!dead) {
           // the 32 CTAs of the row block ADDED their partials into one accumulator (bulk reductions at L2, see the drain below),
-          // laid out [8 pieces][64 columns][128 rows]: 16 coalesced reads, then clear the slice for the step after next
-          float* accp = P.part + ((size_t)((t + 1) & 1) * P.MB + dom) * (size_t)(BM * HIDN) + (size_t)(unit / 64) * (64 * BM) + (size_t)(unit % 64) * BM + r;
+          // laid out [8 pieces][4 warps][64 columns][32 rows]: 16 coalesced reads, then clear the slice for the step after next
+          float* accp = P.part + ((size_t)((t + 1) & 1) * P.MB + dom) * (size_t)(BM * HIDN) + (size_t)(unit / 64) * (64 * BM) + (size_t)q * (64 * 32) +
+                        (size_t)(unit % 64) * 32 + lane;
 #pragma unroll
           for (int i = 0; i < UPC; ++i) {
-            dh[i] += __ldcg(accp + i * BM);
-            __stcg(accp + i * BM, 0.f);
+            dh[i] += __ldcg(accp + i * 32);
+            __stcg(accp + i * 32, 0.f);
           }
         }
       }
@@ -523,11 +524,12 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
         }
       }
       if (t == 0) break;
-      // Drain: the [128 x 512] fp32 partial of dh_{t-1} leaves TMEM in eight [64 columns][128 rows] pieces; each is staged in
-      // shared memory (conflict-free: consecutive threads = consecutive rows) and ADDED into the row block's accumulator by ONE
-      // bulk reduction (cp.reduce.async.bulk .add.f32: the 32-way sum happens at L2, the SM issues 8 instructions per step
-      // instead of 16 384 vector atomics).  Two staging buffers: piece p+2 waits until the reduction of piece p has read its.
-      float* dst = P.part + ((size_t)(t & 1) * P.MB + dom) * (size_t)(BM * HIDN);
+      // Drain: the [128 x 512] fp32 partial of dh_{t-1} leaves TMEM in eight 64-column pieces.  Every WARP runs its own pipeline
+      // over its 32 rows: stage [64 columns][32 rows] in shared memory (conflict-free: consecutive lanes = consecutive rows),
+      // ADD it into the row block's accumulator with one bulk reduction (cp.reduce.async.bulk .add.f32: the 32-way sum happens at
+      // L2, a warp issues 8 instructions per step instead of 4096 vector atomics), two staging buffers per warp -- piece p+2
+      // waits until the reduction of piece p has read its buffer.  No CTA barrier and no single issuing thread inside the drain.
+      float* dst = P.part + ((size_t)(t & 1) * P.MB + dom) * (size_t)(BM * HIDN) + (size_t)q * (64 * 32);
 #pragma unroll 1
       for (int qt = 0; qt < 4; ++qt) {
         wait_bar(bar_tfull + 8 * qt, (uint32_t)(T - 1 - t) & 1u, ef, dead);
@@ -543,29 +545,33 @@ __global__ void __launch_bounds__(192, 1) lstm_bwd_kernel(const BwdParams* __res
             tmem_wait_ld();
           }
           if (pc >= 2) {
-            if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
           }
-          float* sb = stage_ptr + buf * (BWD_STAGE / 4) + r;
+          const uint32_t sb_off = (uint32_t)(q * 2 + buf) * (64 * 32 * 4);
+          float* sb = stage_ptr + sb_off / 4 + lane;
 #pragma unroll
-          for (int i = 0; i < 64; ++i) sb[i * BM] = dead ? 0.f : __uint_as_float(v[i]);
+          for (int i = 0; i < 64; ++i) sb[i * 32] = dead ? 0.f : __uint_as_float(v[i]);
           fence_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (threadIdx.x == 64) {
+          __syncwarp();
+          if (lane == 0) {
             asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst + (size_t)pc * (64 * BM)),
-                         "r"(stage_base + (uint32_t)buf * BWD_STAGE), "r"(BWD_STAGE)
+                         "r"(stage_base + sb_off), "r"(64 * 32 * 4)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
         if (qt & 1) HBL_STAMP(tr, t, 3 + qt);
       }
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's eight reductions have been performed
+        fence_async_global();
+      }
       tc_fence_before();
       fence_async_global();   // the dgate rows of this step are read through TMA by the layer wavefront's GEMM while this kernel runs
       asm volatile("bar.sync 1, 128;" ::: "memory");
       HBL_STAMP(tr, t, 7);
       if (threadIdx.x == 64) {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all eight reductions have been performed
         HBL_STAMP(tr, t, 8);
         fence_async_global();
         red_release_add(ctr, 1u);
