@@ -6,22 +6,31 @@
 //   input projection   GX = X W_ih^T + (b_ih + b_hh) over ALL steps at once      tcgen05 GEMM template (hb_gemm.cuh, EPI_F32)
 //   recurrence         ONE persistent kernel per layer (lstm_fwd_kernel): every CTA keeps a 64-column slice
 //                      ([i|f|g|o] x 16 hidden units) of W_hh resident in shared memory as bf16 hi/lo, per step pulls
-//                      h_{t-1} (bf16 hi/lo, TMA) of its 128-row block, runs 96 tcgen05.mma (bf16x3, fp32 accumulate in
-//                      TMEM), applies the cell update with c kept in registers across all T steps, and publishes its
-//                      slice of h_t; the 32 CTAs of a row block meet at a global-memory step counter.  Online and target
-//                      network run in the same launch.
+//                      h_{t-1} (bf16 hi/lo, TMA, multicast inside 4-CTA clusters) of its 128-row block, runs 64 tcgen05.mma
+//                      (bf16x3 in two instructions per K-step: h_hi x [W_hi | W_lo] as one N = 128 tile + h_lo x W_hi, fp32
+//                      accumulate in TMEM), applies the cell update with c kept in registers across all T steps, and
+//                      publishes its slice of h_t; the 32 CTAs of a row block meet at a global-memory step counter.
+//                      Online and target network run in the same launch.
 //   backward           lstm_bwd_kernel, same residency idea with the contraction split over K: a CTA turns dh_t of its 16
 //                      units into its 64 dgate columns, multiplies them (as the A operand, written to swizzled shared
 //                      memory) with its resident 64 x 512 slice of W_hh and ADDS its [128 x 512] partial of dh_{t-1} into
-//                      the row block's accumulator with red.global.add.v4.f32 (the 32-way sum happens at L2); after the
-//                      step barrier a consumer reads its 64 bytes and clears them.
+//                      the row block's accumulator with bulk reductions (cp.reduce.async.bulk .add.f32 from shared-memory
+//                      staging, one pipeline per warp: the 32-way sum happens at L2); after the step barrier a consumer
+//                      reads its 64 bytes and clears them.
+//   layer wavefront    the two layers' recurrences run side by side on internal streams, one 8-step time chunk apart, with
+//                      the chunk's input projection / dX GEMM on the SMs they leave free; with one row block the weight
+//                      gradients are accumulated chunk by chunk on a fourth stream as well (hb_lstm_forward / _backward).
 //   dX, dW, db         dX = dG W_ih and the four weight gradients dG^T X / dG^T H_{t-1} as GEMM-template launches (the four
-//                      as problems of ONE launch); the recurrence kernels leave h and dG row-major as bf16 hi/lo, a tiled
-//                      transpose (lstm_transpose_pair) adds the other orientation after each recurrence; db by a reduction.
+//                      as problems of ONE launch, or per chunk inside the wavefront); the recurrence kernels leave h and dG
+//                      row-major as bf16 hi/lo, a tiled transpose (lstm_transpose_pair) adds the other orientation; db by a
+//                      reduction.
+//   row accesses       a lane of the cell updates owns a ROW: every global access is 32 bytes wide (ld/st.global.v8), i.e. a
+//                      whole sector per lane -- 16-byte accesses cost twice the LSU sector transactions.
 //
-// Measured (B200, T = 80, rows = 256): forward recurrence 10 us / step for both networks, backward 19 us /
-// step -- bound by the per-step dependency chain through L2 (publish -> counter -> TMA ring -> MMA -> TMEM), not by the
-// tensor pipe (13-17 % busy); whole LSTM part of an update 6.3 ms vs cuDNN 8.4 ms (TF32) / 18.1 ms (fp32).
+// Measured (B200, T = 80): forward recurrence 7.0 us / step, backward 12.2 us / step stand-alone (round 1: 10.3 /
+// 19) -- bound by moving 256 KB per SM and step (h_{t-1} in, the dh partial out through L2 reductions) and the per-step
+// handshake, not by the tensor pipe; whole update of the learner 3.0 ms (IQL, 128 rows) / 4.2 ms (VDN, 256 rows), of which
+// the recurrences are 1.9 / 2.4 ms.
 //
 // Arithmetic: fp32-class everywhere (bf16x3 products accumulated in fp32, pointwise math in fp32); parity target: CPU fp32
 // torch.nn.LSTM forward / autograd within 1e-4 (tests/test_lstm_train_parity.py).
