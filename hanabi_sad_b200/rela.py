@@ -165,8 +165,9 @@ class RNNPrioritizedReplay:
         for r in list(cls._live or ()):
             try:
                 r._top_up()
-            except Exception:      # a replay that cannot be topped up now (too few entries yet) is simply drawn from later
-                pass
+            except RuntimeError as ex:   # a replay that holds too few entries yet is simply drawn from later; anything else is real
+                if "fewer than the batch size" not in str(ex):
+                    raise
 
     def _attach(self, engine, lock):
         self._engines.append((engine, lock))
