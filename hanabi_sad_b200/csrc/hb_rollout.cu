@@ -28,7 +28,7 @@
 #else
 #define HB_TICK_NT(P_) ((P_) >= 4 ? 96 : 32)
 #endif
-#define HB_TICK_MIN_CTAS(NT_) ((NT_) >= 96 ? 16 : ((NT_) >= 64 ? 24 : 32))
+#define HB_TICK_MIN_CTAS(NT_) ((NT_) >= 96 ? 10 : ((NT_) >= 64 ? 24 : 32))   // 96 threads: 68 registers, no spills (16 CTAs / SM left 40)
 
 struct HbTickArgs {
   HbGame* games;
